@@ -1,0 +1,235 @@
+/*
+ * madrigal_b200.h — C ABI of the B200-native (sm_100a) drug-pair scoring path.
+ *
+ * This is the drop-in boundary for ONE path of biopharmaai/Madrigal (the reference):
+ *
+ *     modality tokens -> fusion transformer -> fused drug embedding z
+ *                     -> per-outcome bilinear decoder  z_A . W_k . z_B^T
+ *                     -> per-outcome rank normalisation
+ *
+ * The reference is pure Python/PyTorch and has no FFI layer; its boundary for this path is a set of
+ * Python call signatures.  Each entry point below names the reference symbol (file:line under the
+ * reference root) whose arithmetic it replaces.  madrigal_b200/*.py holds Python modules with the reference's
+ * class names / constructor arguments / state_dict keys that bind these entry points through ctypes; the stub a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns every buffer, the library
+ *     never allocates, frees or retains device memory beyond the call;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden synchronisation;
+ *   - return value 0 = success, non-zero = MdgStatus; mdg_last_error() returns a thread-local message;
+ *   - there is NO CPU fallback and NO alternative backend: unsupported shapes fail with MDG_ERR_UNSUPPORTED;
+ *   - row-major ("C") layouts throughout, fp32 inputs exactly as the reference holds them.
+ */
+#ifndef MADRIGAL_B200_H_
+#define MADRIGAL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDG_ABI_VERSION 1
+
+typedef enum MdgStatus {
+  MDG_OK = 0,
+  MDG_ERR_INVALID_ARGUMENT = 1, /* NULL pointer, negative size, inconsistent shapes */
+  MDG_ERR_UNSUPPORTED = 2,      /* shape/config outside what the sm_100a kernels implement */
+  MDG_ERR_WORKSPACE = 3,        /* workspace too small */
+  MDG_ERR_CUDA = 4,             /* CUDA runtime/driver error (message in mdg_last_error) */
+  MDG_ERR_NO_DEVICE = 5         /* no sm_100 device visible */
+} MdgStatus;
+
+/* Thread-local, never NULL. */
+const char* mdg_last_error(void);
+int mdg_abi_version(void);
+/* 0 if device `device` (or the current one if <0) is compute capability 10.x, else MDG_ERR_NO_DEVICE. */
+int mdg_check_device(int device);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Bilinear decoder, all pairs  (reference: BilinearDDIScorer.bilinear/forward, madrigal/models/models.py:537-547;
+ *                               caller-side sigmoid, madrigal/evaluate/predict.py:235,358)
+ *
+ *   S[l, i, j] = sum_{a,b} z_rows[i, a] * W[l, a, b] * z_cols[j, b]        l < L, i < Nr, j < Nc
+ *
+ * `W` is the weight AS THE REFERENCE READS IT (through the Symmetric parametrisation if one is registered,
+ * models.py:522-524,922) — i.e. `label_range` slicing is done by the caller by offsetting W and `L`.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+typedef enum MdgPrecision {
+  MDG_PREC_BF16 = 0, /* operands rounded to bf16 once, fp32 accumulation in TMEM (north-star bar: 1e-2)          */
+  MDG_PREC_FP32 = 1  /* bf16x3 split operands (hi*hi + lo*hi + hi*lo), fp32 accumulation (north-star bar: 1e-3) */
+} MdgPrecision;
+
+typedef enum MdgOutMode {
+  MDG_OUT_LOGIT_F32 = 0,   /* out: float   [L, Nr, Nc]  raw logits                                        */
+  MDG_OUT_SIGMOID_F32 = 1, /* out: float   [L, Nr, Nc]  1/(1+exp(-logit))          (predict.py:358)       */
+  MDG_OUT_RANK_U16 = 2     /* out: uint16  [L, Nr, Nc]  searchsorted(table[l], logit, side='right')       */
+} MdgOutMode;
+
+typedef enum MdgPairs {
+  MDG_PAIRS_FULL = 0,     /* every (i, j)                                                                          */
+  MDG_PAIRS_SYMMETRIC = 1 /* z_rows == z_cols only: compute i > j, write [i,j] and [j,i], diagonal = 0 — the shape
+                             of the reference normaliser's output (notebooks/normalize_scores.py:67-70)            */
+} MdgPairs;
+
+/* Prepared per-outcome reference-quantile table for the fused rank epilogue (see mdg_rank_table_build). */
+#define MDG_RANK_BUCKET_BITS 13
+#define MDG_RANK_SUB_BITS 4
+#define MDG_RANK_LUT_ENTRIES (1 << MDG_RANK_BUCKET_BITS) /* uint32 entries per outcome (32 KB) */
+#define MDG_RANK_MAX_Q 65535
+
+typedef struct MdgRankTable {
+  const float* thresholds; /* [L, Q] ascending, snapped to the lookup grid (what np.searchsorted is run against) */
+  const uint32_t* lut;     /* [L, MDG_RANK_LUT_ENTRIES]                                                          */
+  const float* affine;     /* [L, 2]  (scale, bias) of the logit -> grid map                                     */
+  int32_t L;
+  int32_t Q;
+} MdgRankTable;
+
+/*
+ * Snap ascending reference quantiles onto the epilogue's lookup grid and build the lookup structure.
+ *   quantiles      [L, Q] fp32, ascending per row (e.g. order statistics of the strict-lower-triangle logits of a
+ *                  reference panel — the distribution notebooks/normalize_scores.py:36-60 ranks against)
+ *   thresholds_out [L, Q] fp32: the snapped table.  |thresholds_out - quantiles| <= ~2 grid cells
+ *                  (cell = 1.02*(q_max-q_min)/2^17), strictly ascending wherever fp32 allows.
+ *   lut_out        [L, MDG_RANK_LUT_ENTRIES] uint32, affine_out [L, 2] fp32.
+ * Contract: for every finite fp32 x, the fused epilogue's rank for outcome l equals
+ *           np.searchsorted(thresholds_out[l], x, side='right') bit for bit.
+ */
+int mdg_rank_table_build(const float* quantiles, int32_t L, int32_t Q, float* thresholds_out, uint32_t* lut_out,
+                         float* affine_out, void* stream);
+
+/* Stand-alone lookup of already materialised logits through a prepared table (same device function as the fused
+ * epilogue).  logits [L, n] -> ranks [L, n] uint16. */
+int mdg_rank_lookup(const float* logits, int64_t n_per_outcome, const MdgRankTable* table, uint16_t* ranks,
+                    void* stream);
+
+size_t mdg_pair_score_workspace_bytes(int64_t Nr, int64_t Nc, int64_t D, int64_t L, int precision);
+
+/*
+ * All-pairs decoder with fused epilogue.
+ *   z_rows [Nr, D], z_cols [Nc, D], W [L, D, D] fp32.  D in {64, 128, 192, 256}.
+ *   normalize_rows != 0: L2-normalise each z row first (F.normalize, models.py:947-949).
+ *   table: required for MDG_OUT_RANK_U16 (table->L must be >= L; row l of the table is used for W[l]).
+ *   out: [L, Nr, Nc] of the mode's element type.
+ *   workspace: >= mdg_pair_score_workspace_bytes(...) bytes, 256-byte aligned.
+ */
+int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
+                   int64_t L, int precision, int out_mode, int pairs, int normalize_rows,
+                   const MdgRankTable* table, void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernel launches the last successful mdg_pair_score call on this thread enqueued (for bench accounting). */
+int mdg_last_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Exact in-sample normalised rank  (reference: classwise_normalized_rank_3d_numpy + run_slice,
+ *                                   notebooks/normalize_scores.py:36-74)
+ *
+ * For each outcome l: rank the strict lower triangle (i > j) of scores[l] (1-based, ascending), divide by
+ * N(N-1)/2, write the value at [i,j] and [j,i], zero diagonal.  Ties: the reference's order among equal scores
+ * is numpy-introsort-defined; this implementation gives equal scores the rank of the first of them in (i,j)
+ * row-major order + their stable position (== np.argsort(kind='stable')), which satisfies
+ * searchsorted_left + 1 <= rank <= searchsorted_right.
+ *   scores [L, N, N] fp32 -> out [L, N, N] fp32.
+ *   workspace: >= mdg_exact_rank_workspace_bytes(N) bytes.
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t mdg_exact_rank_workspace_bytes(int64_t N);
+int mdg_exact_rank(const float* scores, int64_t L, int64_t N, float* out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fusion encoder  (reference: TransformerFusion.forward, madrigal/models/models.py:401-455, with
+ *                  nn.TransformerEncoderLayer / nn.MultiheadAttention eval-mode semantics of torch 1.13)
+ *
+ * Weight pointers are the reference state_dict tensors, unmodified (fp32, torch [out,in] layout).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+typedef enum MdgAgg { MDG_AGG_CLS = 0, MDG_AGG_XATTN = 1, MDG_AGG_MEAN = 2, MDG_AGG_MAX = 3 } MdgAgg;
+typedef enum MdgActn { MDG_ACTN_RELU = 0, MDG_ACTN_GELU = 1 } MdgActn;
+
+#define MDG_MAX_LAYERS 8
+#define MDG_MAX_TOKENS 32
+
+typedef struct MdgFusionLayer {
+  const float* in_proj_weight;  /* [3*Dl, Dl]  self_attn.in_proj_weight  */
+  const float* in_proj_bias;    /* [3*Dl]                                */
+  const float* out_proj_weight; /* [Dl, Dl]    self_attn.out_proj.weight */
+  const float* out_proj_bias;   /* [Dl]                                  */
+  const float* linear1_weight;  /* [F, Dl]                               */
+  const float* linear1_bias;    /* [F]                                   */
+  const float* linear2_weight;  /* [Dl, F]                               */
+  const float* linear2_bias;    /* [Dl]                                  */
+  const float* norm1_weight;    /* [Dl] */
+  const float* norm1_bias;
+  const float* norm2_weight;
+  const float* norm2_bias;
+} MdgFusionLayer;
+
+typedef struct MdgFusionWeights {
+  const float* embed2latent_weight; /* [Dl, E] */
+  const float* embed2latent_bias;   /* [Dl]    */
+  const float* latent2embed_weight; /* [E, Dl] */
+  const float* latent2embed_bias;   /* [E]     */
+  MdgFusionLayer layers[MDG_MAX_LAYERS];
+  /* x-attn pooling (models.py:370-385, 422-443); NULL unless agg == MDG_AGG_XATTN */
+  const float* x_attn_query;           /* [1, Dl] */
+  const float* x_attn_kv_norm_weight;  /* [Dl] */
+  const float* x_attn_kv_norm_bias;
+  const float* x_attn_query_norm_weight;
+  const float* x_attn_query_norm_bias;
+  const float* x_attn_in_proj_weight;  /* [3*Dl, Dl] */
+  const float* x_attn_in_proj_bias;
+  const float* x_attn_out_proj_weight; /* [Dl, Dl] */
+  const float* x_attn_out_proj_bias;
+} MdgFusionWeights;
+
+typedef struct MdgFusionCfg {
+  int32_t embed_dim;  /* E  */
+  int32_t num_layers; /* <= MDG_MAX_LAYERS */
+  int32_t num_heads;  /* H  */
+  int32_t head_dim;   /* Dl = H * head_dim */
+  int32_t ffn_dim;    /* F  */
+  int32_t actn;       /* MdgActn */
+  int32_t norm_first; /* 0/1 */
+  int32_t agg;        /* MdgAgg */
+  int32_t num_tokens; /* T <= MDG_MAX_TOKENS */
+} MdgFusionCfg;
+
+/*
+ *   tokens        [B, T, E] fp32, position-encoded (what models.py:853 passes as `pos_enc_sequence`)
+ *   key_mask      [B, T] uint8, non-zero = token missing  (`fusion_mask`, True = masked key)
+ *   src_mask      [T, T] uint8 or NULL, non-zero = query row may not attend key column (`src_mask`)
+ *   pool_key_mask [T] uint8 or NULL: x-attn pooling's constant key mask (`x_attn_key_padding_mask`, models.py:382-385)
+ *   z_out         [B, E] fp32
+ *   workspace     >= mdg_fusion_workspace_bytes(cfg, B) bytes
+ */
+size_t mdg_fusion_workspace_bytes(const MdgFusionCfg* cfg, int64_t B);
+int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const float* tokens,
+                      const uint8_t* key_mask, const uint8_t* src_mask, const uint8_t* pool_key_mask, float* z_out,
+                      int64_t B, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Unimodal MLP bypass  (reference: MLPAdaptor as `uni_fuser`, models.py:459-518, 855-865; norm='ln', order='nd')
+ *   x [B, dims[0]] -> y [B, dims[n_linear]];  linear i: weight [dims[i+1], dims[i]], bias [dims[i+1]];
+ *   LayerNorm (ln_weight[i], ln_bias[i], over dims[i]) precedes linear i for 1 <= i < n_linear-1 when non-NULL;
+ *   activation after every linear but the last.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define MDG_MAX_MLP_LINEAR 8
+typedef struct MdgMlp {
+  int32_t n_linear;
+  int32_t dims[MDG_MAX_MLP_LINEAR + 1];
+  int32_t actn; /* MdgActn */
+  const float* weight[MDG_MAX_MLP_LINEAR];
+  const float* bias[MDG_MAX_MLP_LINEAR];
+  const float* ln_weight[MDG_MAX_MLP_LINEAR];
+  const float* ln_bias[MDG_MAX_MLP_LINEAR];
+} MdgMlp;
+int mdg_mlp_forward(const MdgMlp* mlp, const float* x, float* y, int64_t B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MADRIGAL_B200_H_ */

@@ -1,0 +1,8 @@
+"""madrigal_b200 — B200-native (sm_100a) drug-pair scoring path of Madrigal behind the reference's call signatures.
+
+Only the path is here: fusion encoder -> bilinear decoder -> rank normalisation.  Every operator
+calls the C ABI in include/madrigal_b200.h through ctypes; nothing falls back to PyTorch or the CPU.
+"""
+from .decoder import BilinearDDIScorer, RankTable, Symmetric, pair_score  # noqa: F401
+
+__all__ = ["BilinearDDIScorer", "RankTable", "Symmetric", "pair_score"]

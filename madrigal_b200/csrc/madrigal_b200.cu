@@ -1,0 +1,346 @@
+// C-ABI entry points of libmadrigal_b200.so (see include/madrigal_b200.h for the contract and the reference
+// symbols each entry point replaces).  Host-side glue only: argument checking, workspace carving, TMA descriptor
+// encoding and kernel launches on the caller's stream.  No allocation, no synchronisation, no CPU compute path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/madrigal_b200.h"
+#include "exact_rank.cuh"
+#include "fusion_encode.cuh"
+#include "pair_score.cuh"
+#include "rank_table.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_last_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define MDG_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) return fail(MDG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 3-D tensor map over a row-major [batch, rows, inner] array; box = [1, box_rows, box_inner].
+int make_map_3d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* ptr, uint64_t inner,
+                uint64_t rows, uint64_t batch, uint64_t row_stride_elems, uint64_t batch_stride_elems,
+                uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(MDG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {inner, rows, batch};
+  cuuint64_t strides[2] = {row_stride_elems * elem_bytes, batch_stride_elems * elem_bytes};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MDG_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu batch=%llu strides=%llu,%llu box=%u,%u",
+                (int)r, (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)batch,
+                (unsigned long long)strides[0], (unsigned long long)strides[1], box_inner, box_rows);
+  return MDG_OK;
+}
+
+int num_sms() {
+  static int n[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
+  }
+  return n[dev];
+}
+
+struct PairWorkspace {
+  __nv_bfloat16* zr;
+  __nv_bfloat16* zc;
+  __nv_bfloat16* wt;
+  __nv_bfloat16* y;
+  int64_t nr_pad, nc_pad, ka;
+  size_t total;
+};
+
+PairWorkspace carve_pair_ws(void* ws, int64_t Nr, int64_t Nc, int64_t D, int64_t L, int precision) {
+  PairWorkspace w;
+  w.ka = (precision == MDG_PREC_FP32) ? 2 * D : D;
+  w.nr_pad = round_up(Nr, 128);
+  w.nc_pad = round_up(Nc, 128);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 1023) / 1024 * 1024;
+    return o;
+  };
+  size_t o_zr = take(static_cast<size_t>(w.nr_pad) * w.ka * 2);
+  size_t o_zc = take(static_cast<size_t>(w.nc_pad) * w.ka * 2);
+  size_t o_wt = take(static_cast<size_t>(L) * D * w.ka * 2);
+  size_t o_y = take(static_cast<size_t>(L) * w.nr_pad * w.ka * 2);
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  w.zr = reinterpret_cast<__nv_bfloat16*>(b + o_zr);
+  w.zc = reinterpret_cast<__nv_bfloat16*>(b + o_zc);
+  w.wt = reinterpret_cast<__nv_bfloat16*>(b + o_wt);
+  w.y = reinterpret_cast<__nv_bfloat16*>(b + o_y);
+  w.total = off;
+  return w;
+}
+
+int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                       mdg::PairScoreParams& p, cudaStream_t stream) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  MDG_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    MDG_CUDA(cudaFuncSetAttribute(mdg::pair_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  mdg::kPairSmemBytes));
+    attr_set[dev] = true;
+  }
+  // task decomposition: enough tasks for ~8 per CTA, chunks of >= 4 column blocks
+  const int sms = num_sms();
+  p.n_blocks = static_cast<int>((p.cols + mdg::kBN - 1) / mdg::kBN);
+  p.m_blocks = static_cast<int>((p.rows + mdg::kBM * p.msub - 1) / (mdg::kBM * p.msub));
+  int64_t row_tasks = static_cast<int64_t>(p.L) * p.m_blocks;
+  int want_chunks = static_cast<int>((8LL * sms + row_tasks - 1) / row_tasks);
+  if (want_chunks < 1) want_chunks = 1;
+  int nchunk = (p.n_blocks + want_chunks - 1) / want_chunks;
+  if (nchunk < 4) nchunk = 4;
+  if (nchunk > p.n_blocks) nchunk = p.n_blocks;
+  if (nchunk < 1) nchunk = 1;
+  p.nchunk = nchunk;
+  p.chunks_per_row = (p.n_blocks + nchunk - 1) / nchunk;
+  int64_t tasks = row_tasks * p.chunks_per_row;
+  if (tasks > 0x7fffffffLL) return fail(MDG_ERR_UNSUPPORTED, "too many tasks (%lld)", (long long)tasks);
+  p.num_tasks = static_cast<int>(tasks);
+  if (p.num_tasks == 0) return MDG_OK;
+  int grid = p.num_tasks < sms ? p.num_tasks : sms;
+  mdg::pair_score_kernel<<<grid, mdg::kPairThreads, mdg::kPairSmemBytes, stream>>>(tmA, tmB, tmOut, p);
+  MDG_CUDA(cudaGetLastError());
+  ++g_last_launches;
+  return MDG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mdg_last_error(void) { return g_err; }
+int mdg_abi_version(void) { return MDG_ABI_VERSION; }
+int mdg_last_launch_count(void) { return g_last_launches; }
+
+int mdg_check_device(int device) {
+  int dev = device;
+  if (dev < 0) MDG_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  MDG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(MDG_ERR_NO_DEVICE, "device %d is sm_%d0, this library is sm_100a only", dev, major);
+  return MDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ rank table
+int mdg_rank_table_build(const float* quantiles, int32_t L, int32_t Q, float* thresholds_out, uint32_t* lut_out,
+                         float* affine_out, void* stream) {
+  if (!quantiles || !thresholds_out || !lut_out || !affine_out)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_rank_table_build: NULL pointer");
+  if (L <= 0 || Q <= 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_rank_table_build: L=%d Q=%d", L, Q);
+  if (Q > MDG_RANK_MAX_Q) return fail(MDG_ERR_UNSUPPORTED, "Q=%d exceeds %d (uint16 ranks)", Q, MDG_RANK_MAX_Q);
+  if (static_cast<const void*>(quantiles) == static_cast<const void*>(thresholds_out))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_rank_table_build: quantiles and thresholds_out must not alias");
+  mdg::rank_table_build_kernel<<<L, 256, 0, static_cast<cudaStream_t>(stream)>>>(quantiles, Q, thresholds_out, lut_out,
+                                                                                  affine_out);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
+}
+
+int mdg_rank_lookup(const float* logits, int64_t n_per_outcome, const MdgRankTable* table, uint16_t* ranks,
+                    void* stream) {
+  if (!logits || !table || !ranks || !table->lut || !table->affine)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_rank_lookup: NULL pointer");
+  if (n_per_outcome < 0 || table->L <= 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_rank_lookup: bad sizes");
+  if (n_per_outcome == 0) return MDG_OK;
+  int64_t blocks = (n_per_outcome + 255) / 256;
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(table->L));
+  mdg::rank_lookup_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, n_per_outcome, table->lut,
+                                                                                table->affine, ranks);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ decoder
+size_t mdg_pair_score_workspace_bytes(int64_t Nr, int64_t Nc, int64_t D, int64_t L, int precision) {
+  if (Nr < 0 || Nc < 0 || D <= 0 || L < 0) return 0;
+  return carve_pair_ws(nullptr, Nr, Nc, D, L, precision).total;
+}
+
+int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
+                   int64_t L, int precision, int out_mode, int pairs, int normalize_rows, const MdgRankTable* table,
+                   void* out, void* workspace, size_t workspace_bytes, void* stream_v) {
+  g_last_launches = 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!z_rows || !z_cols || !W || !out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: NULL pointer");
+  if (Nr < 0 || Nc < 0 || L < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: negative size");
+  if (D != 64 && D != 128 && D != 192 && D != 256)
+    return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: D=%lld (supported: 64, 128, 192, 256)", (long long)D);
+  if (precision != MDG_PREC_BF16 && precision != MDG_PREC_FP32)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: precision=%d", precision);
+  if (out_mode < MDG_OUT_LOGIT_F32 || out_mode > MDG_OUT_RANK_U16)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: out_mode=%d", out_mode);
+  if (pairs != MDG_PAIRS_FULL) return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: pairs=%d not implemented", pairs);
+  if (Nr > (1 << 30) || Nc > (1 << 30) || L > (1 << 24))
+    return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: sizes too large");
+  if (out_mode == MDG_OUT_RANK_U16) {
+    if (!table || !table->lut || !table->affine)
+      return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: MDG_OUT_RANK_U16 needs a rank table");
+    if (table->L < L) return fail(MDG_ERR_INVALID_ARGUMENT, "rank table has %d outcomes, need %lld", table->L, (long long)L);
+  }
+  if (Nr == 0 || Nc == 0 || L == 0) return MDG_OK;
+  if (!workspace) return fail(MDG_ERR_WORKSPACE, "mdg_pair_score: NULL workspace");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
+    return fail(MDG_ERR_WORKSPACE, "mdg_pair_score: workspace must be 256-byte aligned");
+  PairWorkspace ws = carve_pair_ws(workspace, Nr, Nc, D, L, precision);
+  if (workspace_bytes < ws.total)
+    return fail(MDG_ERR_WORKSPACE, "mdg_pair_score: workspace %zu < required %zu", workspace_bytes, ws.total);
+  int rc = mdg_check_device(-1);
+  if (rc) return rc;
+
+  const int split = precision == MDG_PREC_FP32;
+  const int nterm = split ? 3 : 1;
+  const int msub = split ? 1 : 2;
+  const int kb = static_cast<int>(D / 64);
+  const int64_t ka = ws.ka;
+
+  // ---- operand preparation: fp32 -> bf16 (hi | lo), W transposed to K-major
+  {
+    const int wpb = 8;
+    mdg::convert_z_kernel<<<static_cast<unsigned>((ws.nr_pad + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+        z_rows, static_cast<int>(Nr), static_cast<int>(ws.nr_pad), static_cast<int>(D), split, normalize_rows, ws.zr);
+    MDG_CUDA(cudaGetLastError());
+    ++g_last_launches;
+    mdg::convert_z_kernel<<<static_cast<unsigned>((ws.nc_pad + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+        z_cols, static_cast<int>(Nc), static_cast<int>(ws.nc_pad), static_cast<int>(D), split, normalize_rows, ws.zc);
+    MDG_CUDA(cudaGetLastError());
+    ++g_last_launches;
+    dim3 g(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>(L));
+    mdg::convert_w_kernel<<<g, 256, 0, stream>>>(W, static_cast<int>(D), split, ws.wt);
+    MDG_CUDA(cudaGetLastError());
+    ++g_last_launches;
+  }
+
+  CUtensorMap tmA, tmB, tmOut;
+  // ---- GEMM 1:  Y[l] = z_rows . W[l]      A = zr [1, nr_pad, ka], B = wt [L, D, ka], out = y [L, nr_pad, ka]
+  {
+    rc = make_map_3d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.zr, ka, ws.nr_pad, 1, ka, ws.nr_pad * ka, 64, 128,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.wt, ka, D, L, ka, D * ka, 64, 128,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_3d(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.y, ka, ws.nr_pad, L, ka, ws.nr_pad * ka, 32, 32,
+                     CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    mdg::PairScoreParams p;
+    memset(&p, 0, sizeof(p));
+    p.L = static_cast<int>(L);
+    p.rows = static_cast<int>(ws.nr_pad);
+    p.cols = static_cast<int>(D);
+    p.kb = kb;
+    p.nterm = nterm;
+    p.msub = msub;
+    p.a_batched = 0;
+    p.b_batched = 1;
+    p.epi_mode = mdg::EPI_BF16_SPLIT;
+    p.use_tma_store = 1;
+    p.lo_col_offset = static_cast<int>(D);
+    p.write_lo = split;
+    p.out = ws.y;
+    p.out_ld = ka;
+    p.out_batch_stride = ws.nr_pad * ka;
+    rc = launch_pair_kernel(tmA, tmB, tmOut, p, stream);
+    if (rc) return rc;
+  }
+  // ---- GEMM 2:  S[l] = Y[l] . z_cols^T    A = y [L, nr_pad, ka], B = zc [1, nc_pad, ka], out [L, Nr, Nc]
+  {
+    rc = make_map_3d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.y, ka, ws.nr_pad, L, ka, ws.nr_pad * ka, 64, 128,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.zc, ka, ws.nc_pad, 1, ka, ws.nc_pad * ka, 64, 128,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    mdg::PairScoreParams p;
+    memset(&p, 0, sizeof(p));
+    p.L = static_cast<int>(L);
+    p.rows = static_cast<int>(Nr);
+    p.cols = static_cast<int>(Nc);
+    p.kb = kb;
+    p.nterm = nterm;
+    p.msub = msub;
+    p.a_batched = 1;
+    p.b_batched = 0;
+    p.out = out;
+    p.out_ld = Nc;
+    p.out_batch_stride = Nr * Nc;
+    int elem = 4;
+    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if (out_mode == MDG_OUT_LOGIT_F32) {
+      p.epi_mode = mdg::EPI_F32;
+    } else if (out_mode == MDG_OUT_SIGMOID_F32) {
+      p.epi_mode = mdg::EPI_SIGMOID;
+    } else {
+      p.epi_mode = mdg::EPI_RANK_U16;
+      p.lut = table->lut;
+      p.affine = table->affine;
+      elem = 2;
+      dt = CU_TENSOR_MAP_DATA_TYPE_UINT16;
+    }
+    // TMA store needs 16-byte aligned base and row pitch; otherwise guarded direct stores from registers
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && ((Nc * elem) % 16 == 0) &&
+                        (getenv("MDG_FORCE_DIRECT_STORE") == nullptr);
+    p.use_tma_store = tma_ok ? 1 : 0;
+    if (tma_ok) {
+      rc = make_map_3d(&tmOut, dt, elem, out, Nc, Nr, L, Nc, Nr * Nc, 64 / elem, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    } else {
+      tmOut = tmA;  // unused
+    }
+    rc = launch_pair_kernel(tmA, tmB, tmOut, p, stream);
+    if (rc) return rc;
+  }
+  return MDG_OK;
+}
+
+}  // extern "C"
+
+#include "capi_fusion.inl"

@@ -1,0 +1,518 @@
+// All-pairs bilinear decoder on tcgen05 / TMEM / TMA  (reference: BilinearDDIScorer.bilinear,
+// madrigal/models/models.py:537-539:  matmul(matmul(z1, W[L,D,D]), z2.T) -> [L, N1, N2]).
+//
+// The reference's association order is kept: GEMM 1  Y_l = z_rows . W_l   ([Nr,D] per outcome, small),
+// then GEMM 2  S_l = Y_l . z_cols^T  ([Nr,Nc] per outcome, the N^2 part).  Both are "NT" GEMMs with K-major bf16
+// operands, so ONE persistent warp-specialised kernel runs both, with a different epilogue:
+//
+//   warp 0      TMA producer   : A panels (resident for a whole task) + B panels (3-stage ring), 128B-swizzled
+//   warp 1      UMMA issuer    : tcgen05.mma cta_group::1 kind::f16, 128x128x16, fp32 accumulators in TMEM,
+//                                2 accumulator stages x up to 2 row sub-tiles = 512 TMEM columns
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue       : tcgen05.ld -> registers -> {fp32 | sigmoid | u16 quantile rank | bf16 hi/lo}
+//                                -> 64-byte-swizzled staging in smem -> TMA store (or guarded direct stores)
+//
+// A task = (outcome l, 128*msub-row block, chunk of 128-column blocks).  Within a task the A operand stays in
+// shared memory and only B streams, so L2->SM traffic per output is K*2/(128*msub) bytes.
+//
+// Precision: MDG_PREC_BF16 -> one bf16 term (msub = 2).  MDG_PREC_FP32 -> bf16x3 split: operands are stored as
+// [hi | lo] along K and the K loop runs hi*hi + lo*hi + hi*lo into one accumulator (msub = 1).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "mdg_ptx.cuh"
+#include "rank_table.cuh"
+
+namespace mdg {
+
+constexpr int kBM = 128;
+constexpr int kBN = 128;
+constexpr int kBK = 64;  // bf16 elements per K block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kPanelBytes = kBM * kBK * 2;  // 16 KB: one [128 x 64] bf16 panel
+constexpr int kMaxAPanels = 8;              // 128 KB resident A
+constexpr int kBStages = 3;
+constexpr int kNumEpiWarps = 8;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kPairThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 384
+constexpr int kStagingBytesPerWarp = 2048;                         // 32 rows x 64 B
+constexpr int kTmemCols = 512;
+
+constexpr int kSmemA = 0;
+constexpr int kSmemB = kSmemA + kMaxAPanels * kPanelBytes;                  // 131072
+constexpr int kSmemStaging = kSmemB + kBStages * kPanelBytes;               // 180224
+constexpr int kSmemLut = kSmemStaging + kNumEpiWarps * kStagingBytesPerWarp;  // 196608
+constexpr int kSmemBar = kSmemLut + kRankLutEntries * 4;                    // 229376
+constexpr int kSmemTotal = kSmemBar + 128;
+constexpr int kPairSmemBytes = kSmemTotal + 1024;  // + slack for manual 1024-byte alignment
+static_assert(kPairSmemBytes <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+enum EpiMode : int { EPI_F32 = 0, EPI_SIGMOID = 1, EPI_RANK_U16 = 2, EPI_BF16_SPLIT = 3 };
+
+struct PairScoreParams {
+  int L;          // outcomes in this launch
+  int rows;       // valid output rows
+  int cols;       // valid output columns
+  int kb;         // 64-wide K blocks per precision term (D / 64)
+  int nterm;      // 1 (bf16) or 3 (bf16x3)
+  int msub;       // 128-row sub-tiles per CTA tile
+  int a_batched;  // A's batch coordinate is l (else 0)
+  int b_batched;
+  int n_blocks;
+  int m_blocks;
+  int nchunk;
+  int chunks_per_row;
+  int num_tasks;
+  int epi_mode;
+  int use_tma_store;
+  int lo_col_offset;  // EPI_BF16_SPLIT: column offset of the lo half in the output rows
+  int write_lo;
+  int symmetric;      // MDG_PAIRS_SYMMETRIC: skip column blocks entirely above the diagonal, mask i <= j to 0
+  void* out;          // direct-store path
+  long long out_ld;   // elements per output row
+  long long out_batch_stride;
+  const uint32_t* lut;  // [L, kRankLutEntries]
+  const float* affine;  // [L, 2]
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// rank lookup against the LUT staged in shared memory (same arithmetic as rank_lookup_raw)
+__device__ __forceinline__ uint32_t rank_lookup_smem(uint32_t lut_smem, float x, float scale, float bias) {
+  uint32_t kb = rank_key_bits(x, scale, bias);
+  uint32_t off = (kb >> (kRankBucketShift - 2)) & ((kRankLutEntries - 1) << 2);
+  uint32_t e = lds_u32(lut_smem + off);
+  uint32_t sh = (~(kb >> kRankCellShift) & 15u) | 16u;
+  return e + __popc(e >> sh);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct TaskCoord {
+  int l, m0, nb0, nb1;
+};
+__device__ __forceinline__ TaskCoord decode_task(const PairScoreParams& p, int t) {
+  TaskCoord c;
+  int per_l = p.m_blocks * p.chunks_per_row;
+  c.l = t / per_l;
+  int rem = t - c.l * per_l;
+  int mb = rem / p.chunks_per_row;
+  int ch = rem - mb * p.chunks_per_row;
+  c.m0 = mb * kBM * p.msub;
+  c.nb0 = ch * p.nchunk;
+  c.nb1 = min(c.nb0 + p.nchunk, p.n_blocks);
+  if (p.symmetric) {
+    // only column blocks that intersect the strict lower triangle of this row block: n0 < m0 + rows_in_tile
+    int last = (c.m0 + kBM * p.msub - 1) / kBN;  // block containing the diagonal of the last row
+    c.nb1 = min(c.nb1, last + 1);
+    if (c.nb1 < c.nb0) c.nb1 = c.nb0;
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(kPairThreads, 1)
+pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ PairScoreParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+
+  const uint32_t sA = base + kSmemA, sB = base + kSmemB, sStaging = base + kSmemStaging, sLut = base + kSmemLut,
+                 sBar = base + kSmemBar;
+  const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8;
+  auto bar_b_full = [&](int i) { return sBar + 16 + 8 * i; };
+  auto bar_b_empty = [&](int i) { return sBar + 40 + 8 * i; };
+  auto bar_t_full = [&](int i) { return sBar + 64 + 8 * i; };
+  auto bar_t_empty = [&](int i) { return sBar + 80 + 8 * i; };
+  const uint32_t tmem_slot = sBar + 96;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = lane_id();
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_empty, 1);
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(bar_b_full(i), 1);
+      mbar_init(bar_b_empty(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_t_full(i), 1);
+      mbar_init(bar_t_empty(i), kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.use_tma_store) tma_prefetch_desc(&tmOut);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kSmemBar + 96);
+
+  const int kb = p.kb;
+  const int n_apanels = (p.nterm == 1) ? p.msub * kb : 2 * kb;
+  const int kb_b = (p.nterm == 1) ? kb : 2 * kb;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t b_phase = 0;
+      int it = 0;  // executed tasks (parity of the A barriers)
+      for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
+        const TaskCoord c = decode_task(p, t);
+        if (c.nb1 <= c.nb0) continue;  // (symmetric mode) nothing to do; all roles skip identically
+        mbar_wait(bar_a_empty, (it & 1) ^ 1, 1);
+        mbar_arrive_expect_tx(bar_a_full, n_apanels * kPanelBytes);
+        for (int pn = 0; pn < n_apanels; ++pn) {
+          int row, kc;
+          if (p.nterm == 1) {
+            int ms = pn / kb;
+            row = c.m0 + ms * kBM;
+            kc = (pn - ms * kb) * kBK;
+          } else {
+            row = c.m0;
+            kc = pn * kBK;
+          }
+          tma_load_3d(sA + pn * kPanelBytes, &tmA, bar_a_full, kc, row, p.a_batched ? c.l : 0);
+        }
+        for (int nb = c.nb0; nb < c.nb1; ++nb) {
+          for (int kbi = 0; kbi < kb_b; ++kbi) {
+            mbar_wait(bar_b_empty(stage), b_phase ^ 1, 2);
+            mbar_arrive_expect_tx(bar_b_full(stage), kPanelBytes);
+            tma_load_3d(sB + stage * kPanelBytes, &tmB, bar_b_full(stage), kbi * kBK, nb * kBN,
+                        p.b_batched ? c.l : 0);
+            if (++stage == kBStages) {
+              stage = 0;
+              b_phase ^= 1;
+            }
+          }
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ UMMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_f32(kBM, kBN);
+      int stage = 0;
+      uint32_t b_phase = 0;
+      int acc_stage = 0;
+      uint32_t acc_phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
+        const TaskCoord c = decode_task(p, t);
+        if (c.nb1 <= c.nb0) continue;
+        mbar_wait(bar_a_full, it & 1, 3);
+        for (int nb = c.nb0; nb < c.nb1; ++nb) {
+          mbar_wait(bar_t_empty(acc_stage), acc_phase ^ 1, 4);
+          tc_fence_after_sync();
+          uint32_t started = 0;  // bit ms set once accumulator ms holds a partial sum for this tile
+          for (int kbi = 0; kbi < kb_b; ++kbi) {
+            mbar_wait(bar_b_full(stage), b_phase, 5);
+            tc_fence_after_sync();
+            const uint64_t bdesc = umma_desc_kmajor_sw128(sB + stage * kPanelBytes);
+            int npan, pan[2], accs[2];
+            if (p.nterm == 1) {
+              npan = p.msub;
+              pan[0] = kbi;
+              accs[0] = 0;
+              pan[1] = kb + kbi;
+              accs[1] = 1;
+            } else if (kbi < kb) {  // B = hi:  A_hi[k], A_lo[k]
+              npan = 2;
+              pan[0] = kbi;
+              pan[1] = kb + kbi;
+              accs[0] = accs[1] = 0;
+            } else {  // B = lo:  A_hi[k]
+              npan = 1;
+              pan[0] = kbi - kb;
+              accs[0] = 0;
+              pan[1] = 0;
+              accs[1] = 0;
+            }
+            for (int i = 0; i < npan; ++i) {
+              const uint64_t adesc = umma_desc_kmajor_sw128(sA + pan[i] * kPanelBytes);
+              const uint32_t d = tmem_base + static_cast<uint32_t>((acc_stage * 2 + accs[i]) * kBN);
+#pragma unroll
+              for (int k = 0; k < kBK / kUmmaK; ++k) {
+                const uint32_t acc = ((started >> accs[i]) & 1u) | (k > 0 ? 1u : 0u);
+                umma_bf16(d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc, acc);
+              }
+              started |= 1u << accs[i];
+            }
+            umma_commit(bar_b_empty(stage));  // frees this B stage once the MMAs above have read it
+            if (++stage == kBStages) {
+              stage = 0;
+              b_phase ^= 1;
+            }
+          }
+          umma_commit(bar_t_full(acc_stage));  // accumulators of this tile complete
+          acc_stage ^= 1;
+          if (acc_stage == 0) acc_phase ^= 1;
+        }
+        umma_commit(bar_a_empty);  // every MMA of this task has finished reading the resident A panels
+        ++it;
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
+    // ============================================================ epilogue warps
+    const int ew = warp - kFirstEpiWarp;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;   // 0 / 1
+    const int ms = (p.msub == 2) ? half : 0;
+    const int col_begin = (p.msub == 2) ? 0 : half * (kBN / 2);
+    const int col_end = (p.msub == 2) ? kBN : col_begin + kBN / 2;
+    const uint32_t my_staging = sStaging + ew * kStagingBytesPerWarp;
+    const uint32_t swz = static_cast<uint32_t>((lane >> 1) & 3);  // 64-byte swizzle: chunk ^= (row >> 1) & 3
+    const uint32_t my_row_smem = my_staging + lane * 64;
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    int cur_l = -1;
+    float scale = 0.f, bias = 0.f;
+    bool store_pending = false;
+
+    for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
+      const TaskCoord c = decode_task(p, t);
+      if (c.nb1 <= c.nb0) continue;
+      if (p.epi_mode == EPI_RANK_U16 && c.l != cur_l) {
+        named_bar_sync(1, kNumEpiWarps * 32);  // everyone is done with the previous outcome's LUT
+        const uint4* src = reinterpret_cast<const uint4*>(p.lut + static_cast<size_t>(c.l) * kRankLutEntries);
+        const int tid = ew * 32 + lane;
+#pragma unroll 4
+        for (int i = tid; i < kRankLutEntries / 4; i += kNumEpiWarps * 32) {
+          uint4 v = __ldg(src + i);
+          st_shared_v4(sLut + i * 16, v.x, v.y, v.z, v.w);
+        }
+        scale = __ldg(p.affine + 2 * c.l);
+        bias = __ldg(p.affine + 2 * c.l + 1);
+        cur_l = c.l;
+        named_bar_sync(1, kNumEpiWarps * 32);
+      }
+      const int row0 = c.m0 + ms * kBM + quad * 32;  // first of this warp's 32 rows
+      const int my_row = row0 + lane;
+      for (int nb = c.nb0; nb < c.nb1; ++nb) {
+        mbar_wait(bar_t_full(acc_stage), acc_phase, 6);
+        tc_fence_after_sync();
+        const bool tile_live = row0 < p.rows && !(p.symmetric && nb * kBN > row0 + 31);
+        if (tile_live) {
+          for (int cc = col_begin; cc < col_end; cc += 32) {
+            const int n0 = nb * kBN + cc;
+            if (n0 >= p.cols) break;
+            if (p.symmetric && n0 > row0 + 31) break;  // chunk entirely above the diagonal
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                   static_cast<uint32_t>((acc_stage * 2 + ms) * kBN + cc);
+            tmem_ld_32x32(taddr, v);
+            tmem_ld_wait();
+
+            if (p.epi_mode == EPI_RANK_U16) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                uint32_t r0 = rank_lookup_smem(sLut, __uint_as_float(v[2 * j]), scale, bias);
+                uint32_t r1 = rank_lookup_smem(sLut, __uint_as_float(v[2 * j + 1]), scale, bias);
+                if (p.symmetric) {  // reference zeroes i <= j (normalize_scores.py:69)
+                  if (n0 + 2 * j >= my_row) r0 = 0;
+                  if (n0 + 2 * j + 1 >= my_row) r1 = 0;
+                }
+                pk[j] = __byte_perm(r0, r1, 0x5410);
+              }
+              if (p.use_tma_store) {
+                if (store_pending) {
+                  if (lane == 0) tma_store_wait_read<0>();
+                  __syncwarp();
+                }
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                  st_shared_v4(my_row_smem + ((static_cast<uint32_t>(ch) ^ swz) << 4), pk[4 * ch], pk[4 * ch + 1],
+                               pk[4 * ch + 2], pk[4 * ch + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_3d(&tmOut, my_staging, n0, row0, c.l);
+                  tma_store_commit();
+                }
+                store_pending = true;
+              } else if (my_row < p.rows) {
+                uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + c.l * p.out_batch_stride + my_row * p.out_ld + n0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (n0 + 2 * j < p.cols) o[2 * j] = static_cast<uint16_t>(pk[j] & 0xFFFFu);
+                  if (n0 + 2 * j + 1 < p.cols) o[2 * j + 1] = static_cast<uint16_t>(pk[j] >> 16);
+                }
+              }
+            } else if (p.epi_mode == EPI_BF16_SPLIT) {
+              // hi = bf16(y), lo = bf16(y - hi): the A operand of the second GEMM, K-major rows [hi | lo]
+              for (int part = 0; part < (p.write_lo ? 2 : 1); ++part) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+                  if (part == 1) {
+                    a -= __bfloat162float(__float2bfloat16_rn(a));
+                    b -= __bfloat162float(__float2bfloat16_rn(b));
+                  }
+                  pk[j] = pack_bf16x2(a, b);
+                }
+                const int ncol = n0 + part * p.lo_col_offset;
+                if (p.use_tma_store) {
+                  if (store_pending) {
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                  }
+#pragma unroll
+                  for (int ch = 0; ch < 4; ++ch)
+                    st_shared_v4(my_row_smem + ((static_cast<uint32_t>(ch) ^ swz) << 4), pk[4 * ch], pk[4 * ch + 1],
+                                 pk[4 * ch + 2], pk[4 * ch + 3]);
+                  fence_proxy_async_smem();
+                  __syncwarp();
+                  if (lane == 0) {
+                    tma_store_3d(&tmOut, my_staging, ncol, row0, c.l);
+                    tma_store_commit();
+                  }
+                  store_pending = true;
+                } else if (my_row < p.rows) {
+                  uint32_t* o = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) +
+                                                            c.l * p.out_batch_stride + my_row * p.out_ld + ncol);
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (n0 + 2 * j < p.cols) o[j] = pk[j];  // cols and offsets are even in this mode
+                }
+              }
+            } else {
+              // fp32 logits or sigmoid
+              if (p.epi_mode == EPI_SIGMOID) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  float x = __uint_as_float(v[j]);
+                  v[j] = __float_as_uint(1.0f / (1.0f + expf(-x)));
+                }
+              }
+              if (p.symmetric) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j >= my_row) v[j] = 0u;
+              }
+              if (p.use_tma_store) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {  // two 16-column (64-byte) fills
+                  if (n0 + hf * 16 >= p.cols) break;
+                  if (store_pending) {
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                  }
+#pragma unroll
+                  for (int ch = 0; ch < 4; ++ch)
+                    st_shared_v4(my_row_smem + ((static_cast<uint32_t>(ch) ^ swz) << 4), v[hf * 16 + 4 * ch],
+                                 v[hf * 16 + 4 * ch + 1], v[hf * 16 + 4 * ch + 2], v[hf * 16 + 4 * ch + 3]);
+                  fence_proxy_async_smem();
+                  __syncwarp();
+                  if (lane == 0) {
+                    tma_store_3d(&tmOut, my_staging, n0 + hf * 16, row0, c.l);
+                    tma_store_commit();
+                  }
+                  store_pending = true;
+                }
+              } else if (my_row < p.rows) {
+                float* o = reinterpret_cast<float*>(p.out) + c.l * p.out_batch_stride + my_row * p.out_ld + n0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < p.cols) o[j] = __uint_as_float(v[j]);
+              }
+            }
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_t_empty(acc_stage));
+        acc_stage ^= 1;
+        if (acc_stage == 0) acc_phase ^= 1;
+      }
+    }
+    if (store_pending && lane == 0) tma_store_wait_all<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ operand prep
+// z [N, D] fp32 -> bf16 [Npad, Ka]  with Ka = D (hi only) or 2D ([hi | lo]); rows >= N are zero.
+// Optional row L2 normalisation (F.normalize: x / max(||x||_2, 1e-12), models.py:947-949).  One warp per row.
+__global__ void __launch_bounds__(256) convert_z_kernel(const float* __restrict__ z, int N, int Npad, int D,
+                                                        int split, int normalize, __nv_bfloat16* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= Npad) return;
+  const int Ka = split ? 2 * D : D;
+  __nv_bfloat16* o = out + static_cast<size_t>(row) * Ka;
+  float vals[8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int d = lane + 32 * i;
+    float x = (row < N && d < D) ? z[static_cast<size_t>(row) * D + d] : 0.f;
+    vals[i] = x;
+    ss += x * x;
+  }
+  if (normalize) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    float denom = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vals[i] = vals[i] / denom;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int d = lane + 32 * i;
+    if (d < D) {
+      __nv_bfloat16 hi = __float2bfloat16_rn(vals[i]);
+      o[d] = hi;
+      if (split) o[D + d] = __float2bfloat16_rn(vals[i] - __bfloat162float(hi));
+    }
+  }
+}
+
+// W [L, D, D] fp32 (W[l][a][b]) -> Wt bf16 [L, D, Ka] with Wt[l][b][a] (+ lo half at K offset D): the B operand of
+// GEMM 1 in K-major form.  32x32 shared-memory tile transpose.
+__global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict__ W, int D, int split,
+                                                        __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int l = blockIdx.z;
+  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* w = W + static_cast<size_t>(l) * D * D;
+  const int Ka = split ? 2 * D : D;
+  __nv_bfloat16* o = out + static_cast<size_t>(l) * D * Ka;
+  for (int r = ty; r < 32; r += 8) {
+    int a = a0 + r, b = b0 + tx;
+    tile[r][tx] = (a < D && b < D) ? w[static_cast<size_t>(a) * D + b] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int b = b0 + r, a = a0 + tx;
+    if (a < D && b < D) {
+      float x = tile[tx][r];
+      __nv_bfloat16 hi = __float2bfloat16_rn(x);
+      o[static_cast<size_t>(b) * Ka + a] = hi;
+      if (split) o[static_cast<size_t>(b) * Ka + D + a] = __float2bfloat16_rn(x - __bfloat162float(hi));
+    }
+  }
+}
+
+}  // namespace mdg

@@ -1,0 +1,158 @@
+"""Bilinear decoder drop-ins (reference: madrigal/models/models.py:521-547) over the C ABI.
+
+`BilinearDDIScorer` keeps the reference's constructor, parameter names (`weight [L, D, D]`, unused `bias [L]`) and
+`forward(input1, input2, label_range=None) -> [L', N1, N2]` contract, so a reference `state_dict` loads unchanged and
+`register_parametrization(decoder, 'weight', Symmetric())` works as in models.py:922.  The arithmetic runs in
+`mdg_pair_score` (tcgen05 GEMMs); there is no PyTorch fallback.
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import MdgRankTable
+
+_PRECISION = {"bf16": _lib.MDG_PREC_BF16, "fp32": _lib.MDG_PREC_FP32}
+_OUT = {"logit": (_lib.MDG_OUT_LOGIT_F32, torch.float32), "sigmoid": (_lib.MDG_OUT_SIGMOID_F32, torch.float32),
+        "rank": (_lib.MDG_OUT_RANK_U16, torch.uint16)}
+
+_workspaces = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (operand copies in bf16 + the intermediate z.W_l)."""
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _workspaces.pop(key, None)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"madrigal_b200: `{name}` must be a CUDA tensor (no CPU path exists)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"madrigal_b200: `{name}` must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+class RankTable:
+    """Per-outcome reference-quantile table prepared for the fused rank epilogue (mdg_rank_table_build).
+
+    `thresholds[l]` is what `np.searchsorted(..., side='right')` must be run against to reproduce the ranks.
+    """
+
+    def __init__(self, quantiles: torch.Tensor):
+        q = _require_cuda_f32(quantiles, "quantiles")
+        if q.dim() != 2:
+            raise ValueError("quantiles must be [L, Q]")
+        L, Q = q.shape
+        if Q > _lib.MDG_RANK_MAX_Q:
+            raise ValueError(f"Q={Q} exceeds {_lib.MDG_RANK_MAX_Q}")
+        self.L, self.Q = L, Q
+        self.thresholds = torch.empty_like(q)
+        self.lut = torch.empty((L, _lib.MDG_RANK_LUT_ENTRIES), dtype=torch.int32, device=q.device)
+        self.affine = torch.empty((L, 2), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            _lib.check(_lib.lib().mdg_rank_table_build(q.data_ptr(), L, Q, self.thresholds.data_ptr(),
+                                                       self.lut.data_ptr(), self.affine.data_ptr(),
+                                                       _stream_ptr(q.device)), "mdg_rank_table_build")
+
+    def struct(self, l0: int = 0, l1: Optional[int] = None) -> MdgRankTable:
+        l1 = self.L if l1 is None else l1
+        return MdgRankTable(self.thresholds[l0:l1].data_ptr(), self.lut[l0:l1].data_ptr(),
+                            self.affine[l0:l1].data_ptr(), l1 - l0, self.Q)
+
+    def lookup(self, logits: torch.Tensor) -> torch.Tensor:
+        """ranks[l, ...] = searchsorted(thresholds[l], logits[l, ...], 'right') for materialised logits."""
+        x = _require_cuda_f32(logits, "logits")
+        if x.shape[0] != self.L:
+            raise ValueError("logits.shape[0] must equal the number of outcomes in the table")
+        out = torch.empty(x.shape, dtype=torch.uint16, device=x.device)
+        st = self.struct()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mdg_rank_lookup(x.data_ptr(), x[0].numel(), ctypes.byref(st), out.data_ptr(),
+                                                  _stream_ptr(x.device)), "mdg_rank_lookup")
+        return out
+
+
+def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight: torch.Tensor, *, precision: str = "fp32",
+               out: str = "logit", table: Optional[RankTable] = None, table_offset: int = 0,
+               normalize: bool = False, out_tensor: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """All-pairs bilinear scores  S[l,i,j] = z_rows[i] . W[l] . z_cols[j]  with a fused epilogue.
+
+    out='logit' | 'sigmoid' -> float32 [L, Nr, Nc];  out='rank' -> uint16 quantile ranks against `table`
+    (rows table_offset .. table_offset+L of the table).
+    """
+    zr = _require_cuda_f32(z_rows, "z_rows")
+    zc = _require_cuda_f32(z_cols, "z_cols")
+    W = _require_cuda_f32(weight, "weight")
+    if zr.dim() != 2 or zc.dim() != 2 or W.dim() != 3:
+        raise ValueError("expected z_rows [Nr,D], z_cols [Nc,D], weight [L,D,D]")
+    Nr, D = zr.shape
+    Nc = zc.shape[0]
+    L = W.shape[0]
+    if zc.shape[1] != D or W.shape[1] != D or W.shape[2] != D:
+        raise ValueError(f"shape mismatch: z_rows {tuple(zr.shape)}, z_cols {tuple(zc.shape)}, weight {tuple(W.shape)}")
+    mode, dtype = _OUT[out]
+    prec = _PRECISION[precision]
+    if out_tensor is None:
+        out_tensor = torch.empty((L, Nr, Nc), dtype=dtype, device=zr.device)
+    else:
+        if out_tensor.shape != (L, Nr, Nc) or out_tensor.dtype != dtype or not out_tensor.is_contiguous():
+            raise ValueError("out_tensor has the wrong shape/dtype/layout")
+    tbl = None
+    if out == "rank":
+        if table is None:
+            raise ValueError("out='rank' needs a RankTable")
+        tbl = table.struct(table_offset, table_offset + L)
+    fn = _lib.lib()
+    nbytes = fn.mdg_pair_score_workspace_bytes(Nr, Nc, D, L, prec)
+    ws = _workspace(zr.device, nbytes)
+    with torch.cuda.device(zr.device):
+        _lib.check(fn.mdg_pair_score(zr.data_ptr(), zc.data_ptr(), W.data_ptr(), Nr, Nc, D, L, prec, mode,
+                                     _lib.MDG_PAIRS_FULL, int(bool(normalize)),
+                                     ctypes.byref(tbl) if tbl is not None else None, out_tensor.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _stream_ptr(zr.device)), "mdg_pair_score")
+    return out_tensor
+
+
+class Symmetric(nn.Module):
+    """Parametrisation making each W_l exactly symmetric from its upper triangle (models.py:522-524)."""
+
+    def forward(self, W: torch.Tensor) -> torch.Tensor:
+        upper = torch.triu(W)
+        return upper + torch.triu(W, diagonal=1).transpose(-1, -2)
+
+
+class BilinearDDIScorer(nn.Bilinear):
+    """Drop-in for the reference decoder (models.py:526-547): same ctor, same parameters, same forward contract.
+
+    `precision` ('fp32' default = bf16x3 split, 1e-3 bar; 'bf16' = single bf16 term, 1e-2 bar) is an attribute so
+    the reference's call sites (`model.decoder(z, z, (start, end))`, predict.py:428, 544) run unmodified.
+    """
+
+    def __init__(self, input_dim1: int, input_dim2: int, output_dim: int, precision: str = "fp32"):
+        if input_dim1 != input_dim2:
+            raise NotImplementedError("madrigal_b200 decoder needs input_dim1 == input_dim2 (as every Madrigal config)")
+        super().__init__(in1_features=input_dim1, in2_features=input_dim2, out_features=output_dim)
+        self.precision = precision
+
+    def bilinear(self, input1: torch.Tensor, input2: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        return pair_score(input1, input2, weight, precision=self.precision, out="logit")
+
+    def forward(self, input1: torch.Tensor, input2: torch.Tensor, label_range: Optional[Tuple[int, int]] = None):
+        weight = self.weight  # through the parametrisation, if one is registered
+        if label_range is not None:
+            assert len(label_range) == 2
+            weight = weight[label_range[0]:label_range[1], :, :]
+        return self.bilinear(input1, input2, weight)
