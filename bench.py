@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the drug-pair scoring path (BASELINE.json metric: scored (outcome, drugA, drugB) triples/sec, fused
+rank).  Contract: one JSON line on stdout from rank 0.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (N = 1): BASELINE.json configs[1] — 4,096 drugs x 86 outcomes, hidden 256, all-pairs fused scoring + uint16
+quantile rank on one B200.  N > 1: the same per-GPU workload with DISTINCT outcomes per rank (weak scaling, outcomes
+sharded); the only collective is the all-gather of the fused-embedding table.
+
+A "step" = one pass of the hot path over the whole batch: [all-gather z] -> operand prep -> GEMM 1 (z.W_l) -> GEMM 2 +
+fused rank epilogue writing uint16 ranks for every (outcome, drugA, drugB).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_DRUGS = 4096
+N_OUTCOMES = 86
+HIDDEN = 256
+Q_TABLE = 16384
+PANEL = 2048
+METRIC = "scored (outcome, drugA, drugB) triples/sec, fused rank"
+UNIT = "triples/s"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": f"BASELINE configs[1]: {N_DRUGS} drugs x {N_OUTCOMES} outcomes per GPU, hidden {HIDDEN}, "
+                    f"all-pairs bf16-input/fp32-accumulate scoring + fused uint16 rank (Q={Q_TABLE} reference "
+                    f"quantiles/outcome from a {PANEL}-drug panel)",
+        "drugs": N_DRUGS, "outcomes_per_gpu": N_OUTCOMES, "outcomes_total": N_OUTCOMES * n_gpus, "hidden": HIDDEN,
+        "pairs": "full N x N (ordered pairs, the reference's [L,N,N] tensor)",
+        "parallelism": f"outcomes sharded over {n_gpus} GPU(s); z all-gathered once per step" if n_gpus > 1 else "1 GPU",
+        "l2": "no explicit flush: each step streams 2.9 GB of output through the 126 MB L2, evicting the inputs",
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm for this path on the host cores (oracle port; the Python reference cannot
+# travel to the GPU box).  decoder = fp32 matmul, normaliser = run_slice per outcome in a multiprocessing.Pool()
+# exactly as notebooks/normalize_scores.py:78-85.
+# ----------------------------------------------------------------------------------------------------------------
+_CPU_STATE = {}
+
+
+def _cpu_worker_init(z, W):
+    _CPU_STATE["z"], _CPU_STATE["W"] = z, W
+
+
+def _cpu_one_outcome(l):
+    from oracle import oracle
+    z, W = _CPU_STATE["z"], _CPU_STATE["W"]
+    raw = oracle.bilinear_scores(z, z, W, (l, l + 1))          # models.py:537-547
+    norm = oracle.normalize_scores(raw)                         # normalize_scores.py:62-74
+    return float(norm[0, 1, 0])
+
+
+def cpu_reference_pass(n_outcomes, cores):
+    """Score + rank-normalise `n_outcomes` outcomes of the 4,096-drug workload on `cores` processes; seconds."""
+    import multiprocessing as mp
+    from synth import decoder_inputs
+    z, W = decoder_inputs(N_DRUGS, HIDDEN, n_outcomes, seed=0)
+    t0 = time.perf_counter()
+    ctx = mp.get_context("fork")
+    with ctx.Pool(processes=cores, initializer=_cpu_worker_init, initargs=(z, W)) as pool:
+        pool.map(_cpu_one_outcome, range(n_outcomes))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(cores=None):
+    cores = cores or os.cpu_count() or 1
+    n_out = max(1, min(cores, 8))  # one outcome per worker: ~10-20 s of CPU work
+    dt = cpu_reference_pass(n_out, cores)
+    return {"value": n_out * N_DRUGS * N_DRUGS / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_out} of {N_OUTCOMES} outcomes x {N_DRUGS}^2 pairs: fp32 decoder (numpy matmul) + the "
+                      f"reference's exact argsort rank normaliser, one outcome per process in Pool({cores}); {dt:.1f} s"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_out = max(1, min(cores, 8))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_pass(1, 1)
+    times = [cpu_reference_pass(n_out, cores) for _ in range(args.steps)]
+    dt = float(np.mean(times))
+    value = n_out * N_DRUGS * N_DRUGS / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"each step = {n_out} of {N_OUTCOMES} outcomes x {N_DRUGS}^2 pairs (decoder + exact "
+                                   f"rank normaliser, Pool({cores})); the reference is Python and cannot be installed "
+                                   f"on the GPU box, so this is the oracle port of its algorithm"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def start_clock_sampler(gpu_index):
+    path = tempfile.mktemp(prefix="mdg_clocks_", suffix=".csv")
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                 "-lms", "100"], stdout=open(path, "w"), stderr=subprocess.DEVNULL)
+    except Exception:
+        return None, path
+    return proc, path
+
+
+def stop_clock_sampler(proc, path):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    if proc is None:
+        return out
+    proc.terminate()
+    try:
+        proc.wait(timeout=5)
+    except Exception:
+        proc.kill()
+    sm, reasons, smax = [], set(), None
+    try:
+        for ln in open(path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(path)
+    except Exception:
+        pass
+    if sm:
+        top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
+        out["sm_mhz"] = float(np.median(top))
+        out["sm_max_mhz"] = smax
+        out["reasons"] = sorted(reasons)
+    return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import madrigal_b200 as mb
+    from madrigal_b200 import _lib, normalize, scoring
+    from synth import decoder_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.lib().mdg_check_device(local_rank), "mdg_check_device")
+
+    # ---- synthetic inputs (seeded): shared drug catalogue, per-rank outcomes
+    z_np, _ = decoder_inputs(N_DRUGS, HIDDEN, 1, seed=0)
+    _, W_np = decoder_inputs(1, HIDDEN, N_OUTCOMES, seed=100 + rank)
+    z_full = torch.from_numpy(z_np).to(dev)
+    W = torch.from_numpy(W_np).to(dev)
+    r0, r1 = scoring.row_shard(N_DRUGS, rank, world)
+    z_shard = z_full[r0:r1].contiguous()
+    # setup (untimed): per-outcome reference quantiles from a drug panel -> prepared rank table
+    table = normalize.build_rank_table(z_full, W, Q_TABLE, panel=PANEL, precision="bf16")
+    out = torch.empty((N_OUTCOMES, N_DRUGS, N_DRUGS), dtype=torch.uint16, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        z = scoring.all_gather_embeddings(z_shard, N_DRUGS) if world > 1 else z_full
+        mb.pair_score(z, z, W, precision="bf16", out="rank", table=table, out_tensor=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches_per_step = _lib.lib().mdg_last_launch_count() + (1 if world > 1 else 0)
+
+    proc, cpath = start_clock_sampler(local_rank) if rank == 0 else (None, None)
+    _lib.check(_lib.lib().mdg_profile_enable(min(args.steps, 256)), "mdg_profile_enable")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    buf = (ctypes.c_float * 256)()
+    n_rec = _lib.lib().mdg_profile_read(buf, 256)
+    _lib.lib().mdg_profile_enable(0)
+    kern_ms = float(np.mean(buf[:n_rec])) if n_rec > 0 else None
+    clocks = stop_clock_sampler(proc, cpath) if rank == 0 else None
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / args.steps
+    triples_per_step = world * N_OUTCOMES * N_DRUGS * N_DRUGS
+    value = triples_per_step / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, through the public scoring driver
+    e2e_steps = max(1, min(args.steps, 3))
+    z_host = torch.from_numpy(z_np).pin_memory()
+    W_host = torch.from_numpy(W_np).pin_memory()
+    out_host = torch.empty((N_OUTCOMES, N_DRUGS, N_DRUGS), dtype=torch.uint16).pin_memory()
+
+    def e2e_step():
+        zd = z_host.to(dev, non_blocking=True)
+        Wd = W_host.to(dev, non_blocking=True)
+        if world > 1:
+            zd = scoring.all_gather_embeddings(zd[r0:r1].contiguous(), N_DRUGS)
+        scoring.score_all_pairs_to_host(zd, Wd, out_host, out="rank", table=table, precision="bf16", chunk=10)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = triples_per_step / (te.item() * 1e-3)
+    h2d = z_host.numel() * 4 + W_host.numel() * 4
+    d2h = out_host.numel() * 2
+
+    if rank == 0:
+        peaks = load_peaks()
+        per_gpu_triples = N_OUTCOMES * N_DRUGS * N_DRUGS
+        roofline = None
+        if kern_ms:
+            flops = 2.0 * HIDDEN * per_gpu_triples  # 2*D flop per triple for the dominant (N^2) GEMM
+            achieved = flops / (kern_ms * 1e-3) / 1e12
+            traffic = None
+            prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+            if os.path.exists(prof):
+                try:
+                    traffic = json.load(open(prof)).get("pair_score_kernel", {}).get("dram_bytes_per_launch")
+                except Exception:
+                    traffic = None
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
+                        "kernel": "pair_score_kernel (GEMM 2 + fused rank epilogue)", "kernel_ms": kern_ms,
+                        "peak_source": peaks["src"] + ", sustained bf16",
+                        "hbm_view": {"achieved_gbs": per_gpu_triples * 2 / (kern_ms * 1e-3) / 1e9,
+                                     "peak_gbs": peaks["hbm_gbs"],
+                                     "frac": per_gpu_triples * 2 / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks, "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": te.item()},
+            "gpu_launches": launches_per_step * args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

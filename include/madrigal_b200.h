@@ -124,6 +124,13 @@ int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int
 /* Number of kernel launches the last successful mdg_pair_score call on this thread enqueued (for bench accounting). */
 int mdg_last_launch_count(void);
 
+/* Measurement hooks (bench.py's roofline line).  mdg_profile_enable(n > 0): the next n mdg_pair_score calls on this
+ * thread record a CUDA event pair, on the caller's stream, around their dominant kernel (the N^2 GEMM + epilogue);
+ * n = 0 disables.  mdg_profile_read synchronises on those events (the only call in this library that does), writes
+ * the per-launch durations in ms to a HOST array, resets the counter and returns how many were written (-1: error). */
+int mdg_profile_enable(int max_records);
+int mdg_profile_read(float* ms_out_host, int max_records);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Exact in-sample normalised rank  (reference: classwise_normalized_rank_3d_numpy + run_slice,
  *                                   notebooks/normalize_scores.py:36-74)

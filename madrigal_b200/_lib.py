@@ -63,6 +63,8 @@ SIGNATURES = {
     "mdg_pair_score": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                c_int, POINTER(MdgRankTable), c_void_p, c_void_p, c_size_t, c_void_p]),
     "mdg_last_launch_count": (c_int, []),
+    "mdg_profile_enable": (c_int, [c_int]),
+    "mdg_profile_read": (c_int, [POINTER(c_float), c_int]),
     "mdg_exact_rank_workspace_bytes": (c_size_t, [c_int64]),
     "mdg_exact_rank": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mdg_fusion_workspace_bytes": (c_size_t, [POINTER(MdgFusionCfg), c_int64]),

@@ -36,6 +36,14 @@ int fail(int code, const char* fmt, ...) {
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// ---- optional per-launch timing of the dominant kernel (GEMM 2 of mdg_pair_score) for bench.py's roofline line
+constexpr int kMaxProfile = 256;
+thread_local cudaEvent_t g_prof_start[kMaxProfile];
+thread_local cudaEvent_t g_prof_stop[kMaxProfile];
+thread_local int g_prof_cap = 0;    // 0 = disabled
+thread_local int g_prof_count = 0;  // records taken since enable/reset
+thread_local int g_prof_created = 0;
+
 // ---- driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -335,10 +343,39 @@ int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int
     } else {
       tmOut = tmA;  // unused
     }
+    const bool prof = g_prof_cap > 0 && g_prof_count < g_prof_cap;
+    if (prof) MDG_CUDA(cudaEventRecord(g_prof_start[g_prof_count], stream));
     rc = launch_pair_kernel(tmA, tmB, tmOut, p, stream);
     if (rc) return rc;
+    if (prof) {
+      MDG_CUDA(cudaEventRecord(g_prof_stop[g_prof_count], stream));
+      ++g_prof_count;
+    }
   }
   return MDG_OK;
+}
+
+int mdg_profile_enable(int max_records) {
+  if (max_records < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_profile_enable: max_records=%d", max_records);
+  if (max_records > kMaxProfile) max_records = kMaxProfile;
+  for (; g_prof_created < max_records; ++g_prof_created) {
+    MDG_CUDA(cudaEventCreate(&g_prof_start[g_prof_created]));
+    MDG_CUDA(cudaEventCreate(&g_prof_stop[g_prof_created]));
+  }
+  g_prof_cap = max_records;
+  g_prof_count = 0;
+  return MDG_OK;
+}
+
+int mdg_profile_read(float* ms_out_host, int max_records) {
+  if (!ms_out_host || max_records < 0) return -1;
+  int n = g_prof_count < max_records ? g_prof_count : max_records;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(g_prof_stop[i]) != cudaSuccess) return -1;
+    if (cudaEventElapsedTime(&ms_out_host[i], g_prof_start[i], g_prof_stop[i]) != cudaSuccess) return -1;
+  }
+  g_prof_count = 0;
+  return n;
 }
 
 }  // extern "C"

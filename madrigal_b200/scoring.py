@@ -1,0 +1,114 @@
+"""All-pairs scoring drivers (reference: madrigal/evaluate/predict.py:381-463, 502-579 and the catalogue loop in
+notebooks/generate_embeddings.ipynb cell 10) and the multi-GPU partition of SURVEY.md §8e.
+
+The reference loops outcomes in chunks of 10 (`label_range`), runs the decoder on the GPU, copies every chunk to the
+host and writes it into an np.memmap (predict.py:420-429).  `score_all_pairs_to_host` keeps that call pattern —
+chunked outcomes, host destination buffer — but the chunk is produced by one fused kernel (logits never exist in HBM
+when ranks are requested) and the device->host copy of chunk c overlaps the compute of chunk c+1 on a second stream.
+File I/O itself (memmap/.npy naming) is out of scope.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from .decoder import RankTable, pair_score
+
+_OUT_DTYPE = {"logit": torch.float32, "sigmoid": torch.float32, "rank": torch.uint16}
+
+
+def outcome_shard(L: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous, balanced partition of L outcomes over `world_size` ranks (sizes differ by at most 1)."""
+    base, rem = divmod(L, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def row_shard(N: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous partition of N drugs over ranks for the encoder stage."""
+    return outcome_shard(N, rank, world_size)
+
+
+def all_gather_embeddings(z_shard: torch.Tensor, N: int, group=None) -> torch.Tensor:
+    """The path's ONLY collective: replicate the fused-embedding table [N, D] from per-rank row shards.
+
+    Shards are the `row_shard` partition (sizes differ by at most one row), padded to equal length for
+    `all_gather_into_tensor` (NCCL over NVLink on GPUs; gloo in the CPU tests).
+    """
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = -(-N // world)
+    D = z_shard.shape[1]
+    padded = torch.zeros((per, D), dtype=z_shard.dtype, device=z_shard.device)
+    padded[: z_shard.shape[0]] = z_shard
+    gathered = torch.empty((world * per, D), dtype=z_shard.dtype, device=z_shard.device)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    parts = []
+    for r in range(world):
+        s, e = row_shard(N, r, world)
+        parts.append(gathered[r * per: r * per + (e - s)])
+    del rank
+    return torch.cat(parts, dim=0)
+
+
+def score_all_pairs(z: torch.Tensor, weight: torch.Tensor, *, out: str = "rank", table: Optional[RankTable] = None,
+                    precision: str = "bf16", label_range: Optional[Tuple[int, int]] = None,
+                    normalize: bool = False, out_tensor: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device-resident all-pairs scores for outcomes `label_range` of `weight` (the decoder call of predict.py:428)."""
+    l0, l1 = (0, weight.shape[0]) if label_range is None else label_range
+    return pair_score(z, z, weight[l0:l1], precision=precision, out=out, table=table, table_offset=l0,
+                      normalize=normalize, out_tensor=out_tensor)
+
+
+def score_all_pairs_to_host(z: torch.Tensor, weight: torch.Tensor, out_host: torch.Tensor, *, out: str = "rank",
+                            table: Optional[RankTable] = None, precision: str = "bf16", chunk: int = 10,
+                            normalize: bool = False) -> torch.Tensor:
+    """predict.py:420-429 call pattern: outcomes in chunks of `chunk`, each chunk scored on the GPU and copied into
+    `out_host` ([L, N, N], pinned for overlap).  Double-buffered: copy of chunk c overlaps compute of chunk c+1."""
+    L, N = weight.shape[0], z.shape[0]
+    dtype = _OUT_DTYPE[out]
+    if tuple(out_host.shape) != (L, N, N) or out_host.dtype != dtype:
+        raise ValueError(f"out_host must be {dtype} [{L}, {N}, {N}]")
+    dev = z.device
+    compute = torch.cuda.current_stream(dev)
+    copy = _copy_stream(dev)
+    bufs = [torch.empty((min(chunk, L), N, N), dtype=dtype, device=dev) for _ in range(2)]
+    done_copy = [None, None]
+    for ci, l0 in enumerate(range(0, L, chunk)):
+        l1 = min(l0 + chunk, L)
+        b = ci & 1
+        if done_copy[b] is not None:
+            compute.wait_event(done_copy[b])  # buffer b is free once its previous copy finished
+        dst = bufs[b][: l1 - l0]
+        pair_score(z, z, weight[l0:l1], precision=precision, out=out, table=table, table_offset=l0,
+                   normalize=normalize, out_tensor=dst)
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        with torch.cuda.stream(copy):
+            copy.wait_event(ready)
+            out_host[l0:l1].copy_(dst, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            done_copy[b] = ev
+    compute.wait_stream(copy)
+    return out_host
+
+
+_copy_streams = {}
+
+
+def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
+    key = (dev.type, dev.index)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=dev)
+    return _copy_streams[key]
+
+
+def ensemble_mean_sigmoid(z_list, weight_list, *, precision: str = "bf16",
+                          label_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """predict.py:493, 612: mean over checkpoints of sigmoid(raw scores), per checkpoint's (z, W)."""
+    acc = None
+    for z, W in zip(z_list, weight_list):
+        s = score_all_pairs(z, W, out="sigmoid", precision=precision, label_range=label_range)
+        acc = s if acc is None else acc.add_(s)
+    return acc.div_(len(z_list))

@@ -134,3 +134,192 @@ def quantile_rank(thresholds: np.ndarray, logits: np.ndarray, side: str = "right
 def ensemble_mean_sigmoid(logits_per_ckpt: Sequence[np.ndarray]) -> np.ndarray:
     """predict.py:493, 612: mean over checkpoints of sigmoid(raw scores)."""
     return np.mean(np.stack([sigmoid(x) for x in logits_per_ckpt], axis=0), axis=0).astype(F32)
+
+
+# ------------------------------------------------------------------------------------------- fusion transformer (a-1)
+def _layer_norm(x, w, b, eps=1e-5):
+    """F.layer_norm over the last dim (biased variance, eps 1e-5 = nn.LayerNorm default; models.py:366, 372-373)."""
+    mu = x.mean(axis=-1, keepdims=True)
+    var = ((x - mu) ** 2).mean(axis=-1, keepdims=True)
+    return (x - mu) / np.sqrt(var + eps) * w + b
+
+
+def _linear(x, w, b):
+    return x @ w.T + b
+
+
+def _activation(x, actn):
+    if actn == "relu":
+        return np.maximum(x, 0)
+    if actn == "gelu":  # exact erf GELU (F.gelu default, selected by transformer_actn: gelu)
+        return 0.5 * x * (1.0 + _erf(x / math.sqrt(2.0)))
+    raise NotImplementedError(actn)
+
+
+def _mha(q_in, kv_in, in_w, in_b, out_w, out_b, num_heads, add_mask):
+    """nn.MultiheadAttention forward (packed in_proj, q scaled by 1/sqrt(head_dim), additive -inf mask, softmax
+    over keys, out_proj).  q_in [B,Tq,Dl], kv_in [B,Tk,Dl], add_mask broadcastable to [B,1,Tq,Tk] (0 / -inf)."""
+    B, Tq, Dl = q_in.shape
+    Tk = kv_in.shape[1]
+    hd = Dl // num_heads
+    q = _linear(q_in, in_w[:Dl], in_b[:Dl]).reshape(B, Tq, num_heads, hd).transpose(0, 2, 1, 3)
+    k = _linear(kv_in, in_w[Dl:2 * Dl], in_b[Dl:2 * Dl]).reshape(B, Tk, num_heads, hd).transpose(0, 2, 1, 3)
+    v = _linear(kv_in, in_w[2 * Dl:], in_b[2 * Dl:]).reshape(B, Tk, num_heads, hd).transpose(0, 2, 1, 3)
+    s = (q * q.dtype.type(1.0 / math.sqrt(hd))) @ k.transpose(0, 1, 3, 2) + add_mask
+    s = s - s.max(axis=-1, keepdims=True)
+    p = np.exp(s)
+    p = p / p.sum(axis=-1, keepdims=True)
+    o = (p @ v).transpose(0, 2, 1, 3).reshape(B, Tq, Dl)
+    return _linear(o, out_w, out_b)
+
+
+def fusion_forward(sd: Dict[str, np.ndarray], cfg: dict, fusion_sequence: np.ndarray, fusion_mask: np.ndarray,
+                   src_mask: Optional[np.ndarray] = None, pool_key_mask: Optional[np.ndarray] = None,
+                   dtype=F32) -> np.ndarray:
+    """TransformerFusion.forward in eval mode, models.py:401-455 (dropouts = identity).
+
+    sd: the module's state_dict as numpy arrays (keys as in the reference: embed2latent.*, transformer_encoder.
+    layers.{i}.*, latent2embed.*, x_attn_*).  cfg keys: num_layers, num_heads, head_dim, ffn_dim, actn, norm_first,
+    agg.  fusion_sequence [B,T,E] (already position-encoded), fusion_mask [B,T] bool True = missing,
+    src_mask [T,T] bool True = blocked, pool_key_mask [T] bool = the module's constant x_attn_key_padding_mask
+    (models.py:382-385).  Encoder layers follow torch 1.13 nn.TransformerEncoderLayer._sa_block/_ff_block with
+    norm_first either way, no final norm (models.py:366-367).  The result does not depend on transformer_batch_first
+    except for the reference's x-attn indexing bug at models.py:443 (only batch_first=False is meaningful there).
+    """
+    g = lambda k: sd[k].astype(dtype)
+    x = fusion_sequence.astype(dtype)
+    B, T, _ = x.shape
+    H = cfg["num_heads"]
+    neg = np.zeros((B, 1, 1, T), dtype=dtype)
+    neg[np.asarray(fusion_mask, bool)[:, None, None, :]] = -np.inf
+    if src_mask is not None:
+        sm = np.zeros((1, 1, T, T), dtype=dtype)
+        sm[np.asarray(src_mask, bool)[None, None]] = -np.inf
+        neg = neg + sm
+    h = _linear(x, g("embed2latent.weight"), g("embed2latent.bias"))  # models.py:411
+    for i in range(cfg["num_layers"]):  # models.py:412
+        p = f"transformer_encoder.layers.{i}."
+        sa = lambda y: _mha(y, y, g(p + "self_attn.in_proj_weight"), g(p + "self_attn.in_proj_bias"),
+                            g(p + "self_attn.out_proj.weight"), g(p + "self_attn.out_proj.bias"), H, neg)
+        ff = lambda y: _linear(_activation(_linear(y, g(p + "linear1.weight"), g(p + "linear1.bias")), cfg["actn"]),
+                               g(p + "linear2.weight"), g(p + "linear2.bias"))
+        n1 = lambda y: _layer_norm(y, g(p + "norm1.weight"), g(p + "norm1.bias"))
+        n2 = lambda y: _layer_norm(y, g(p + "norm2.weight"), g(p + "norm2.bias"))
+        if cfg["norm_first"]:
+            h = h + sa(n1(h))
+            h = h + ff(n2(h))
+        else:
+            h = n1(h + sa(h))
+            h = n2(h + ff(h))
+    agg = cfg["agg"]
+    l2e = lambda y: _linear(y, g("latent2embed.weight"), g("latent2embed.bias"))
+    if agg == "cls":  # models.py:415-421
+        return l2e(h)[:, 0, :].astype(dtype)
+    if agg == "x-attn":  # models.py:422-443
+        kv = _layer_norm(h, g("x_attn_kv_norm.weight"), g("x_attn_kv_norm.bias"))
+        q = np.broadcast_to(g("x_attn_query")[None, :, :], (B, 1, h.shape[-1]))
+        if cfg["norm_first"]:
+            q = _layer_norm(q, g("x_attn_query_norm.weight"), g("x_attn_query_norm.bias"))
+        pm = np.zeros((1, 1, 1, T), dtype=dtype)
+        if pool_key_mask is not None:
+            pm[:, :, :, np.asarray(pool_key_mask, bool)] = -np.inf
+        out = _mha(q, kv, g("x_attn_mha_layer.in_proj_weight"), g("x_attn_mha_layer.in_proj_bias"),
+                   g("x_attn_mha_layer.out_proj.weight"), g("x_attn_mha_layer.out_proj.bias"), H, pm)
+        out = out + q
+        if not cfg["norm_first"]:
+            out = _layer_norm(out, g("x_attn_query_norm.weight"), g("x_attn_query_norm.bias"))
+        return l2e(out)[:, 0, :].astype(dtype)
+    e = l2e(h)  # models.py:415
+    keep = ~np.asarray(fusion_mask, bool)
+    if agg == "mean":  # models.py:444-447: scatter_mean over unmasked tokens
+        cnt = np.maximum(keep.sum(axis=1, keepdims=True), 1).astype(dtype)
+        return ((e * keep[:, :, None]).sum(axis=1) / cnt).astype(dtype)
+    if agg == "max":  # models.py:448-451: scatter_max over unmasked tokens (empty -> 0)
+        m = np.where(keep[:, :, None], e, -np.inf).max(axis=1)
+        return np.where(np.isinf(m), 0, m).astype(dtype)
+    raise NotImplementedError(agg)
+
+
+# ------------------------------------------------------------------------------------------ positional encodings (a-2)
+def sinusoidal_pe(d_model: int, max_len: int, seq_len: int) -> np.ndarray:
+    """PositionEncodingSinusoidal buffer, models.py:560-577: [1, seq_len, d_model], zero beyond max_len."""
+    position = np.arange(max_len, dtype=F32)[:, None]
+    div_term = np.exp(np.arange(0, d_model, 2, dtype=F32) * F32(-math.log(10000.0) / d_model)).astype(F32)
+    pe = np.zeros((1, seq_len, d_model), dtype=F32)
+    pe[0, :max_len, 0::2] = np.sin(position * div_term)
+    pe[0, :max_len, 1::2] = np.cos(position * div_term)
+    return pe
+
+
+# ------------------------------------------------------------------------------------------- unimodal MLP bypass (a-3)
+def mlp_adaptor(layers: Sequence[dict], x: np.ndarray, dtype=F32) -> np.ndarray:
+    """MLPAdaptor.forward (eval), models.py:459-518, as a list of ops in nn.Sequential order.
+
+    Each entry: {'op': 'linear', 'w', 'b'} | {'op': 'ln', 'w', 'b'} | {'op': 'act', 'actn'}.
+    """
+    h = x.astype(dtype)
+    for L in layers:
+        if L["op"] == "linear":
+            h = _linear(h, L["w"].astype(dtype), L["b"].astype(dtype))
+        elif L["op"] == "ln":
+            h = _layer_norm(h, L["w"].astype(dtype), L["b"].astype(dtype))
+        elif L["op"] == "act":
+            h = _activation(h, L["actn"])
+        else:
+            raise NotImplementedError(L["op"])
+    return h.astype(dtype)
+
+
+# ----------------------------------------------------------------------------------------------- token assembly (a-2)
+def assemble_fusion_inputs(all_embeds: np.ndarray, batch_masks: np.ndarray, *, n_non_tx: int, num_tx_bottlenecks: int,
+                           agg: str, tx_bottleneck_tokens: Optional[np.ndarray] = None,
+                           cls: Optional[np.ndarray] = None, pe: Optional[np.ndarray] = None,
+                           pos_emb_type: str = "sinusoidal", pos_max_len: Optional[int] = None,
+                           normalize: bool = False):
+    """The fusion section of NovelDDIEncoder.encode for fusion='transformer', models.py:793-853.
+
+    all_embeds [B, M, E] in the order [non-TX..., TX...] (models.py:772), batch_masks [B, M] bool True = missing.
+    Returns (pos-encoded sequence [B,T,E], fusion mask [B,T], src_mask [T,T] or None).
+    """
+    seq = all_embeds.astype(F32)
+    masks = np.asarray(batch_masks, bool)
+    B, M, E = seq.shape
+    n_tx = M - n_non_tx
+    src_mask = None
+    nb = num_tx_bottlenecks
+    if nb > 0:  # models.py:799-816
+        seq = np.concatenate([seq[:, :n_non_tx], np.broadcast_to(tx_bottleneck_tokens[None], (B, nb, E)),
+                              seq[:, n_non_tx:]], axis=1)
+        masks = np.concatenate([masks[:, :n_non_tx], np.zeros((B, nb), bool), masks[:, n_non_tx:]], axis=1)
+        T = seq.shape[1]
+        src_mask = np.zeros((T, T), bool)
+        src_mask[:n_non_tx, T - n_tx:] = True
+        src_mask[T - n_tx:, :n_non_tx] = True
+    if agg == "cls":  # models.py:818-842
+        seq = np.concatenate([np.broadcast_to(cls[None], (B, 1, E)), seq], axis=1)
+        masks = np.concatenate([np.zeros((B, 1), bool), masks], axis=1)
+        if src_mask is not None:
+            T = src_mask.shape[0]
+            sm = np.zeros((T + 1, T + 1), bool)
+            sm[1:, 1:] = src_mask
+            src_mask = sm
+    if normalize:  # models.py:849-850, F.normalize(p=2, dim=-1, eps=1e-12)
+        n = np.sqrt((seq ** 2).sum(axis=-1, keepdims=True))
+        seq = seq / np.maximum(n, F32(1e-12))
+    seq = seq.copy()
+    if pe is not None:  # models.py:852
+        if pos_emb_type == "sinusoidal":
+            seq = seq + pe  # buffer already has the sequence length (models.py:571-579, 586)
+        else:
+            seq[:, :pos_max_len, :] += pe  # models.py:602
+    return seq.astype(F32), masks, src_mask
+
+
+def split_unimodal(batch_masks: np.ndarray):
+    """fusion='transformer_uni_proj' routing, models.py:781-790: rows with exactly one visible modality bypass the
+    transformer.  Returns (multimodal bool [B], index of the single visible modality for the unimodal rows)."""
+    vis = ~np.asarray(batch_masks, bool)
+    assert (vis.sum(axis=1) > 0).all()  # models.py:783
+    multi = vis.sum(axis=1) > 1
+    uni_idx = np.where(vis[~multi])[1]
+    return multi, uni_idx

@@ -20,3 +20,91 @@ def decoder_inputs(N: int, D: int, L: int, seed: int = 0, symmetric: bool = True
     if symmetric:
         P = np.triu(P) + np.swapaxes(np.triu(P, 1), -1, -2)
     return z, P
+
+
+# ------------------------------------------------------------------------------------------------ fusion encoder
+CELL_LINES = ['a375', 'a549', 'asc', 'ha1e', 'hcc515', 'hec108', 'hela', 'hepg2', 'ht29', 'huvec', 'mcf7', 'npc',
+              'pc3', 'thp1', 'vcap', 'yapc']  # madrigal/utils.py:28 (ORDERED)
+NUM_NON_TX = 3  # str, kg, cv (madrigal/utils.py:30-36)
+
+
+def _uniform(rng, shape, fan_in):
+    b = 1.0 / np.sqrt(fan_in)
+    return rng.uniform(-b, b, size=shape).astype(F32)
+
+
+def fusion_state_dict(cfg: dict, seed: int = 0):
+    """Random-init TransformerFusion state_dict (reference key names, models.py:365-381) from a numpy seed.
+
+    cfg: embed_dim, num_layers, num_heads, head_dim, ffn_dim, agg.  Linear weights/biases ~ U(+-1/sqrt(fan_in))
+    (nn.Linear's default distribution); LayerNorm affine params perturbed away from (1, 0) so they are exercised.
+    """
+    rng = np.random.default_rng(seed)
+    E, Dl, Fd = cfg["embed_dim"], cfg["num_heads"] * cfg["head_dim"], cfg["ffn_dim"]
+    sd = {"embed2latent.weight": _uniform(rng, (Dl, E), E), "embed2latent.bias": _uniform(rng, (Dl,), E)}
+
+    def ln(prefix):
+        sd[prefix + ".weight"] = (1.0 + 0.1 * rng.standard_normal(Dl)).astype(F32)
+        sd[prefix + ".bias"] = (0.1 * rng.standard_normal(Dl)).astype(F32)
+
+    def mha(prefix):
+        sd[prefix + ".in_proj_weight"] = _uniform(rng, (3 * Dl, Dl), Dl)
+        sd[prefix + ".in_proj_bias"] = _uniform(rng, (3 * Dl,), Dl)
+        sd[prefix + ".out_proj.weight"] = _uniform(rng, (Dl, Dl), Dl)
+        sd[prefix + ".out_proj.bias"] = _uniform(rng, (Dl,), Dl)
+
+    for i in range(cfg["num_layers"]):
+        p = f"transformer_encoder.layers.{i}"
+        mha(p + ".self_attn")
+        sd[p + ".linear1.weight"] = _uniform(rng, (Fd, Dl), Dl)
+        sd[p + ".linear1.bias"] = _uniform(rng, (Fd,), Dl)
+        sd[p + ".linear2.weight"] = _uniform(rng, (Dl, Fd), Fd)
+        sd[p + ".linear2.bias"] = _uniform(rng, (Dl,), Fd)
+        ln(p + ".norm1")
+        ln(p + ".norm2")
+    sd["latent2embed.weight"] = _uniform(rng, (E, Dl), Dl)
+    sd["latent2embed.bias"] = _uniform(rng, (E,), Dl)
+    if cfg["agg"] == "x-attn":
+        ln("x_attn_kv_norm")
+        ln("x_attn_query_norm")
+        mha("x_attn_mha_layer")
+        sd["x_attn_query"] = rng.standard_normal((1, Dl)).astype(F32)
+    return sd
+
+
+def fusion_inputs(B: int, T: int, E: int, seed: int = 0, always_visible=(0,), p_missing: float = 0.5):
+    """tokens [B,T,E] ~ N(0,1); mask [B,T] True = missing, Bernoulli(p_missing), `always_visible` never masked;
+    masked slots overwritten with a different finite draw (their content must not matter)."""
+    rng = np.random.default_rng(seed + 1000)
+    tokens = rng.standard_normal((B, T, E)).astype(F32)
+    mask = rng.random((B, T)) < p_missing
+    mask[:, list(always_visible)] = False
+    garbage = (3.0 * rng.standard_normal((B, T, E))).astype(F32)
+    tokens = np.where(mask[:, :, None], garbage, tokens)
+    return tokens, mask
+
+
+def mlp_adaptor_params(in_dim, hidden_dims, out_dim, seed=0):
+    """MLPAdaptor (norm='ln', order='nd') parameters in nn.Sequential order as a list of op dicts (see
+    oracle.mlp_adaptor): Linear, act, [LN, Linear, act]*, Linear  (models.py:471-481, 499-514)."""
+    rng = np.random.default_rng(seed + 2000)
+    ops = [{"op": "linear", "w": _uniform(rng, (hidden_dims[0], in_dim), in_dim),
+            "b": _uniform(rng, (hidden_dims[0],), in_dim)}, {"op": "act"}]
+    for i in range(len(hidden_dims) - 1):
+        ops.append({"op": "ln", "w": (1.0 + 0.1 * rng.standard_normal(hidden_dims[i])).astype(F32),
+                    "b": (0.1 * rng.standard_normal(hidden_dims[i])).astype(F32)})
+        ops.append({"op": "linear", "w": _uniform(rng, (hidden_dims[i + 1], hidden_dims[i]), hidden_dims[i]),
+                    "b": _uniform(rng, (hidden_dims[i + 1],), hidden_dims[i])})
+        ops.append({"op": "act"})
+    ops.append({"op": "linear", "w": _uniform(rng, (out_dim, hidden_dims[-1]), hidden_dims[-1]),
+                "b": _uniform(rng, (out_dim,), hidden_dims[-1])})
+    return ops
+
+
+def params_checksum(arrays) -> float:
+    """Order-dependent float64 checksum used by the golden fixtures to detect RNG-stream drift."""
+    tot = 0.0
+    for k, a in enumerate(arrays):
+        a = np.asarray(a, dtype=np.float64).reshape(-1)
+        tot += float((a * np.cos(np.arange(a.size) * 0.37 + k)).sum())
+    return tot

@@ -1,0 +1,66 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/madrigal_b200.h declares.
+No compute call is made (there is no GPU here and the library has no CPU path)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from madrigal_b200 import _lib
+from madrigal_b200.build import LIB_PATH, REPO_ROOT, build_library
+
+
+@pytest.fixture(scope="module")
+def handle():
+    build_library()
+    assert os.path.exists(LIB_PATH)
+    return _lib.lib()
+
+
+def _declared_functions():
+    text = open(os.path.join(REPO_ROOT, "include", "madrigal_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported(handle):
+    names = _declared_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES and the header disagree"
+
+
+def test_abi_version_and_error_string(handle):
+    assert handle.mdg_abi_version() == 1
+    assert isinstance(handle.mdg_last_error(), bytes)
+
+
+def test_invalid_arguments_fail_without_touching_the_gpu(handle):
+    # argument validation happens before any CUDA call
+    rc = handle.mdg_pair_score(None, None, None, 4, 4, 128, 1, 0, 0, 0, 0, None, None, None, 0, None)
+    assert rc == 1 and b"NULL" in handle.mdg_last_error()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf)
+    rc = handle.mdg_pair_score(p, p, p, 4, 4, 100, 1, 0, 0, 0, 0, None, p, None, 0, None)
+    assert rc == 2 and b"D=100" in handle.mdg_last_error()
+    rc = handle.mdg_pair_score(p, p, p, 4, 4, 128, 1, 0, 2, 0, 0, None, p, None, 0, None)
+    assert rc == 1 and b"rank table" in handle.mdg_last_error()
+    rc = handle.mdg_rank_table_build(p, 1, 70000, p + 16, p, p, None)
+    assert rc != 0
+
+
+def test_workspace_size_is_monotone(handle):
+    a = handle.mdg_pair_score_workspace_bytes(1024, 1024, 128, 86, 0)
+    b = handle.mdg_pair_score_workspace_bytes(1024, 1024, 128, 86, 1)
+    c = handle.mdg_pair_score_workspace_bytes(4096, 4096, 256, 86, 0)
+    assert 0 < a < b and a < c
+
+
+def test_python_ops_refuse_cpu_tensors():
+    import torch
+    import madrigal_b200 as mb
+    z = torch.zeros(4, 128)
+    W = torch.zeros(1, 128, 128)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mb.pair_score(z, z, W)

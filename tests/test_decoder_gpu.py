@@ -1,0 +1,211 @@
+"""GPU parity: mdg_pair_score (tcgen05 decoder + fused epilogues) through the C ABI vs the CPU oracle.
+
+Tolerances (north-star / BASELINE.md §4), written out:
+  * MDG_PREC_FP32 (bf16x3 split):  |got - ref| <= 1e-3 * max(|ref|, rms(ref))   element-wise, ref = fp64 oracle
+  * MDG_PREC_BF16:                 |got - ref_bf16| <= 1e-2 * max(|ref_bf16|, rms) element-wise, where ref_bf16 is
+                                   the oracle run on the bf16-rounded inputs ("bf16-input / fp32-accumulate"), and
+                                   max|got - ref| <= 1e-2 * max|ref| against the un-rounded fp32 reference
+  * ranks: bit-exact vs np.searchsorted(thresholds, logits, 'right') on identical logits.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def mb(cuda_device):
+    import madrigal_b200
+    from madrigal_b200 import _lib
+    _lib.check(_lib.lib().mdg_check_device(0), "mdg_check_device")
+    return madrigal_b200
+
+
+def to_bf16_f32(a):
+    return torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def assert_close(got, ref, tol, what=""):
+    ref = ref.astype(np.float64)
+    err = np.abs(got.astype(np.float64) - ref)
+    rms = np.sqrt(np.mean(ref ** 2))
+    ratio = (err / (tol * np.maximum(np.abs(ref), rms))).max()
+    assert np.isfinite(got).all() and ratio <= 1.0, f"{what}: max err/bound = {ratio:.3f}, max|err| = {err.max():.3e}"
+
+
+def gpu(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+CASES = [  # N1, N2, D, L
+    (128, 128, 64, 1), (256, 384, 256, 3), (200, 328, 128, 2), (130, 75, 192, 2), (1, 1, 64, 1), (5, 700, 128, 1),
+    (513, 257, 256, 2),
+]
+
+
+@pytest.mark.parametrize("N1,N2,D,L", CASES)
+def test_logits_fp32_mode(mb, cuda_device, N1, N2, D, L):
+    z1, W = synth.decoder_inputs(N1, D, L, seed=N1 + D)
+    z2, _ = synth.decoder_inputs(N2, D, 1, seed=N2 + D + 1)
+    ref = oracle.bilinear_scores(z1, z2, W, dtype=np.float64)
+    got = mb.pair_score(gpu(z1, cuda_device), gpu(z2, cuda_device), gpu(W, cuda_device), precision="fp32").cpu().numpy()
+    assert got.shape == (L, N1, N2)
+    assert_close(got, ref, 1e-3, "fp32 mode")
+
+
+@pytest.mark.parametrize("N1,N2,D,L", CASES)
+def test_logits_bf16_mode(mb, cuda_device, N1, N2, D, L):
+    z1, W = synth.decoder_inputs(N1, D, L, seed=N1 + D)
+    z2, _ = synth.decoder_inputs(N2, D, 1, seed=N2 + D + 1)
+    got = mb.pair_score(gpu(z1, cuda_device), gpu(z2, cuda_device), gpu(W, cuda_device), precision="bf16").cpu().numpy()
+    ref_b = oracle.bilinear_scores(to_bf16_f32(z1), to_bf16_f32(z2), to_bf16_f32(W), dtype=np.float64)
+    assert_close(got, ref_b, 1e-2, "bf16 mode vs oracle on bf16-rounded inputs")
+    ref = oracle.bilinear_scores(z1, z2, W, dtype=np.float64)
+    assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max()
+
+
+def test_direct_store_path_matches_tma_store_path(mb, cuda_device, monkeypatch):
+    z1, W = synth.decoder_inputs(256, 128, 2, seed=3)
+    a = mb.pair_score(gpu(z1, cuda_device), gpu(z1, cuda_device), gpu(W, cuda_device), precision="fp32").cpu()
+    monkeypatch.setenv("MDG_FORCE_DIRECT_STORE", "1")
+    b = mb.pair_score(gpu(z1, cuda_device), gpu(z1, cuda_device), gpu(W, cuda_device), precision="fp32").cpu()
+    assert torch.equal(a, b)
+
+
+def test_golden_decoder_fixtures(mb, cuda_device):
+    """The committed outputs of the reference's own NovelDDIMultilabel/BilinearDDIScorer (tests/golden)."""
+    meta = json.load(open(os.path.join(HERE, "golden", "golden_meta.json")))["decoder"]
+    g = np.load(os.path.join(HERE, "golden", "golden_decoder.npz"))
+    for case in meta:
+        z1, P = synth.decoder_inputs(case["N1"], case["D"], case["L"], case["seed"], symmetric=False, unit_scale=False)
+        z2, _ = synth.decoder_inputs(case["N2"], case["D"], 1, case["seed"] + 50, symmetric=False, unit_scale=False)
+        if not np.isclose(synth.params_checksum([z1, z2, P]), case["checksum"], rtol=1e-9):
+            pytest.skip("numpy Generator stream drift")
+        if case["D"] % 64:
+            # D=32 fixtures: embed into D=64 with zero padding (the bilinear form is unchanged)
+            pad = 64 - case["D"]
+            z1, z2 = np.pad(z1, ((0, 0), (0, pad))), np.pad(z2, ((0, 0), (0, pad)))
+            P = np.pad(P, ((0, 0), (0, pad), (0, pad)))
+        dec = mb.BilinearDDIScorer(z1.shape[1], z1.shape[1], case["L"]).to(cuda_device)
+        torch.nn.utils.parametrize.register_parametrization(dec, "weight", mb.Symmetric())  # models.py:922
+        with torch.no_grad():
+            dec.parametrizations.weight.original.copy_(gpu(P, cuda_device))
+            a, b = gpu(z1, cuda_device), gpu(z2, cuda_device)
+            if case["normalize"]:
+                a, b = torch.nn.functional.normalize(a), torch.nn.functional.normalize(b)
+            lr = tuple(case["label_range"]) if case["label_range"] else None
+            got = dec(a, b, lr).cpu().numpy()
+        assert_close(got, g[f"{case['name']}.scores"], 1e-3, case["name"])
+
+
+def test_label_range_and_state_dict_keys(mb, cuda_device):
+    dec = mb.BilinearDDIScorer(128, 128, 6).to(cuda_device)
+    torch.nn.utils.parametrize.register_parametrization(dec, "weight", mb.Symmetric())
+    assert sorted(dec.state_dict().keys()) == ["bias", "parametrizations.weight.original"]
+    z = torch.randn(40, 128, device=cuda_device)
+    with torch.no_grad():
+        full = dec(z, z)
+        part = dec(z, z, (2, 5))
+    assert part.shape == (3, 40, 40) and torch.equal(part, full[2:5])
+    with pytest.raises(AssertionError):
+        dec(z, z, (1, 2, 3))
+
+
+def test_normalize_rows_flag(mb, cuda_device):
+    z1, W = synth.decoder_inputs(100, 128, 2, seed=5, unit_scale=False)
+    ref = oracle.bilinear_scores(oracle.l2_normalize(z1), oracle.l2_normalize(z1), W, dtype=np.float64)
+    got = mb.pair_score(gpu(z1, cuda_device), gpu(z1, cuda_device), gpu(W, cuda_device), precision="fp32",
+                        normalize=True).cpu().numpy()
+    assert_close(got, ref, 1e-3, "normalize_rows")
+
+
+def test_sigmoid_mode(mb, cuda_device):
+    z1, W = synth.decoder_inputs(300, 256, 2, seed=9, unit_scale=False)  # logits O(1): exercises the curve
+    ref = oracle.sigmoid(oracle.bilinear_scores(z1, z1, W, dtype=np.float64))
+    got = mb.pair_score(gpu(z1, cuda_device), gpu(z1, cuda_device), gpu(W, cuda_device), precision="fp32",
+                        out="sigmoid").cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-3
+
+
+@pytest.mark.parametrize("N,D,L,Q,prec", [(192, 128, 2, 1024, "bf16"), (256, 256, 3, 16384, "bf16"),
+                                          (64, 64, 2, 2016, "fp32"), (333, 192, 2, 4096, "fp32"),
+                                          (150, 128, 1, 65535, "bf16")])
+def test_fused_rank_is_bit_exact_searchsorted(mb, cuda_device, N, D, L, Q, prec):
+    z, W = synth.decoder_inputs(N, D, L, seed=N)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    logits = mb.pair_score(zt, zt, Wt, precision=prec, out="logit")
+    lg = logits.cpu().numpy()
+    M = N * (N - 1) // 2
+    quant = oracle.reference_quantiles(lg, min(Q, M))
+    table = mb.RankTable(gpu(quant, cuda_device))
+    thr = table.thresholds.cpu().numpy()
+    assert (np.diff(thr, axis=1) >= 0).all()
+    span = quant[:, -1:] - quant[:, :1]
+    assert (np.abs(thr - quant) <= 8 * 1.02 * span / 131072 + 1e-12).all()  # snapped by at most a few grid cells
+    ref = oracle.quantile_rank(thr, lg, "right")
+    assert np.array_equal(table.lookup(logits).cpu().numpy(), ref)
+    fused = mb.pair_score(zt, zt, Wt, precision=prec, out="rank", table=table).cpu().numpy()
+    assert fused.dtype == np.uint16 and np.array_equal(fused, ref)
+
+
+def test_rank_with_full_sample_table_reproduces_reference_normaliser(mb, cuda_device):
+    """Q = M: the quantile lookup IS the reference's in-sample rank (normalize_scores.py:36-72) for untied scores."""
+    N, D, L = 48, 64, 2
+    z, W = synth.decoder_inputs(N, D, L, seed=11)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    lg = mb.pair_score(zt, zt, Wt, precision="fp32").cpu().numpy()
+    M = N * (N - 1) // 2
+    table = mb.RankTable(gpu(oracle.reference_quantiles(lg, M), cuda_device))
+    fused = mb.pair_score(zt, zt, Wt, precision="fp32", out="rank", table=table).cpu().numpy()
+    ref_norm = oracle.normalize_scores(lg)  # the reference normaliser's output on the same logits
+    i, j = np.tril_indices(N, -1)
+    for l in range(L):
+        v = lg[l][i, j]
+        if len(np.unique(v)) != M:
+            pytest.skip("tied logits")
+        snapped_same_order = np.array_equal(np.argsort(table.thresholds[l].cpu().numpy(), kind="stable"), np.arange(M))
+        assert snapped_same_order
+        ref_rank = np.rint(ref_norm[l][i, j].astype(np.float64) * M).astype(np.int64)
+        got = fused[l][i, j].astype(np.int64)
+        # snapping moves a threshold by <= a few grid cells: ranks agree except where two scores are closer than that
+        assert np.abs(got - ref_rank).max() <= 2
+        assert (got == ref_rank).mean() > 0.98
+
+
+def test_rank_edge_values(mb, cuda_device):
+    q = torch.linspace(-1, 1, 1000, device=cuda_device)[None, :].contiguous()
+    table = mb.RankTable(q)
+    x = torch.tensor([[-1e30, -1.5, -1.0, 0.0, 1.0, 1.5, 1e30, 3.4e38, -3.4e38]], device=cuda_device)
+    got = table.lookup(x).cpu().numpy()
+    ref = oracle.quantile_rank(table.thresholds.cpu().numpy(), x.cpu().numpy(), "right")
+    assert np.array_equal(got, ref)
+    assert got[0, 0] == 0 and got[0, 6] == 1000
+
+
+def test_config1_full_size_properties(mb, cuda_device):
+    """BASELINE config 1 (1,024 drugs x 86 outcomes, D=128): fp32 parity on a slice + size-independent properties."""
+    N, D, L = 1024, 128, 86
+    z, W = synth.decoder_inputs(N, D, L, seed=0)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    got = mb.pair_score(zt, zt, Wt, precision="fp32")
+    ref = oracle.bilinear_scores(z, z, W, (10, 14), dtype=np.float64)
+    assert_close(got[10:14].cpu().numpy(), ref, 1e-3, "config 1 slice")
+    # symmetry (W symmetric, same z on both sides) up to fp32 accumulation order
+    assert (got - got.transpose(1, 2)).abs().max().item() <= 1e-5
+    # linearity in W: S(W1 + W2) = S(W1) + S(W2)
+    s12 = mb.pair_score(zt, zt, (Wt[:4] + Wt[4:8]).contiguous(), precision="fp32")
+    assert (s12 - (got[:4] + got[4:8])).abs().max().item() <= 2e-5
+    # checksum of checksums: sum_ij S_l[i,j] = (sum_i z_i) W_l (sum_j z_j)
+    zs = z.astype(np.float64).sum(0)
+    expect = np.einsum("a,lab,b->l", zs, W.astype(np.float64), zs)
+    total = got.double().sum(dim=(1, 2)).cpu().numpy()
+    assert np.abs(total - expect).max() <= 1e-3 * np.abs(expect).max() + 1e-2
