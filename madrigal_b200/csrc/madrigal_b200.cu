@@ -126,16 +126,25 @@ PairWorkspace carve_pair_ws(void* ws, int64_t Nr, int64_t Nc, int64_t D, int64_t
   return w;
 }
 
-int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                       mdg::PairScoreParams& p, cudaStream_t stream) {
+template <int EPI, int NE>
+int launch_pair_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                         const mdg::PairScoreParams& p, int grid, cudaStream_t stream) {
+  using SM = mdg::PairSmem<NE>;
   static bool attr_set[64] = {false};
   int dev = 0;
   MDG_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    MDG_CUDA(cudaFuncSetAttribute(mdg::pair_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  mdg::kPairSmemBytes));
+    MDG_CUDA(cudaFuncSetAttribute(mdg::pair_score_kernel<EPI, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  SM::kBytes));
     attr_set[dev] = true;
   }
+  mdg::pair_score_kernel<EPI, NE><<<grid, SM::kThreads, SM::kBytes, stream>>>(tmA, tmB, tmOut, p);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
+}
+
+int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                       mdg::PairScoreParams& p, int epi_mode, cudaStream_t stream) {
   // task decomposition: enough tasks for ~8 per CTA, chunks of >= 4 column blocks
   const int sms = num_sms();
   p.n_blocks = static_cast<int>((p.cols + mdg::kBN - 1) / mdg::kBN);
@@ -153,9 +162,23 @@ int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if (tasks > 0x7fffffffLL) return fail(MDG_ERR_UNSUPPORTED, "too many tasks (%lld)", (long long)tasks);
   p.num_tasks = static_cast<int>(tasks);
   if (p.num_tasks == 0) return MDG_OK;
-  int grid = p.num_tasks < sms ? p.num_tasks : sms;
-  mdg::pair_score_kernel<<<grid, mdg::kPairThreads, mdg::kPairSmemBytes, stream>>>(tmA, tmB, tmOut, p);
-  MDG_CUDA(cudaGetLastError());
+  const int grid = p.num_tasks < sms ? p.num_tasks : sms;
+  static const int rank_warps = [] {
+    const char* e = getenv("MDG_RANK_EPI_WARPS");  // tuning knob: 8 or 16 epilogue warps for the rank epilogue
+    return (e && atoi(e) == 8) ? 8 : 16;
+  }();
+  int rc;
+  switch (epi_mode) {
+    case mdg::EPI_F32: rc = launch_pair_instance<mdg::EPI_F32, 8>(tmA, tmB, tmOut, p, grid, stream); break;
+    case mdg::EPI_SIGMOID: rc = launch_pair_instance<mdg::EPI_SIGMOID, 8>(tmA, tmB, tmOut, p, grid, stream); break;
+    case mdg::EPI_BF16_SPLIT: rc = launch_pair_instance<mdg::EPI_BF16_SPLIT, 8>(tmA, tmB, tmOut, p, grid, stream); break;
+    case mdg::EPI_RANK_U16:
+      rc = (rank_warps == 8) ? launch_pair_instance<mdg::EPI_RANK_U16, 8>(tmA, tmB, tmOut, p, grid, stream)
+                             : launch_pair_instance<mdg::EPI_RANK_U16, 16>(tmA, tmB, tmOut, p, grid, stream);
+      break;
+    default: return fail(MDG_ERR_INVALID_ARGUMENT, "bad epilogue mode %d", epi_mode);
+  }
+  if (rc) return rc;
   ++g_last_launches;
   return MDG_OK;
 }
@@ -289,14 +312,13 @@ int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int
     p.msub = msub;
     p.a_batched = 0;
     p.b_batched = 1;
-    p.epi_mode = mdg::EPI_BF16_SPLIT;
     p.use_tma_store = 1;
     p.lo_col_offset = static_cast<int>(D);
     p.write_lo = split;
     p.out = ws.y;
     p.out_ld = ka;
     p.out_batch_stride = ws.nr_pad * ka;
-    rc = launch_pair_kernel(tmA, tmB, tmOut, p, stream);
+    rc = launch_pair_kernel(tmA, tmB, tmOut, p, mdg::EPI_BF16_SPLIT, stream);
     if (rc) return rc;
   }
   // ---- GEMM 2:  S[l] = Y[l] . z_cols^T    A = y [L, nr_pad, ka], B = zc [1, nc_pad, ka], out [L, Nr, Nc]
@@ -322,12 +344,11 @@ int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int
     p.out_batch_stride = Nr * Nc;
     int elem = 4;
     CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    if (out_mode == MDG_OUT_LOGIT_F32) {
-      p.epi_mode = mdg::EPI_F32;
-    } else if (out_mode == MDG_OUT_SIGMOID_F32) {
-      p.epi_mode = mdg::EPI_SIGMOID;
-    } else {
-      p.epi_mode = mdg::EPI_RANK_U16;
+    int epi = mdg::EPI_F32;
+    if (out_mode == MDG_OUT_SIGMOID_F32) {
+      epi = mdg::EPI_SIGMOID;
+    } else if (out_mode == MDG_OUT_RANK_U16) {
+      epi = mdg::EPI_RANK_U16;
       p.lut = table->lut;
       p.affine = table->affine;
       elem = 2;
@@ -345,7 +366,7 @@ int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int
     }
     const bool prof = g_prof_cap > 0 && g_prof_count < g_prof_cap;
     if (prof) MDG_CUDA(cudaEventRecord(g_prof_start[g_prof_count], stream));
-    rc = launch_pair_kernel(tmA, tmB, tmOut, p, stream);
+    rc = launch_pair_kernel(tmA, tmB, tmOut, p, epi, stream);
     if (rc) return rc;
     if (prof) {
       MDG_CUDA(cudaEventRecord(g_prof_stop[g_prof_count], stream));

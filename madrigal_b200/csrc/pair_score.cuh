@@ -9,7 +9,7 @@
 //   warp 1      UMMA issuer    : tcgen05.mma cta_group::1 kind::f16, 128x128x16, fp32 accumulators in TMEM,
 //                                2 accumulator stages x up to 2 row sub-tiles = 512 TMEM columns
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue       : tcgen05.ld -> registers -> {fp32 | sigmoid | u16 quantile rank | bf16 hi/lo}
+//   warps 4..   epilogue       : tcgen05.ld -> registers -> {fp32 | sigmoid | u16 quantile rank | bf16 hi/lo}
 //                                -> 64-byte-swizzled staging in smem -> TMA store (or guarded direct stores)
 //
 // A task = (outcome l, 128*msub-row block, chunk of 128-column blocks).  Within a task the A operand stays in
@@ -31,23 +31,27 @@ constexpr int kBK = 64;  // bf16 elements per K block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kPanelBytes = kBM * kBK * 2;  // 16 KB: one [128 x 64] bf16 panel
 constexpr int kMaxAPanels = 8;              // 128 KB resident A
-constexpr int kBStages = 3;
-constexpr int kNumEpiWarps = 8;
 constexpr int kFirstEpiWarp = 4;
-constexpr int kPairThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 384
-constexpr int kStagingBytesPerWarp = 2048;                         // 32 rows x 64 B
+constexpr int kStagingBytesPerWarp = 2048;  // 32 rows x 64 B
 constexpr int kTmemCols = 512;
 
-constexpr int kSmemA = 0;
-constexpr int kSmemB = kSmemA + kMaxAPanels * kPanelBytes;                  // 131072
-constexpr int kSmemStaging = kSmemB + kBStages * kPanelBytes;               // 180224
-constexpr int kSmemLut = kSmemStaging + kNumEpiWarps * kStagingBytesPerWarp;  // 196608
-constexpr int kSmemBar = kSmemLut + kRankLutEntries * 4;                    // 229376
-constexpr int kSmemTotal = kSmemBar + 128;
-constexpr int kPairSmemBytes = kSmemTotal + 1024;  // + slack for manual 1024-byte alignment
-static_assert(kPairSmemBytes <= 232448, "exceeds 227 KB of shared memory per CTA");
-
 enum EpiMode : int { EPI_F32 = 0, EPI_SIGMOID = 1, EPI_RANK_U16 = 2, EPI_BF16_SPLIT = 3 };
+
+// Shared-memory plan for a kernel instance with NE epilogue warps (staging is per warp, so more epilogue warps
+// trade one B stage for staging space).
+template <int NE>
+struct PairSmem {
+  static constexpr int kBStages = (NE > 8) ? 2 : 3;
+  static constexpr int kA = 0;
+  static constexpr int kB = kA + kMaxAPanels * kPanelBytes;
+  static constexpr int kStaging = kB + kBStages * kPanelBytes;
+  static constexpr int kLut = kStaging + NE * kStagingBytesPerWarp;
+  static constexpr int kBar = kLut + kRankLutEntries * 4;
+  static constexpr int kTotal = kBar + 128;
+  static constexpr int kBytes = kTotal + 1024;  // + slack for manual 1024-byte alignment
+  static constexpr int kThreads = (kFirstEpiWarp + NE) * 32;
+  static_assert(kBytes <= 232448, "exceeds 227 KB of shared memory per CTA");
+};
 
 struct PairScoreParams {
   int L;          // outcomes in this launch
@@ -63,11 +67,9 @@ struct PairScoreParams {
   int nchunk;
   int chunks_per_row;
   int num_tasks;
-  int epi_mode;
   int use_tma_store;
   int lo_col_offset;  // EPI_BF16_SPLIT: column offset of the lo half in the output rows
   int write_lo;
-  int symmetric;      // MDG_PAIRS_SYMMETRIC: skip column blocks entirely above the diagonal, mask i <= j to 0
   void* out;          // direct-store path
   long long out_ld;   // elements per output row
   long long out_batch_stride;
@@ -81,13 +83,13 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   return v;
 }
 
-// rank lookup against the LUT staged in shared memory (same arithmetic as rank_lookup_raw)
+// Rank lookup against the LUT staged in shared memory (same arithmetic as rank_lookup_raw).  mul.hi keeps the
+// bucket extraction on the (idle) FMA pipe instead of the ALU pipe the epilogue is bound by.
 __device__ __forceinline__ uint32_t rank_lookup_smem(uint32_t lut_smem, float x, float scale, float bias) {
-  uint32_t kb = rank_key_bits(x, scale, bias);
-  uint32_t off = (kb >> (kRankBucketShift - 2)) & ((kRankLutEntries - 1) << 2);
-  uint32_t e = lds_u32(lut_smem + off);
-  uint32_t sh = (~(kb >> kRankCellShift) & 15u) | 16u;
-  return e + __popc(e >> sh);
+  const uint32_t kb = rank_key_bits(x, scale, bias);
+  uint32_t bucket;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(bucket) : "r"(kb), "r"(1u << 28));  // kb >> 4
+  return rank_finish(lds_u32(lut_smem + bucket * 4), kb);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -108,25 +110,48 @@ __device__ __forceinline__ TaskCoord decode_task(const PairScoreParams& p, int t
   c.m0 = mb * kBM * p.msub;
   c.nb0 = ch * p.nchunk;
   c.nb1 = min(c.nb0 + p.nchunk, p.n_blocks);
-  if (p.symmetric) {
-    // only column blocks that intersect the strict lower triangle of this row block: n0 < m0 + rows_in_tile
-    int last = (c.m0 + kBM * p.msub - 1) / kBN;  // block containing the diagonal of the last row
-    c.nb1 = min(c.nb1, last + 1);
-    if (c.nb1 < c.nb0) c.nb1 = c.nb0;
-  }
   return c;
 }
 
-__global__ void __launch_bounds__(kPairThreads, 1)
+// One warp's 32 rows x 64 bytes: registers -> 64B-swizzled staging -> TMA store (bulk group per chunk).
+struct StagedStore {
+  uint32_t staging;  // this warp's 2 KB buffer
+  uint32_t my_row;   // staging + lane * 64
+  uint32_t swz;      // (lane >> 1) & 3
+  bool pending;
+  __device__ __forceinline__ void store(const CUtensorMap* tm, const uint32_t (&w)[16], int c0, int c1, int c2,
+                                        int lane) {
+    if (pending) {
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      st_shared_v4(my_row + ((static_cast<uint32_t>(ch) ^ swz) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2],
+                   w[4 * ch + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tm, staging, c0, c1, c2);
+      tma_store_commit();
+    }
+    pending = true;
+  }
+};
+
+template <int EPI, int NE>
+__global__ void __launch_bounds__(PairSmem<NE>::kThreads, 1)
 pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ PairScoreParams p) {
+  using SM = PairSmem<NE>;
+  constexpr int kBStages = SM::kBStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw_addr);
 
-  const uint32_t sA = base + kSmemA, sB = base + kSmemB, sStaging = base + kSmemStaging, sLut = base + kSmemLut,
-                 sBar = base + kSmemBar;
+  const uint32_t sA = base + SM::kA, sB = base + SM::kB, sStaging = base + SM::kStaging, sLut = base + SM::kLut,
+                 sBar = base + SM::kBar;
   const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8;
   auto bar_b_full = [&](int i) { return sBar + 16 + 8 * i; };
   auto bar_b_empty = [&](int i) { return sBar + 40 + 8 * i; };
@@ -146,7 +171,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_t_full(i), 1);
-      mbar_init(bar_t_empty(i), kNumEpiWarps);
+      mbar_init(bar_t_empty(i), NE);
     }
     fence_mbar_init();
   }
@@ -159,7 +184,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kSmemBar + 96);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + SM::kBar + 96);
 
   const int kb = p.kb;
   const int n_apanels = (p.nterm == 1) ? p.msub * kb : 2 * kb;
@@ -171,9 +196,8 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t b_phase = 0;
       int it = 0;  // executed tasks (parity of the A barriers)
-      for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
+      for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x, ++it) {
         const TaskCoord c = decode_task(p, t);
-        if (c.nb1 <= c.nb0) continue;  // (symmetric mode) nothing to do; all roles skip identically
         mbar_wait(bar_a_empty, (it & 1) ^ 1, 1);
         mbar_arrive_expect_tx(bar_a_full, n_apanels * kPanelBytes);
         for (int pn = 0; pn < n_apanels; ++pn) {
@@ -200,7 +224,6 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         }
-        ++it;
       }
     }
   } else if (warp == 1) {
@@ -212,9 +235,8 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int acc_stage = 0;
       uint32_t acc_phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
+      for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x, ++it) {
         const TaskCoord c = decode_task(p, t);
-        if (c.nb1 <= c.nb0) continue;
         mbar_wait(bar_a_full, it & 1, 3);
         for (int nb = c.nb0; nb < c.nb1; ++nb) {
           mbar_wait(bar_t_empty(acc_stage), acc_phase ^ 1, 4);
@@ -224,34 +246,32 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(bar_b_full(stage), b_phase, 5);
             tc_fence_after_sync();
             const uint64_t bdesc = umma_desc_kmajor_sw128(sB + stage * kPanelBytes);
-            int npan, pan[2], accs[2];
-            if (p.nterm == 1) {
+            int npan, pan0, pan1, acc0 = 0, acc1 = 0;
+            if (p.nterm == 1) {  // one bf16 term, msub row sub-tiles share this B panel
               npan = p.msub;
-              pan[0] = kbi;
-              accs[0] = 0;
-              pan[1] = kb + kbi;
-              accs[1] = 1;
+              pan0 = kbi;
+              pan1 = kb + kbi;
+              acc1 = 1;
             } else if (kbi < kb) {  // B = hi:  A_hi[k], A_lo[k]
               npan = 2;
-              pan[0] = kbi;
-              pan[1] = kb + kbi;
-              accs[0] = accs[1] = 0;
+              pan0 = kbi;
+              pan1 = kb + kbi;
             } else {  // B = lo:  A_hi[k]
               npan = 1;
-              pan[0] = kbi - kb;
-              accs[0] = 0;
-              pan[1] = 0;
-              accs[1] = 0;
+              pan0 = kbi - kb;
+              pan1 = 0;
             }
             for (int i = 0; i < npan; ++i) {
-              const uint64_t adesc = umma_desc_kmajor_sw128(sA + pan[i] * kPanelBytes);
-              const uint32_t d = tmem_base + static_cast<uint32_t>((acc_stage * 2 + accs[i]) * kBN);
+              const int pn = i ? pan1 : pan0;
+              const int ac = i ? acc1 : acc0;
+              const uint64_t adesc = umma_desc_kmajor_sw128(sA + pn * kPanelBytes);
+              const uint32_t d = tmem_base + static_cast<uint32_t>((acc_stage * 2 + ac) * kBN);
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k) {
-                const uint32_t acc = ((started >> accs[i]) & 1u) | (k > 0 ? 1u : 0u);
+                const uint32_t acc = ((started >> ac) & 1u) | (k > 0 ? 1u : 0u);
                 umma_bf16(d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc, acc);
               }
-              started |= 1u << accs[i];
+              started |= 1u << ac;
             }
             umma_commit(bar_b_empty(stage));  // frees this B stage once the MMAs above have read it
             if (++stage == kBStages) {
@@ -264,88 +284,69 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (acc_stage == 0) acc_phase ^= 1;
         }
         umma_commit(bar_a_empty);  // every MMA of this task has finished reading the resident A panels
-        ++it;
       }
     }
   } else if (warp >= kFirstEpiWarp) {
     // ============================================================ epilogue warps
     const int ew = warp - kFirstEpiWarp;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;   // 0 / 1
-    const int ms = (p.msub == 2) ? half : 0;
-    const int col_begin = (p.msub == 2) ? 0 : half * (kBN / 2);
-    const int col_end = (p.msub == 2) ? kBN : col_begin + kBN / 2;
-    const uint32_t my_staging = sStaging + ew * kStagingBytesPerWarp;
-    const uint32_t swz = static_cast<uint32_t>((lane >> 1) & 3);  // 64-byte swizzle: chunk ^= (row >> 1) & 3
-    const uint32_t my_row_smem = my_staging + lane * 64;
+    const int grp = ew >> 2;    // which slice of the quadrant's msub*128 accumulator columns
+    constexpr int kGroups = NE / 4;
+    const int cols_per_warp = p.msub * kBN / kGroups;
+    const int ms = (grp * cols_per_warp) / kBN;
+    const int col_begin = (grp * cols_per_warp) % kBN;
+    const int col_end = col_begin + cols_per_warp;
+    StagedStore ss;
+    ss.staging = sStaging + ew * kStagingBytesPerWarp;
+    ss.my_row = ss.staging + lane * 64;
+    ss.swz = static_cast<uint32_t>((lane >> 1) & 3);  // 64-byte swizzle: chunk ^= (row >> 1) & 3
+    ss.pending = false;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     int cur_l = -1;
     float scale = 0.f, bias = 0.f;
-    bool store_pending = false;
 
     for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
       const TaskCoord c = decode_task(p, t);
-      if (c.nb1 <= c.nb0) continue;
-      if (p.epi_mode == EPI_RANK_U16 && c.l != cur_l) {
-        named_bar_sync(1, kNumEpiWarps * 32);  // everyone is done with the previous outcome's LUT
+      if (EPI == EPI_RANK_U16 && c.l != cur_l) {
+        named_bar_sync(1, NE * 32);  // everyone is done with the previous outcome's LUT
         const uint4* src = reinterpret_cast<const uint4*>(p.lut + static_cast<size_t>(c.l) * kRankLutEntries);
         const int tid = ew * 32 + lane;
 #pragma unroll 4
-        for (int i = tid; i < kRankLutEntries / 4; i += kNumEpiWarps * 32) {
+        for (int i = tid; i < kRankLutEntries / 4; i += NE * 32) {
           uint4 v = __ldg(src + i);
           st_shared_v4(sLut + i * 16, v.x, v.y, v.z, v.w);
         }
         scale = __ldg(p.affine + 2 * c.l);
         bias = __ldg(p.affine + 2 * c.l + 1);
         cur_l = c.l;
-        named_bar_sync(1, kNumEpiWarps * 32);
+        named_bar_sync(1, NE * 32);
       }
       const int row0 = c.m0 + ms * kBM + quad * 32;  // first of this warp's 32 rows
       const int my_row = row0 + lane;
       for (int nb = c.nb0; nb < c.nb1; ++nb) {
         mbar_wait(bar_t_full(acc_stage), acc_phase, 6);
         tc_fence_after_sync();
-        const bool tile_live = row0 < p.rows && !(p.symmetric && nb * kBN > row0 + 31);
-        if (tile_live) {
+        if (row0 < p.rows) {
           for (int cc = col_begin; cc < col_end; cc += 32) {
             const int n0 = nb * kBN + cc;
             if (n0 >= p.cols) break;
-            if (p.symmetric && n0 > row0 + 31) break;  // chunk entirely above the diagonal
             uint32_t v[32];
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    static_cast<uint32_t>((acc_stage * 2 + ms) * kBN + cc);
             tmem_ld_32x32(taddr, v);
             tmem_ld_wait();
 
-            if (p.epi_mode == EPI_RANK_U16) {
+            if constexpr (EPI == EPI_RANK_U16) {
               uint32_t pk[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                uint32_t r0 = rank_lookup_smem(sLut, __uint_as_float(v[2 * j]), scale, bias);
-                uint32_t r1 = rank_lookup_smem(sLut, __uint_as_float(v[2 * j + 1]), scale, bias);
-                if (p.symmetric) {  // reference zeroes i <= j (normalize_scores.py:69)
-                  if (n0 + 2 * j >= my_row) r0 = 0;
-                  if (n0 + 2 * j + 1 >= my_row) r1 = 0;
-                }
+                const uint32_t r0 = rank_lookup_smem(sLut, __uint_as_float(v[2 * j]), scale, bias);
+                const uint32_t r1 = rank_lookup_smem(sLut, __uint_as_float(v[2 * j + 1]), scale, bias);
                 pk[j] = __byte_perm(r0, r1, 0x5410);
               }
               if (p.use_tma_store) {
-                if (store_pending) {
-                  if (lane == 0) tma_store_wait_read<0>();
-                  __syncwarp();
-                }
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-                  st_shared_v4(my_row_smem + ((static_cast<uint32_t>(ch) ^ swz) << 4), pk[4 * ch], pk[4 * ch + 1],
-                               pk[4 * ch + 2], pk[4 * ch + 3]);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                  tma_store_3d(&tmOut, my_staging, n0, row0, c.l);
-                  tma_store_commit();
-                }
-                store_pending = true;
+                ss.store(&tmOut, pk, n0, row0, c.l, lane);
               } else if (my_row < p.rows) {
                 uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + c.l * p.out_batch_stride + my_row * p.out_ld + n0;
 #pragma unroll
@@ -354,7 +355,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   if (n0 + 2 * j + 1 < p.cols) o[2 * j + 1] = static_cast<uint16_t>(pk[j] >> 16);
                 }
               }
-            } else if (p.epi_mode == EPI_BF16_SPLIT) {
+            } else if constexpr (EPI == EPI_BF16_SPLIT) {
               // hi = bf16(y), lo = bf16(y - hi): the A operand of the second GEMM, K-major rows [hi | lo]
               for (int part = 0; part < (p.write_lo ? 2 : 1); ++part) {
                 uint32_t pk[16];
@@ -369,21 +370,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 const int ncol = n0 + part * p.lo_col_offset;
                 if (p.use_tma_store) {
-                  if (store_pending) {
-                    if (lane == 0) tma_store_wait_read<0>();
-                    __syncwarp();
-                  }
-#pragma unroll
-                  for (int ch = 0; ch < 4; ++ch)
-                    st_shared_v4(my_row_smem + ((static_cast<uint32_t>(ch) ^ swz) << 4), pk[4 * ch], pk[4 * ch + 1],
-                                 pk[4 * ch + 2], pk[4 * ch + 3]);
-                  fence_proxy_async_smem();
-                  __syncwarp();
-                  if (lane == 0) {
-                    tma_store_3d(&tmOut, my_staging, ncol, row0, c.l);
-                    tma_store_commit();
-                  }
-                  store_pending = true;
+                  ss.store(&tmOut, pk, ncol, row0, c.l, lane);
                 } else if (my_row < p.rows) {
                   uint32_t* o = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) +
                                                             c.l * p.out_batch_stride + my_row * p.out_ld + ncol);
@@ -394,37 +381,19 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             } else {
               // fp32 logits or sigmoid
-              if (p.epi_mode == EPI_SIGMOID) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  float x = __uint_as_float(v[j]);
-                  v[j] = __float_as_uint(1.0f / (1.0f + expf(-x)));
-                }
-              }
-              if (p.symmetric) {
+              if constexpr (EPI == EPI_SIGMOID) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (n0 + j >= my_row) v[j] = 0u;
+                  v[j] = __float_as_uint(__fdividef(1.0f, 1.0f + __expf(-__uint_as_float(v[j]))));
               }
               if (p.use_tma_store) {
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {  // two 16-column (64-byte) fills
                   if (n0 + hf * 16 >= p.cols) break;
-                  if (store_pending) {
-                    if (lane == 0) tma_store_wait_read<0>();
-                    __syncwarp();
-                  }
+                  uint32_t w[16];
 #pragma unroll
-                  for (int ch = 0; ch < 4; ++ch)
-                    st_shared_v4(my_row_smem + ((static_cast<uint32_t>(ch) ^ swz) << 4), v[hf * 16 + 4 * ch],
-                                 v[hf * 16 + 4 * ch + 1], v[hf * 16 + 4 * ch + 2], v[hf * 16 + 4 * ch + 3]);
-                  fence_proxy_async_smem();
-                  __syncwarp();
-                  if (lane == 0) {
-                    tma_store_3d(&tmOut, my_staging, n0 + hf * 16, row0, c.l);
-                    tma_store_commit();
-                  }
-                  store_pending = true;
+                  for (int j = 0; j < 16; ++j) w[j] = v[hf * 16 + j];
+                  ss.store(&tmOut, w, n0 + hf * 16, row0, c.l, lane);
                 }
               } else if (my_row < p.rows) {
                 float* o = reinterpret_cast<float*>(p.out) + c.l * p.out_batch_stride + my_row * p.out_ld + n0;
@@ -442,7 +411,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (acc_stage == 0) acc_phase ^= 1;
       }
     }
-    if (store_pending && lane == 0) tma_store_wait_all<0>();
+    if (ss.pending && lane == 0) tma_store_wait_all<0>();
     __syncwarp();
   }
 

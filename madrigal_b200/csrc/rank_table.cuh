@@ -7,9 +7,9 @@
 // table of that set bounds |rank/Q - reference normalised rank| by 1/Q ("rank semantics").
 //
 // How the lookup is made O(1) and still exact:
-//   key(x)  = 23-bit fixed-point image of x under a per-outcome affine map, computed with two FFMAs; it is a
-//             monotone non-decreasing function of x because each fp32 rounding is monotone;
-//   cell(x) = key(x) >> 6   (17 bits = 8192 buckets x 16 sub-cells);
+//   cell(x) = round(sat(x*scale + bias) * (2^17 - 1)): a 17-bit fixed-point image of x (8192 buckets x 16 sub-cells)
+//             under a per-outcome affine map, computed with two FFMAs; monotone non-decreasing in x because each
+//             fp32 rounding is monotone;
 //   every threshold is SNAPPED by the builder to   t_i = min{ fp32 f : cell(f) >= c_i }   for a strictly increasing
 //   cell sequence c_i, so that   x >= t_i  <=>  cell(x) >= c_i   (=> by monotonicity, <= by minimality);
 //   hence #{t_i <= x} = #{c_i <= cell(x)} = lut[bucket].base + popc(occupied sub-cells <= sub(x)).
@@ -24,31 +24,35 @@ namespace mdg {
 constexpr int kRankBucketBits = MDG_RANK_BUCKET_BITS;
 constexpr int kRankSubBits = MDG_RANK_SUB_BITS;
 constexpr int kRankCellBits = kRankBucketBits + kRankSubBits;  // 17
-constexpr int kRankKeyBits = 23;
-constexpr int kRankCellShift = kRankKeyBits - kRankCellBits;   // 6
-constexpr int kRankBucketShift = kRankKeyBits - kRankBucketBits;  // 10
 constexpr int kRankCells = 1 << kRankCellBits;
 constexpr int kRankLutEntries = MDG_RANK_LUT_ENTRIES;
 static_assert(kRankSubBits == 4, "LUT entry packs a 16-bit occupancy bitmap");
 
-// bits(w) with w in [1, 2): low 23 bits are the key. Monotone non-decreasing in x for scale > 0.
+// cell(x) = round(sat(x*scale + bias) * (2^17 - 1)) in [0, 2^17), produced directly as an INTEGER bit pattern:
+// multiplying by the subnormal constant (2^17 - 1) * 2^-149 yields a subnormal result whose bit pattern is the
+// rounded integer (subnormals are exact multiples of 2^-149; FMUL rounds to nearest-even at full speed, no FTZ).
+// One FFMA + one FMUL, monotone non-decreasing in x for scale > 0.
 __device__ __forceinline__ uint32_t rank_key_bits(float x, float scale, float bias) {
-  float y = __saturatef(fmaf(x, scale, bias));     // [0, 1]
-  float w = fmaf(y, 0.99999988079071044921875f /* 1 - 2^-23 */, 1.0f);  // [1, 2 - 2^-23]
-  return __float_as_uint(w);
+  const float y = __saturatef(fmaf(x, scale, bias));  // [0, 1]
+  const float c = __uint_as_float(static_cast<uint32_t>(kRankCells - 1));  // subnormal: (2^17 - 1) * 2^-149
+  return __float_as_uint(__fmul_rn(y, c));
 }
 __device__ __forceinline__ uint32_t rank_cell(float x, float scale, float bias) {
-  return (rank_key_bits(x, scale, bias) & 0x7FFFFFu) >> kRankCellShift;
+  return rank_key_bits(x, scale, bias);
 }
 
-// Generic-pointer version (global or shared LUT). Returns base + count with garbage in the high half-word:
-// callers take the low 16 bits (the fused epilogue does it for free when packing two ranks with PRMT).
+// LUT entry: base (thresholds in earlier buckets) in the low half-word, occupancy bitmap in the high half-word with
+// sub-cell j at bit 31 - j, so   #{occupied sub-cells <= sub} = popc(entry >> (31 - sub)).
+// Returns base + count with garbage in the high half-word: callers take the low 16 bits (the fused epilogue does
+// it for free when packing two ranks with PRMT).
+__device__ __forceinline__ uint32_t rank_finish(uint32_t entry, uint32_t key_bits) {
+  uint32_t sh;  // 31 - sub = (~key & 15) | 16 in ONE LOP3
+  asm("lop3.b32 %0, %1, %2, %3, 0xAE;" : "=r"(sh) : "r"(key_bits), "r"(15u), "r"(16u));
+  return entry + __popc(entry >> sh);
+}
 __device__ __forceinline__ uint32_t rank_lookup_raw(const uint32_t* lut, float x, float scale, float bias) {
   uint32_t kb = rank_key_bits(x, scale, bias);
-  uint32_t bucket = (kb >> kRankBucketShift) & (kRankLutEntries - 1);
-  uint32_t e = lut[bucket];
-  uint32_t sh = (~(kb >> kRankCellShift) & 15u) | 16u;  // 31 - sub
-  return e + __popc(e >> sh);
+  return rank_finish(lut[kb >> kRankSubBits], kb);
 }
 
 // ------------------------------------------------------------------------------------------------ builder
