@@ -145,12 +145,17 @@ int launch_pair_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
 
 int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                        mdg::PairScoreParams& p, int epi_mode, cudaStream_t stream) {
-  // task decomposition: enough tasks for ~8 per CTA, chunks of >= 4 column blocks
+  // task decomposition: enough tasks for ~16 per CTA (tail <= ~6%), chunks of >= 4 column blocks
   const int sms = num_sms();
   p.n_blocks = static_cast<int>((p.cols + mdg::kBN - 1) / mdg::kBN);
   p.m_blocks = static_cast<int>((p.rows + mdg::kBM * p.msub - 1) / (mdg::kBM * p.msub));
   int64_t row_tasks = static_cast<int64_t>(p.L) * p.m_blocks;
-  int want_chunks = static_cast<int>((8LL * sms + row_tasks - 1) / row_tasks);
+  static const int tasks_per_cta = [] {
+    const char* e = getenv("MDG_TASKS_PER_CTA");  // tuning knob
+    int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 16;
+  }();
+  int want_chunks = static_cast<int>((static_cast<int64_t>(tasks_per_cta) * sms + row_tasks - 1) / row_tasks);
   if (want_chunks < 1) want_chunks = 1;
   int nchunk = (p.n_blocks + want_chunks - 1) / want_chunks;
   if (nchunk < 4) nchunk = 4;

@@ -186,6 +186,11 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + SM::kBar + 96);
 
+  // Tasks are outcome-major and dealt round-robin, so the CTAs running at any moment cover a few adjacent outcomes:
+  // their output tiles stay within a compact address range (measured: giving each CTA a contiguous task range
+  // instead spreads the concurrent writes over all outcomes and is 20% slower) and they share z_cols through L2.
+  const int t_begin = static_cast<int>(blockIdx.x), t_end = p.num_tasks, t_step = static_cast<int>(gridDim.x);
+
   const int kb = p.kb;
   const int n_apanels = (p.nterm == 1) ? p.msub * kb : 2 * kb;
   const int kb_b = (p.nterm == 1) ? kb : 2 * kb;
@@ -196,7 +201,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t b_phase = 0;
       int it = 0;  // executed tasks (parity of the A barriers)
-      for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x, ++it) {
+      for (int t = t_begin; t < t_end; t += t_step, ++it) {
         const TaskCoord c = decode_task(p, t);
         mbar_wait(bar_a_empty, (it & 1) ^ 1, 1);
         mbar_arrive_expect_tx(bar_a_full, n_apanels * kPanelBytes);
@@ -235,7 +240,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int acc_stage = 0;
       uint32_t acc_phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x, ++it) {
+      for (int t = t_begin; t < t_end; t += t_step, ++it) {
         const TaskCoord c = decode_task(p, t);
         mbar_wait(bar_a_full, it & 1, 3);
         for (int nb = c.nb0; nb < c.nb1; ++nb) {
@@ -306,7 +311,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int cur_l = -1;
     float scale = 0.f, bias = 0.f;
 
-    for (int t = blockIdx.x; t < p.num_tasks; t += gridDim.x) {
+    for (int t = t_begin; t < t_end; t += t_step) {
       const TaskCoord c = decode_task(p, t);
       if (EPI == EPI_RANK_U16 && c.l != cur_l) {
         named_bar_sync(1, NE * 32);  // everyone is done with the previous outcome's LUT
