@@ -211,12 +211,30 @@ typedef struct MdgFusionCfg {
  *   src_mask      [T, T] uint8 or NULL, non-zero = query row may not attend key column (`src_mask`)
  *   pool_key_mask [T] uint8 or NULL: x-attn pooling's constant key mask (`x_attn_key_padding_mask`, models.py:382-385)
  *   z_out         [B, E] fp32
- *   workspace     >= mdg_fusion_workspace_bytes(cfg, B) bytes
+ *   precision     MdgPrecision of the nn.Linear GEMMs (LayerNorm, softmax, residual stream are always fp32)
+ *   workspace     >= mdg_fusion_workspace_bytes(cfg, B, precision) bytes, 256-byte aligned
  */
-size_t mdg_fusion_workspace_bytes(const MdgFusionCfg* cfg, int64_t B);
+size_t mdg_fusion_workspace_bytes(const MdgFusionCfg* cfg, int64_t B, int precision);
 int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const float* tokens,
                       const uint8_t* key_mask, const uint8_t* src_mask, const uint8_t* pool_key_mask, float* z_out,
-                      int64_t B, void* workspace, size_t workspace_bytes, void* stream);
+                      int64_t B, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Token assembly feeding mdg_fusion_encode  (reference: NovelDDIEncoder.encode, models.py:772-852).
+ *   embeds [B, M, E] stacked modality embeddings in the order [non-TX..., TX...] (models.py:772), masks [B, M] uint8
+ *   (non-zero = modality missing).  Sequence: [cls?][non-TX][bottleneck tokens][TX]; bottleneck / CLS tokens are
+ *   never masked (models.py:805, 823).  cls_token NULL = no CLS.  normalize: L2-normalise each token (models.py:849).
+ *   pos_enc [pos_len, E] is added to the first pos_len tokens (sinusoidal buffer or learnable parameter).
+ *   seq_out [B, T, E], seq_mask_out [B, T] with T = M + num_bottlenecks + (cls ? 1 : 0). */
+int mdg_assemble_tokens(const float* embeds, const uint8_t* masks, int64_t B, int32_t M, int32_t E, int32_t n_non_tx,
+                        int32_t num_bottlenecks, const float* bottleneck_tokens, const float* cls_token,
+                        const float* pos_enc, int32_t pos_len, int32_t normalize, float* seq_out,
+                        uint8_t* seq_mask_out, void* stream);
+
+/* Masked pooling over tokens: mode 0 = mean, 1 = max, 2 = sum of the un-masked tokens of each drug (reference:
+ * fusion='mean' / 'add', models.py:870-878, and the 'mean'/'max' aggregations' scatter_mean/scatter_max).
+ *   tokens [B, T, E], masks [B, T] (non-zero = missing) -> z_out [B, E]; a drug with no visible token gives 0. */
+int mdg_masked_pool(const float* tokens, const uint8_t* masks, int64_t B, int32_t T, int32_t E, int32_t mode,
+                    float* z_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Unimodal MLP bypass  (reference: MLPAdaptor as `uni_fuser`, models.py:459-518, 855-865; norm='ln', order='nd')
@@ -234,7 +252,9 @@ typedef struct MdgMlp {
   const float* ln_weight[MDG_MAX_MLP_LINEAR];
   const float* ln_bias[MDG_MAX_MLP_LINEAR];
 } MdgMlp;
-int mdg_mlp_forward(const MdgMlp* mlp, const float* x, float* y, int64_t B, void* stream);
+size_t mdg_mlp_workspace_bytes(const MdgMlp* mlp, int64_t B, int precision);
+int mdg_mlp_forward(const MdgMlp* mlp, const float* x, float* y, int64_t B, int precision, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,15 +1,421 @@
-// Temporary: entry points declared in the header but not implemented yet fail loudly.
+// C-ABI entry points of the fusion encoder, the unimodal MLP bypass and token assembly (host orchestration).
+// Every nn.Linear is one launch of the tcgen05 GEMM kernel (EPI_LINEAR); see fusion_encode.cuh for the glue kernels.
+
+namespace {
+
+inline int kpad_of(int K) { return static_cast<int>(round_up(K, 64)); }
+inline long long ka_of(int K, int split) { return static_cast<long long>(kpad_of(K)) * (split ? 2 : 1); }
+
+struct WsPlanner {
+  size_t off = 0;
+  uint8_t* base = nullptr;
+  template <typename T>
+  T* take(size_t count) {
+    size_t o = off;
+    off += (count * sizeof(T) + 255) / 256 * 256;
+    return base ? reinterpret_cast<T*>(base + o) : nullptr;
+  }
+};
+
+// y[rows, N] = act(A . W^T + bias) (+ residual), A = bf16 operand rows [hi | lo](k_pad), W likewise ([N] rows).
+int run_linear(const __nv_bfloat16* A, long long rows, const __nv_bfloat16* W, int N, int K, int split,
+               const float* bias, int act, const float* residual, long long res_ld, float* out_f32, long long out_ld,
+               __nv_bfloat16* out_bf16, int out_bf16_K, cudaStream_t stream) {
+  if (rows == 0 || N == 0) return MDG_OK;
+  const int k_pad = kpad_of(K);
+  const long long ka = ka_of(K, split);
+  CUtensorMap tmA, tmB;
+  int rc = make_map_3d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, ka, rows, 1, ka, rows * ka, 64, 128,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_map_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, ka, N, 1, ka, static_cast<long long>(N) * ka, 64,
+                   128, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  mdg::PairScoreParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = 1;
+  p.rows = static_cast<int>(rows);
+  p.cols = N;
+  p.kb = k_pad / 64;
+  p.nterm = split ? 3 : 1;
+  p.k_pad = k_pad;
+  const int panels_needed = split ? 2 * p.kb : p.kb;  // for one 128-row sub-tile
+  if (panels_needed <= mdg::kMaxAPanels) {
+    p.stream_a = 0;
+    p.msub = (!split && 2 * p.kb <= mdg::kMaxAPanels) ? 2 : 1;
+  } else {
+    p.stream_a = 1;
+    p.msub = 1;
+  }
+  p.use_tma_store = 0;
+  p.bias = bias;
+  p.act = act;
+  p.residual = residual;
+  p.res_ld = res_ld;
+  p.out_f32 = out_f32;
+  p.out_ld = out_ld;
+  p.out_bf16 = out_bf16;
+  p.bf16_ld = out_bf16 ? ka_of(out_bf16_K, split) : 0;
+  p.bf16_lo_off = out_bf16 ? kpad_of(out_bf16_K) : 0;
+  p.write_lo = split;
+  return launch_pair_kernel(tmA, tmB, tmA, p, mdg::EPI_LINEAR, stream);
+}
+
+int convert_rows(const float* x, long long rows, int K, long long ld_in, long long row_stride, int split,
+                 __nv_bfloat16* out, cudaStream_t stream) {
+  if (rows == 0) return MDG_OK;
+  const int wpb = 8;
+  mdg::convert_rows_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      x, rows, K, ld_in, row_stride, kpad_of(K), split, out);
+  MDG_CUDA(cudaGetLastError());
+  ++g_last_launches;
+  return MDG_OK;
+}
+
+int ln_convert(const float* h, long long rows, int D, const float* addvec, const float* w, const float* b, int do_ln,
+               float* out_f32, __nv_bfloat16* out_bf16, int split, cudaStream_t stream) {
+  if (rows == 0) return MDG_OK;
+  const int wpb = 8;
+  mdg::ln_convert_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      h, rows, D, addvec, w, b, do_ln, out_f32, out_bf16, kpad_of(D), split);
+  MDG_CUDA(cudaGetLastError());
+  ++g_last_launches;
+  return MDG_OK;
+}
+
+struct FusionPlan {
+  int E, Dl, F, H, hd, T, layers, split;
+  long long chunk_drugs, chunk_rows;
+  // workspace pieces
+  __nv_bfloat16 *w_e2l, *w_l2e, *w_xin, *w_xout;
+  __nv_bfloat16 *w_in[MDG_MAX_LAYERS], *w_out[MDG_MAX_LAYERS], *w_l1[MDG_MAX_LAYERS], *w_l2[MDG_MAX_LAYERS];
+  __nv_bfloat16 *xb, *nb, *ob, *fb, *pb;
+  float *h, *qkv, *p32, *q_res, *q_proj;
+  size_t ob_bytes, fb_bytes, pb_bytes;
+  size_t total;
+};
+
+int plan_fusion(const MdgFusionCfg* cfg, long long B, int precision, void* ws, FusionPlan* pl) {
+  if (!cfg) return fail(MDG_ERR_INVALID_ARGUMENT, "fusion: NULL cfg");
+  pl->E = cfg->embed_dim;
+  pl->H = cfg->num_heads;
+  pl->hd = cfg->head_dim;
+  pl->Dl = cfg->num_heads * cfg->head_dim;
+  pl->F = cfg->ffn_dim;
+  pl->T = cfg->num_tokens;
+  pl->layers = cfg->num_layers;
+  pl->split = precision == MDG_PREC_FP32;
+  if (pl->E <= 0 || pl->H <= 0 || pl->hd <= 0 || pl->F <= 0 || pl->T <= 0 || pl->layers < 0)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "fusion: non-positive dimension in cfg");
+  if (pl->T > MDG_MAX_TOKENS) return fail(MDG_ERR_UNSUPPORTED, "fusion: T=%d > %d tokens", pl->T, MDG_MAX_TOKENS);
+  if (pl->layers > MDG_MAX_LAYERS) return fail(MDG_ERR_UNSUPPORTED, "fusion: %d layers > %d", pl->layers, MDG_MAX_LAYERS);
+  if (pl->Dl > 4096 || pl->F > 8192 || pl->E > 4096) return fail(MDG_ERR_UNSUPPORTED, "fusion: dimension too large");
+  if (cfg->agg < MDG_AGG_CLS || cfg->agg > MDG_AGG_MAX) return fail(MDG_ERR_UNSUPPORTED, "fusion: unknown agg %d", cfg->agg);
+  if (cfg->actn != MDG_ACTN_RELU && cfg->actn != MDG_ACTN_GELU)
+    return fail(MDG_ERR_UNSUPPORTED, "fusion: unsupported activation %d", cfg->actn);
+  const int s = pl->split;
+  long long max_rows = 32768;
+  long long cd = max_rows / pl->T;
+  if (cd < 1) cd = 1;
+  if (cd > B) cd = B > 0 ? B : 1;
+  pl->chunk_drugs = cd;
+  pl->chunk_rows = cd * pl->T;
+  WsPlanner w;
+  w.base = static_cast<uint8_t*>(ws);
+  const int E = pl->E, Dl = pl->Dl, F = pl->F;
+  pl->w_e2l = w.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(E, s));
+  pl->w_l2e = w.take<__nv_bfloat16>(static_cast<size_t>(E) * ka_of(Dl, s));
+  pl->w_xin = w.take<__nv_bfloat16>(static_cast<size_t>(2 * Dl) * ka_of(Dl, s));
+  pl->w_xout = w.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(Dl, s));
+  for (int i = 0; i < pl->layers; ++i) {
+    pl->w_in[i] = w.take<__nv_bfloat16>(static_cast<size_t>(3 * Dl) * ka_of(Dl, s));
+    pl->w_out[i] = w.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(Dl, s));
+    pl->w_l1[i] = w.take<__nv_bfloat16>(static_cast<size_t>(F) * ka_of(Dl, s));
+    pl->w_l2[i] = w.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(F, s));
+  }
+  const size_t R = static_cast<size_t>(pl->chunk_rows), C = static_cast<size_t>(pl->chunk_drugs);
+  pl->xb = w.take<__nv_bfloat16>(R * ka_of(E, s));
+  pl->nb = w.take<__nv_bfloat16>(R * ka_of(Dl, s));
+  pl->ob_bytes = R * ka_of(Dl, s) * 2;
+  pl->ob = w.take<__nv_bfloat16>(R * ka_of(Dl, s));
+  pl->fb_bytes = R * ka_of(F, s) * 2;
+  pl->fb = w.take<__nv_bfloat16>(R * ka_of(F, s));
+  pl->pb_bytes = C * ka_of(Dl, s) * 2;
+  pl->pb = w.take<__nv_bfloat16>(C * ka_of(Dl, s));
+  pl->h = w.take<float>(R * Dl);
+  pl->qkv = w.take<float>(R * 3 * Dl > R * static_cast<size_t>(E) ? R * 3 * Dl : R * static_cast<size_t>(E));
+  pl->p32 = w.take<float>(C * Dl);
+  pl->q_res = w.take<float>(Dl);
+  pl->q_proj = w.take<float>(Dl);
+  pl->total = w.off;
+  return MDG_OK;
+}
+
+int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_mask, const uint8_t* src_mask,
+                     long long Bc, cudaStream_t stream) {
+  const size_t per_warp = (2 * static_cast<size_t>(pl.T) * (pl.hd + 1) + pl.hd) * sizeof(float);
+  int warps = static_cast<int>((96 * 1024) / per_warp);
+  if (warps > 8) warps = 8;
+  if (warps < 1) return fail(MDG_ERR_UNSUPPORTED, "attention tile T=%d head_dim=%d needs %zu B of shared memory", pl.T, pl.hd, per_warp);
+  const size_t smem = per_warp * warps;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  MDG_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    MDG_CUDA(cudaFuncSetAttribute(mdg::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set[dev] = true;
+  }
+  long long items = Bc * pl.H;
+  long long blocks = (items + warps - 1) / warps;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  mdg::attention_kernel<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
+      qkv, key_mask, src_mask, Bc, pl.T, pl.H, pl.hd, pl.ob, kpad_of(pl.Dl), pl.split);
+  MDG_CUDA(cudaGetLastError());
+  ++g_last_launches;
+  return MDG_OK;
+}
+
+}  // namespace
+
 extern "C" {
+
+size_t mdg_fusion_workspace_bytes(const MdgFusionCfg* cfg, int64_t B, int precision) {
+  FusionPlan pl;
+  if (plan_fusion(cfg, B, precision, nullptr, &pl) != MDG_OK) return 0;
+  return pl.total;
+}
+
+int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const float* tokens,
+                      const uint8_t* key_mask, const uint8_t* src_mask, const uint8_t* pool_key_mask, float* z_out,
+                      int64_t B, int precision, void* workspace, size_t workspace_bytes, void* stream_v) {
+  g_last_launches = 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!w || !cfg || !tokens || !key_mask || !z_out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: NULL pointer");
+  if (B < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: B=%lld", (long long)B);
+  if (precision != MDG_PREC_BF16 && precision != MDG_PREC_FP32)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: precision=%d", precision);
+  FusionPlan pl;
+  int rc = plan_fusion(cfg, B, precision, workspace, &pl);
+  if (rc) return rc;
+  if (B == 0) return MDG_OK;
+  if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
+    return fail(MDG_ERR_WORKSPACE, "mdg_fusion_encode: workspace must be non-NULL and 256-byte aligned");
+  if (workspace_bytes < pl.total)
+    return fail(MDG_ERR_WORKSPACE, "mdg_fusion_encode: workspace %zu < required %zu", workspace_bytes, pl.total);
+  const bool xattn = cfg->agg == MDG_AGG_XATTN;
+  if (!w->embed2latent_weight || !w->embed2latent_bias || !w->latent2embed_weight || !w->latent2embed_bias)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: NULL embed2latent/latent2embed weights");
+  if (xattn && (!w->x_attn_query || !w->x_attn_kv_norm_weight || !w->x_attn_kv_norm_bias ||
+                !w->x_attn_query_norm_weight || !w->x_attn_query_norm_bias || !w->x_attn_in_proj_weight ||
+                !w->x_attn_in_proj_bias || !w->x_attn_out_proj_weight || !w->x_attn_out_proj_bias))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: agg=x-attn needs the x_attn_* weights");
+  rc = mdg_check_device(-1);
+  if (rc) return rc;
+
+  const int E = pl.E, Dl = pl.Dl, F = pl.F, T = pl.T, s = pl.split;
+  const int act = cfg->actn == MDG_ACTN_GELU ? 2 : 1;
+
+  // ---- weights: fp32 [out, in] (already K-major) -> bf16 operand rows, once per call
+  if ((rc = convert_rows(w->embed2latent_weight, Dl, E, E, 1, s, pl.w_e2l, stream))) return rc;
+  if ((rc = convert_rows(w->latent2embed_weight, E, Dl, Dl, 1, s, pl.w_l2e, stream))) return rc;
+  for (int i = 0; i < pl.layers; ++i) {
+    const MdgFusionLayer& L = w->layers[i];
+    if (!L.in_proj_weight || !L.in_proj_bias || !L.out_proj_weight || !L.out_proj_bias || !L.linear1_weight ||
+        !L.linear1_bias || !L.linear2_weight || !L.linear2_bias || !L.norm1_weight || !L.norm1_bias ||
+        !L.norm2_weight || !L.norm2_bias)
+      return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: NULL weight in layer %d", i);
+    if ((rc = convert_rows(L.in_proj_weight, 3 * Dl, Dl, Dl, 1, s, pl.w_in[i], stream))) return rc;
+    if ((rc = convert_rows(L.out_proj_weight, Dl, Dl, Dl, 1, s, pl.w_out[i], stream))) return rc;
+    if ((rc = convert_rows(L.linear1_weight, F, Dl, Dl, 1, s, pl.w_l1[i], stream))) return rc;
+    if ((rc = convert_rows(L.linear2_weight, Dl, F, F, 1, s, pl.w_l2[i], stream))) return rc;
+  }
+  if (xattn) {
+    if ((rc = convert_rows(w->x_attn_in_proj_weight + static_cast<size_t>(Dl) * Dl, 2 * Dl, Dl, Dl, 1, s, pl.w_xin, stream))) return rc;
+    if ((rc = convert_rows(w->x_attn_out_proj_weight, Dl, Dl, Dl, 1, s, pl.w_xout, stream))) return rc;
+    mdg::xattn_query_kernel<<<1, 256, 0, stream>>>(w->x_attn_query, w->x_attn_query_norm_weight,
+                                                   w->x_attn_query_norm_bias, cfg->norm_first,
+                                                   w->x_attn_in_proj_weight, w->x_attn_in_proj_bias, Dl, pl.hd,
+                                                   pl.q_res, pl.q_proj);
+    MDG_CUDA(cudaGetLastError());
+    ++g_last_launches;
+  }
+  // zero the K-padding columns of operand buffers that kernels fill only up to their logical width
+  if (kpad_of(Dl) != Dl) {
+    MDG_CUDA(cudaMemsetAsync(pl.ob, 0, pl.ob_bytes, stream));
+    MDG_CUDA(cudaMemsetAsync(pl.pb, 0, pl.pb_bytes, stream));
+  }
+  if (kpad_of(F) != F) MDG_CUDA(cudaMemsetAsync(pl.fb, 0, pl.fb_bytes, stream));
+
+  for (long long b0 = 0; b0 < B; b0 += pl.chunk_drugs) {
+    const long long Bc = (B - b0 < pl.chunk_drugs) ? (B - b0) : pl.chunk_drugs;
+    const long long R = Bc * T;
+    const float* tok = tokens + b0 * T * E;
+    const uint8_t* km = key_mask + b0 * T;
+    // embed2latent (models.py:411)
+    if ((rc = convert_rows(tok, R, E, E, 1, s, pl.xb, stream))) return rc;
+    if ((rc = run_linear(pl.xb, R, pl.w_e2l, Dl, E, s, w->embed2latent_bias, 0, nullptr, 0, pl.h, Dl, nullptr, 0, stream))) return rc;
+    // transformer encoder layers (models.py:412; nn.TransformerEncoderLayer._sa_block/_ff_block, no final norm)
+    for (int i = 0; i < pl.layers; ++i) {
+      const MdgFusionLayer& L = w->layers[i];
+      if (cfg->norm_first) {
+        if ((rc = ln_convert(pl.h, R, Dl, nullptr, L.norm1_weight, L.norm1_bias, 1, nullptr, pl.nb, s, stream))) return rc;
+      } else {
+        if ((rc = ln_convert(pl.h, R, Dl, nullptr, nullptr, nullptr, 0, nullptr, pl.nb, s, stream))) return rc;
+      }
+      if ((rc = run_linear(pl.nb, R, pl.w_in[i], 3 * Dl, Dl, s, L.in_proj_bias, 0, nullptr, 0, pl.qkv, 3 * Dl, nullptr, 0, stream))) return rc;
+      if ((rc = launch_attention(pl, pl.qkv, km, src_mask, Bc, stream))) return rc;
+      if ((rc = run_linear(pl.ob, R, pl.w_out[i], Dl, Dl, s, L.out_proj_bias, 0, pl.h, Dl, pl.h, Dl, nullptr, 0, stream))) return rc;
+      if (cfg->norm_first) {
+        if ((rc = ln_convert(pl.h, R, Dl, nullptr, L.norm2_weight, L.norm2_bias, 1, nullptr, pl.nb, s, stream))) return rc;
+      } else {
+        if ((rc = ln_convert(pl.h, R, Dl, nullptr, L.norm1_weight, L.norm1_bias, 1, pl.h, pl.nb, s, stream))) return rc;
+      }
+      if ((rc = run_linear(pl.nb, R, pl.w_l1[i], F, Dl, s, L.linear1_bias, act, nullptr, 0, nullptr, 0, pl.fb, F, stream))) return rc;
+      if ((rc = run_linear(pl.fb, R, pl.w_l2[i], Dl, F, s, L.linear2_bias, 0, pl.h, Dl, pl.h, Dl, nullptr, 0, stream))) return rc;
+      if (!cfg->norm_first) {
+        if ((rc = ln_convert(pl.h, R, Dl, nullptr, L.norm2_weight, L.norm2_bias, 1, pl.h, nullptr, s, stream))) return rc;
+      }
+    }
+    float* z = z_out + b0 * E;
+    if (cfg->agg == MDG_AGG_CLS) {
+      // latent2embed of token 0 only (models.py:415-421)
+      if ((rc = convert_rows(pl.h, Bc, Dl, Dl, T, s, pl.pb, stream))) return rc;
+      if ((rc = run_linear(pl.pb, Bc, pl.w_l2e, E, Dl, s, w->latent2embed_bias, 0, nullptr, 0, z, E, nullptr, 0, stream))) return rc;
+    } else if (cfg->agg == MDG_AGG_XATTN) {
+      // models.py:422-443
+      if ((rc = ln_convert(pl.h, R, Dl, nullptr, w->x_attn_kv_norm_weight, w->x_attn_kv_norm_bias, 1, nullptr, pl.nb, s, stream))) return rc;
+      if ((rc = run_linear(pl.nb, R, pl.w_xin, 2 * Dl, Dl, s, w->x_attn_in_proj_bias + Dl, 0, nullptr, 0, pl.qkv, 2 * Dl, nullptr, 0, stream))) return rc;
+      {
+        long long blocks = (Bc * pl.H + 7) / 8;
+        const long long cap = static_cast<long long>(num_sms()) * 16;
+        if (blocks > cap) blocks = cap;
+        mdg::pool_attention_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+            pl.qkv, pl.q_proj, pool_key_mask, Bc, T, pl.H, pl.hd, pl.pb, kpad_of(Dl), s);
+        MDG_CUDA(cudaGetLastError());
+        ++g_last_launches;
+      }
+      if ((rc = run_linear(pl.pb, Bc, pl.w_xout, Dl, Dl, s, w->x_attn_out_proj_bias, 0, nullptr, 0, pl.p32, Dl, nullptr, 0, stream))) return rc;
+      if ((rc = ln_convert(pl.p32, Bc, Dl, pl.q_res, w->x_attn_query_norm_weight, w->x_attn_query_norm_bias,
+                           cfg->norm_first ? 0 : 1, nullptr, pl.pb, s, stream))) return rc;
+      if ((rc = run_linear(pl.pb, Bc, pl.w_l2e, E, Dl, s, w->latent2embed_bias, 0, nullptr, 0, z, E, nullptr, 0, stream))) return rc;
+    } else {
+      // mean / max over the unmasked tokens of latent2embed(h) (models.py:415, 444-451)
+      if ((rc = ln_convert(pl.h, R, Dl, nullptr, nullptr, nullptr, 0, nullptr, pl.nb, s, stream))) return rc;
+      if ((rc = run_linear(pl.nb, R, pl.w_l2e, E, Dl, s, w->latent2embed_bias, 0, nullptr, 0, pl.qkv, E, nullptr, 0, stream))) return rc;
+      const long long n = Bc * E;
+      mdg::masked_pool_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+          pl.qkv, km, Bc, T, E, cfg->agg == MDG_AGG_MAX, z);
+      MDG_CUDA(cudaGetLastError());
+      ++g_last_launches;
+    }
+  }
+  return MDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ unimodal MLP
+static int plan_mlp(const MdgMlp* m, long long B, int precision, void* ws, __nv_bfloat16** wts, __nv_bfloat16** act_b,
+                    float** act_f, size_t* total) {
+  if (!m || m->n_linear < 1 || m->n_linear > MDG_MAX_MLP_LINEAR) return fail(MDG_ERR_INVALID_ARGUMENT, "mlp: bad n_linear");
+  const int s = precision == MDG_PREC_FP32;
+  WsPlanner w;
+  w.base = static_cast<uint8_t*>(ws);
+  int maxd = 0;
+  for (int i = 0; i <= m->n_linear; ++i) {
+    if (m->dims[i] <= 0 || m->dims[i] > 8192) return fail(MDG_ERR_UNSUPPORTED, "mlp: dims[%d]=%d", i, m->dims[i]);
+    if (m->dims[i] > maxd) maxd = m->dims[i];
+  }
+  for (int i = 0; i < m->n_linear; ++i)
+    wts[i] = w.take<__nv_bfloat16>(static_cast<size_t>(m->dims[i + 1]) * ka_of(m->dims[i], s));
+  *act_b = w.take<__nv_bfloat16>(static_cast<size_t>(B > 0 ? B : 1) * ka_of(maxd, s));
+  *act_f = w.take<float>(static_cast<size_t>(B > 0 ? B : 1) * maxd);
+  *total = w.off;
+  return MDG_OK;
+}
+
+size_t mdg_mlp_workspace_bytes(const MdgMlp* mlp, int64_t B, int precision) {
+  __nv_bfloat16* wts[MDG_MAX_MLP_LINEAR];
+  __nv_bfloat16* ab;
+  float* af;
+  size_t total = 0;
+  if (plan_mlp(mlp, B, precision, nullptr, wts, &ab, &af, &total) != MDG_OK) return 0;
+  return total;
+}
+
+int mdg_mlp_forward(const MdgMlp* mlp, const float* x, float* y, int64_t B, int precision, void* workspace,
+                    size_t workspace_bytes, void* stream_v) {
+  g_last_launches = 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!mlp || !x || !y) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_mlp_forward: NULL pointer");
+  if (B < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_mlp_forward: B < 0");
+  if (mlp->actn != MDG_ACTN_RELU && mlp->actn != MDG_ACTN_GELU) return fail(MDG_ERR_UNSUPPORTED, "mlp: activation %d", mlp->actn);
+  __nv_bfloat16* wts[MDG_MAX_MLP_LINEAR];
+  __nv_bfloat16* ab;
+  float* af;
+  size_t total = 0;
+  int rc = plan_mlp(mlp, B, precision, workspace, wts, &ab, &af, &total);
+  if (rc) return rc;
+  if (B == 0) return MDG_OK;
+  if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0 || workspace_bytes < total)
+    return fail(MDG_ERR_WORKSPACE, "mdg_mlp_forward: workspace (%zu B) too small or misaligned, need %zu", workspace_bytes, total);
+  if ((rc = mdg_check_device(-1))) return rc;
+  const int s = precision == MDG_PREC_FP32;
+  const int act = mlp->actn == MDG_ACTN_GELU ? 2 : 1;
+  const int n = mlp->n_linear;
+  for (int i = 0; i < n; ++i) {
+    if (!mlp->weight[i] || !mlp->bias[i]) return fail(MDG_ERR_INVALID_ARGUMENT, "mlp: NULL weight %d", i);
+    if ((rc = convert_rows(mlp->weight[i], mlp->dims[i + 1], mlp->dims[i], mlp->dims[i], 1, s, wts[i], stream))) return rc;
+  }
+  // layer i input: x (i == 0) or the fp32 activation of layer i-1 (optionally LayerNorm'ed first, models.py:499-514)
+  for (int i = 0; i < n; ++i) {
+    const int K = mlp->dims[i], N = mlp->dims[i + 1];
+    const float* in = (i == 0) ? x : af;
+    const bool ln = i > 0 && mlp->ln_weight[i] != nullptr;
+    if ((rc = ln_convert(in, B, K, nullptr, mlp->ln_weight[i], mlp->ln_bias[i], ln ? 1 : 0, nullptr, ab, s, stream))) return rc;
+    const bool last = (i == n - 1);
+    if ((rc = run_linear(ab, B, wts[i], N, K, s, mlp->bias[i], last ? 0 : act, nullptr, 0, last ? y : af, N, nullptr, 0, stream))) return rc;
+  }
+  return MDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ token assembly
+int mdg_assemble_tokens(const float* embeds, const uint8_t* masks, int64_t B, int32_t M, int32_t E, int32_t n_non_tx,
+                        int32_t num_bottlenecks, const float* bottleneck_tokens, const float* cls_token,
+                        const float* pos_enc, int32_t pos_len, int32_t normalize, float* seq_out,
+                        uint8_t* seq_mask_out, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!embeds || !masks || !seq_out || !seq_mask_out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_assemble_tokens: NULL pointer");
+  if (B < 0 || M <= 0 || E <= 0 || n_non_tx < 0 || n_non_tx > M || num_bottlenecks < 0 || pos_len < 0)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_assemble_tokens: bad sizes");
+  if (num_bottlenecks > 0 && !bottleneck_tokens) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_assemble_tokens: NULL bottleneck tokens");
+  const int has_cls = cls_token != nullptr;
+  const int T = M + num_bottlenecks + has_cls;
+  if (T > MDG_MAX_TOKENS) return fail(MDG_ERR_UNSUPPORTED, "mdg_assemble_tokens: T=%d > %d", T, MDG_MAX_TOKENS);
+  if (pos_len > T) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_assemble_tokens: pos_len %d > T %d", pos_len, T);
+  if (B == 0) return MDG_OK;
+  const long long rows = static_cast<long long>(B) * T;
+  mdg::assemble_tokens_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+      embeds, masks, B, M, E, n_non_tx, num_bottlenecks, has_cls, bottleneck_tokens, cls_token, pos_enc, pos_len,
+      normalize, seq_out, seq_mask_out);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
+}
+
+int mdg_masked_pool(const float* tokens, const uint8_t* masks, int64_t B, int32_t T, int32_t E, int32_t mode,
+                    float* z_out, void* stream_v) {
+  if (!tokens || !masks || !z_out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_masked_pool: NULL pointer");
+  if (B < 0 || T <= 0 || E <= 0 || mode < 0 || mode > 2) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_masked_pool: bad arguments");
+  if (B == 0) return MDG_OK;
+  const long long n = static_cast<long long>(B) * E;
+  mdg::masked_pool_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      tokens, masks, B, T, E, mode, z_out);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
+}
+
 size_t mdg_exact_rank_workspace_bytes(int64_t) { return 0; }
 int mdg_exact_rank(const float*, int64_t, int64_t, float*, void*, size_t, void*) {
   return fail(MDG_ERR_UNSUPPORTED, "mdg_exact_rank: not implemented yet");
 }
-size_t mdg_fusion_workspace_bytes(const MdgFusionCfg*, int64_t) { return 0; }
-int mdg_fusion_encode(const MdgFusionWeights*, const MdgFusionCfg*, const float*, const uint8_t*, const uint8_t*,
-                      const uint8_t*, float*, int64_t, void*, size_t, void*) {
-  return fail(MDG_ERR_UNSUPPORTED, "mdg_fusion_encode: not implemented yet");
-}
-int mdg_mlp_forward(const MdgMlp*, const float*, float*, int64_t, void*) {
-  return fail(MDG_ERR_UNSUPPORTED, "mdg_mlp_forward: not implemented yet");
-}
-}
+
+}  // extern "C"

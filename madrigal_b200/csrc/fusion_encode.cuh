@@ -1,1 +1,286 @@
+// Fusion-encoder glue kernels (reference: TransformerFusion.forward, madrigal/models/models.py:401-455, with the
+// eval-mode arithmetic of torch 1.13 nn.TransformerEncoderLayer / nn.MultiheadAttention, restated in
+// oracle/oracle.py:fusion_forward).  All nn.Linear layers run on the tcgen05 GEMM kernel in pair_score.cuh
+// (EPI_LINEAR); the kernels here are the non-GEMM parts: operand conversion, LayerNorm, the tiny per-(drug, head)
+// masked attention (T <= 32 tokens: one warp, keys on lanes, warp-shuffle softmax), pooling and token assembly.
 #pragma once
+#include <cuda_bf16.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace mdg {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+
+__device__ __forceinline__ void store_bf16_split(__nv_bfloat16* row, int k, int k_pad, int split, float x) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  row[k] = hi;
+  if (split) row[k_pad + k] = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// x [rows, K] fp32 (row pitch ld_in) -> bf16 GEMM operand rows [hi(k_pad) | lo(k_pad)], zero for k >= K.
+// Optional gather: row r reads input row r * row_stride (used to pick the CLS token of every drug).
+__global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restrict__ x, long long rows, int K,
+                                                           long long ld_in, long long row_stride, int k_pad,
+                                                           int split, __nv_bfloat16* __restrict__ out) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * row_stride * ld_in;
+  __nv_bfloat16* o = out + row * static_cast<long long>(split ? 2 * k_pad : k_pad);
+  for (int k = lane; k < k_pad; k += 32) store_bf16_split(o, k, k_pad, split, k < K ? xr[k] : 0.f);
+}
+
+// LayerNorm (eps 1e-5, biased variance) of each row of h [rows, D] (+ optional per-column vector `addvec` first),
+// written as a bf16 GEMM operand and/or back to fp32.  do_ln == 0: conversion only.  One warp per row.
+__global__ void __launch_bounds__(256) ln_convert_kernel(const float* __restrict__ h, long long rows, int D,
+                                                         const float* __restrict__ addvec,
+                                                         const float* __restrict__ w, const float* __restrict__ b,
+                                                         int do_ln, float* __restrict__ out_f32,
+                                                         __nv_bfloat16* __restrict__ out_bf16, int k_pad, int split) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* hr = h + row * D;
+  float mean = 0.f, rstd = 1.f;
+  if (do_ln) {
+    float s = 0.f;
+    for (int k = lane; k < D; k += 32) s += hr[k] + (addvec ? addvec[k] : 0.f);
+    mean = warp_sum(s) / D;
+    float v = 0.f;
+    for (int k = lane; k < D; k += 32) {
+      const float d = hr[k] + (addvec ? addvec[k] : 0.f) - mean;
+      v += d * d;
+    }
+    rstd = 1.0f / sqrtf(warp_sum(v) / D + 1e-5f);
+  }
+  __nv_bfloat16* ob = out_bf16 ? out_bf16 + row * static_cast<long long>(split ? 2 * k_pad : k_pad) : nullptr;
+  const int kmax = ob ? k_pad : D;
+  for (int k = lane; k < kmax; k += 32) {
+    float y = 0.f;
+    if (k < D) {
+      y = hr[k] + (addvec ? addvec[k] : 0.f);
+      if (do_ln) y = (y - mean) * rstd * w[k] + b[k];
+      if (out_f32) out_f32[row * D + k] = y;
+    }
+    if (ob) store_bf16_split(ob, k, k_pad, split, y);
+  }
+}
+
+// Masked multi-head self-attention core for one (drug, head) per warp.
+//   qkv [B*T, 3*Dl] fp32 (packed in_proj output: q | k | v), key_mask [B, T] (non-zero = masked key),
+//   src_mask [T, T] or NULL (non-zero = query row i may not attend key j)
+//   -> out: bf16 operand rows [B*T, (hi | lo)(k_pad)], head h at columns h*hd .. h*hd+hd-1.
+// Lanes hold keys (T <= 32).  K/V tiles of the (drug, head) are staged in shared memory (row pitch hd+1: lane-per-
+// key reads are bank-conflict-free), the query row is broadcast from shared memory, softmax is a warp shuffle
+// max/sum.  Scores use q * (1/sqrt(hd)) as nn.MultiheadAttention does; masked scores are -inf.
+__global__ void attention_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ key_mask,
+                                 const uint8_t* __restrict__ src_mask, long long B, int T, int H, int hd,
+                                 __nv_bfloat16* __restrict__ out, int k_pad, int split) {
+  extern __shared__ float att_smem[];
+  const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pitch = hd + 1;
+  float* Ks = att_smem + static_cast<size_t>(wid) * (2 * T * pitch + hd);
+  float* Vs = Ks + T * pitch;
+  float* Qs = Vs + T * pitch;
+  const int Dl = H * hd;
+  const float qscale = 1.0f / sqrtf(static_cast<float>(hd));
+  const long long total = B * H;
+  for (long long item = static_cast<long long>(blockIdx.x) * warps + wid; item < total;
+       item += static_cast<long long>(gridDim.x) * warps) {
+    const long long b = item / H;
+    const int h = static_cast<int>(item - b * H);
+    const float* base = qkv + (b * T) * 3LL * Dl + h * hd;
+    __syncwarp();
+    for (int idx = lane; idx < T * hd; idx += 32) {
+      const int j = idx / hd, d = idx - j * hd;
+      Ks[j * pitch + d] = base[static_cast<long long>(j) * 3 * Dl + Dl + d];
+      Vs[j * pitch + d] = base[static_cast<long long>(j) * 3 * Dl + 2 * Dl + d];
+    }
+    const bool key_ok = lane < T && key_mask[b * T + lane] == 0;
+    for (int i = 0; i < T; ++i) {
+      __syncwarp();
+      for (int d = lane; d < hd; d += 32) Qs[d] = base[static_cast<long long>(i) * 3 * Dl + d] * qscale;
+      __syncwarp();
+      float s = -CUDART_INF_F;
+      if (key_ok && !(src_mask != nullptr && src_mask[i * T + lane] != 0)) {
+        s = 0.f;
+        const float* kr = Ks + lane * pitch;
+        for (int d = 0; d < hd; ++d) s = fmaf(Qs[d], kr[d], s);
+      }
+      const float m = warp_max(s);
+      float pexp = (s == -CUDART_INF_F) ? 0.f : expf(s - m);
+      const float denom = warp_sum(pexp);
+      const float pj = pexp / denom;  // NaN if every key is masked, like torch.softmax over all -inf
+      __nv_bfloat16* orow = out + (b * T + i) * static_cast<long long>(split ? 2 * k_pad : k_pad) + h * hd;
+      for (int d0 = 0; d0 < hd; d0 += 32) {
+        const int d = d0 + lane;
+        float acc = 0.f;
+        for (int j = 0; j < T; ++j) {
+          const float pb = __shfl_sync(0xffffffffu, pj, j);
+          if (d < hd) acc = fmaf(pb, Vs[j * pitch + d], acc);
+        }
+        if (d < hd) store_bf16_split(orow, d, k_pad, split, acc);
+      }
+    }
+  }
+}
+
+// x-attn pooling attention (models.py:422-440): one learned query per head (already projected and scaled, q_proj
+// [Dl]), keys/values kv [B*T, 2*Dl] (k | v), constant key mask pool_mask [T].  out: fp32-exact bf16 operand rows
+// [B, (hi | lo)(k_pad)] = concatenated heads, input of the MHA out_proj GEMM.
+__global__ void pool_attention_kernel(const float* __restrict__ kv, const float* __restrict__ q_proj,
+                                      const uint8_t* __restrict__ pool_mask, long long B, int T, int H, int hd,
+                                      __nv_bfloat16* __restrict__ out, int k_pad, int split) {
+  const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Dl = H * hd;
+  const long long total = B * H;
+  for (long long item = static_cast<long long>(blockIdx.x) * warps + wid; item < total;
+       item += static_cast<long long>(gridDim.x) * warps) {
+    const long long b = item / H;
+    const int h = static_cast<int>(item - b * H);
+    const float* base = kv + (b * T) * 2LL * Dl + h * hd;
+    float s = -CUDART_INF_F;
+    if (lane < T && !(pool_mask != nullptr && pool_mask[lane] != 0)) {
+      s = 0.f;
+      const float* kr = base + static_cast<long long>(lane) * 2 * Dl;
+      for (int d = 0; d < hd; ++d) s = fmaf(q_proj[h * hd + d], kr[d], s);
+    }
+    const float m = warp_max(s);
+    const float pexp = (s == -CUDART_INF_F) ? 0.f : expf(s - m);
+    const float pj = pexp / warp_sum(pexp);
+    __nv_bfloat16* orow = out + b * static_cast<long long>(split ? 2 * k_pad : k_pad) + h * hd;
+    for (int d0 = 0; d0 < hd; d0 += 32) {
+      const int d = d0 + lane;
+      float acc = 0.f;
+      for (int j = 0; j < T; ++j) {
+        const float pb = __shfl_sync(0xffffffffu, pj, j);
+        if (d < hd) acc = fmaf(pb, base[static_cast<long long>(j) * 2 * Dl + Dl + d], acc);
+      }
+      if (d < hd) store_bf16_split(orow, d, k_pad, split, acc);
+    }
+  }
+}
+
+// The x-attn query path, once per call (models.py:423-429 + the q part of the packed in_proj):
+//   q_res  = norm_first ? LN_q(x_attn_query) : x_attn_query          (added back after attention, models.py:440)
+//   q_proj = (W_q . q_res + b_q) / sqrt(hd)
+// Single block; W_q = first Dl rows of in_proj_weight.
+__global__ void __launch_bounds__(256) xattn_query_kernel(const float* __restrict__ query,
+                                                          const float* __restrict__ lnw,
+                                                          const float* __restrict__ lnb, int norm_first,
+                                                          const float* __restrict__ in_w,
+                                                          const float* __restrict__ in_b, int Dl, int hd,
+                                                          float* __restrict__ q_res, float* __restrict__ q_proj) {
+  __shared__ float red[2];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, warps = blockDim.x >> 5;
+  float mean = 0.f, rstd = 1.f;
+  if (norm_first) {
+    if (wid == 0) {
+      float s = 0.f;
+      for (int k = lane; k < Dl; k += 32) s += query[k];
+      const float mu = warp_sum(s) / Dl;
+      float v = 0.f;
+      for (int k = lane; k < Dl; k += 32) v += (query[k] - mu) * (query[k] - mu);
+      const float var = warp_sum(v) / Dl;
+      if (lane == 0) {
+        red[0] = mu;
+        red[1] = 1.0f / sqrtf(var + 1e-5f);
+      }
+    }
+    __syncthreads();
+    mean = red[0];
+    rstd = red[1];
+  }
+  for (int k = tid; k < Dl; k += blockDim.x)
+    q_res[k] = norm_first ? (query[k] - mean) * rstd * lnw[k] + lnb[k] : query[k];
+  __syncthreads();
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int n = wid; n < Dl; n += warps) {
+    float s = 0.f;
+    for (int k = lane; k < Dl; k += 32) s = fmaf(in_w[static_cast<long long>(n) * Dl + k], q_res[k], s);
+    s = warp_sum(s);
+    if (lane == 0) q_proj[n] = (s + in_b[n]) * scale;
+  }
+}
+
+// 'mean' / 'max' aggregation (models.py:444-451): masked mean / max over the unmasked tokens of each drug.
+//   e [B*T, E] fp32 (latent2embed output), key_mask [B, T] -> z [B, E].  Empty -> 0 (torch_scatter fill value).
+__global__ void __launch_bounds__(256) masked_pool_kernel(const float* __restrict__ e,
+                                                          const uint8_t* __restrict__ key_mask, long long B, int T,
+                                                          int E, int is_max, float* __restrict__ z) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= B * E) return;
+  const long long b = idx / E;
+  const int d = static_cast<int>(idx - b * E);
+  // is_max: 0 = mean, 1 = max, 2 = sum ('add' fusion, models.py:875-878); optional per-token L2 normalisation
+  float acc = is_max == 1 ? -CUDART_INF_F : 0.f;
+  int cnt = 0;
+  for (int t = 0; t < T; ++t) {
+    if (key_mask[b * T + t] == 0) {
+      const float v = e[(b * T + t) * E + d];
+      acc = is_max == 1 ? fmaxf(acc, v) : acc + v;
+      ++cnt;
+    }
+  }
+  z[idx] = cnt == 0 ? 0.f : (is_max == 0 ? acc / cnt : acc);
+}
+
+// Token assembly (reference: NovelDDIEncoder.encode, models.py:772-852): builds the position-encoded fusion sequence
+// and its key mask from the stacked modality embeddings.
+//   embeds [B, M, E] (order [non-TX..., TX...], models.py:772), masks [B, M] (non-zero = missing)
+//   sequence layout: [cls?] [non-TX (n_non_tx)] [bottleneck (nb)] [TX (M - n_non_tx)]
+//   normalize: L2-normalise every token (eps 1e-12) BEFORE the positional encoding (models.py:849-852)
+//   pe [pe_len, E]: added to the first pe_len tokens (sinusoidal buffers are zero beyond max_len; learnable: :602)
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ embeds,
+                                                              const uint8_t* __restrict__ masks, long long B, int M,
+                                                              int E, int n_non_tx, int nb, int has_cls,
+                                                              const float* __restrict__ bottleneck,
+                                                              const float* __restrict__ cls,
+                                                              const float* __restrict__ pe, int pe_len,
+                                                              int normalize, float* __restrict__ seq,
+                                                              uint8_t* __restrict__ seq_mask) {
+  const int T = M + nb + has_cls;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B * T) return;
+  const int lane = threadIdx.x & 31;
+  const long long b = row / T;
+  const int t = static_cast<int>(row - b * T);
+  const int u = t - has_cls;  // position without CLS
+  const float* src;
+  uint8_t mk = 0;
+  if (u < 0) {
+    src = cls;
+  } else if (u < n_non_tx) {
+    src = embeds + (b * M + u) * E;
+    mk = masks[b * M + u];
+  } else if (u < n_non_tx + nb) {
+    src = bottleneck + static_cast<long long>(u - n_non_tx) * E;
+  } else {
+    src = embeds + (b * M + (u - nb)) * E;
+    mk = masks[b * M + (u - nb)];
+  }
+  float denom = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int k = lane; k < E; k += 32) ss += src[k] * src[k];
+    denom = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  }
+  for (int k = lane; k < E; k += 32) {
+    float v = src[k] / denom;
+    if (pe != nullptr && t < pe_len) v += pe[static_cast<long long>(t) * E + k];
+    seq[row * E + k] = v;
+  }
+  if (lane == 0) seq_mask[row] = mk != 0;
+}
+
+}  // namespace mdg

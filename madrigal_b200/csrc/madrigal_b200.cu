@@ -177,6 +177,7 @@ int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     case mdg::EPI_F32: rc = launch_pair_instance<mdg::EPI_F32, 8>(tmA, tmB, tmOut, p, grid, stream); break;
     case mdg::EPI_SIGMOID: rc = launch_pair_instance<mdg::EPI_SIGMOID, 8>(tmA, tmB, tmOut, p, grid, stream); break;
     case mdg::EPI_BF16_SPLIT: rc = launch_pair_instance<mdg::EPI_BF16_SPLIT, 8>(tmA, tmB, tmOut, p, grid, stream); break;
+    case mdg::EPI_LINEAR: rc = launch_pair_instance<mdg::EPI_LINEAR, 8>(tmA, tmB, tmOut, p, grid, stream); break;
     case mdg::EPI_RANK_U16:
       rc = (rank_warps == 8) ? launch_pair_instance<mdg::EPI_RANK_U16, 8>(tmA, tmB, tmOut, p, grid, stream)
                              : launch_pair_instance<mdg::EPI_RANK_U16, 16>(tmA, tmB, tmOut, p, grid, stream);
@@ -404,6 +405,7 @@ int mdg_profile_read(float* ms_out_host, int max_records) {
   return n;
 }
 
+#include "capi_fusion_fwd.inl"
 }  // extern "C"
 
 #include "capi_fusion.inl"

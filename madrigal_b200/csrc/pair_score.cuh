@@ -35,7 +35,7 @@ constexpr int kFirstEpiWarp = 4;
 constexpr int kStagingBytesPerWarp = 2048;  // 32 rows x 64 B
 constexpr int kTmemCols = 512;
 
-enum EpiMode : int { EPI_F32 = 0, EPI_SIGMOID = 1, EPI_RANK_U16 = 2, EPI_BF16_SPLIT = 3 };
+enum EpiMode : int { EPI_F32 = 0, EPI_SIGMOID = 1, EPI_RANK_U16 = 2, EPI_BF16_SPLIT = 3, EPI_LINEAR = 4 };
 
 // Shared-memory plan for a kernel instance with NE epilogue warps (staging is per warp, so more epilogue warps
 // trade one B stage for staging space).
@@ -75,6 +75,18 @@ struct PairScoreParams {
   long long out_batch_stride;
   const uint32_t* lut;  // [L, kRankLutEntries]
   const float* affine;  // [L, 2]
+  // ---- streamed-A mode (K too large for the resident A buffer): A and B panels share the stage ring, msub = 1
+  int stream_a;
+  int k_pad;  // elements between the hi and lo halves of an operand row (bf16x3), = padded K
+  // ---- EPI_LINEAR (the fusion encoder's nn.Linear layers):  y = act(acc + bias) [+ residual]
+  const float* bias;      // [cols] or NULL
+  const float* residual;  // fp32 [rows, res_ld] or NULL (may alias out_f32)
+  long long res_ld;
+  float* out_f32;  // fp32 [rows, out_ld] or NULL
+  __nv_bfloat16* out_bf16;  // bf16 [rows, bf16_ld] (hi at column n, lo at column bf16_lo_off + n) or NULL
+  long long bf16_ld;
+  int bf16_lo_off;
+  int act;  // 0 none, 1 relu, 2 exact-erf gelu
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
@@ -201,6 +213,27 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t b_phase = 0;
       int it = 0;  // executed tasks (parity of the A barriers)
+      if (p.stream_a) {
+        const int ksteps = (p.nterm == 1) ? kb : 3 * kb;
+        for (int t = t_begin; t < t_end; t += t_step) {
+          const TaskCoord c = decode_task(p, t);
+          for (int nb = c.nb0; nb < c.nb1; ++nb) {
+            for (int s = 0; s < ksteps; ++s) {
+              const int term = s / kb, k = s - term * kb;  // 0: hi*hi, 1: lo*hi, 2: hi*lo
+              mbar_wait(bar_b_empty(stage), b_phase ^ 1, 2);
+              mbar_arrive_expect_tx(bar_b_full(stage), 2 * kPanelBytes);
+              tma_load_3d(sA + stage * kPanelBytes, &tmA, bar_b_full(stage), (term == 1 ? p.k_pad : 0) + k * kBK,
+                          c.m0, p.a_batched ? c.l : 0);
+              tma_load_3d(sB + stage * kPanelBytes, &tmB, bar_b_full(stage), (term == 2 ? p.k_pad : 0) + k * kBK,
+                          nb * kBN, p.b_batched ? c.l : 0);
+              if (++stage == kBStages) {
+                stage = 0;
+                b_phase ^= 1;
+              }
+            }
+          }
+        }
+      } else
       for (int t = t_begin; t < t_end; t += t_step, ++it) {
         const TaskCoord c = decode_task(p, t);
         mbar_wait(bar_a_empty, (it & 1) ^ 1, 1);
@@ -240,6 +273,35 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int acc_stage = 0;
       uint32_t acc_phase = 0;
       int it = 0;
+      if (p.stream_a) {
+        const int ksteps = (p.nterm == 1) ? kb : 3 * kb;
+        for (int t = t_begin; t < t_end; t += t_step) {
+          const TaskCoord c = decode_task(p, t);
+          for (int nb = c.nb0; nb < c.nb1; ++nb) {
+            mbar_wait(bar_t_empty(acc_stage), acc_phase ^ 1, 4);
+            tc_fence_after_sync();
+            const uint32_t d = tmem_base + static_cast<uint32_t>(acc_stage * 2 * kBN);
+            for (int s = 0; s < ksteps; ++s) {
+              mbar_wait(bar_b_full(stage), b_phase, 5);
+              tc_fence_after_sync();
+              const uint64_t adesc = umma_desc_kmajor_sw128(sA + stage * kPanelBytes);
+              const uint64_t bdesc = umma_desc_kmajor_sw128(sB + stage * kPanelBytes);
+#pragma unroll
+              for (int k = 0; k < kBK / kUmmaK; ++k)
+                umma_bf16(d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                          (s > 0 || k > 0) ? 1u : 0u);
+              umma_commit(bar_b_empty(stage));
+              if (++stage == kBStages) {
+                stage = 0;
+                b_phase ^= 1;
+              }
+            }
+            umma_commit(bar_t_full(acc_stage));
+            acc_stage ^= 1;
+            if (acc_stage == 0) acc_phase ^= 1;
+          }
+        }
+      } else
       for (int t = t_begin; t < t_end; t += t_step, ++it) {
         const TaskCoord c = decode_task(p, t);
         mbar_wait(bar_a_full, it & 1, 3);
@@ -358,6 +420,76 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int j = 0; j < 16; ++j) {
                   if (n0 + 2 * j < p.cols) o[2 * j] = static_cast<uint16_t>(pk[j] & 0xFFFFu);
                   if (n0 + 2 * j + 1 < p.cols) o[2 * j + 1] = static_cast<uint16_t>(pk[j] >> 16);
+                }
+              }
+            } else if constexpr (EPI == EPI_LINEAR) {
+              // y = act(acc + bias) (+ residual); fp32 and/or bf16 (hi | lo) outputs, guarded direct stores
+              const bool full = (n0 + 32 <= p.cols);
+              float y[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float a = __uint_as_float(v[j]);
+                if (p.bias != nullptr && (full || n0 + j < p.cols)) a += __ldg(p.bias + n0 + j);
+                if (p.act == 1) a = fmaxf(a, 0.f);
+                if (p.act == 2) a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
+                y[j] = a;
+              }
+              if (my_row < p.rows) {
+                if (p.residual != nullptr) {
+                  const float* r = p.residual + static_cast<long long>(my_row) * p.res_ld + n0;
+                  if (full && (p.res_ld & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float4 q = *reinterpret_cast<const float4*>(r + 4 * j);
+                      y[4 * j] += q.x; y[4 * j + 1] += q.y; y[4 * j + 2] += q.z; y[4 * j + 3] += q.w;
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                      if (n0 + j < p.cols) y[j] += r[j];
+                  }
+                }
+                if (p.out_f32 != nullptr) {
+                  float* o = p.out_f32 + static_cast<long long>(my_row) * p.out_ld + n0;
+                  if (full && (p.out_ld & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                      *reinterpret_cast<float4*>(o + 4 * j) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                      if (n0 + j < p.cols) o[j] = y[j];
+                  }
+                }
+                if (p.out_bf16 != nullptr) {
+                  __nv_bfloat16* o = p.out_bf16 + static_cast<long long>(my_row) * p.bf16_ld + n0;
+                  for (int part = 0; part < (p.write_lo ? 2 : 1); ++part) {
+                    __nv_bfloat16* op = o + part * p.bf16_lo_off;
+                    if (full && (p.bf16_ld & 7) == 0 && (p.bf16_lo_off & 7) == 0) {
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                          float a = y[8 * j + 2 * q], b = y[8 * j + 2 * q + 1];
+                          if (part == 1) {
+                            a -= __bfloat162float(__float2bfloat16_rn(a));
+                            b -= __bfloat162float(__float2bfloat16_rn(b));
+                          }
+                          w[q] = pack_bf16x2(a, b);
+                        }
+                        *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+                      }
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 32; ++j)
+                        if (n0 + j < p.cols) {
+                          float a = y[j];
+                          if (part == 1) a -= __bfloat162float(__float2bfloat16_rn(a));
+                          op[j] = __float2bfloat16_rn(a);
+                        }
+                    }
+                  }
                 }
               }
             } else if constexpr (EPI == EPI_BF16_SPLIT) {

@@ -1,0 +1,233 @@
+"""GPU parity: fusion encoder (mdg_fusion_encode), unimodal MLP (mdg_mlp_forward) and token assembly
+(mdg_assemble_tokens) through the C ABI vs the CPU oracle and the committed reference goldens.
+
+Tolerances: precision='fp32' (bf16x3 split GEMMs, fp32 everything else): |got - ref| <= 1e-3 * max(|ref|, rms(ref));
+precision='bf16': 3e-2 of rms (bf16 operands through 2 transformer layers; the north-star states no encoder bar for
+bf16, the decoder's 1e-2 applies to single GEMM chains).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+META = json.load(open(os.path.join(HERE, "golden", "golden_meta.json")))
+
+
+@pytest.fixture(scope="module")
+def mb(cuda_device):
+    import madrigal_b200
+    return madrigal_b200
+
+
+def gpu(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def assert_close(got, ref, tol, what=""):
+    ref = np.asarray(ref, np.float64)
+    err = np.abs(np.asarray(got, np.float64) - ref)
+    rms = np.sqrt(np.mean(ref ** 2))
+    ratio = (err / (tol * np.maximum(np.abs(ref), rms))).max()
+    assert np.isfinite(got).all() and ratio <= 1.0, f"{what}: max err/bound = {ratio:.3f} (max|err| {err.max():.3e}, rms {rms:.3e})"
+
+
+def make_module(mb, case, dev, precision="fp32"):
+    mod = mb.TransformerFusion(case["embed_dim"], case["nb"], case["num_layers"], case["num_heads"], case["head_dim"],
+                               case["ffn_dim"], transformer_actn=case["actn"], transformer_norm_first=case["norm_first"],
+                               transformer_batch_first=False, transformer_agg=case["agg"], precision=precision)
+    sd = synth.fusion_state_dict(case, case["seed"])
+    mod.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)  # reference key names
+    return mod.to(dev).eval(), sd
+
+
+@pytest.mark.parametrize("case", META["fusion"], ids=lambda c: c["name"])
+def test_fusion_vs_reference_golden(mb, cuda_device, case):
+    g = np.load(os.path.join(HERE, "golden", "golden_fusion.npz"))
+    mod, sd = make_module(mb, case, cuda_device)
+    tokens, mask = synth.fusion_inputs(case["B"], case["T"], case["embed_dim"], case["seed"],
+                                       always_visible=tuple(case["always_visible"]))
+    if not np.isclose(synth.params_checksum([sd[k] for k in sorted(sd)] + [tokens]), case["checksum"], rtol=1e-9):
+        pytest.skip("numpy Generator stream drift")
+    name = case["name"]
+    src = gpu(g[f"{name}.src_mask"], cuda_device) if f"{name}.src_mask" in g.files else None
+    if f"{name}.pool_mask" in g.files:
+        mod.x_attn_key_padding_mask = torch.from_numpy(g[f"{name}.pool_mask"])[None, :]
+    with torch.no_grad():
+        z = mod(gpu(tokens, cuda_device), gpu(mask, cuda_device), src).cpu().numpy()
+    assert_close(z, g[f"{name}.z"], 1e-3, name)
+
+
+@pytest.mark.parametrize("agg,norm_first,actn,T,nb,B,dims", [
+    ("mean", True, "gelu", 4, 0, 300, (128, 8, 32, 512)),      # BASELINE config 5 shape: T=4, Dl=256, F=2*Dl
+    ("cls", False, "relu", 5, 0, 257, (128, 8, 64, 256)),
+    ("x-attn", True, "gelu", 23, 4, 40, (128, 8, 64, 256)),    # production DrugBank shape
+    ("max", True, "relu", 21, 2, 33, (64, 2, 256, 512)),       # head_dim 256 (TWOSIDES)
+    ("x-attn", False, "gelu", 19, 0, 64, (256, 8, 32, 1024)),
+])
+def test_fusion_vs_oracle(mb, cuda_device, agg, norm_first, actn, T, nb, B, dims):
+    E, H, hd, F = dims
+    case = dict(embed_dim=E, num_layers=2, num_heads=H, head_dim=hd, ffn_dim=F, actn=actn, norm_first=norm_first,
+                agg=agg, nb=nb, seed=17 + T)
+    mod, sd = make_module(mb, case, cuda_device)
+    tokens, mask = synth.fusion_inputs(B, T, E, case["seed"], always_visible=(0,) + tuple(range(3, 3 + nb)))
+    src = None
+    if nb > 0:
+        src = np.zeros((T, T), bool)
+        src[:3, T - 16:] = True
+        src[T - 16:, :3] = True
+    pool = None
+    if agg == "x-attn":
+        pool = np.zeros(T, bool)
+        if nb > 0:
+            pool[:3] = True
+            pool[-16:] = True
+        mod.x_attn_key_padding_mask = torch.from_numpy(pool)[None, :]
+    ref = oracle.fusion_forward(sd, case, tokens, mask, src, pool, dtype=np.float64)
+    with torch.no_grad():
+        z = mod(gpu(tokens, cuda_device), gpu(mask, cuda_device), None if src is None else gpu(src, cuda_device))
+        assert_close(z.cpu().numpy(), ref, 1e-3, "fp32 mode")
+        # masked-slot contents are don't-care (only for aggregations that never read masked tokens' outputs)
+        if agg in ("mean", "max") or nb > 0:
+            tok2 = np.where(mask[:, :, None], np.float32(9.0), tokens)
+            z2 = mod(gpu(tok2, cuda_device), gpu(mask, cuda_device), None if src is None else gpu(src, cuda_device))
+            assert (z2 - z).abs().max().item() <= 1e-5 * max(1.0, z.abs().max().item())
+        mod.precision = "bf16"
+        zb = mod(gpu(tokens, cuda_device), gpu(mask, cuda_device), None if src is None else gpu(src, cuda_device))
+    rms = np.sqrt(np.mean(ref ** 2))
+    assert np.abs(zb.cpu().numpy() - ref).max() <= 3e-2 * max(rms, np.abs(ref).max() * 0.1)
+
+
+def test_fusion_chunking_and_empty(mb, cuda_device):
+    """More drugs than one internal chunk (32768 token rows) and B == 0."""
+    case = dict(embed_dim=64, num_layers=1, num_heads=2, head_dim=32, ffn_dim=64, actn="relu", norm_first=True,
+                agg="mean", nb=0, seed=5)
+    mod, sd = make_module(mb, case, cuda_device)
+    B, T = 9000, 4  # 36000 rows -> 2 chunks
+    tokens, mask = synth.fusion_inputs(B, T, 64, 5)
+    with torch.no_grad():
+        z = mod(gpu(tokens, cuda_device), gpu(mask, cuda_device)).cpu().numpy()
+        idx = np.r_[0:50, 8150:8250, 8950:9000]
+        ref = oracle.fusion_forward(sd, case, tokens[idx], mask[idx], dtype=np.float64)
+        assert_close(z[idx], ref, 1e-3, "chunked")
+        z0 = mod(torch.empty((0, T, 64), device=cuda_device), torch.empty((0, T), dtype=torch.bool, device=cuda_device))
+        assert z0.shape == (0, 64)
+
+
+def test_unsupported_configs_fail_loudly(mb, cuda_device):
+    with pytest.raises(NotImplementedError):
+        mb.TransformerFusion(32, 0, 1, 2, 16, 32, transformer_agg="median")
+    with pytest.raises(NotImplementedError):
+        mb.TransformerFusion(32, 0, 1, 2, 16, 32, transformer_actn="tanh")
+    mod = mb.TransformerFusion(32, 0, 1, 2, 16, 32, transformer_agg="mean").to(cuda_device)
+    with pytest.raises(RuntimeError, match="T=40"):
+        mod(torch.zeros(2, 40, 32, device=cuda_device), torch.zeros(2, 40, dtype=torch.bool, device=cuda_device))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mod(torch.zeros(2, 4, 32), torch.zeros(2, 4, dtype=torch.bool))
+
+
+@pytest.mark.parametrize("case", [c for c in META["posenc_mlp"] if c["name"].startswith("mlp")], ids=lambda c: c["name"])
+def test_mlp_adaptor_vs_reference_golden(mb, cuda_device, case):
+    g = np.load(os.path.join(HERE, "golden", "golden_posenc_mlp.npz"))
+    mod = mb.MLPAdaptor(case["E"], case["hidden"], case["E"], case["p"], "ln", case["actn"], "nd")
+    assert list(mod.state_dict().keys()) == case["keys"]  # same `fc.N.*` key layout as the reference module
+    ops = synth.mlp_adaptor_params(case["E"], case["hidden"], case["E"], case["seed"])
+    lin = [o for o in ops if o["op"] in ("linear", "ln")]
+    mods = [x for x in mod.fc if isinstance(x, (torch.nn.Linear, torch.nn.LayerNorm))]
+    for o, x in zip(lin, mods):
+        x.weight.data = torch.from_numpy(o["w"])
+        x.bias.data = torch.from_numpy(o["b"])
+    mod = mod.to(cuda_device)
+    x = np.random.default_rng(case["seed"]).standard_normal((7, case["E"])).astype(np.float32)
+    with torch.no_grad():
+        y = mod(gpu(x, cuda_device)).cpu().numpy()
+    assert_close(y, g[f"{case['name']}.y"], 1e-3, case["name"])
+
+
+@pytest.mark.parametrize("case", META["encode"], ids=lambda c: c["name"])
+def test_fusion_encoder_vs_reference_encode_golden(mb, cuda_device, case):
+    """FusionEncoder (assembly kernel + encoder + unimodal bypass) vs the reference's own NovelDDIEncoder.encode."""
+    g = np.load(os.path.join(HERE, "golden", "golden_encode.npz"))
+    name, E, seed, B = case["name"], case["E"], case["seed"], case["B"]
+    rng = np.random.default_rng(seed)
+    embeds = rng.standard_normal((B, 19, E)).astype(np.float32)
+    masks = rng.random((B, 19)) < 0.55
+    masks[:, 0] = False
+    if "uni_proj" in case["fusion"]:
+        masks[1, :] = True
+        masks[1, 0] = False
+        masks[4, :] = True
+        masks[4, 2] = False
+    hp = dict(transformer_num_layers=2, transformer_att_heads=4, transformer_head_dim=8, transformer_ffn_dim=64,
+              transformer_dropout=0.1, transformer_actn="gelu", transformer_norm_first=True,
+              transformer_batch_first=False, transformer_agg=case["agg"])
+    proj = dict(proj_hidden_dims=[48, 40], proj_dropout=0.2, proj_norm="ln", proj_actn="relu", proj_order="nd")
+    enc = mb.FusionEncoder(E, case["nb"], 0.1, hp, proj, fusion=case["fusion"], normalize=case["normalize"],
+                           pos_emb_type="learnable" if case["pos"] == "learnable" else "sinusoidal")
+    cfg = dict(embed_dim=E, num_layers=2, num_heads=4, head_dim=8, ffn_dim=64, agg=case["agg"])
+    sd = synth.fusion_state_dict(cfg, seed)
+    if not np.isclose(synth.params_checksum([sd[k] for k in sorted(sd)] + [embeds]), case["checksum"], rtol=1e-9):
+        pytest.skip("numpy Generator stream drift")
+    enc.transformer.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    get = lambda k: torch.from_numpy(g[f"{name}.{k}"]) if f"{name}.{k}" in g.files else None
+    with torch.no_grad():
+        if case["nb"] > 0:
+            enc.tx_bottleneck_tokens.copy_(get("tx_bottleneck_tokens"))
+        if case["agg"] == "cls":
+            enc.cls.copy_(get("cls"))
+        if case["pos"] == "learnable":
+            enc.pos_encoder.pe.copy_(get("pos_encoder.pe"))
+        if case["fusion"] == "transformer_uni_proj":
+            ops = synth.mlp_adaptor_params(E, [48, 40], E, seed)
+            lin = [o for o in ops if o["op"] in ("linear", "ln")]
+            for o, x in zip(lin, [x for x in enc.uni_fuser.fc if isinstance(x, (torch.nn.Linear, torch.nn.LayerNorm))]):
+                x.weight.copy_(torch.from_numpy(o["w"]))
+                x.bias.copy_(torch.from_numpy(o["b"]))
+        enc = enc.to(cuda_device).eval()
+        z = enc(gpu(embeds, cuda_device), gpu(masks, cuda_device)).cpu().numpy()
+    assert_close(z, g[f"{name}.z"], 1e-3, name)
+
+
+def test_model_wrapper_end_to_end(mb, cuda_device):
+    """NovelDDIMultilabel drop-in: tokens -> z (FusionEncoder) -> logits, vs the oracle chain."""
+    E, L, B = 128, 5, 96
+    hp = dict(transformer_num_layers=2, transformer_att_heads=8, transformer_head_dim=32, transformer_ffn_dim=256,
+              transformer_dropout=0.1, transformer_actn="gelu", transformer_norm_first=True,
+              transformer_batch_first=False, transformer_agg="x-attn")
+    proj = dict(proj_hidden_dims=[64, 64], proj_dropout=0.0, proj_norm="ln", proj_actn="relu", proj_order="nd")
+    torch.manual_seed(0)
+    enc = mb.FusionEncoder(E, 4, 0.1, hp, proj, fusion="transformer", normalize=False, pos_emb_type="sinusoidal")
+    model = mb.NovelDDIMultilabel(mb.PrecomputedEmbeddingEncoder(enc), E, L, normalize=True).to(cuda_device).eval()
+    keys = set(model.state_dict().keys())
+    assert {"decoder.parametrizations.weight.original", "decoder.bias", "encoder.fusion_encoder.tx_bottleneck_tokens",
+            "encoder.fusion_encoder.transformer.x_attn_query"} <= keys
+    rng = np.random.default_rng(3)
+    embeds = rng.standard_normal((B, 19, E)).astype(np.float32)
+    masks = rng.random((B, 19)) < 0.5
+    masks[:, 0] = False
+    batch = {"drugs": None, "strs": None, "cv": None, "tx": {"all_embeds": gpu(embeds, cuda_device)}}
+    with torch.no_grad():
+        logits = model(batch, batch, gpu(masks, cuda_device), gpu(masks, cuda_device), None, label_range=(1, 4))
+    # oracle chain on the same parameters
+    sd = {k[len("encoder.fusion_encoder.transformer."):]: v.cpu().numpy() for k, v in model.state_dict().items()
+          if k.startswith("encoder.fusion_encoder.transformer.")}
+    cfg = dict(num_layers=2, num_heads=8, head_dim=32, ffn_dim=256, actn="gelu", norm_first=True, agg="x-attn")
+    seq, fmask, src = oracle.assemble_fusion_inputs(
+        embeds, masks, n_non_tx=3, num_tx_bottlenecks=4, agg="x-attn",
+        tx_bottleneck_tokens=model.encoder.fusion_encoder.tx_bottleneck_tokens.detach().cpu().numpy(),
+        pe=oracle.sinusoidal_pe(E, 3, 23), pos_emb_type="sinusoidal")
+    pool = np.zeros(23, bool)
+    pool[:3] = True
+    pool[-16:] = True
+    z = oracle.fusion_forward(sd, cfg, seq, fmask, src, pool, dtype=np.float64)
+    zn = z / np.maximum(np.linalg.norm(z, axis=1, keepdims=True), 1e-12)
+    W = oracle.symmetric(model.decoder.parametrizations.weight.original.detach().cpu().numpy().astype(np.float64))
+    ref = oracle.bilinear_scores(zn, zn, W, (1, 4), dtype=np.float64)
+    assert logits.shape == (3, B, B)
+    assert_close(logits.cpu().numpy(), ref, 2e-3, "tokens -> logits")
