@@ -127,8 +127,10 @@ class TransformerFusion(nn.Module):
         prec = _PRECISION[self.precision]
         fn = _lib.lib()
         z = torch.empty((B, E), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return z
         nbytes = fn.mdg_fusion_workspace_bytes(ctypes.byref(cfg), B, prec)
-        if nbytes == 0 and B > 0:
+        if nbytes == 0:  # unsupported configuration: let the C side produce the error message
             _lib.check(fn.mdg_fusion_encode(ctypes.byref(w), ctypes.byref(cfg), x.data_ptr(), km.data_ptr(), _ptr(sm),
                                             _ptr(pm), z.data_ptr(), B, prec, None, 0, None), "mdg_fusion_encode")
         ws = _workspace(x.device, nbytes)
@@ -172,6 +174,9 @@ class MLPAdaptor(nn.Module):
         lead = x2.shape[:-1]
         x2 = x2.reshape(-1, x2.shape[-1]).contiguous()
         B = x2.shape[0]
+        if B == 0:
+            return torch.empty((*lead, [l for l in self.fc if isinstance(l, nn.Linear)][-1].out_features),
+                               dtype=torch.float32, device=x2.device)
         m = MdgMlp()
         linears = [l for l in self.fc if isinstance(l, nn.Linear)]
         m.n_linear = len(linears)
