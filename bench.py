@@ -15,9 +15,7 @@ import argparse
 import ctypes
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -29,6 +27,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 N_DRUGS = 4096
 N_OUTCOMES = 86
 HIDDEN = 256
+N_TOKENS = 4          # BASELINE: "up to four modality tokens per drug (structure, KG, transcriptomic, cell-viability)"
+ENC = dict(embed_dim=HIDDEN, num_layers=2, num_heads=8, head_dim=32, ffn_dim=512, actn="gelu", norm_first=True,
+           agg="x-attn", nb=0)  # latent 256 = 8 x 32, FFN 2 x latent, pre-LN + GELU + x-attn pooling as shipped configs
 Q_TABLE = 16384
 PANEL = 2048
 METRIC = "scored (outcome, drugA, drugB) triples/sec, fused rank"
@@ -37,12 +38,14 @@ UNIT = "triples/s"
 
 def workload_config(n_gpus):
     return {
-        "workload": f"BASELINE configs[1]: {N_DRUGS} drugs x {N_OUTCOMES} outcomes per GPU, hidden {HIDDEN}, "
-                    f"all-pairs bf16-input/fp32-accumulate scoring + fused uint16 rank (Q={Q_TABLE} reference "
-                    f"quantiles/outcome from a {PANEL}-drug panel)",
+        "workload": f"BASELINE configs[1]: {N_DRUGS} drugs x {N_OUTCOMES} outcomes per GPU, hidden {HIDDEN}: fusion "
+                    f"encoder ({N_TOKENS} modality tokens/drug, random missing-modality masks, 2 layers, 8 heads, "
+                    f"latent 256, FFN 512, x-attn pooling) -> all-pairs bf16-input/fp32-accumulate bilinear scoring "
+                    f"-> fused uint16 rank (Q={Q_TABLE} reference quantiles/outcome from a {PANEL}-drug panel)",
         "drugs": N_DRUGS, "outcomes_per_gpu": N_OUTCOMES, "outcomes_total": N_OUTCOMES * n_gpus, "hidden": HIDDEN,
         "pairs": "full N x N (ordered pairs, the reference's [L,N,N] tensor)",
-        "parallelism": f"outcomes sharded over {n_gpus} GPU(s); z all-gathered once per step" if n_gpus > 1 else "1 GPU",
+        "parallelism": (f"drugs sharded over {n_gpus} GPUs for the encoder, one all-gather of z per step, outcomes "
+                        f"sharded for the decoder") if n_gpus > 1 else "1 GPU",
         "l2": "no explicit flush: each step streams 2.9 GB of output through the 126 MB L2, evicting the inputs",
     }
 
@@ -70,9 +73,15 @@ def _cpu_one_outcome(l):
 def cpu_reference_pass(n_outcomes, cores):
     """Score + rank-normalise `n_outcomes` outcomes of the 4,096-drug workload on `cores` processes; seconds."""
     import multiprocessing as mp
-    from synth import decoder_inputs
-    z, W = decoder_inputs(N_DRUGS, HIDDEN, n_outcomes, seed=0)
+    import synth
+    from oracle import oracle
+    tokens, masks = synth.fusion_inputs(N_DRUGS, N_TOKENS, HIDDEN, seed=0)
+    sd = synth.fusion_state_dict(ENC, seed=7)
+    _, W = synth.decoder_inputs(1, HIDDEN, n_outcomes, seed=100)
     t0 = time.perf_counter()
+    # fusion encoder for the whole catalogue (TransformerFusion.forward restated, fp32, BLAS threads) ...
+    z = oracle.fusion_forward(sd, ENC, tokens, masks, None, np.zeros(N_TOKENS, bool))
+    # ... then decoder + exact rank normalisation, one outcome per process
     ctx = mp.get_context("fork")
     with ctx.Pool(processes=cores, initializer=_cpu_worker_init, initargs=(z, W)) as pool:
         pool.map(_cpu_one_outcome, range(n_outcomes))
@@ -84,8 +93,9 @@ def cpu_baseline(cores=None):
     n_out = max(1, min(cores, 8))  # one outcome per worker: ~10-20 s of CPU work
     dt = cpu_reference_pass(n_out, cores)
     return {"value": n_out * N_DRUGS * N_DRUGS / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_out} of {N_OUTCOMES} outcomes x {N_DRUGS}^2 pairs: fp32 decoder (numpy matmul) + the "
-                      f"reference's exact argsort rank normaliser, one outcome per process in Pool({cores}); {dt:.1f} s"}
+            "sample": f"{n_out} of {N_OUTCOMES} outcomes x {N_DRUGS}^2 pairs: fp32 fusion encoder for all {N_DRUGS} drugs "
+                      f"+ fp32 decoder (numpy matmul) + the reference's exact argsort rank normaliser, one outcome per "
+                      f"process in Pool({cores}); {dt:.1f} s"}
 
 
 def run_reference_arm(args):
@@ -114,50 +124,51 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def start_clock_sampler(gpu_index):
-    path = tempfile.mktemp(prefix="mdg_clocks_", suffix=".csv")
-    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    try:
-        proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                 "-lms", "100"], stdout=open(path, "w"), stderr=subprocess.DEVNULL)
-    except Exception:
-        return None, path
-    return proc, path
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML from a background thread DURING the timed region."""
 
+    def __init__(self, gpu_index, period_s=0.02):
+        import threading
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+            return
+        self._period = period_s
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
-def stop_clock_sampler(proc, path):
-    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-    if proc is None:
-        return out
-    proc.terminate()
-    try:
-        proc.wait(timeout=5)
-    except Exception:
-        proc.kill()
-    sm, reasons, smax = [], set(), None
-    try:
-        for ln in open(path):
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
+    def _run(self):
+        nv = self._nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
             try:
-                sm.append(float(f[0]))
-                smax = float(f[1])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(path)
-    except Exception:
-        pass
-    if sm:
-        top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
-        out["sm_mhz"] = float(np.median(top))
-        out["sm_max_mhz"] = smax
-        out["reasons"] = sorted(reasons)
-    return out
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self._period)
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        sm = sorted(self.samples)
+        return {"sm_mhz": float(np.median(sm[len(sm) // 2:])) if sm else None,  # upper half = samples under load
+                "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def load_peaks():
@@ -188,21 +199,38 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.lib().mdg_check_device(local_rank), "mdg_check_device")
 
-    # ---- synthetic inputs (seeded): shared drug catalogue, per-rank outcomes
-    z_np, _ = decoder_inputs(N_DRUGS, HIDDEN, 1, seed=0)
+    # ---- synthetic inputs (seeded): shared drug catalogue (modality tokens + masks), per-rank outcomes
+    import synth
+    tok_np, mask_np = synth.fusion_inputs(N_DRUGS, N_TOKENS, HIDDEN, seed=0)
     _, W_np = decoder_inputs(1, HIDDEN, N_OUTCOMES, seed=100 + rank)
-    z_full = torch.from_numpy(z_np).to(dev)
+    encoder = mb.TransformerFusion(HIDDEN, 0, ENC["num_layers"], ENC["num_heads"], ENC["head_dim"], ENC["ffn_dim"],
+                                   transformer_actn=ENC["actn"], transformer_norm_first=True,
+                                   transformer_batch_first=False, transformer_agg="x-attn", precision="bf16")
+    encoder.load_state_dict({k: torch.from_numpy(v) for k, v in synth.fusion_state_dict(ENC, seed=7).items()})
+    encoder.x_attn_key_padding_mask = torch.zeros(1, N_TOKENS, dtype=torch.bool)  # nb = 0: every token is a key
+    encoder = encoder.to(dev).eval()
+    tokens = torch.from_numpy(tok_np).to(dev)
+    masks = torch.from_numpy(mask_np).to(dev)
     W = torch.from_numpy(W_np).to(dev)
     r0, r1 = scoring.row_shard(N_DRUGS, rank, world)
-    z_shard = z_full[r0:r1].contiguous()
+    tok_shard, mask_shard = tokens[r0:r1].contiguous(), masks[r0:r1].contiguous()
+    with torch.no_grad():
+        z_full = encoder(tokens, masks)
     # setup (untimed): per-outcome reference quantiles from a drug panel -> prepared rank table
     table = normalize.build_rank_table(z_full, W, Q_TABLE, panel=PANEL, precision="bf16")
     out = torch.empty((N_OUTCOMES, N_DRUGS, N_DRUGS), dtype=torch.uint16, device=dev)
     torch.cuda.synchronize()
+    launches = {"n": 0}
 
+    @torch.no_grad()
     def step():
-        z = scoring.all_gather_embeddings(z_shard, N_DRUGS) if world > 1 else z_full
+        z = encoder(tok_shard, mask_shard)                       # fusion encoder on this rank's drugs
+        launches["n"] = encoder.last_launch_count
+        if world > 1:
+            z = scoring.all_gather_embeddings(z, N_DRUGS)        # the path's only collective
+            launches["n"] += 1
         mb.pair_score(z, z, W, precision="bf16", out="rank", table=table, out_tensor=out)
+        launches["n"] += _lib.lib().mdg_last_launch_count()
 
     def barrier():
         if world > 1:
@@ -212,9 +240,9 @@ def run_gpu_arm(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    launches_per_step = _lib.lib().mdg_last_launch_count() + (1 if world > 1 else 0)
+    launches_per_step = launches["n"]
 
-    proc, cpath = start_clock_sampler(local_rank) if rank == 0 else (None, None)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     _lib.check(_lib.lib().mdg_profile_enable(min(args.steps, 256)), "mdg_profile_enable")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -228,7 +256,7 @@ def run_gpu_arm(args):
     n_rec = _lib.lib().mdg_profile_read(buf, 256)
     _lib.lib().mdg_profile_enable(0)
     kern_ms = float(np.mean(buf[:n_rec])) if n_rec > 0 else None
-    clocks = stop_clock_sampler(proc, cpath) if rank == 0 else None
+    clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -239,15 +267,17 @@ def run_gpu_arm(args):
 
     # ---- e2e: host buffers in, host buffers out, through the public scoring driver
     e2e_steps = max(1, min(args.steps, 3))
-    z_host = torch.from_numpy(z_np).pin_memory()
+    tok_host = torch.from_numpy(tok_np[r0:r1]).pin_memory()
+    mask_host = torch.from_numpy(mask_np[r0:r1]).pin_memory()
     W_host = torch.from_numpy(W_np).pin_memory()
     out_host = torch.empty((N_OUTCOMES, N_DRUGS, N_DRUGS), dtype=torch.uint16).pin_memory()
 
+    @torch.no_grad()
     def e2e_step():
-        zd = z_host.to(dev, non_blocking=True)
+        zd = encoder(tok_host.to(dev, non_blocking=True), mask_host.to(dev, non_blocking=True))
         Wd = W_host.to(dev, non_blocking=True)
         if world > 1:
-            zd = scoring.all_gather_embeddings(zd[r0:r1].contiguous(), N_DRUGS)
+            zd = scoring.all_gather_embeddings(zd, N_DRUGS)
         scoring.score_all_pairs_to_host(zd, Wd, out_host, out="rank", table=table, precision="bf16", chunk=10)
 
     e2e_step()
@@ -261,7 +291,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = triples_per_step / (te.item() * 1e-3)
-    h2d = z_host.numel() * 4 + W_host.numel() * 4
+    h2d = tok_host.numel() * 4 + mask_host.numel() + W_host.numel() * 4
     d2h = out_host.numel() * 2
 
     if rank == 0:

@@ -147,6 +147,12 @@ size_t mdg_exact_rank_workspace_bytes(int64_t N);
 int mdg_exact_rank(const float* scores, int64_t L, int64_t N, float* out, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* Reference-quantile builder: Q order statistics (ranks ceil(i*M/Q), i = 1..Q, M = N(N-1)/2) of each outcome's
+ * strict-lower-triangle scores — the distribution normalize_scores.py ranks against — as ascending fp32 rows, the
+ * input of mdg_rank_table_build.   scores [L, N, N] -> quantiles_out [L, Q].  Same workspace as mdg_exact_rank. */
+int mdg_lower_triangle_quantiles(const float* scores, int64_t L, int64_t N, int32_t Q, float* quantiles_out,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Fusion encoder  (reference: TransformerFusion.forward, madrigal/models/models.py:401-455, with
  *                  nn.TransformerEncoderLayer / nn.MultiheadAttention eval-mode semantics of torch 1.13)
@@ -215,7 +221,13 @@ typedef struct MdgFusionCfg {
  *   workspace     >= mdg_fusion_workspace_bytes(cfg, B, precision) bytes, 256-byte aligned
  */
 size_t mdg_fusion_workspace_bytes(const MdgFusionCfg* cfg, int64_t B, int precision);
-int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const float* tokens,
+/* Optional: convert the weights to the GEMM operand format ONCE (caller-owned buffer of mdg_fusion_prepared_bytes,
+ * 256-byte aligned) and pass it to every mdg_fusion_encode call.  With prepared == NULL the conversion is redone on
+ * every call and the workspace must be mdg_fusion_workspace_bytes + mdg_fusion_prepared_bytes large. */
+size_t mdg_fusion_prepared_bytes(const MdgFusionCfg* cfg, int precision);
+int mdg_fusion_prepare(const MdgFusionWeights* w, const MdgFusionCfg* cfg, int precision, void* prepared,
+                       size_t prepared_bytes, void* stream);
+int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const void* prepared, const float* tokens,
                       const uint8_t* key_mask, const uint8_t* src_mask, const uint8_t* pool_key_mask, float* z_out,
                       int64_t B, int precision, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -67,9 +67,14 @@ SIGNATURES = {
     "mdg_profile_read": (c_int, [POINTER(c_float), c_int]),
     "mdg_exact_rank_workspace_bytes": (c_size_t, [c_int64]),
     "mdg_exact_rank": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mdg_lower_triangle_quantiles": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_size_t,
+                                             c_void_p]),
     "mdg_fusion_workspace_bytes": (c_size_t, [POINTER(MdgFusionCfg), c_int64, c_int]),
+    "mdg_fusion_prepared_bytes": (c_size_t, [POINTER(MdgFusionCfg), c_int]),
+    "mdg_fusion_prepare": (c_int, [POINTER(MdgFusionWeights), POINTER(MdgFusionCfg), c_int, c_void_p, c_size_t,
+                                   c_void_p]),
     "mdg_fusion_encode": (c_int, [POINTER(MdgFusionWeights), POINTER(MdgFusionCfg), c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "mdg_assemble_tokens": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                     c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "mdg_masked_pool": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

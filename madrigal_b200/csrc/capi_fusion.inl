@@ -47,7 +47,6 @@ int run_linear(const __nv_bfloat16* A, long long rows, const __nv_bfloat16* W, i
     p.stream_a = 1;
     p.msub = 1;
   }
-  p.use_tma_store = 0;
   p.bias = bias;
   p.act = act;
   p.residual = residual;
@@ -58,7 +57,23 @@ int run_linear(const __nv_bfloat16* A, long long rows, const __nv_bfloat16* W, i
   p.bf16_ld = out_bf16 ? ka_of(out_bf16_K, split) : 0;
   p.bf16_lo_off = out_bf16 ? kpad_of(out_bf16_K) : 0;
   p.write_lo = split;
-  return launch_pair_kernel(tmA, tmB, tmA, p, mdg::EPI_LINEAR, stream);
+  // outputs go through swizzled staging + TMA stores whenever base and row pitch are 16-byte aligned
+  CUtensorMap tmO1 = tmA, tmO2 = tmA;
+  p.use_tma_store = 0;
+  p.use_tma_store2 = 0;
+  if (out_f32 && reinterpret_cast<uintptr_t>(out_f32) % 16 == 0 && (out_ld * 4) % 16 == 0) {
+    rc = make_map_3d(&tmO1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out_f32, N, rows, 1, out_ld, rows * out_ld, 16, 32,
+                     CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    p.use_tma_store = 1;
+  }
+  if (out_bf16 && reinterpret_cast<uintptr_t>(out_bf16) % 16 == 0) {
+    rc = make_map_3d(&tmO2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_bf16, p.bf16_ld, rows, 1, p.bf16_ld,
+                     rows * p.bf16_ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    p.use_tma_store2 = 1;
+  }
+  return launch_pair_kernel(tmA, tmB, tmO1, p, mdg::EPI_LINEAR, stream, &tmO2);
 }
 
 int convert_rows(const float* x, long long rows, int K, long long ld_in, long long row_stride, int split,
@@ -92,10 +107,10 @@ struct FusionPlan {
   __nv_bfloat16 *xb, *nb, *ob, *fb, *pb;
   float *h, *qkv, *p32, *q_res, *q_proj;
   size_t ob_bytes, fb_bytes, pb_bytes;
-  size_t total;
+  size_t total, prepared_total;
 };
 
-int plan_fusion(const MdgFusionCfg* cfg, long long B, int precision, void* ws, FusionPlan* pl) {
+int plan_fusion(const MdgFusionCfg* cfg, long long B, int precision, void* ws, void* prepared, FusionPlan* pl) {
   if (!cfg) return fail(MDG_ERR_INVALID_ARGUMENT, "fusion: NULL cfg");
   pl->E = cfg->embed_dim;
   pl->H = cfg->num_heads;
@@ -114,25 +129,37 @@ int plan_fusion(const MdgFusionCfg* cfg, long long B, int precision, void* ws, F
   if (cfg->actn != MDG_ACTN_RELU && cfg->actn != MDG_ACTN_GELU)
     return fail(MDG_ERR_UNSUPPORTED, "fusion: unsupported activation %d", cfg->actn);
   const int s = pl->split;
-  long long max_rows = 32768;
+  static const long long max_rows_cfg = [] {
+    const char* e = getenv("MDG_FUSION_CHUNK_ROWS");  // tuning knob: token rows processed per internal chunk
+    long long v = e ? atoll(e) : 0;
+    return v >= 128 ? v : 262144LL;
+  }();
+  long long max_rows = max_rows_cfg;
   long long cd = max_rows / pl->T;
   if (cd < 1) cd = 1;
   if (cd > B) cd = B > 0 ? B : 1;
   pl->chunk_drugs = cd;
   pl->chunk_rows = cd * pl->T;
+  const int E = pl->E, Dl = pl->Dl, F = pl->F;
+  // (a) prepared weights: bf16 operand copies + the x-attn query vectors (depend on the parameters only)
+  WsPlanner pw;
+  pw.base = static_cast<uint8_t*>(prepared);
+  pl->w_e2l = pw.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(E, s));
+  pl->w_l2e = pw.take<__nv_bfloat16>(static_cast<size_t>(E) * ka_of(Dl, s));
+  pl->w_xin = pw.take<__nv_bfloat16>(static_cast<size_t>(2 * Dl) * ka_of(Dl, s));
+  pl->w_xout = pw.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(Dl, s));
+  for (int i = 0; i < pl->layers; ++i) {
+    pl->w_in[i] = pw.take<__nv_bfloat16>(static_cast<size_t>(3 * Dl) * ka_of(Dl, s));
+    pl->w_out[i] = pw.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(Dl, s));
+    pl->w_l1[i] = pw.take<__nv_bfloat16>(static_cast<size_t>(F) * ka_of(Dl, s));
+    pl->w_l2[i] = pw.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(F, s));
+  }
+  pl->q_res = pw.take<float>(Dl);
+  pl->q_proj = pw.take<float>(Dl);
+  pl->prepared_total = pw.off;
+  // (b) per-call activation workspace
   WsPlanner w;
   w.base = static_cast<uint8_t*>(ws);
-  const int E = pl->E, Dl = pl->Dl, F = pl->F;
-  pl->w_e2l = w.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(E, s));
-  pl->w_l2e = w.take<__nv_bfloat16>(static_cast<size_t>(E) * ka_of(Dl, s));
-  pl->w_xin = w.take<__nv_bfloat16>(static_cast<size_t>(2 * Dl) * ka_of(Dl, s));
-  pl->w_xout = w.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(Dl, s));
-  for (int i = 0; i < pl->layers; ++i) {
-    pl->w_in[i] = w.take<__nv_bfloat16>(static_cast<size_t>(3 * Dl) * ka_of(Dl, s));
-    pl->w_out[i] = w.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(Dl, s));
-    pl->w_l1[i] = w.take<__nv_bfloat16>(static_cast<size_t>(F) * ka_of(Dl, s));
-    pl->w_l2[i] = w.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(F, s));
-  }
   const size_t R = static_cast<size_t>(pl->chunk_rows), C = static_cast<size_t>(pl->chunk_drugs);
   pl->xb = w.take<__nv_bfloat16>(R * ka_of(E, s));
   pl->nb = w.take<__nv_bfloat16>(R * ka_of(Dl, s));
@@ -145,15 +172,34 @@ int plan_fusion(const MdgFusionCfg* cfg, long long B, int precision, void* ws, F
   pl->h = w.take<float>(R * Dl);
   pl->qkv = w.take<float>(R * 3 * Dl > R * static_cast<size_t>(E) ? R * 3 * Dl : R * static_cast<size_t>(E));
   pl->p32 = w.take<float>(C * Dl);
-  pl->q_res = w.take<float>(Dl);
-  pl->q_proj = w.take<float>(Dl);
   pl->total = w.off;
   return MDG_OK;
 }
 
 int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_mask, const uint8_t* src_mask,
                      long long Bc, cudaStream_t stream) {
-  const size_t per_warp = (2 * static_cast<size_t>(pl.T) * (pl.hd + 1) + pl.hd) * sizeof(float);
+  if (pl.T <= 8 && pl.hd <= 64) {  // few tokens: head dimension on lanes, registers only
+    const long long items = Bc * pl.H;
+    long long blocks = (items + 7) / 8;
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    const int kp = kpad_of(pl.Dl);
+#define MDG_ATT_SMALL(TT, DPT)                                                                              \
+  mdg::attention_small_kernel<TT, DPT><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(                  \
+      qkv, key_mask, src_mask, Bc, pl.T, pl.H, pl.hd, pl.ob, kp, pl.split)
+    if (pl.T <= 4 && pl.hd <= 32) MDG_ATT_SMALL(4, 1);
+    else if (pl.T <= 4) MDG_ATT_SMALL(4, 2);
+    else if (pl.hd <= 32) MDG_ATT_SMALL(8, 1);
+    else MDG_ATT_SMALL(8, 2);
+#undef MDG_ATT_SMALL
+    MDG_CUDA(cudaGetLastError());
+    ++g_last_launches;
+    return MDG_OK;
+  }
+  int TP = 1;
+  while (TP < pl.T) TP <<= 1;
+  const int G = 32 / TP;
+  const size_t per_warp = static_cast<size_t>(G) * (2 * static_cast<size_t>(pl.T) * (pl.hd + 1) + pl.hd) * sizeof(float);
   int warps = static_cast<int>((96 * 1024) / per_warp);
   if (warps > 8) warps = 8;
   if (warps < 1) return fail(MDG_ERR_UNSUPPORTED, "attention tile T=%d head_dim=%d needs %zu B of shared memory", pl.T, pl.hd, per_warp);
@@ -165,12 +211,12 @@ int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_
     MDG_CUDA(cudaFuncSetAttribute(mdg::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set[dev] = true;
   }
-  long long items = Bc * pl.H;
-  long long blocks = (items + warps - 1) / warps;
+  const long long groups = (Bc * pl.H + G - 1) / G;
+  long long blocks = (groups + warps - 1) / warps;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
   mdg::attention_kernel<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
-      qkv, key_mask, src_mask, Bc, pl.T, pl.H, pl.hd, pl.ob, kpad_of(pl.Dl), pl.split);
+      qkv, key_mask, src_mask, Bc, pl.T, TP, pl.H, pl.hd, pl.ob, kpad_of(pl.Dl), pl.split);
   MDG_CUDA(cudaGetLastError());
   ++g_last_launches;
   return MDG_OK;
@@ -182,55 +228,49 @@ extern "C" {
 
 size_t mdg_fusion_workspace_bytes(const MdgFusionCfg* cfg, int64_t B, int precision) {
   FusionPlan pl;
-  if (plan_fusion(cfg, B, precision, nullptr, &pl) != MDG_OK) return 0;
+  if (plan_fusion(cfg, B, precision, nullptr, nullptr, &pl) != MDG_OK) return 0;
   return pl.total;
 }
 
-int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const float* tokens,
-                      const uint8_t* key_mask, const uint8_t* src_mask, const uint8_t* pool_key_mask, float* z_out,
-                      int64_t B, int precision, void* workspace, size_t workspace_bytes, void* stream_v) {
-  g_last_launches = 0;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!w || !cfg || !tokens || !key_mask || !z_out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: NULL pointer");
-  if (B < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: B=%lld", (long long)B);
-  if (precision != MDG_PREC_BF16 && precision != MDG_PREC_FP32)
-    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: precision=%d", precision);
+size_t mdg_fusion_prepared_bytes(const MdgFusionCfg* cfg, int precision) {
   FusionPlan pl;
-  int rc = plan_fusion(cfg, B, precision, workspace, &pl);
-  if (rc) return rc;
-  if (B == 0) return MDG_OK;
-  if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
-    return fail(MDG_ERR_WORKSPACE, "mdg_fusion_encode: workspace must be non-NULL and 256-byte aligned");
-  if (workspace_bytes < pl.total)
-    return fail(MDG_ERR_WORKSPACE, "mdg_fusion_encode: workspace %zu < required %zu", workspace_bytes, pl.total);
-  const bool xattn = cfg->agg == MDG_AGG_XATTN;
+  if (plan_fusion(cfg, 1, precision, nullptr, nullptr, &pl) != MDG_OK) return 0;
+  return pl.prepared_total;
+}
+
+static int check_fusion_weights(const MdgFusionWeights* w, const MdgFusionCfg* cfg) {
   if (!w->embed2latent_weight || !w->embed2latent_bias || !w->latent2embed_weight || !w->latent2embed_bias)
-    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: NULL embed2latent/latent2embed weights");
-  if (xattn && (!w->x_attn_query || !w->x_attn_kv_norm_weight || !w->x_attn_kv_norm_bias ||
-                !w->x_attn_query_norm_weight || !w->x_attn_query_norm_bias || !w->x_attn_in_proj_weight ||
-                !w->x_attn_in_proj_bias || !w->x_attn_out_proj_weight || !w->x_attn_out_proj_bias))
-    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: agg=x-attn needs the x_attn_* weights");
-  rc = mdg_check_device(-1);
-  if (rc) return rc;
-
-  const int E = pl.E, Dl = pl.Dl, F = pl.F, T = pl.T, s = pl.split;
-  const int act = cfg->actn == MDG_ACTN_GELU ? 2 : 1;
-
-  // ---- weights: fp32 [out, in] (already K-major) -> bf16 operand rows, once per call
-  if ((rc = convert_rows(w->embed2latent_weight, Dl, E, E, 1, s, pl.w_e2l, stream))) return rc;
-  if ((rc = convert_rows(w->latent2embed_weight, E, Dl, Dl, 1, s, pl.w_l2e, stream))) return rc;
-  for (int i = 0; i < pl.layers; ++i) {
+    return fail(MDG_ERR_INVALID_ARGUMENT, "fusion: NULL embed2latent/latent2embed weights");
+  for (int i = 0; i < cfg->num_layers; ++i) {
     const MdgFusionLayer& L = w->layers[i];
     if (!L.in_proj_weight || !L.in_proj_bias || !L.out_proj_weight || !L.out_proj_bias || !L.linear1_weight ||
         !L.linear1_bias || !L.linear2_weight || !L.linear2_bias || !L.norm1_weight || !L.norm1_bias ||
         !L.norm2_weight || !L.norm2_bias)
-      return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: NULL weight in layer %d", i);
+      return fail(MDG_ERR_INVALID_ARGUMENT, "fusion: NULL weight in layer %d", i);
+  }
+  if (cfg->agg == MDG_AGG_XATTN &&
+      (!w->x_attn_query || !w->x_attn_kv_norm_weight || !w->x_attn_kv_norm_bias || !w->x_attn_query_norm_weight ||
+       !w->x_attn_query_norm_bias || !w->x_attn_in_proj_weight || !w->x_attn_in_proj_bias ||
+       !w->x_attn_out_proj_weight || !w->x_attn_out_proj_bias))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "fusion: agg=x-attn needs the x_attn_* weights");
+  return MDG_OK;
+}
+
+// weights: fp32 [out, in] (already K-major) -> bf16 GEMM operand rows; x-attn query path
+static int fusion_prepare_impl(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const FusionPlan& pl,
+                               cudaStream_t stream) {
+  int rc;
+  const int E = pl.E, Dl = pl.Dl, F = pl.F, s = pl.split;
+  if ((rc = convert_rows(w->embed2latent_weight, Dl, E, E, 1, s, pl.w_e2l, stream))) return rc;
+  if ((rc = convert_rows(w->latent2embed_weight, E, Dl, Dl, 1, s, pl.w_l2e, stream))) return rc;
+  for (int i = 0; i < pl.layers; ++i) {
+    const MdgFusionLayer& L = w->layers[i];
     if ((rc = convert_rows(L.in_proj_weight, 3 * Dl, Dl, Dl, 1, s, pl.w_in[i], stream))) return rc;
     if ((rc = convert_rows(L.out_proj_weight, Dl, Dl, Dl, 1, s, pl.w_out[i], stream))) return rc;
     if ((rc = convert_rows(L.linear1_weight, F, Dl, Dl, 1, s, pl.w_l1[i], stream))) return rc;
     if ((rc = convert_rows(L.linear2_weight, Dl, F, F, 1, s, pl.w_l2[i], stream))) return rc;
   }
-  if (xattn) {
+  if (cfg->agg == MDG_AGG_XATTN) {
     if ((rc = convert_rows(w->x_attn_in_proj_weight + static_cast<size_t>(Dl) * Dl, 2 * Dl, Dl, Dl, 1, s, pl.w_xin, stream))) return rc;
     if ((rc = convert_rows(w->x_attn_out_proj_weight, Dl, Dl, Dl, 1, s, pl.w_xout, stream))) return rc;
     mdg::xattn_query_kernel<<<1, 256, 0, stream>>>(w->x_attn_query, w->x_attn_query_norm_weight,
@@ -240,6 +280,57 @@ int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
     MDG_CUDA(cudaGetLastError());
     ++g_last_launches;
   }
+  return MDG_OK;
+}
+
+int mdg_fusion_prepare(const MdgFusionWeights* w, const MdgFusionCfg* cfg, int precision, void* prepared,
+                       size_t prepared_bytes, void* stream_v) {
+  g_last_launches = 0;
+  if (!w || !cfg || !prepared) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_prepare: NULL pointer");
+  if (precision != MDG_PREC_BF16 && precision != MDG_PREC_FP32)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_prepare: precision=%d", precision);
+  FusionPlan pl;
+  int rc = plan_fusion(cfg, 1, precision, nullptr, prepared, &pl);
+  if (rc) return rc;
+  if (reinterpret_cast<uintptr_t>(prepared) % 256 != 0 || prepared_bytes < pl.prepared_total)
+    return fail(MDG_ERR_WORKSPACE, "mdg_fusion_prepare: buffer (%zu B) too small or misaligned, need %zu", prepared_bytes, pl.prepared_total);
+  if ((rc = check_fusion_weights(w, cfg))) return rc;
+  if ((rc = mdg_check_device(-1))) return rc;
+  return fusion_prepare_impl(w, cfg, pl, static_cast<cudaStream_t>(stream_v));
+}
+
+int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const void* prepared, const float* tokens,
+                      const uint8_t* key_mask, const uint8_t* src_mask, const uint8_t* pool_key_mask, float* z_out,
+                      int64_t B, int precision, void* workspace, size_t workspace_bytes, void* stream_v) {
+  g_last_launches = 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!w || !cfg) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: NULL pointer");
+  if (B < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: B=%lld", (long long)B);
+  if (precision != MDG_PREC_BF16 && precision != MDG_PREC_FP32)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: precision=%d", precision);
+  // without a prepared-weights buffer the operand copies live at the head of the workspace (converted every call)
+  FusionPlan pl;
+  int rc = plan_fusion(cfg, B, precision, nullptr, nullptr, &pl);
+  if (rc) return rc;
+  if (B == 0) return MDG_OK;
+  if (!tokens || !key_mask || !z_out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_fusion_encode: NULL pointer");
+  const size_t head = prepared ? 0 : pl.prepared_total;
+  if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
+    return fail(MDG_ERR_WORKSPACE, "mdg_fusion_encode: workspace must be non-NULL and 256-byte aligned");
+  if (workspace_bytes < pl.total + head)
+    return fail(MDG_ERR_WORKSPACE, "mdg_fusion_encode: workspace %zu < required %zu", workspace_bytes, pl.total + head);
+  if (prepared && reinterpret_cast<uintptr_t>(prepared) % 256 != 0)
+    return fail(MDG_ERR_WORKSPACE, "mdg_fusion_encode: prepared buffer must be 256-byte aligned");
+  rc = plan_fusion(cfg, B, precision, static_cast<uint8_t*>(workspace) + head,
+                   prepared ? const_cast<void*>(prepared) : workspace, &pl);
+  if (rc) return rc;
+  if ((rc = check_fusion_weights(w, cfg))) return rc;
+  rc = mdg_check_device(-1);
+  if (rc) return rc;
+
+  const int E = pl.E, Dl = pl.Dl, F = pl.F, T = pl.T, s = pl.split;
+  const int act = cfg->actn == MDG_ACTN_GELU ? 2 : 1;
+  if (!prepared && (rc = fusion_prepare_impl(w, cfg, pl, stream))) return rc;
   // zero the K-padding columns of operand buffers that kernels fill only up to their logical width
   if (kpad_of(Dl) != Dl) {
     MDG_CUDA(cudaMemsetAsync(pl.ob, 0, pl.ob_bytes, stream));
@@ -413,9 +504,74 @@ int mdg_masked_pool(const float* tokens, const uint8_t* masks, int64_t B, int32_
   return MDG_OK;
 }
 
-size_t mdg_exact_rank_workspace_bytes(int64_t) { return 0; }
-int mdg_exact_rank(const float*, int64_t, int64_t, float*, void*, size_t, void*) {
-  return fail(MDG_ERR_UNSUPPORTED, "mdg_exact_rank: not implemented yet");
+// ------------------------------------------------------------------------------------------------ exact rank
+size_t mdg_exact_rank_workspace_bytes(int64_t N) {
+  if (N < 2 || N > 92000) return 0;
+  return mdg::plan_exact_rank(nullptr, N).total;
+}
+
+static int exact_rank_sort(const float* scores_l, long long N, const mdg::ExactRankWs& w, cudaStream_t stream) {
+  const unsigned long long M = static_cast<unsigned long long>(N) * (N - 1) / 2;
+  long long blocks = static_cast<long long>((M + 255) / 256);
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  mdg::tri_gather_keys_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(scores_l, static_cast<int>(N), M,
+                                                                                  w.keys_in, w.idx_in);
+  MDG_CUDA(cudaGetLastError());
+  size_t tb = w.cub_bytes;
+  MDG_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.keys_in, w.keys_out, w.idx_in, w.idx_out,
+                                           static_cast<long long>(M), 0, 32, stream));
+  return MDG_OK;
+}
+
+int mdg_exact_rank(const float* scores, int64_t L, int64_t N, float* out, void* workspace, size_t workspace_bytes,
+                   void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!scores || !out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_exact_rank: NULL pointer");
+  if (L < 0 || N < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_exact_rank: negative size");
+  if (L == 0 || N == 0) return MDG_OK;
+  if (N == 1) {
+    MDG_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(L) * sizeof(float), stream));
+    return MDG_OK;
+  }
+  if (N > 92000) return fail(MDG_ERR_UNSUPPORTED, "mdg_exact_rank: N=%lld (pair index exceeds 32 bits)", (long long)N);
+  mdg::ExactRankWs w = mdg::plan_exact_rank(workspace, N);
+  if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0 || workspace_bytes < w.total)
+    return fail(MDG_ERR_WORKSPACE, "mdg_exact_rank: workspace (%zu B) too small or misaligned, need %zu", workspace_bytes, w.total);
+  const unsigned long long M = static_cast<unsigned long long>(N) * (N - 1) / 2;
+  long long blocks = static_cast<long long>((M + 255) / 256);
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  for (int64_t l = 0; l < L; ++l) {
+    int rc = exact_rank_sort(scores + static_cast<size_t>(l) * N * N, N, w, stream);
+    if (rc) return rc;
+    mdg::tri_scatter_rank_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        w.idx_out, static_cast<int>(N), M, out + static_cast<size_t>(l) * N * N);
+    MDG_CUDA(cudaGetLastError());
+  }
+  return MDG_OK;
+}
+
+int mdg_lower_triangle_quantiles(const float* scores, int64_t L, int64_t N, int32_t Q, float* quantiles_out,
+                                 void* workspace, size_t workspace_bytes, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!scores || !quantiles_out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_lower_triangle_quantiles: NULL pointer");
+  if (L < 0 || N < 2 || Q < 1) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_lower_triangle_quantiles: bad sizes");
+  if (N > 92000) return fail(MDG_ERR_UNSUPPORTED, "mdg_lower_triangle_quantiles: N too large");
+  const unsigned long long M = static_cast<unsigned long long>(N) * (N - 1) / 2;
+  if (static_cast<unsigned long long>(Q) > M) return fail(MDG_ERR_INVALID_ARGUMENT, "Q=%d exceeds the %llu pairs", Q, M);
+  if (L == 0) return MDG_OK;
+  mdg::ExactRankWs w = mdg::plan_exact_rank(workspace, N);
+  if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0 || workspace_bytes < w.total)
+    return fail(MDG_ERR_WORKSPACE, "mdg_lower_triangle_quantiles: workspace too small or misaligned, need %zu", w.total);
+  for (int64_t l = 0; l < L; ++l) {
+    int rc = exact_rank_sort(scores + static_cast<size_t>(l) * N * N, N, w, stream);
+    if (rc) return rc;
+    mdg::pick_quantiles_kernel<<<(Q + 255) / 256, 256, 0, stream>>>(w.keys_out, M, Q,
+                                                                     quantiles_out + static_cast<size_t>(l) * Q);
+    MDG_CUDA(cudaGetLastError());
+  }
+  return MDG_OK;
 }
 
 }  // extern "C"

@@ -1,1 +1,98 @@
+// Exact in-sample normalised rank (reference: classwise_normalized_rank_3d_numpy + run_slice,
+// notebooks/normalize_scores.py:36-74): per outcome, rank the M = N(N-1)/2 strict-lower-triangle scores
+// (argsort(argsort) + 1), divide by M in float64, store float32 at [i,j] and [j,i], zero diagonal.
+//
+// The sort itself is CUB's device radix sort (library code, like the reference's use of numpy's sort); the gather,
+// the key transform and the rank scatter are ours.  Keys are the order-preserving uint32 image of fp32; the radix
+// sort is stable, so equal scores are ranked in (i, j) row-major order == np.argsort(kind='stable').
 #pragma once
+#include <cub/device/device_radix_sort.cuh>
+#include <stdint.h>
+
+namespace mdg {
+
+__device__ __forceinline__ void tri_unflatten(unsigned long long p, unsigned int* i_out, unsigned int* j_out) {
+  // p = i(i-1)/2 + j with 0 <= j < i
+  unsigned long long i = static_cast<unsigned long long>((1.0 + sqrt(1.0 + 8.0 * static_cast<double>(p))) * 0.5);
+  while (i * (i - 1) / 2 > p) --i;
+  while ((i + 1) * i / 2 <= p) ++i;
+  *i_out = static_cast<unsigned int>(i);
+  *j_out = static_cast<unsigned int>(p - i * (i - 1) / 2);
+}
+
+__global__ void __launch_bounds__(256) tri_gather_keys_kernel(const float* __restrict__ scores, int N,
+                                                              unsigned long long M, uint32_t* __restrict__ keys,
+                                                              uint32_t* __restrict__ idx) {
+  for (unsigned long long p = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; p < M;
+       p += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    unsigned int i, j;
+    tri_unflatten(p, &i, &j);
+    float x = scores[static_cast<size_t>(i) * N + j];
+    if (x == 0.f) x = 0.f;  // -0.0 and +0.0 are one value for the reference's float comparison
+    const uint32_t u = __float_as_uint(x);
+    keys[p] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    idx[p] = static_cast<uint32_t>(p);
+  }
+}
+
+__global__ void __launch_bounds__(256) tri_scatter_rank_kernel(const uint32_t* __restrict__ sorted_idx, int N,
+                                                               unsigned long long M, float* __restrict__ out) {
+  for (unsigned long long r = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; r < M;
+       r += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    unsigned int i, j;
+    tri_unflatten(sorted_idx[r], &i, &j);
+    // normalize_scores.py:57: rank / (N*(N-1)/2) in float64, stored into a float32 memmap (:72)
+    const float v = static_cast<float>(static_cast<double>(r + 1) / static_cast<double>(M));
+    out[static_cast<size_t>(i) * N + j] = v;
+    out[static_cast<size_t>(j) * N + i] = v;
+  }
+  for (unsigned long long d = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+       d < static_cast<unsigned long long>(N); d += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+    out[d * N + d] = 0.f;  // normalize_scores.py:69
+}
+
+// Q order statistics (ranks ceil(i*M/Q), i = 1..Q) of the sorted keys -> ascending fp32 quantiles
+__global__ void __launch_bounds__(256) pick_quantiles_kernel(const uint32_t* __restrict__ sorted_keys,
+                                                             unsigned long long M, int Q, float* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const unsigned long long rank = (static_cast<unsigned long long>(q + 1) * M + Q - 1) / Q;  // 1-based
+  const uint32_t o = sorted_keys[rank - 1];
+  const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+  out[q] = __uint_as_float(u);
+}
+
+struct ExactRankWs {
+  uint32_t *keys_in, *keys_out, *idx_in, *idx_out;
+  void* cub_temp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+inline ExactRankWs plan_exact_rank(void* ws, long long N) {
+  ExactRankWs w;
+  const unsigned long long M = static_cast<unsigned long long>(N) * (N - 1) / 2;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<const uint32_t*>(nullptr),
+                                  static_cast<uint32_t*>(nullptr), static_cast<const uint32_t*>(nullptr),
+                                  static_cast<uint32_t*>(nullptr), static_cast<long long>(M));
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) / 256 * 256;
+    return o;
+  };
+  const size_t arr = static_cast<size_t>(M ? M : 1) * 4;
+  size_t o0 = take(arr), o1 = take(arr), o2 = take(arr), o3 = take(arr), o4 = take(cub_bytes ? cub_bytes : 1);
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  w.keys_in = reinterpret_cast<uint32_t*>(b + o0);
+  w.keys_out = reinterpret_cast<uint32_t*>(b + o1);
+  w.idx_in = reinterpret_cast<uint32_t*>(b + o2);
+  w.idx_out = reinterpret_cast<uint32_t*>(b + o3);
+  w.cub_temp = b + o4;
+  w.cub_bytes = cub_bytes;
+  w.total = off;
+  return w;
+}
+
+}  // namespace mdg

@@ -76,22 +76,89 @@ __global__ void __launch_bounds__(256) ln_convert_kernel(const float* __restrict
   }
 }
 
-// Masked multi-head self-attention core for one (drug, head) per warp.
+// Masked multi-head self-attention core.
 //   qkv [B*T, 3*Dl] fp32 (packed in_proj output: q | k | v), key_mask [B, T] (non-zero = masked key),
 //   src_mask [T, T] or NULL (non-zero = query row i may not attend key j)
 //   -> out: bf16 operand rows [B*T, (hi | lo)(k_pad)], head h at columns h*hd .. h*hd+hd-1.
-// Lanes hold keys (T <= 32).  K/V tiles of the (drug, head) are staged in shared memory (row pitch hd+1: lane-per-
-// key reads are bank-conflict-free), the query row is broadcast from shared memory, softmax is a warp shuffle
-// max/sum.  Scores use q * (1/sqrt(hd)) as nn.MultiheadAttention does; masked scores are -inf.
+// A warp processes 32/TP (drug, head) items at once, TP = T rounded up to a power of two: lane = (item slot, key).
+// K/V tiles are staged in shared memory (row pitch hd+1), the query row is broadcast from shared memory, softmax is
+// a segmented warp-shuffle max/sum over the TP lanes of an item.  Scores use q * (1/sqrt(hd)) as
+// nn.MultiheadAttention does; masked scores are -inf.
 __global__ void attention_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ key_mask,
-                                 const uint8_t* __restrict__ src_mask, long long B, int T, int H, int hd,
+                                 const uint8_t* __restrict__ src_mask, long long B, int T, int TP, int H, int hd,
                                  __nv_bfloat16* __restrict__ out, int k_pad, int split) {
   extern __shared__ float att_smem[];
   const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = 32 / TP;  // items per warp
   const int pitch = hd + 1;
-  float* Ks = att_smem + static_cast<size_t>(wid) * (2 * T * pitch + hd);
+  const int item_floats = 2 * T * pitch + hd;
+  float* wbase = att_smem + static_cast<size_t>(wid) * G * item_floats;
+  const int slot = lane / TP, j = lane - slot * TP;
+  float* Ks = wbase + slot * item_floats;
   float* Vs = Ks + T * pitch;
   float* Qs = Vs + T * pitch;
+  const int Dl = H * hd;
+  const float qscale = 1.0f / sqrtf(static_cast<float>(hd));
+  const long long total = B * H;
+  const long long groups = (total + G - 1) / G;
+  for (long long grp = static_cast<long long>(blockIdx.x) * warps + wid; grp < groups;
+       grp += static_cast<long long>(gridDim.x) * warps) {
+    const long long item = grp * G + slot;
+    const bool live = item < total;
+    const long long b = live ? item / H : 0;
+    const int h = live ? static_cast<int>(item - b * H) : 0;
+    const float* base = qkv + (b * T) * 3LL * Dl + h * hd;
+    __syncwarp();
+    if (live) {
+      for (int idx = j; idx < T * hd; idx += TP) {
+        const int r = idx / hd, d = idx - r * hd;
+        Ks[r * pitch + d] = base[static_cast<long long>(r) * 3 * Dl + Dl + d];
+        Vs[r * pitch + d] = base[static_cast<long long>(r) * 3 * Dl + 2 * Dl + d];
+      }
+    }
+    const bool key_ok = live && j < T && key_mask[b * T + j] == 0;
+    for (int i = 0; i < T; ++i) {
+      __syncwarp();
+      if (live)
+        for (int d = j; d < hd; d += TP) Qs[d] = base[static_cast<long long>(i) * 3 * Dl + d] * qscale;
+      __syncwarp();
+      float sc = -CUDART_INF_F;
+      if (key_ok && !(src_mask != nullptr && src_mask[i * T + j] != 0)) {
+        sc = 0.f;
+        const float* kr = Ks + j * pitch;
+        for (int d = 0; d < hd; ++d) sc = fmaf(Qs[d], kr[d], sc);
+      }
+      float m = sc;
+      for (int o = TP >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float pexp = (sc == -CUDART_INF_F) ? 0.f : expf(sc - m);
+      float denom = pexp;
+      for (int o = TP >> 1; o > 0; o >>= 1) denom += __shfl_xor_sync(0xffffffffu, denom, o);
+      const float pj = pexp / denom;  // NaN if every key is masked, like torch.softmax over all -inf
+      __nv_bfloat16* orow = out + (b * T + i) * static_cast<long long>(split ? 2 * k_pad : k_pad) + h * hd;
+      for (int d0 = 0; d0 < hd; d0 += TP) {
+        const int d = d0 + j;
+        float acc = 0.f;
+        for (int jj = 0; jj < T; ++jj) {
+          const float pb = __shfl_sync(0xffffffffu, pj, slot * TP + jj);
+          if (d < hd) acc = fmaf(pb, Vs[jj * pitch + d], acc);
+        }
+        if (live && d < hd) store_bf16_split(orow, d, k_pad, split, acc);
+      }
+    }
+  }
+}
+
+// Few-token variant (T <= TT <= 8, hd <= 32*DPT): one (drug, head) per warp with the HEAD DIMENSION on lanes.  q/k/v
+// rows are read straight from global memory as coalesced 128-byte rows into registers (no shared memory), the T*T
+// scores are warp-shuffle reductions, softmax and the P.V product are lane-local.  This is the shape of BASELINE
+// config 5 (4 modality tokens) where the keys-on-lanes kernel above would leave 28 of 32 lanes idle.
+template <int TT, int DPT>
+__global__ void __launch_bounds__(256) attention_small_kernel(const float* __restrict__ qkv,
+                                                              const uint8_t* __restrict__ key_mask,
+                                                              const uint8_t* __restrict__ src_mask, long long B,
+                                                              int T, int H, int hd, __nv_bfloat16* __restrict__ out,
+                                                              int k_pad, int split) {
+  const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Dl = H * hd;
   const float qscale = 1.0f / sqrtf(static_cast<float>(hd));
   const long long total = B * H;
@@ -100,36 +167,51 @@ __global__ void attention_kernel(const float* __restrict__ qkv, const uint8_t* _
     const long long b = item / H;
     const int h = static_cast<int>(item - b * H);
     const float* base = qkv + (b * T) * 3LL * Dl + h * hd;
-    __syncwarp();
-    for (int idx = lane; idx < T * hd; idx += 32) {
-      const int j = idx / hd, d = idx - j * hd;
-      Ks[j * pitch + d] = base[static_cast<long long>(j) * 3 * Dl + Dl + d];
-      Vs[j * pitch + d] = base[static_cast<long long>(j) * 3 * Dl + 2 * Dl + d];
-    }
-    const bool key_ok = lane < T && key_mask[b * T + lane] == 0;
-    for (int i = 0; i < T; ++i) {
-      __syncwarp();
-      for (int d = lane; d < hd; d += 32) Qs[d] = base[static_cast<long long>(i) * 3 * Dl + d] * qscale;
-      __syncwarp();
-      float s = -CUDART_INF_F;
-      if (key_ok && !(src_mask != nullptr && src_mask[i * T + lane] != 0)) {
-        s = 0.f;
-        const float* kr = Ks + lane * pitch;
-        for (int d = 0; d < hd; ++d) s = fmaf(Qs[d], kr[d], s);
+    float q[TT][DPT], k[TT][DPT], v[TT][DPT];
+    bool kok[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      kok[t] = t < T && key_mask[b * T + t] == 0;
+#pragma unroll
+      for (int e = 0; e < DPT; ++e) {
+        const int d = lane + 32 * e;
+        const bool ok = t < T && d < hd;
+        const float* r = base + static_cast<long long>(t) * 3 * Dl + d;
+        q[t][e] = ok ? r[0] * qscale : 0.f;
+        k[t][e] = ok ? r[Dl] : 0.f;
+        v[t][e] = ok ? r[2 * Dl] : 0.f;
       }
-      const float m = warp_max(s);
-      float pexp = (s == -CUDART_INF_F) ? 0.f : expf(s - m);
-      const float denom = warp_sum(pexp);
-      const float pj = pexp / denom;  // NaN if every key is masked, like torch.softmax over all -inf
-      __nv_bfloat16* orow = out + (b * T + i) * static_cast<long long>(split ? 2 * k_pad : k_pad) + h * hd;
-      for (int d0 = 0; d0 < hd; d0 += 32) {
-        const int d = d0 + lane;
-        float acc = 0.f;
-        for (int j = 0; j < T; ++j) {
-          const float pb = __shfl_sync(0xffffffffu, pj, j);
-          if (d < hd) acc = fmaf(pb, Vs[j * pitch + d], acc);
+    }
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+      if (i < T) {
+        float sc[TT];
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < TT; ++j) {
+          float part = 0.f;
+#pragma unroll
+          for (int e = 0; e < DPT; ++e) part = fmaf(q[i][e], k[j][e], part);
+          part = warp_sum(part);
+          const bool vis = kok[j] && !(src_mask != nullptr && src_mask[i * T + j] != 0);
+          sc[j] = vis ? part : -CUDART_INF_F;
+          m = fmaxf(m, sc[j]);
         }
-        if (d < hd) store_bf16_split(orow, d, k_pad, split, acc);
+        float denom = 0.f;
+#pragma unroll
+        for (int j = 0; j < TT; ++j) {
+          sc[j] = (sc[j] == -CUDART_INF_F) ? 0.f : expf(sc[j] - m);
+          denom += sc[j];
+        }
+        __nv_bfloat16* orow = out + (b * T + i) * static_cast<long long>(split ? 2 * k_pad : k_pad) + h * hd;
+#pragma unroll
+        for (int e = 0; e < DPT; ++e) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < TT; ++j) acc = fmaf(sc[j] / denom, v[j][e], acc);
+          const int d = lane + 32 * e;
+          if (d < hd) store_bf16_split(orow, d, k_pad, split, acc);
+        }
       }
     }
   }

@@ -128,7 +128,7 @@ PairWorkspace carve_pair_ws(void* ws, int64_t Nr, int64_t Nc, int64_t D, int64_t
 
 template <int EPI, int NE>
 int launch_pair_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                         const mdg::PairScoreParams& p, int grid, cudaStream_t stream) {
+                         const CUtensorMap& tmOut2, const mdg::PairScoreParams& p, int grid, cudaStream_t stream) {
   using SM = mdg::PairSmem<NE>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -138,13 +138,15 @@ int launch_pair_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
                                   SM::kBytes));
     attr_set[dev] = true;
   }
-  mdg::pair_score_kernel<EPI, NE><<<grid, SM::kThreads, SM::kBytes, stream>>>(tmA, tmB, tmOut, p);
+  mdg::pair_score_kernel<EPI, NE><<<grid, SM::kThreads, SM::kBytes, stream>>>(tmA, tmB, tmOut, tmOut2, p);
   MDG_CUDA(cudaGetLastError());
   return MDG_OK;
 }
 
 int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                       mdg::PairScoreParams& p, int epi_mode, cudaStream_t stream) {
+                       mdg::PairScoreParams& p, int epi_mode, cudaStream_t stream,
+                       const CUtensorMap* tmOut2_opt = nullptr) {
+  const CUtensorMap& tmOut2 = tmOut2_opt ? *tmOut2_opt : tmOut;
   // task decomposition: enough tasks for ~16 per CTA (tail <= ~6%), chunks of >= 4 column blocks
   const int sms = num_sms();
   p.n_blocks = static_cast<int>((p.cols + mdg::kBN - 1) / mdg::kBN);
@@ -172,15 +174,22 @@ int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     const char* e = getenv("MDG_RANK_EPI_WARPS");  // tuning knob: 8 or 16 epilogue warps for the rank epilogue
     return (e && atoi(e) == 8) ? 8 : 16;
   }();
+  static const int linear_warps = [] {
+    const char* e = getenv("MDG_LINEAR_EPI_WARPS");  // tuning knob
+    return (e && atoi(e) == 16) ? 16 : 8;
+  }();
   int rc;
   switch (epi_mode) {
-    case mdg::EPI_F32: rc = launch_pair_instance<mdg::EPI_F32, 8>(tmA, tmB, tmOut, p, grid, stream); break;
-    case mdg::EPI_SIGMOID: rc = launch_pair_instance<mdg::EPI_SIGMOID, 8>(tmA, tmB, tmOut, p, grid, stream); break;
-    case mdg::EPI_BF16_SPLIT: rc = launch_pair_instance<mdg::EPI_BF16_SPLIT, 8>(tmA, tmB, tmOut, p, grid, stream); break;
-    case mdg::EPI_LINEAR: rc = launch_pair_instance<mdg::EPI_LINEAR, 8>(tmA, tmB, tmOut, p, grid, stream); break;
+    case mdg::EPI_F32: rc = launch_pair_instance<mdg::EPI_F32, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
+    case mdg::EPI_SIGMOID: rc = launch_pair_instance<mdg::EPI_SIGMOID, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
+    case mdg::EPI_BF16_SPLIT: rc = launch_pair_instance<mdg::EPI_BF16_SPLIT, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
+    case mdg::EPI_LINEAR:
+      rc = (linear_warps == 8) ? launch_pair_instance<mdg::EPI_LINEAR, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream)
+                               : launch_pair_instance<mdg::EPI_LINEAR, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
+      break;
     case mdg::EPI_RANK_U16:
-      rc = (rank_warps == 8) ? launch_pair_instance<mdg::EPI_RANK_U16, 8>(tmA, tmB, tmOut, p, grid, stream)
-                             : launch_pair_instance<mdg::EPI_RANK_U16, 16>(tmA, tmB, tmOut, p, grid, stream);
+      rc = (rank_warps == 8) ? launch_pair_instance<mdg::EPI_RANK_U16, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream)
+                             : launch_pair_instance<mdg::EPI_RANK_U16, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
       break;
     default: return fail(MDG_ERR_INVALID_ARGUMENT, "bad epilogue mode %d", epi_mode);
   }

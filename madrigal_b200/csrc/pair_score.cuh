@@ -67,7 +67,8 @@ struct PairScoreParams {
   int nchunk;
   int chunks_per_row;
   int num_tasks;
-  int use_tma_store;
+  int use_tma_store;   // tmOut is valid (all modes; LINEAR: the fp32 output)
+  int use_tma_store2;  // tmOut2 is valid (LINEAR: the bf16 operand output)
   int lo_col_offset;  // EPI_BF16_SPLIT: column offset of the lo half in the output rows
   int write_lo;
   void* out;          // direct-store path
@@ -125,36 +126,45 @@ __device__ __forceinline__ TaskCoord decode_task(const PairScoreParams& p, int t
   return c;
 }
 
-// One warp's 32 rows x 64 bytes: registers -> 64B-swizzled staging -> TMA store (bulk group per chunk).
+// One warp's 32 rows x 64 bytes: registers -> 64B-swizzled staging -> TMA store (one bulk group per chunk).  Two
+// staging buffers alternate so a store only waits for the store before the previous one to have read its buffer.
 struct StagedStore {
-  uint32_t staging;  // this warp's 2 KB buffer
-  uint32_t my_row;   // staging + lane * 64
+  uint32_t buf[2];  // this warp's 2 KB staging buffers (buf[1] == buf[0]: single-buffered)
+  uint32_t row_off;  // lane * 64
   uint32_t swz;      // (lane >> 1) & 3
-  bool pending;
+  int cur;
+  int pending;       // committed bulk groups not yet known to have been read
   __device__ __forceinline__ void store(const CUtensorMap* tm, const uint32_t (&w)[16], int c0, int c1, int c2,
                                         int lane) {
-    if (pending) {
-      if (lane == 0) tma_store_wait_read<0>();
+    const bool dbl = buf[0] != buf[1];
+    if (pending >= (dbl ? 2 : 1)) {
+      if (lane == 0) {
+        if (dbl) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+      }
       __syncwarp();
+      pending = dbl ? 1 : 0;
     }
+    const uint32_t base = buf[cur] + row_off;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
-      st_shared_v4(my_row + ((static_cast<uint32_t>(ch) ^ swz) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2],
+      st_shared_v4(base + ((static_cast<uint32_t>(ch) ^ swz) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2],
                    w[4 * ch + 3]);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_3d(tm, staging, c0, c1, c2);
+      tma_store_3d(tm, buf[cur], c0, c1, c2);
       tma_store_commit();
     }
-    pending = true;
+    ++pending;
+    if (dbl) cur ^= 1;
   }
 };
 
 template <int EPI, int NE>
 __global__ void __launch_bounds__(PairSmem<NE>::kThreads, 1)
 pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ PairScoreParams p) {
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                  const __grid_constant__ PairScoreParams p) {
   using SM = PairSmem<NE>;
   constexpr int kBStages = SM::kBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -191,6 +201,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.use_tma_store) tma_prefetch_desc(&tmOut);
+    if (p.use_tma_store2) tma_prefetch_desc(&tmOut2);
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before_sync();
@@ -364,10 +375,13 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int col_begin = (grp * cols_per_warp) % kBN;
     const int col_end = col_begin + cols_per_warp;
     StagedStore ss;
-    ss.staging = sStaging + ew * kStagingBytesPerWarp;
-    ss.my_row = ss.staging + lane * 64;
+    ss.buf[0] = sStaging + ew * kStagingBytesPerWarp;
+    // the LUT region is idle outside the rank epilogue: use it as a second staging buffer per warp
+    ss.buf[1] = (EPI == EPI_RANK_U16) ? ss.buf[0] : sLut + ew * kStagingBytesPerWarp;
+    ss.row_off = static_cast<uint32_t>(lane) * 64;
     ss.swz = static_cast<uint32_t>((lane >> 1) & 3);  // 64-byte swizzle: chunk ^= (row >> 1) & 3
-    ss.pending = false;
+    ss.cur = 0;
+    ss.pending = 0;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     int cur_l = -1;
@@ -402,7 +416,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    static_cast<uint32_t>((acc_stage * 2 + ms) * kBN + cc);
             tmem_ld_32x32(taddr, v);
-            tmem_ld_wait();
+            if constexpr (EPI != EPI_LINEAR) tmem_ld_wait();  // LINEAR overlaps its global loads with the TMEM load
 
             if constexpr (EPI == EPI_RANK_U16) {
               uint32_t pk[16];
@@ -426,69 +440,94 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               // y = act(acc + bias) (+ residual); fp32 and/or bf16 (hi | lo) outputs, guarded direct stores
               const bool full = (n0 + 32 <= p.cols);
               float y[32];
+              // bias first, as independent vector loads (one exposed latency instead of 32 dependent ones)
+              if (p.bias != nullptr) {
+                if (full && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+                  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float a = __uint_as_float(v[j]);
-                if (p.bias != nullptr && (full || n0 + j < p.cols)) a += __ldg(p.bias + n0 + j);
-                if (p.act == 1) a = fmaxf(a, 0.f);
-                if (p.act == 2) a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
-                y[j] = a;
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 q = __ldg(b4 + j);
+                    y[4 * j] = q.x; y[4 * j + 1] = q.y; y[4 * j + 2] = q.z; y[4 * j + 3] = q.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) y[j] = (n0 + j < p.cols) ? __ldg(p.bias + n0 + j) : 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = 0.f;
               }
-              if (my_row < p.rows) {
-                if (p.residual != nullptr) {
-                  const float* r = p.residual + static_cast<long long>(my_row) * p.res_ld + n0;
-                  if (full && (p.res_ld & 3) == 0) {
+              // residual, likewise issued before the accumulator is needed
+              float rs[32];
+              const bool row_ok = my_row < p.rows;
+              if (p.residual != nullptr && row_ok) {
+                const float* r = p.residual + static_cast<long long>(my_row) * p.res_ld + n0;
+                if (full && (p.res_ld & 3) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                      const float4 q = *reinterpret_cast<const float4*>(r + 4 * j);
-                      y[4 * j] += q.x; y[4 * j + 1] += q.y; y[4 * j + 2] += q.z; y[4 * j + 3] += q.w;
-                    }
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                      if (n0 + j < p.cols) y[j] += r[j];
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 q = *reinterpret_cast<const float4*>(r + 4 * j);
+                    rs[4 * j] = q.x; rs[4 * j + 1] = q.y; rs[4 * j + 2] = q.z; rs[4 * j + 3] = q.w;
                   }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) rs[j] = (n0 + j < p.cols) ? r[j] : 0.f;
                 }
-                if (p.out_f32 != nullptr) {
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) rs[j] = 0.f;
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(v[j]);
+              if (p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+              } else if (p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = 0.5f * y[j] * (1.0f + erff(y[j] * 0.70710678118654752440f));
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) y[j] += rs[j];
+              if (p.out_f32 != nullptr) {
+                if (p.use_tma_store) {
+#pragma unroll
+                  for (int hf = 0; hf < 2; ++hf) {  // two 16-column (64-byte) fills
+                    if (n0 + hf * 16 >= p.cols) break;
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(y[hf * 16 + j]);
+                    ss.store(&tmOut, w, n0 + hf * 16, row0, 0, lane);
+                  }
+                } else if (row_ok) {
                   float* o = p.out_f32 + static_cast<long long>(my_row) * p.out_ld + n0;
-                  if (full && (p.out_ld & 3) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                      *reinterpret_cast<float4*>(o + 4 * j) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-                  } else {
+                  for (int j = 0; j < 32; ++j)
+                    if (n0 + j < p.cols) o[j] = y[j];
+                }
+              }
+              if (p.out_bf16 != nullptr) {
+                for (int part = 0; part < (p.write_lo ? 2 : 1); ++part) {
+                  if (p.use_tma_store2) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      float a = y[2 * j], b = y[2 * j + 1];
+                      if (part == 1) {
+                        a -= __bfloat162float(__float2bfloat16_rn(a));
+                        b -= __bfloat162float(__float2bfloat16_rn(b));
+                      }
+                      pk[j] = pack_bf16x2(a, b);
+                    }
+                    ss.store(&tmOut2, pk, n0 + part * p.bf16_lo_off, row0, 0, lane);
+                  } else if (row_ok) {
+                    __nv_bfloat16* op = p.out_bf16 + static_cast<long long>(my_row) * p.bf16_ld + n0 + part * p.bf16_lo_off;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                      if (n0 + j < p.cols) o[j] = y[j];
-                  }
-                }
-                if (p.out_bf16 != nullptr) {
-                  __nv_bfloat16* o = p.out_bf16 + static_cast<long long>(my_row) * p.bf16_ld + n0;
-                  for (int part = 0; part < (p.write_lo ? 2 : 1); ++part) {
-                    __nv_bfloat16* op = o + part * p.bf16_lo_off;
-                    if (full && (p.bf16_ld & 7) == 0 && (p.bf16_lo_off & 7) == 0) {
-#pragma unroll
-                      for (int j = 0; j < 4; ++j) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                          float a = y[8 * j + 2 * q], b = y[8 * j + 2 * q + 1];
-                          if (part == 1) {
-                            a -= __bfloat162float(__float2bfloat16_rn(a));
-                            b -= __bfloat162float(__float2bfloat16_rn(b));
-                          }
-                          w[q] = pack_bf16x2(a, b);
-                        }
-                        *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+                      if (n0 + j < p.cols) {
+                        float a = y[j];
+                        if (part == 1) a -= __bfloat162float(__float2bfloat16_rn(a));
+                        op[j] = __float2bfloat16_rn(a);
                       }
-                    } else {
-#pragma unroll
-                      for (int j = 0; j < 32; ++j)
-                        if (n0 + j < p.cols) {
-                          float a = y[j];
-                          if (part == 1) a -= __bfloat162float(__float2bfloat16_rn(a));
-                          op[j] = __float2bfloat16_rn(a);
-                        }
-                    }
                   }
                 }
               }
@@ -548,7 +587,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (acc_stage == 0) acc_phase ^= 1;
       }
     }
-    if (ss.pending && lane == 0) tma_store_wait_all<0>();
+    if (ss.pending > 0 && lane == 0) tma_store_wait_all<0>();
     __syncwarp();
   }
 

@@ -100,14 +100,42 @@ class TransformerFusion(nn.Module):
             w.x_attn_out_proj_bias = _ptr(self.x_attn_mha_layer.out_proj.bias)
         return w
 
+    def _prepared_weights(self, device, T):
+        """Weights struct + bf16 operand copies, cached until a parameter changes (version counter / storage)."""
+        params = list(self.parameters())
+        key = (self.precision, str(device), tuple((p.data_ptr(), p._version) for p in params))
+        cache = getattr(self, "_mdg_cache", None)
+        if cache is None or cache[0] != key:
+            for p in params:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("madrigal_b200: module parameters must be contiguous float32 CUDA tensors")
+            w = self._weights()
+            cfg = MdgFusionCfg(self.embed_dim, len(self.transformer_encoder.layers), self.num_heads, self.head_dim,
+                               self.ffn_dim, _lib.MDG_ACTN[self.actn], int(self.norm_first),
+                               _lib.MDG_AGG[self.transformer_agg], 1)
+            prec = _PRECISION[self.precision]
+            fn = _lib.lib()
+            nbytes = fn.mdg_fusion_prepared_bytes(ctypes.byref(cfg), prec)
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                _lib.check(fn.mdg_fusion_prepare(ctypes.byref(w), ctypes.byref(cfg), prec, buf.data_ptr(), buf.numel(),
+                                                 _stream_ptr(device)), "mdg_fusion_prepare")
+            pm = None
+            if self.transformer_agg == 'x-attn':
+                pm = self.x_attn_key_padding_mask.reshape(-1).to(device=device, dtype=torch.uint8).contiguous()
+            cache = (key, w, buf, pm, self.x_attn_key_padding_mask if pm is not None else None)
+            self._mdg_cache = cache
+        if cache[3] is not None and cache[4] is not self.x_attn_key_padding_mask:  # attribute was replaced
+            pm = self.x_attn_key_padding_mask.reshape(-1).to(device=device, dtype=torch.uint8).contiguous()
+            cache = (cache[0], cache[1], cache[2], pm, self.x_attn_key_padding_mask)
+            self._mdg_cache = cache
+        return cache[1], cache[2], cache[3]
+
     def forward(self, fusion_sequence: torch.Tensor, fusion_mask: torch.Tensor, src_mask: Optional[torch.Tensor] = None):
         x = _require_cuda_f32(fusion_sequence, "fusion_sequence")
         if x.dim() != 3 or x.shape[2] != self.embed_dim:
             raise ValueError(f"fusion_sequence must be [B, T, {self.embed_dim}]")
         B, T, E = x.shape
-        for p in self.parameters():
-            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
-                raise RuntimeError("madrigal_b200: module parameters must be contiguous float32 CUDA tensors")
         km = _mask_u8(fusion_mask, "fusion_mask")
         if tuple(km.shape) != (B, T):
             raise ValueError("fusion_mask must be [B, T]")
@@ -116,28 +144,22 @@ class TransformerFusion(nn.Module):
             sm = _mask_u8(src_mask, "src_mask")
             if tuple(sm.shape) != (T, T):
                 raise ValueError("src_mask must be [T, T]")
-        pm = None
-        if self.transformer_agg == 'x-attn':
-            pm = self.x_attn_key_padding_mask.reshape(-1).to(device=x.device, dtype=torch.uint8).contiguous()
-            if pm.numel() != T:
-                raise ValueError(f"x_attn_key_padding_mask has {pm.numel()} keys but the sequence has {T} tokens")
+        w, prepared, pm = self._prepared_weights(x.device, T)
+        if pm is not None and pm.numel() != T:
+            raise ValueError(f"x_attn_key_padding_mask has {pm.numel()} keys but the sequence has {T} tokens")
         cfg = MdgFusionCfg(E, len(self.transformer_encoder.layers), self.num_heads, self.head_dim, self.ffn_dim,
                            _lib.MDG_ACTN[self.actn], int(self.norm_first), _lib.MDG_AGG[self.transformer_agg], T)
-        w = self._weights()
         prec = _PRECISION[self.precision]
         fn = _lib.lib()
         z = torch.empty((B, E), dtype=torch.float32, device=x.device)
         if B == 0:
             return z
         nbytes = fn.mdg_fusion_workspace_bytes(ctypes.byref(cfg), B, prec)
-        if nbytes == 0:  # unsupported configuration: let the C side produce the error message
-            _lib.check(fn.mdg_fusion_encode(ctypes.byref(w), ctypes.byref(cfg), x.data_ptr(), km.data_ptr(), _ptr(sm),
-                                            _ptr(pm), z.data_ptr(), B, prec, None, 0, None), "mdg_fusion_encode")
-        ws = _workspace(x.device, nbytes)
+        ws = _workspace(x.device, max(nbytes, 256))  # nbytes == 0: unsupported config, the C side reports why
         with torch.cuda.device(x.device):
-            _lib.check(fn.mdg_fusion_encode(ctypes.byref(w), ctypes.byref(cfg), x.data_ptr(), km.data_ptr(), _ptr(sm),
-                                            _ptr(pm), z.data_ptr(), B, prec, ws.data_ptr(), ws.numel(),
-                                            _stream_ptr(x.device)), "mdg_fusion_encode")
+            _lib.check(fn.mdg_fusion_encode(ctypes.byref(w), ctypes.byref(cfg), prepared.data_ptr(), x.data_ptr(),
+                                            km.data_ptr(), _ptr(sm), _ptr(pm), z.data_ptr(), B, prec, ws.data_ptr(),
+                                            ws.numel(), _stream_ptr(x.device)), "mdg_fusion_encode")
         self.last_launch_count = fn.mdg_last_launch_count()
         return z
 

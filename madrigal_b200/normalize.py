@@ -8,14 +8,50 @@ Two formulations:
 `build_reference_quantiles` produces the per-outcome table rows: Q order statistics (ranks ceil(i*M/Q)) of the strict
 lower triangle of each outcome's score matrix over a reference panel of drugs — the distribution the reference ranks
 against (normalize_scores.py:67: entries with col >= row are excluded).  It is SETUP, run once per model/catalogue,
-outside any timed region; it materialises one outcome chunk of fp32 logits at a time and uses torch.sort for the
-order statistics (plumbing — the GPU histogram-select builder is a SURVEY §8f-2 "next" row).
+outside any timed region; it materialises one outcome chunk of fp32 logits at a time and takes the order statistics
+with mdg_lower_triangle_quantiles (gather + CUB radix sort + pick).
 """
 from typing import Optional
 
 import torch
 
-from .decoder import RankTable, pair_score
+from . import _lib
+from .decoder import RankTable, _require_cuda_f32, _stream_ptr, _workspace, pair_score
+
+
+def exact_normalized_ranks(scores: torch.Tensor) -> torch.Tensor:
+    """Drop-in for `run_slice` over all outcomes (normalize_scores.py:62-74): [L, N, N] fp32 raw scores -> [L, N, N]
+    fp32 symmetric in-sample normalised ranks with zero diagonal (mdg_exact_rank)."""
+    s = _require_cuda_f32(scores, "scores")
+    if s.dim() != 3 or s.shape[1] != s.shape[2]:
+        raise ValueError("scores must be [L, N, N]")
+    L, N, _ = s.shape
+    out = torch.empty_like(s)
+    fn = _lib.lib()
+    ws = _workspace(s.device, fn.mdg_exact_rank_workspace_bytes(N))
+    with torch.cuda.device(s.device):
+        _lib.check(fn.mdg_exact_rank(s.data_ptr(), L, N, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     _stream_ptr(s.device)), "mdg_exact_rank")
+    return out
+
+
+def classwise_normalized_rank_3d(tensor: torch.Tensor) -> torch.Tensor:
+    """Alias with the reference function's name for scripts ported from notebooks/normalize_scores.py; applies the
+    run_slice masking (col >= row excluded) because that is the only way the reference calls it."""
+    return exact_normalized_ranks(tensor)
+
+
+def lower_triangle_quantiles(scores: torch.Tensor, Q: int) -> torch.Tensor:
+    """[L, N, N] fp32 -> [L, Q] ascending order statistics of each outcome's strict lower triangle."""
+    s = _require_cuda_f32(scores, "scores")
+    L, N, _ = s.shape
+    out = torch.empty((L, Q), dtype=torch.float32, device=s.device)
+    fn = _lib.lib()
+    ws = _workspace(s.device, fn.mdg_exact_rank_workspace_bytes(N))
+    with torch.cuda.device(s.device):
+        _lib.check(fn.mdg_lower_triangle_quantiles(s.data_ptr(), L, N, Q, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                   _stream_ptr(s.device)), "mdg_lower_triangle_quantiles")
+    return out
 
 
 def build_reference_quantiles(z: torch.Tensor, weight: torch.Tensor, Q: int, *, panel: Optional[int] = None,
@@ -29,15 +65,11 @@ def build_reference_quantiles(z: torch.Tensor, weight: torch.Tensor, Q: int, *, 
     if M < 1:
         raise ValueError("need at least 2 drugs for a reference distribution")
     Q = min(Q, M)
-    i, j = torch.tril_indices(n, n, -1, device=z.device)
-    pick = (torch.arange(1, Q + 1, device=z.device, dtype=torch.int64) * M + Q - 1) // Q - 1  # ceil(i*M/Q) - 1
     out = torch.empty((L, Q), dtype=torch.float32, device=z.device)
     for l0 in range(0, L, chunk):
         l1 = min(l0 + chunk, L)
         logits = pair_score(zp, zp, weight[l0:l1], precision=precision, out="logit", normalize=normalize)
-        for l in range(l0, l1):
-            v = logits[l - l0][i, j].sort().values
-            out[l] = v[pick]
+        out[l0:l1] = lower_triangle_quantiles(logits, Q)
     return out
 
 

@@ -1,0 +1,79 @@
+"""GPU parity: exact in-sample normalised rank (mdg_exact_rank) and the reference-quantile builder vs the oracle and
+the committed outputs of the reference's own run_slice (notebooks/normalize_scores.py:62-74).  Integer rank work:
+bit-exact float32 outputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+META = json.load(open(os.path.join(HERE, "golden", "golden_meta.json")))
+
+
+@pytest.fixture(scope="module")
+def norm(cuda_device):
+    from madrigal_b200 import normalize
+    return normalize
+
+
+@pytest.mark.parametrize("case", META["normalizer"], ids=lambda c: c["name"])
+def test_exact_rank_vs_reference_golden(norm, cuda_device, case):
+    g = np.load(os.path.join(HERE, "golden", "golden_normalizer.npz"))
+    rng = np.random.default_rng(case["seed"])
+    raw = rng.standard_normal((case["L"], case["N"], case["N"])).astype(np.float32)
+    if case["ties"]:
+        raw = np.round(raw * 4) / 4
+    got = norm.exact_normalized_ranks(torch.from_numpy(raw).to(cuda_device)).cpu().numpy()
+    ref = g[f"{case['name']}.out"]
+    if not case["ties"]:
+        assert np.array_equal(got, ref)  # bit-identical to the reference's float32 memmap contents
+    else:
+        assert np.array_equal(got, oracle.normalize_scores(raw, kind="stable"))
+        N, M = case["N"], case["N"] * (case["N"] - 1) // 2
+        i, j = np.tril_indices(N, -1)
+        for l in range(case["L"]):
+            v = np.sort(oracle.lower_triangle_values(raw[l]))
+            r = np.rint(got[l][i, j].astype(np.float64) * M).astype(np.int64)
+            assert (r >= np.searchsorted(v, raw[l][i, j], "left") + 1).all()
+            assert (r <= np.searchsorted(v, raw[l][i, j], "right")).all()
+
+
+@pytest.mark.parametrize("L,N", [(2, 257), (1, 2), (3, 1), (1, 700)])
+def test_exact_rank_vs_oracle(norm, cuda_device, L, N):
+    rng = np.random.default_rng(N)
+    raw = rng.standard_normal((L, N, N)).astype(np.float32)
+    raw[:, 0, :] = 0.0  # some exact ties incl. -0.0
+    raw[:, :, 0] *= -0.0 if N > 2 else 1.0
+    got = norm.exact_normalized_ranks(torch.from_numpy(raw).to(cuda_device)).cpu().numpy()
+    ref = oracle.normalize_scores(raw, kind="stable")
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    assert np.array_equal(got, got.swapaxes(1, 2)) and (np.diagonal(got, axis1=1, axis2=2) == 0).all()
+
+
+def test_quantile_builder_vs_oracle(norm, cuda_device):
+    rng = np.random.default_rng(4)
+    raw = rng.standard_normal((3, 200, 200)).astype(np.float32)
+    for Q in (1, 17, 4096, 19900):
+        got = norm.lower_triangle_quantiles(torch.from_numpy(raw).to(cuda_device), Q).cpu().numpy()
+        assert np.array_equal(got, oracle.reference_quantiles(raw, Q))
+
+
+def test_fused_quantile_rank_tracks_exact_rank_within_one_over_q(norm, cuda_device):
+    """End-to-end link between the two formulations: |fused rank / Q - reference normalised rank| <= 1/Q + snapping."""
+    import madrigal_b200 as mb
+    import synth
+    N, D, L, Q = 300, 128, 2, 4096
+    z, W = synth.decoder_inputs(N, D, L, seed=21)
+    zt, Wt = torch.from_numpy(z).to(cuda_device), torch.from_numpy(W).to(cuda_device)
+    logits = mb.pair_score(zt, zt, Wt, precision="fp32")
+    exact = norm.exact_normalized_ranks(logits).cpu().numpy()
+    table = norm.build_rank_table(zt, Wt, Q, precision="fp32")
+    fused = mb.pair_score(zt, zt, Wt, precision="fp32", out="rank", table=table).cpu().numpy().astype(np.float64) / Q
+    i, j = np.tril_indices(N, -1)
+    for l in range(L):
+        assert np.abs(fused[l][i, j] - exact[l][i, j]).max() <= 1.0 / Q + 4.0 / 131072 + 1e-7
