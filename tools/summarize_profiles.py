@@ -1,0 +1,108 @@
+"""Turn the ncu outputs brought back in gpurun_out/ into the committed summaries under profiles/."""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+SRC = os.path.join(ROOT, "gpurun_out")
+ROUND = sys.argv[1] if len(sys.argv) > 1 else "r01"
+os.makedirs(OUT, exist_ok=True)
+
+
+def launch_list():
+    path = os.path.join(SRC, "launches.csv")
+    if not os.path.exists(path):
+        return
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = next(r for r in rows if "Kernel Name" in r)
+    start = rows.index(hdr)
+    ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
+    data = []
+    for r in rows[start + 1:]:
+        try:
+            data.append((r[ki], float(r[vi].replace(",", "")), r[gi], r[bi]))
+        except ValueError:
+            pass
+    # the last DEVICE-RESIDENT bench step: it ends with the full-size rank launch (the e2e steps that follow score the
+    # outcomes in chunks of 10, so their rank launches are ~9x shorter) and starts with the encoder's token conversion
+    rank = [(i, d[1]) for i, d in enumerate(data) if "pair_score_kernel<2" in d[0].replace("(int)", "")]
+    longest = max(v for _, v in rank)
+    rank_idx = max(i for i, v in rank if v > 0.5 * longest)
+    step_start = max(i for i, d in enumerate(data[:rank_idx]) if "convert_rows_kernel" in d[0])
+    step = data[step_start:rank_idx + 1]
+    total = sum(d[1] for d in step)
+    with open(os.path.join(OUT, f"{ROUND}_bench_step_launches.csv"), "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
+        f.write("# one bench step (last one in the run); per-launch times are cold-cache and serialised: compare SHARES\n")
+        f.write("kernel,grid,block,duration_us,share\n")
+        for k, v, g, b in step:
+            name = k.split("(CUtensorMap")[0].split("(const")[0].replace("void ", "").replace("(int)", "")
+            f.write(f"\"{name}\",\"{g}\",\"{b}\",{v / 1e3:.2f},{v / total:.4f}\n")
+        f.write(f"TOTAL,,,{total / 1e3:.2f},1.0\n")
+    agg = collections.OrderedDict()
+    for k, v, g, b in step:
+        name = k.split("(")[0].replace("void ", "")
+        if "pair_score_kernel" in k:
+            name = k.split("(CUtensorMap")[0].replace("void ", "").replace("(int)", "")
+        agg.setdefault(name, [0, 0.0])
+        agg[name][0] += 1
+        agg[name][1] += v
+    print(f"bench step: {len(step)} launches, {total / 1e3:.1f} us under ncu")
+    for k, (n, v) in agg.items():
+        print(f"  {k:60s} x{n:2d} {v / 1e3:9.1f} us  {100 * v / total:5.1f}%")
+    return {k: {"launches": n, "us": v / 1e3, "share": v / total} for k, (n, v) in agg.items()}
+
+
+def full_capture(rep, tag, kernel_key):
+    path = os.path.join(SRC, rep)
+    if not os.path.exists(path):
+        return None
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, unit, val = rows[0], rows[1], rows[2]
+    want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+            "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.per_cycle_active",
+            "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+            "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
+            "smsp__cycles_active.avg"]
+    out = {}
+    lines = []
+    for i, h in enumerate(hdr):
+        if h in want or ("issue_stalled" in h and "per_issue_active" in h):
+            out[h] = (val[i], unit[i])
+            lines.append(f"{h:95s} {val[i]:>18s} {unit[i]}")
+    with open(os.path.join(OUT, f"{ROUND}_{tag}_ncu_full.txt"), "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on, kernel {kernel_key}, one launch from a bench step\n")
+        f.write("\n".join(sorted(lines)) + "\n")
+
+    def num(k, mult={"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}):
+        v, u = out[k]
+        return float(v.replace(",", "")) * mult.get(u, 1.0)
+
+    return {"dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+            "dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
+            "duration_ms_under_ncu": float(out["gpu__time_duration.sum"][0]) * (1e-3 if out["gpu__time_duration.sum"][1] == "us" else 1.0),
+            "tensor_pipe_active_pct": float(out["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0]),
+            "lsu_wavefronts_pct": float(out["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"][0])}
+
+
+if __name__ == "__main__":
+    summary = {"round": ROUND}
+    shares = launch_list()
+    if shares:
+        summary["bench_step_shares"] = shares
+    cap = full_capture("prof_rank.ncu-rep", "pair_score_rank", "pair_score_kernel<EPI_RANK_U16, 16>")
+    if cap:
+        summary["pair_score_kernel"] = cap
+        print("rank kernel:", cap)
+    json.dump(summary, open(os.path.join(OUT, "ncu_summary.json"), "w"), indent=1)
