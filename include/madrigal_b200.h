@@ -71,8 +71,9 @@ typedef enum MdgOutMode {
 
 typedef enum MdgPairs {
   MDG_PAIRS_FULL = 0,     /* every (i, j)                                                                          */
-  MDG_PAIRS_SYMMETRIC = 1 /* z_rows == z_cols only: compute i > j, write [i,j] and [j,i], diagonal = 0 — the shape
-                             of the reference normaliser's output (notebooks/normalize_scores.py:67-70)            */
+  MDG_PAIRS_SYMMETRIC = 1 /* z_rows == z_cols only: only row > col is computed/kept — the pair set the reference
+                             normaliser ranks (notebooks/normalize_scores.py:67).  Implemented for mdg_pair_topk;
+                             mdg_pair_score's dense outputs are MDG_PAIRS_FULL only in this version.              */
 } MdgPairs;
 
 /* Prepared per-outcome reference-quantile table for the fused rank epilogue (see mdg_rank_table_build). */
@@ -120,6 +121,23 @@ size_t mdg_pair_score_workspace_bytes(int64_t Nr, int64_t Nc, int64_t D, int64_t
 int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
                    int64_t L, int precision, int out_mode, int pairs, int normalize_rows,
                    const MdgRankTable* table, void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Per-outcome top-k pairs without materialising any dense output (BASELINE config 4: "per-outcome top-1000").
+ * The decoder's epilogue appends every score >= thresholds[l] to outcome l's candidate list (capacity `cap`); the
+ * lists are then sorted (score descending, ties by pair index ascending) and the first k are written out.
+ *   pairs = MDG_PAIRS_SYMMETRIC: unordered pairs of one catalogue — only row > col is kept and column blocks above
+ *           the diagonal are never computed (the set normalize_scores.py ranks); MDG_PAIRS_FULL: every (row, col).
+ *   thresholds [L] fp32 (device): e.g. a high quantile of the rank table, so that k <= #candidates <= cap.
+ *   scores_out [L, k] fp32, rows_out / cols_out [L, k] int32 (-1 / -inf padding when fewer than k candidates)
+ *   status_out [L] int32: 0 ok, 1 fewer than k candidates (threshold too high), 2 more than cap (too low: the list is
+ *   then an arbitrary subset and must be recomputed).
+ */
+size_t mdg_pair_topk_workspace_bytes(int64_t Nr, int64_t Nc, int64_t D, int64_t L, int precision, int32_t cap);
+int mdg_pair_topk(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
+                  int64_t L, int precision, int pairs, int normalize_rows, const float* thresholds, int32_t k,
+                  int32_t cap, float* scores_out, int32_t* rows_out, int32_t* cols_out, int32_t* status_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of kernel launches the last successful mdg_pair_score call on this thread enqueued (for bench accounting). */
 int mdg_last_launch_count(void);

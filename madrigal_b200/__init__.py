@@ -3,11 +3,11 @@
 Only the path is here: fusion encoder -> bilinear decoder -> rank normalisation.  Every operator
 calls the C ABI in include/madrigal_b200.h through ctypes; nothing falls back to PyTorch or the CPU.
 """
-from .decoder import BilinearDDIScorer, RankTable, Symmetric, pair_score  # noqa: F401
+from .decoder import BilinearDDIScorer, RankTable, Symmetric, pair_score, pair_topk  # noqa: F401
 from .fusion import (FusionEncoder, MLPAdaptor, PositionEncodingLearnable, PositionEncodingSinusoidal,  # noqa: F401
                      TransformerFusion, masked_pool)
 from .model import NovelDDIMultilabel, PrecomputedEmbeddingEncoder  # noqa: F401
 
-__all__ = ["BilinearDDIScorer", "RankTable", "Symmetric", "pair_score", "TransformerFusion", "MLPAdaptor",
+__all__ = ["BilinearDDIScorer", "RankTable", "Symmetric", "pair_score", "pair_topk", "TransformerFusion", "MLPAdaptor",
            "FusionEncoder", "PositionEncodingSinusoidal", "PositionEncodingLearnable", "masked_pool",
            "NovelDDIMultilabel", "PrecomputedEmbeddingEncoder"]

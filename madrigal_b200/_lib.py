@@ -62,6 +62,10 @@ SIGNATURES = {
     "mdg_pair_score_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "mdg_pair_score": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                c_int, POINTER(MdgRankTable), c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mdg_pair_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int32]),
+    "mdg_pair_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int,
+                              c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                              c_void_p]),
     "mdg_last_launch_count": (c_int, []),
     "mdg_profile_enable": (c_int, [c_int]),
     "mdg_profile_read": (c_int, [POINTER(c_float), c_int]),

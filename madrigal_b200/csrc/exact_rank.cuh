@@ -7,6 +7,7 @@
 // sort is stable, so equal scores are ranked in (i, j) row-major order == np.argsort(kind='stable').
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 #include <stdint.h>
 
 namespace mdg {
@@ -60,6 +61,58 @@ __global__ void __launch_bounds__(256) pick_quantiles_kernel(const uint32_t* __r
   const uint32_t o = sorted_keys[rank - 1];
   const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
   out[q] = __uint_as_float(u);
+}
+
+// ---- top-k finalisation: candidates appended by the EPI_TOPK epilogue -> per-outcome top k
+// sort key = (~ordered(score) << 32) | pair index: ascending order = descending score, ties by ascending pair index;
+// unused slots are all-ones and sort last.
+__global__ void __launch_bounds__(256) topk_make_keys_kernel(const unsigned long long* __restrict__ cand,
+                                                             const unsigned int* __restrict__ counts, int cap,
+                                                             unsigned long long* __restrict__ keys,
+                                                             int* __restrict__ offsets, int L) {
+  const int l = blockIdx.y;
+  const unsigned int n = min(counts[l], static_cast<unsigned int>(cap));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (static_cast<unsigned int>(i) < n) {
+      const unsigned long long c = cand[static_cast<size_t>(l) * cap + i];
+      const uint32_t u = static_cast<uint32_t>(c >> 32);
+      const uint32_t o = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      key = (static_cast<unsigned long long>(~o) << 32) | (c & 0xFFFFFFFFull);
+    }
+    keys[static_cast<size_t>(l) * cap + i] = key;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    offsets[l] = l * cap;
+    if (l == L - 1) offsets[L] = L * cap;
+  }
+}
+
+__global__ void __launch_bounds__(256) topk_emit_kernel(const unsigned long long* __restrict__ sorted,
+                                                        const unsigned int* __restrict__ counts, int cap, int k,
+                                                        int ncols, float* __restrict__ scores, int* __restrict__ rows,
+                                                        int* __restrict__ cols, int* __restrict__ status) {
+  const int l = blockIdx.y;
+  const unsigned int n_raw = counts[l];
+  const int n = n_raw < static_cast<unsigned int>(cap) ? static_cast<int>(n_raw) : cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    status[l] = (n_raw > static_cast<unsigned int>(cap)) ? 2 : (n < k ? 1 : 0);  // 2: overflow, 1: fewer than k
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+    float sc = -INFINITY;
+    int r = -1, c = -1;
+    if (i < n) {
+      const unsigned long long key = sorted[static_cast<size_t>(l) * cap + i];
+      const uint32_t o = ~static_cast<uint32_t>(key >> 32);
+      const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+      sc = __uint_as_float(u);
+      const uint32_t idx = static_cast<uint32_t>(key);
+      r = static_cast<int>(idx / static_cast<uint32_t>(ncols));
+      c = static_cast<int>(idx % static_cast<uint32_t>(ncols));
+    }
+    scores[static_cast<size_t>(l) * k + i] = sc;
+    rows[static_cast<size_t>(l) * k + i] = r;
+    cols[static_cast<size_t>(l) * k + i] = c;
+  }
 }
 
 struct ExactRankWs {

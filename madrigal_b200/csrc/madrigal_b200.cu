@@ -183,6 +183,7 @@ int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     case mdg::EPI_F32: rc = launch_pair_instance<mdg::EPI_F32, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
     case mdg::EPI_SIGMOID: rc = launch_pair_instance<mdg::EPI_SIGMOID, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
     case mdg::EPI_BF16_SPLIT: rc = launch_pair_instance<mdg::EPI_BF16_SPLIT, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
+    case mdg::EPI_TOPK: rc = launch_pair_instance<mdg::EPI_TOPK, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
     case mdg::EPI_LINEAR:
       rc = (linear_warps == 8) ? launch_pair_instance<mdg::EPI_LINEAR, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream)
                                : launch_pair_instance<mdg::EPI_LINEAR, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
@@ -251,20 +252,31 @@ size_t mdg_pair_score_workspace_bytes(int64_t Nr, int64_t Nc, int64_t D, int64_t
   return carve_pair_ws(nullptr, Nr, Nc, D, L, precision).total;
 }
 
-int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
-                   int64_t L, int precision, int out_mode, int pairs, int normalize_rows, const MdgRankTable* table,
-                   void* out, void* workspace, size_t workspace_bytes, void* stream_v) {
-  g_last_launches = 0;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!z_rows || !z_cols || !W || !out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: NULL pointer");
+struct TopkArgs {
+  const float* thresh;
+  unsigned int* counts;
+  unsigned long long* cand;
+  int cap;
+};
+constexpr int kOutTopk = 100;  // internal out_mode of mdg_pair_topk
+
+static int pair_score_impl(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
+                           int64_t L, int precision, int out_mode, int pairs, int normalize_rows,
+                           const MdgRankTable* table, void* out, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream, const TopkArgs* topk) {
+  if (!z_rows || !z_cols || !W || (!out && out_mode != kOutTopk))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: NULL pointer");
   if (Nr < 0 || Nc < 0 || L < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: negative size");
   if (D != 64 && D != 128 && D != 192 && D != 256)
     return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: D=%lld (supported: 64, 128, 192, 256)", (long long)D);
   if (precision != MDG_PREC_BF16 && precision != MDG_PREC_FP32)
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: precision=%d", precision);
-  if (out_mode < MDG_OUT_LOGIT_F32 || out_mode > MDG_OUT_RANK_U16)
+  if (out_mode != kOutTopk && (out_mode < MDG_OUT_LOGIT_F32 || out_mode > MDG_OUT_RANK_U16))
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: out_mode=%d", out_mode);
-  if (pairs != MDG_PAIRS_FULL) return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: pairs=%d not implemented", pairs);
+  if (pairs != MDG_PAIRS_FULL && out_mode != kOutTopk)
+    return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: pairs=%d is implemented for the top-k output only", pairs);
+  if (pairs != MDG_PAIRS_FULL && pairs != MDG_PAIRS_SYMMETRIC)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: pairs=%d", pairs);
   if (Nr > (1 << 30) || Nc > (1 << 30) || L > (1 << 24))
     return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: sizes too large");
   if (out_mode == MDG_OUT_RANK_U16) {
@@ -360,7 +372,14 @@ int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int
     int elem = 4;
     CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     int epi = mdg::EPI_F32;
-    if (out_mode == MDG_OUT_SIGMOID_F32) {
+    if (out_mode == kOutTopk) {
+      epi = mdg::EPI_TOPK;
+      p.topk_thresh = topk->thresh;
+      p.topk_count = topk->counts;
+      p.topk_cand = topk->cand;
+      p.topk_cap = topk->cap;
+      p.lower_only = pairs == MDG_PAIRS_SYMMETRIC;
+    } else if (out_mode == MDG_OUT_SIGMOID_F32) {
       epi = mdg::EPI_SIGMOID;
     } else if (out_mode == MDG_OUT_RANK_U16) {
       epi = mdg::EPI_RANK_U16;
@@ -370,8 +389,8 @@ int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int
       dt = CU_TENSOR_MAP_DATA_TYPE_UINT16;
     }
     // TMA store needs 16-byte aligned base and row pitch; otherwise guarded direct stores from registers
-    const bool tma_ok = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && ((Nc * elem) % 16 == 0) &&
-                        (getenv("MDG_FORCE_DIRECT_STORE") == nullptr);
+    const bool tma_ok = out_mode != kOutTopk && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                        ((Nc * elem) % 16 == 0) && (getenv("MDG_FORCE_DIRECT_STORE") == nullptr);
     p.use_tma_store = tma_ok ? 1 : 0;
     if (tma_ok) {
       rc = make_map_3d(&tmOut, dt, elem, out, Nc, Nr, L, Nc, Nr * Nc, 64 / elem, 32, CU_TENSOR_MAP_SWIZZLE_64B);
@@ -388,6 +407,97 @@ int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int
       ++g_prof_count;
     }
   }
+  return MDG_OK;
+}
+
+int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
+                   int64_t L, int precision, int out_mode, int pairs, int normalize_rows, const MdgRankTable* table,
+                   void* out, void* workspace, size_t workspace_bytes, void* stream_v) {
+  g_last_launches = 0;
+  if (out_mode == kOutTopk) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: out_mode=%d", out_mode);
+  return pair_score_impl(z_rows, z_cols, W, Nr, Nc, D, L, precision, out_mode, pairs, normalize_rows, table, out,
+                         workspace, workspace_bytes, static_cast<cudaStream_t>(stream_v), nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------ top-k output
+struct TopkWs {
+  unsigned int* counts;
+  int* offsets;
+  unsigned long long *cand, *keys, *sorted;
+  void* cub_temp;
+  size_t cub_bytes, pair_off, total;
+};
+
+static TopkWs plan_topk(void* ws, int64_t Nr, int64_t Nc, int64_t D, int64_t L, int precision, int cap) {
+  TopkWs t;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) / 256 * 256;
+    return o;
+  };
+  const size_t n = static_cast<size_t>(L > 0 ? L : 1) * cap;
+  size_t cub_bytes = 0;
+  cub::DeviceSegmentedRadixSort::SortKeys(nullptr, cub_bytes, static_cast<const unsigned long long*>(nullptr),
+                                          static_cast<unsigned long long*>(nullptr), static_cast<long long>(n),
+                                          static_cast<int>(L), static_cast<const int*>(nullptr),
+                                          static_cast<const int*>(nullptr));
+  const size_t o_counts = take((L + 1) * 4), o_off = take((L + 2) * 4), o_cand = take(n * 8), o_keys = take(n * 8),
+               o_sorted = take(n * 8), o_cub = take(cub_bytes ? cub_bytes : 1);
+  t.pair_off = off;
+  off += carve_pair_ws(nullptr, Nr, Nc, D, L, precision).total;
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  t.counts = reinterpret_cast<unsigned int*>(b + o_counts);
+  t.offsets = reinterpret_cast<int*>(b + o_off);
+  t.cand = reinterpret_cast<unsigned long long*>(b + o_cand);
+  t.keys = reinterpret_cast<unsigned long long*>(b + o_keys);
+  t.sorted = reinterpret_cast<unsigned long long*>(b + o_sorted);
+  t.cub_temp = b + o_cub;
+  t.cub_bytes = cub_bytes;
+  t.total = off;
+  return t;
+}
+
+size_t mdg_pair_topk_workspace_bytes(int64_t Nr, int64_t Nc, int64_t D, int64_t L, int precision, int32_t cap) {
+  if (Nr < 0 || Nc < 0 || D <= 0 || L < 0 || cap <= 0) return 0;
+  return plan_topk(nullptr, Nr, Nc, D, L, precision, cap).total;
+}
+
+int mdg_pair_topk(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
+                  int64_t L, int precision, int pairs, int normalize_rows, const float* thresholds, int32_t k,
+                  int32_t cap, float* scores_out, int32_t* rows_out, int32_t* cols_out, int32_t* status_out,
+                  void* workspace, size_t workspace_bytes, void* stream_v) {
+  g_last_launches = 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!thresholds || !scores_out || !rows_out || !cols_out || !status_out)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_topk: NULL pointer");
+  if (k <= 0 || cap < k) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_topk: need 0 < k <= cap (k=%d cap=%d)", k, cap);
+  if (Nr * Nc > 0xFFFFFFFFLL) return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_topk: Nr*Nc exceeds 32-bit pair indices");
+  if (static_cast<int64_t>(L) * cap > 0x7FFFFFFFLL) return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_topk: L*cap too large");
+  if (L == 0) return MDG_OK;
+  if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
+    return fail(MDG_ERR_WORKSPACE, "mdg_pair_topk: workspace must be non-NULL and 256-byte aligned");
+  TopkWs t = plan_topk(workspace, Nr, Nc, D, L, precision, cap);
+  if (workspace_bytes < t.total) return fail(MDG_ERR_WORKSPACE, "mdg_pair_topk: workspace %zu < required %zu", workspace_bytes, t.total);
+  MDG_CUDA(cudaMemsetAsync(t.counts, 0, static_cast<size_t>(L) * 4, stream));
+  TopkArgs args{thresholds, t.counts, t.cand, cap};
+  int rc = pair_score_impl(z_rows, z_cols, W, Nr, Nc, D, L, precision, kOutTopk, pairs, normalize_rows, nullptr, nullptr,
+                           static_cast<uint8_t*>(workspace) + t.pair_off, workspace_bytes - t.pair_off, stream, &args);
+  if (rc) return rc;
+  if (Nr == 0 || Nc == 0) {
+    // no pairs: every list is empty
+  }
+  dim3 g(static_cast<unsigned>((cap + 255) / 256 > 64 ? 64 : (cap + 255) / 256), static_cast<unsigned>(L));
+  mdg::topk_make_keys_kernel<<<g, 256, 0, stream>>>(t.cand, t.counts, cap, t.keys, t.offsets, static_cast<int>(L));
+  MDG_CUDA(cudaGetLastError());
+  size_t tb = t.cub_bytes;
+  MDG_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(t.cub_temp, tb, t.keys, t.sorted, static_cast<long long>(L) * cap,
+                                                   static_cast<int>(L), t.offsets, t.offsets + 1, 0, 64, stream));
+  dim3 g2(static_cast<unsigned>((k + 255) / 256), static_cast<unsigned>(L));
+  mdg::topk_emit_kernel<<<g2, 256, 0, stream>>>(t.sorted, t.counts, cap, k, static_cast<int>(Nc), scores_out, rows_out,
+                                                cols_out, status_out);
+  MDG_CUDA(cudaGetLastError());
+  g_last_launches += 3;
   return MDG_OK;
 }
 

@@ -21,6 +21,21 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// One lane of a converged warp (the same lane every time); the predicate is what single-thread instructions
+// (TMA, tcgen05.mma, tcgen05.commit) are guarded with while the surrounding control flow stays warp-uniform, so their
+// operands live in uniform registers instead of going through per-lane election/broadcast sequences.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -35,7 +35,7 @@ constexpr int kFirstEpiWarp = 4;
 constexpr int kStagingBytesPerWarp = 2048;  // 32 rows x 64 B
 constexpr int kTmemCols = 512;
 
-enum EpiMode : int { EPI_F32 = 0, EPI_SIGMOID = 1, EPI_RANK_U16 = 2, EPI_BF16_SPLIT = 3, EPI_LINEAR = 4 };
+enum EpiMode : int { EPI_F32 = 0, EPI_SIGMOID = 1, EPI_RANK_U16 = 2, EPI_BF16_SPLIT = 3, EPI_LINEAR = 4, EPI_TOPK = 5 };
 
 // Shared-memory plan for a kernel instance with NE epilogue warps (staging is per warp, so more epilogue warps
 // trade one B stage for staging space).
@@ -88,6 +88,12 @@ struct PairScoreParams {
   long long bf16_ld;
   int bf16_lo_off;
   int act;  // 0 none, 1 relu, 2 exact-erf gelu
+  // ---- EPI_TOPK: append every score >= topk_thresh[l] to the outcome's candidate list (no dense output at all)
+  const float* topk_thresh;       // [L]
+  unsigned int* topk_count;       // [L] atomic counters (may exceed topk_cap: overflow is detected by the caller)
+  unsigned long long* topk_cand;  // [L, topk_cap]  (score bits << 32 | row * cols + col)
+  int topk_cap;
+  int lower_only;  // keep only row > col (unordered pairs of one catalogue) and skip column blocks above the diagonal
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
@@ -123,6 +129,11 @@ __device__ __forceinline__ TaskCoord decode_task(const PairScoreParams& p, int t
   c.m0 = mb * kBM * p.msub;
   c.nb0 = ch * p.nchunk;
   c.nb1 = min(c.nb0 + p.nchunk, p.n_blocks);
+  if (p.lower_only) {  // column blocks starting at or beyond the last row of this row block hold no row > col pair
+    const int last_row = c.m0 + kBM * p.msub - 1;
+    c.nb1 = min(c.nb1, last_row / kBN + 1);
+    if (c.nb1 < c.nb0) c.nb1 = c.nb0;
+  }
   return c;
 }
 
@@ -219,8 +230,8 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int kb_b = (p.nterm == 1) ? kb : 2 * kb;
 
   if (warp == 0) {
-    // ============================================================ TMA producer
-    if (lane == 0) {
+    // ============================================================ TMA producer (whole warp loops, one lane issues)
+    {
       int stage = 0;
       uint32_t b_phase = 0;
       int it = 0;  // executed tasks (parity of the A barriers)
@@ -232,11 +243,14 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int s = 0; s < ksteps; ++s) {
               const int term = s / kb, k = s - term * kb;  // 0: hi*hi, 1: lo*hi, 2: hi*lo
               mbar_wait(bar_b_empty(stage), b_phase ^ 1, 2);
-              mbar_arrive_expect_tx(bar_b_full(stage), 2 * kPanelBytes);
-              tma_load_3d(sA + stage * kPanelBytes, &tmA, bar_b_full(stage), (term == 1 ? p.k_pad : 0) + k * kBK,
-                          c.m0, p.a_batched ? c.l : 0);
-              tma_load_3d(sB + stage * kPanelBytes, &tmB, bar_b_full(stage), (term == 2 ? p.k_pad : 0) + k * kBK,
-                          nb * kBN, p.b_batched ? c.l : 0);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar_b_full(stage), 2 * kPanelBytes);
+                tma_load_3d(sA + stage * kPanelBytes, &tmA, bar_b_full(stage), (term == 1 ? p.k_pad : 0) + k * kBK,
+                            c.m0, p.a_batched ? c.l : 0);
+                tma_load_3d(sB + stage * kPanelBytes, &tmB, bar_b_full(stage), (term == 2 ? p.k_pad : 0) + k * kBK,
+                            nb * kBN, p.b_batched ? c.l : 0);
+              }
+              __syncwarp();
               if (++stage == kBStages) {
                 stage = 0;
                 b_phase ^= 1;
@@ -248,25 +262,31 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int t = t_begin; t < t_end; t += t_step, ++it) {
         const TaskCoord c = decode_task(p, t);
         mbar_wait(bar_a_empty, (it & 1) ^ 1, 1);
-        mbar_arrive_expect_tx(bar_a_full, n_apanels * kPanelBytes);
-        for (int pn = 0; pn < n_apanels; ++pn) {
-          int row, kc;
-          if (p.nterm == 1) {
-            int ms = pn / kb;
-            row = c.m0 + ms * kBM;
-            kc = (pn - ms * kb) * kBK;
-          } else {
-            row = c.m0;
-            kc = pn * kBK;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_a_full, n_apanels * kPanelBytes);
+          for (int pn = 0; pn < n_apanels; ++pn) {
+            int row, kc;
+            if (p.nterm == 1) {
+              int ms = pn / kb;
+              row = c.m0 + ms * kBM;
+              kc = (pn - ms * kb) * kBK;
+            } else {
+              row = c.m0;
+              kc = pn * kBK;
+            }
+            tma_load_3d(sA + pn * kPanelBytes, &tmA, bar_a_full, kc, row, p.a_batched ? c.l : 0);
           }
-          tma_load_3d(sA + pn * kPanelBytes, &tmA, bar_a_full, kc, row, p.a_batched ? c.l : 0);
         }
+        __syncwarp();
         for (int nb = c.nb0; nb < c.nb1; ++nb) {
           for (int kbi = 0; kbi < kb_b; ++kbi) {
             mbar_wait(bar_b_empty(stage), b_phase ^ 1, 2);
-            mbar_arrive_expect_tx(bar_b_full(stage), kPanelBytes);
-            tma_load_3d(sB + stage * kPanelBytes, &tmB, bar_b_full(stage), kbi * kBK, nb * kBN,
-                        p.b_batched ? c.l : 0);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar_b_full(stage), kPanelBytes);
+              tma_load_3d(sB + stage * kPanelBytes, &tmB, bar_b_full(stage), kbi * kBK, nb * kBN,
+                          p.b_batched ? c.l : 0);
+            }
+            __syncwarp();
             if (++stage == kBStages) {
               stage = 0;
               b_phase ^= 1;
@@ -276,9 +296,17 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ============================================================ UMMA issuer (one thread)
-    if (lane == 0) {
+    // ============================================================ UMMA issuer
+    // The whole warp runs the (warp-uniform) loop; ONE elected lane — the same every time — issues tcgen05.mma and
+    // tcgen05.commit.  Descriptors are uniform values: the constant high word and a per-panel low word (start
+    // address >> 4) that only needs "+ 2" per K step of 16 elements.
+    {
       const uint32_t idesc = umma_idesc_bf16_f32(kBM, kBN);
+      const uint64_t desc_hi = umma_desc_kmajor_sw128(0) & 0xFFFFFFFF00000000ull;
+      const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_kmajor_sw128(0));  // LBO field
+      auto desc_of = [&](uint32_t smem_addr) {
+        return desc_hi | static_cast<uint64_t>(desc_lo0 | ((smem_addr & 0x3FFFFu) >> 4));
+      };
       int stage = 0;
       uint32_t b_phase = 0;
       int acc_stage = 0;
@@ -295,19 +323,23 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int s = 0; s < ksteps; ++s) {
               mbar_wait(bar_b_full(stage), b_phase, 5);
               tc_fence_after_sync();
-              const uint64_t adesc = umma_desc_kmajor_sw128(sA + stage * kPanelBytes);
-              const uint64_t bdesc = umma_desc_kmajor_sw128(sB + stage * kPanelBytes);
+              const uint64_t adesc = desc_of(sA + stage * kPanelBytes);
+              const uint64_t bdesc = desc_of(sB + stage * kPanelBytes);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < kBK / kUmmaK; ++k)
-                umma_bf16(d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                          (s > 0 || k > 0) ? 1u : 0u);
-              umma_commit(bar_b_empty(stage));
+                for (int k = 0; k < kBK / kUmmaK; ++k)
+                  umma_bf16(d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                            (s > 0 || k > 0) ? 1u : 0u);
+                umma_commit(bar_b_empty(stage));
+              }
+              __syncwarp();
               if (++stage == kBStages) {
                 stage = 0;
                 b_phase ^= 1;
               }
             }
-            umma_commit(bar_t_full(acc_stage));
+            if (elect_one()) umma_commit(bar_t_full(acc_stage));
+            __syncwarp();
             acc_stage ^= 1;
             if (acc_stage == 0) acc_phase ^= 1;
           }
@@ -319,49 +351,63 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int nb = c.nb0; nb < c.nb1; ++nb) {
           mbar_wait(bar_t_empty(acc_stage), acc_phase ^ 1, 4);
           tc_fence_after_sync();
-          uint32_t started = 0;  // bit ms set once accumulator ms holds a partial sum for this tile
+          const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc_stage * 2 * kBN);
           for (int kbi = 0; kbi < kb_b; ++kbi) {
             mbar_wait(bar_b_full(stage), b_phase, 5);
             tc_fence_after_sync();
-            const uint64_t bdesc = umma_desc_kmajor_sw128(sB + stage * kPanelBytes);
-            int npan, pan0, pan1, acc0 = 0, acc1 = 0;
-            if (p.nterm == 1) {  // one bf16 term, msub row sub-tiles share this B panel
-              npan = p.msub;
+            const uint64_t bdesc = desc_of(sB + stage * kPanelBytes);
+            // (A panel, accumulator, overwrite?) for up to two MMA groups on this B panel
+            int pan0, pan1, acc1;
+            bool two, first0, first1;
+            if (p.nterm == 1) {  // one bf16 term: msub row sub-tiles share the B panel, one accumulator each
               pan0 = kbi;
               pan1 = kb + kbi;
               acc1 = 1;
-            } else if (kbi < kb) {  // B = hi:  A_hi[k], A_lo[k]
-              npan = 2;
+              two = p.msub == 2;
+              first0 = first1 = (kbi == 0);
+            } else if (kbi < kb) {  // B = hi:  A_hi[k] then A_lo[k], same accumulator
               pan0 = kbi;
               pan1 = kb + kbi;
+              acc1 = 0;
+              two = true;
+              first0 = (kbi == 0);
+              first1 = false;
             } else {  // B = lo:  A_hi[k]
-              npan = 1;
               pan0 = kbi - kb;
               pan1 = 0;
+              acc1 = 0;
+              two = false;
+              first0 = first1 = false;
             }
-            for (int i = 0; i < npan; ++i) {
-              const int pn = i ? pan1 : pan0;
-              const int ac = i ? acc1 : acc0;
-              const uint64_t adesc = umma_desc_kmajor_sw128(sA + pn * kPanelBytes);
-              const uint32_t d = tmem_base + static_cast<uint32_t>((acc_stage * 2 + ac) * kBN);
+            const uint64_t adesc0 = desc_of(sA + pan0 * kPanelBytes);
+            const uint64_t adesc1 = desc_of(sA + pan1 * kPanelBytes);
+            const uint32_t d1 = d0 + static_cast<uint32_t>(acc1 * kBN);
+            if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < kBK / kUmmaK; ++k) {
-                const uint32_t acc = ((started >> ac) & 1u) | (k > 0 ? 1u : 0u);
-                umma_bf16(d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc, acc);
+              for (int k = 0; k < kBK / kUmmaK; ++k)
+                umma_bf16(d0, adesc0 + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                          (first0 && k == 0) ? 0u : 1u);
+              if (two) {
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k)
+                  umma_bf16(d1, adesc1 + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                            (first1 && k == 0) ? 0u : 1u);
               }
-              started |= 1u << ac;
+              umma_commit(bar_b_empty(stage));  // frees this B stage once the MMAs above have read it
             }
-            umma_commit(bar_b_empty(stage));  // frees this B stage once the MMAs above have read it
+            __syncwarp();
             if (++stage == kBStages) {
               stage = 0;
               b_phase ^= 1;
             }
           }
-          umma_commit(bar_t_full(acc_stage));  // accumulators of this tile complete
+          if (elect_one()) umma_commit(bar_t_full(acc_stage));  // accumulators of this tile complete
+          __syncwarp();
           acc_stage ^= 1;
           if (acc_stage == 0) acc_phase ^= 1;
         }
-        umma_commit(bar_a_empty);  // every MMA of this task has finished reading the resident A panels
+        if (elect_one()) umma_commit(bar_a_empty);  // every MMA of this task has read the resident A panels
+        __syncwarp();
       }
     }
   } else if (warp >= kFirstEpiWarp) {
@@ -403,6 +449,8 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         cur_l = c.l;
         named_bar_sync(1, NE * 32);
       }
+      float topk_thr = 0.f;
+      if constexpr (EPI == EPI_TOPK) topk_thr = __ldg(p.topk_thresh + c.l);
       const int row0 = c.m0 + ms * kBM + quad * 32;  // first of this warp's 32 rows
       const int my_row = row0 + lane;
       for (int nb = c.nb0; nb < c.nb1; ++nb) {
@@ -412,6 +460,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int cc = col_begin; cc < col_end; cc += 32) {
             const int n0 = nb * kBN + cc;
             if (n0 >= p.cols) break;
+            if (p.lower_only && n0 > row0 + 31) break;  // every (row, col) of this chunk has col > row
             uint32_t v[32];
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    static_cast<uint32_t>((acc_stage * 2 + ms) * kBN + cc);
@@ -434,6 +483,25 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int j = 0; j < 16; ++j) {
                   if (n0 + 2 * j < p.cols) o[2 * j] = static_cast<uint16_t>(pk[j] & 0xFFFFu);
                   if (n0 + 2 * j + 1 < p.cols) o[2 * j + 1] = static_cast<uint16_t>(pk[j] >> 16);
+                }
+              }
+            } else if constexpr (EPI == EPI_TOPK) {
+              const float thr = topk_thr;
+              bool hit = false;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) hit |= __uint_as_float(v[j]) >= thr;
+              if (__any_sync(0xffffffffu, hit) && hit && my_row < p.rows) {  // rare: candidates are ~k of N^2 scores
+                for (int j = 0; j < 32; ++j) {
+                  const int col = n0 + j;
+                  const float x = __uint_as_float(v[j]);
+                  if (x >= thr && col < p.cols && !(p.lower_only && col >= my_row)) {
+                    const unsigned int slot = atomicAdd(p.topk_count + c.l, 1u);
+                    if (slot < static_cast<unsigned int>(p.topk_cap))
+                      p.topk_cand[static_cast<size_t>(c.l) * p.topk_cap + slot] =
+                          (static_cast<unsigned long long>(v[j]) << 32) |
+                          static_cast<unsigned long long>(static_cast<unsigned int>(my_row) *
+                                                          static_cast<unsigned int>(p.cols) + col);
+                  }
                 }
               }
             } else if constexpr (EPI == EPI_LINEAR) {

@@ -156,3 +156,37 @@ class BilinearDDIScorer(nn.Bilinear):
             assert len(label_range) == 2
             weight = weight[label_range[0]:label_range[1], :, :]
         return self.bilinear(input1, input2, weight)
+
+
+def pair_topk(z_rows: torch.Tensor, z_cols: torch.Tensor, weight: torch.Tensor, thresholds: torch.Tensor, k: int, *,
+              cap: Optional[int] = None, symmetric: bool = True, precision: str = "bf16", normalize: bool = False):
+    """Per-outcome top-k scoring pairs without any dense [L, N, N] output (mdg_pair_topk).
+
+    thresholds [L]: candidates are the scores >= thresholds[l] (e.g. `RankTable.thresholds[:, -1]`, the 1 - 1/Q
+    quantile).  symmetric=True keeps unordered pairs of one catalogue (row > col) and skips tiles above the diagonal.
+    Returns (scores [L,k] fp32 descending, rows [L,k] int32, cols [L,k] int32, status [L] int32: 0 ok / 1 fewer than k
+    candidates / 2 candidate list overflowed `cap`).
+    """
+    zr = _require_cuda_f32(z_rows, "z_rows")
+    zc = _require_cuda_f32(z_cols, "z_cols")
+    W = _require_cuda_f32(weight, "weight")
+    thr = _require_cuda_f32(thresholds, "thresholds")
+    Nr, D = zr.shape
+    Nc, L = zc.shape[0], W.shape[0]
+    if thr.numel() != L:
+        raise ValueError("thresholds must have one entry per outcome")
+    cap = int(cap) if cap is not None else max(4 * k, 4096)
+    dev = zr.device
+    scores = torch.empty((L, k), dtype=torch.float32, device=dev)
+    rows = torch.empty((L, k), dtype=torch.int32, device=dev)
+    cols = torch.empty((L, k), dtype=torch.int32, device=dev)
+    status = torch.empty((L,), dtype=torch.int32, device=dev)
+    prec = _PRECISION[precision]
+    fn = _lib.lib()
+    ws = _workspace(dev, fn.mdg_pair_topk_workspace_bytes(Nr, Nc, D, L, prec, cap))
+    with torch.cuda.device(dev):
+        _lib.check(fn.mdg_pair_topk(zr.data_ptr(), zc.data_ptr(), W.data_ptr(), Nr, Nc, D, L, prec,
+                                    _lib.MDG_PAIRS_SYMMETRIC if symmetric else _lib.MDG_PAIRS_FULL, int(bool(normalize)),
+                                    thr.data_ptr(), k, cap, scores.data_ptr(), rows.data_ptr(), cols.data_ptr(),
+                                    status.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "mdg_pair_topk")
+    return scores, rows, cols, status

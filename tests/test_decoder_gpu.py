@@ -209,3 +209,36 @@ def test_config1_full_size_properties(mb, cuda_device):
     expect = np.einsum("a,lab,b->l", zs, W.astype(np.float64), zs)
     total = got.double().sum(dim=(1, 2)).cpu().numpy()
     assert np.abs(total - expect).max() <= 1e-3 * np.abs(expect).max() + 1e-2
+
+
+@pytest.mark.parametrize("N,D,L,k,symmetric,prec", [(300, 128, 3, 50, True, "fp32"), (513, 256, 2, 1000, True, "bf16"),
+                                                   (200, 64, 2, 100, False, "bf16")])
+def test_topk_matches_dense_logits(mb, cuda_device, N, D, L, k, symmetric, prec):
+    """mdg_pair_topk (no dense output) vs a top-k taken from the dense logits of the same kernel arithmetic."""
+    z, W = synth.decoder_inputs(N, D, L, seed=N + k)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    lg = mb.pair_score(zt, zt, Wt, precision=prec, out="logit").cpu().numpy()
+    want_scores, thr = [], []
+    for l in range(L):
+        if symmetric:
+            i, j = np.tril_indices(N, -1)
+        else:
+            i, j = np.divmod(np.arange(N * N), N)
+        v = lg[l][i, j]
+        order = np.lexsort((i * N + j, -v))[:k]          # score descending, ties by pair index ascending
+        want_scores.append((v[order], i[order], j[order]))
+        thr.append(np.sort(v)[-min(3 * k, v.size)])      # ~3k candidates per outcome
+    thr_t = gpu(np.asarray(thr, np.float32), cuda_device)
+    scores, rows, cols, status = mb.pair_topk(zt, zt, Wt, thr_t, k, cap=4 * k + 64, symmetric=symmetric, precision=prec)
+    assert status.cpu().tolist() == [0] * L
+    for l in range(L):
+        ws, wi, wj = want_scores[l]
+        assert np.array_equal(scores[l].cpu().numpy(), ws)
+        assert np.array_equal(rows[l].cpu().numpy(), wi) and np.array_equal(cols[l].cpu().numpy(), wj)
+    # threshold too high -> status 1 with -inf/-1 padding; too low -> status 2 (overflow reported, never silent)
+    hi = gpu(np.full(L, 1e9, np.float32), cuda_device)
+    s2, r2, _, st2 = mb.pair_topk(zt, zt, Wt, hi, k, symmetric=symmetric, precision=prec)
+    assert st2.cpu().tolist() == [1] * L and torch.isinf(s2).all() and (r2 == -1).all()
+    lo = gpu(np.full(L, -1e9, np.float32), cuda_device)
+    _, _, _, st3 = mb.pair_topk(zt, zt, Wt, lo, k, cap=k, symmetric=symmetric, precision=prec)
+    assert st3.cpu().tolist() == [2] * L
