@@ -71,9 +71,10 @@ typedef enum MdgOutMode {
 
 typedef enum MdgPairs {
   MDG_PAIRS_FULL = 0,     /* every (i, j)                                                                          */
-  MDG_PAIRS_SYMMETRIC = 1 /* z_rows == z_cols only: only row > col is computed/kept — the pair set the reference
-                             normaliser ranks (notebooks/normalize_scores.py:67).  Implemented for mdg_pair_topk;
-                             mdg_pair_score's dense outputs are MDG_PAIRS_FULL only in this version.              */
+  MDG_PAIRS_SYMMETRIC = 1 /* z_rows == z_cols only: only row > col is computed — the pair set the reference normaliser
+                             ranks (notebooks/normalize_scores.py:67).  MDG_OUT_RANK_U16: each rank is written at
+                             [row, col] AND [col, row], diagonal 0 (the normaliser's output layout, :69-70);
+                             mdg_pair_topk: unordered pairs.  Not available for the fp32 logit / sigmoid outputs. */
 } MdgPairs;
 
 /* Prepared per-outcome reference-quantile table for the fused rank epilogue (see mdg_rank_table_build). */

@@ -42,7 +42,9 @@ int run_linear(const __nv_bfloat16* A, long long rows, const __nv_bfloat16* W, i
   const int panels_needed = split ? 2 * p.kb : p.kb;  // for one 128-row sub-tile
   if (panels_needed <= mdg::kMaxAPanels) {
     p.stream_a = 0;
-    p.msub = (!split && 2 * p.kb <= mdg::kMaxAPanels) ? 2 : 1;
+    // two 128-row sub-tiles per CTA halve the B traffic, but a small GEMM wants more, smaller tasks instead
+    const long long tiles256 = ((rows + 255) / 256) * ((N + 127) / 128);
+    p.msub = (!split && 2 * p.kb <= mdg::kMaxAPanels && tiles256 > 2LL * num_sms()) ? 2 : 1;
   } else {
     p.stream_a = 1;
     p.msub = 1;

@@ -98,6 +98,7 @@ struct PairWorkspace {
   __nv_bfloat16* zc;
   __nv_bfloat16* wt;
   __nv_bfloat16* y;
+  unsigned int* sched;  // task counters of the dynamic scheduler (zeroed before each launch)
   int64_t nr_pad, nc_pad, ka;
   size_t total;
 };
@@ -117,7 +118,9 @@ PairWorkspace carve_pair_ws(void* ws, int64_t Nr, int64_t Nc, int64_t D, int64_t
   size_t o_zc = take(static_cast<size_t>(w.nc_pad) * w.ka * 2);
   size_t o_wt = take(static_cast<size_t>(L) * D * w.ka * 2);
   size_t o_y = take(static_cast<size_t>(L) * w.nr_pad * w.ka * 2);
+  size_t o_sched = take(256);
   uint8_t* b = static_cast<uint8_t*>(ws);
+  w.sched = reinterpret_cast<unsigned int*>(b + o_sched);
   w.zr = reinterpret_cast<__nv_bfloat16*>(b + o_zr);
   w.zc = reinterpret_cast<__nv_bfloat16*>(b + o_zc);
   w.wt = reinterpret_cast<__nv_bfloat16*>(b + o_wt);
@@ -160,7 +163,10 @@ int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int want_chunks = static_cast<int>((static_cast<int64_t>(tasks_per_cta) * sms + row_tasks - 1) / row_tasks);
   if (want_chunks < 1) want_chunks = 1;
   int nchunk = (p.n_blocks + want_chunks - 1) / want_chunks;
-  if (nchunk < 4) nchunk = 4;
+  // small problems (fewer tiles than ~4 per SM): one tile per task so that every SM gets work and the critical path
+  // of a CTA is a single A load + one tile; large problems: chunks of >= 4 column blocks amortise the A load
+  const bool small = row_tasks * p.n_blocks <= 4LL * sms;
+  if (nchunk < 4 && !small) nchunk = 4;
   if (nchunk > p.n_blocks) nchunk = p.n_blocks;
   if (nchunk < 1) nchunk = 1;
   p.nchunk = nchunk;
@@ -183,6 +189,9 @@ int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     case mdg::EPI_F32: rc = launch_pair_instance<mdg::EPI_F32, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
     case mdg::EPI_SIGMOID: rc = launch_pair_instance<mdg::EPI_SIGMOID, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
     case mdg::EPI_BF16_SPLIT: rc = launch_pair_instance<mdg::EPI_BF16_SPLIT, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
+    case mdg::EPI_RANK_U16_MIRROR:
+      rc = launch_pair_instance<mdg::EPI_RANK_U16_MIRROR, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
+      break;
     case mdg::EPI_TOPK: rc = launch_pair_instance<mdg::EPI_TOPK, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
     case mdg::EPI_LINEAR:
       rc = (linear_warps == 8) ? launch_pair_instance<mdg::EPI_LINEAR, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream)
@@ -273,8 +282,10 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: precision=%d", precision);
   if (out_mode != kOutTopk && (out_mode < MDG_OUT_LOGIT_F32 || out_mode > MDG_OUT_RANK_U16))
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: out_mode=%d", out_mode);
-  if (pairs != MDG_PAIRS_FULL && out_mode != kOutTopk)
-    return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: pairs=%d is implemented for the top-k output only", pairs);
+  if (pairs != MDG_PAIRS_FULL && out_mode != kOutTopk && out_mode != MDG_OUT_RANK_U16)
+    return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: pairs=%d is implemented for the rank and top-k outputs only", pairs);
+  if (pairs == MDG_PAIRS_SYMMETRIC && (z_rows != z_cols || Nr != Nc))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: MDG_PAIRS_SYMMETRIC needs z_rows == z_cols (one catalogue)");
   if (pairs != MDG_PAIRS_FULL && pairs != MDG_PAIRS_SYMMETRIC)
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: pairs=%d", pairs);
   if (Nr > (1 << 30) || Nc > (1 << 30) || L > (1 << 24))
@@ -369,6 +380,11 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     p.out = out;
     p.out_ld = Nc;
     p.out_batch_stride = Nr * Nc;
+    static const bool static_sched = getenv("MDG_STATIC_SCHED") != nullptr;  // tuning/debug knob
+    if (!static_sched) {
+      MDG_CUDA(cudaMemsetAsync(ws.sched, 0, 256, stream));
+      p.sched_counter = ws.sched;
+    }
     int elem = 4;
     CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     int epi = mdg::EPI_F32;
@@ -387,20 +403,31 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
       p.affine = table->affine;
       elem = 2;
       dt = CU_TENSOR_MAP_DATA_TYPE_UINT16;
+      if (pairs == MDG_PAIRS_SYMMETRIC) {
+        epi = mdg::EPI_RANK_U16_MIRROR;
+        p.lower_only = 1;
+        p.mirror = 1;
+      }
     }
     // TMA store needs 16-byte aligned base and row pitch; otherwise guarded direct stores from registers
     const bool tma_ok = out_mode != kOutTopk && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
                         ((Nc * elem) % 16 == 0) && (getenv("MDG_FORCE_DIRECT_STORE") == nullptr);
     p.use_tma_store = tma_ok ? 1 : 0;
+    CUtensorMap tmOutT = tmA;  // mirror mode: same tensor, un-swizzled 32 x 32 boxes for the transposed tiles
     if (tma_ok) {
       rc = make_map_3d(&tmOut, dt, elem, out, Nc, Nr, L, Nc, Nr * Nc, 64 / elem, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
+      if (p.mirror) {
+        rc = make_map_3d(&tmOutT, dt, elem, out, Nc, Nr, L, Nc, Nr * Nc, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        p.use_tma_store2 = 1;
+      }
     } else {
       tmOut = tmA;  // unused
     }
     const bool prof = g_prof_cap > 0 && g_prof_count < g_prof_cap;
     if (prof) MDG_CUDA(cudaEventRecord(g_prof_start[g_prof_count], stream));
-    rc = launch_pair_kernel(tmA, tmB, tmOut, p, epi, stream);
+    rc = launch_pair_kernel(tmA, tmB, tmOut, p, epi, stream, &tmOutT);
     if (rc) return rc;
     if (prof) {
       MDG_CUDA(cudaEventRecord(g_prof_stop[g_prof_count], stream));

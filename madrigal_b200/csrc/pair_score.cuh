@@ -34,8 +34,12 @@ constexpr int kMaxAPanels = 8;              // 128 KB resident A
 constexpr int kFirstEpiWarp = 4;
 constexpr int kStagingBytesPerWarp = 2048;  // 32 rows x 64 B
 constexpr int kTmemCols = 512;
+constexpr int kTaskRing = 4;  // dynamic-scheduler ring depth
 
-enum EpiMode : int { EPI_F32 = 0, EPI_SIGMOID = 1, EPI_RANK_U16 = 2, EPI_BF16_SPLIT = 3, EPI_LINEAR = 4, EPI_TOPK = 5 };
+enum EpiMode : int {
+  EPI_F32 = 0, EPI_SIGMOID = 1, EPI_RANK_U16 = 2, EPI_BF16_SPLIT = 3, EPI_LINEAR = 4, EPI_TOPK = 5,
+  EPI_RANK_U16_MIRROR = 6  // rank of row > col pairs, written at [row, col] and [col, row]
+};
 
 // Shared-memory plan for a kernel instance with NE epilogue warps (staging is per warp, so more epilogue warps
 // trade one B stage for staging space).
@@ -47,7 +51,7 @@ struct PairSmem {
   static constexpr int kStaging = kB + kBStages * kPanelBytes;
   static constexpr int kLut = kStaging + NE * kStagingBytesPerWarp;
   static constexpr int kBar = kLut + kRankLutEntries * 4;
-  static constexpr int kTotal = kBar + 128;
+  static constexpr int kTotal = kBar + 256;  // mbarriers, TMEM slot, dynamic-scheduler task ring
   static constexpr int kBytes = kTotal + 1024;  // + slack for manual 1024-byte alignment
   static constexpr int kThreads = (kFirstEpiWarp + NE) * 32;
   static_assert(kBytes <= 232448, "exceeds 227 KB of shared memory per CTA");
@@ -93,6 +97,8 @@ struct PairScoreParams {
   unsigned int* topk_count;       // [L] atomic counters (may exceed topk_cap: overflow is detected by the caller)
   unsigned long long* topk_cand;  // [L, topk_cap]  (score bits << 32 | row * cols + col)
   int topk_cap;
+  unsigned int* sched_counter;  // zeroed by the host before the launch: dynamic task scheduler (NULL: static deal)
+  int mirror;      // EPI_RANK_U16 with lower_only: also write each rank at [col, row]; diagonal = 0
   int lower_only;  // keep only row > col (unordered pairs of one catalogue) and skip column blocks above the diagonal
 };
 
@@ -126,6 +132,7 @@ __device__ __forceinline__ TaskCoord decode_task(const PairScoreParams& p, int t
   int rem = t - c.l * per_l;
   int mb = rem / p.chunks_per_row;
   int ch = rem - mb * p.chunks_per_row;
+  if (p.lower_only) mb = p.m_blocks - 1 - mb;  // largest row blocks (most tiles below the diagonal) first
   c.m0 = mb * kBM * p.msub;
   c.nb0 = ch * p.nchunk;
   c.nb1 = min(c.nb0 + p.nchunk, p.n_blocks);
@@ -145,8 +152,8 @@ struct StagedStore {
   uint32_t swz;      // (lane >> 1) & 3
   int cur;
   int pending;       // committed bulk groups not yet known to have been read
-  __device__ __forceinline__ void store(const CUtensorMap* tm, const uint32_t (&w)[16], int c0, int c1, int c2,
-                                        int lane) {
+  // wait until buf[cur] may be overwritten; returns its shared-memory address
+  __device__ __forceinline__ uint32_t acquire(int lane) {
     const bool dbl = buf[0] != buf[1];
     if (pending >= (dbl ? 2 : 1)) {
       if (lane == 0) {
@@ -155,11 +162,10 @@ struct StagedStore {
       __syncwarp();
       pending = dbl ? 1 : 0;
     }
-    const uint32_t base = buf[cur] + row_off;
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
-      st_shared_v4(base + ((static_cast<uint32_t>(ch) ^ swz) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2],
-                   w[4 * ch + 3]);
+    return buf[cur];
+  }
+  // the warp has filled buf[cur]: hand it to the TMA store engine
+  __device__ __forceinline__ void commit(const CUtensorMap* tm, int c0, int c1, int c2, int lane) {
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -167,7 +173,16 @@ struct StagedStore {
       tma_store_commit();
     }
     ++pending;
-    if (dbl) cur ^= 1;
+    if (buf[0] != buf[1]) cur ^= 1;
+  }
+  __device__ __forceinline__ void store(const CUtensorMap* tm, const uint32_t (&w)[16], int c0, int c1, int c2,
+                                        int lane) {
+    const uint32_t base = acquire(lane) + row_off;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      st_shared_v4(base + ((static_cast<uint32_t>(ch) ^ swz) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2],
+                   w[4 * ch + 3]);
+    commit(tm, c0, c1, c2, lane);
   }
 };
 
@@ -206,6 +221,10 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(bar_t_full(i), 1);
       mbar_init(bar_t_empty(i), NE);
     }
+    for (int i = 0; i < 4; ++i) {  // dynamic-scheduler task ring: full (producer -> consumers), empty (1 MMA + NE)
+      mbar_init(sBar + 128 + 8 * i, 1);
+      mbar_init(sBar + 160 + 8 * i, 1 + NE);
+    }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -220,10 +239,61 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + SM::kBar + 96);
 
-  // Tasks are outcome-major and dealt round-robin, so the CTAs running at any moment cover a few adjacent outcomes:
-  // their output tiles stay within a compact address range (measured: giving each CTA a contiguous task range
-  // instead spreads the concurrent writes over all outcomes and is 20% slower) and they share z_cols through L2.
-  const int t_begin = static_cast<int>(blockIdx.x), t_end = p.num_tasks, t_step = static_cast<int>(gridDim.x);
+  // Task order: outcome-major.  Static mode deals tasks round-robin; dynamic mode (sched_counter != NULL) hands them
+  // out in the same order through an atomic counter (needed when tasks are uneven, e.g. lower-triangle mode).
+  // Either way the CTAs running at any moment cover a few adjacent outcomes, so their output tiles stay within a
+  // compact address range (measured: contiguous per-CTA task ranges are 20% slower) and they share z_cols via L2.
+  const uint32_t bar_task_full0 = sBar + 128, bar_task_empty0 = sBar + 160, task_ids0 = sBar + 192;
+  const bool dyn = p.sched_counter != nullptr;
+  struct TaskIter {
+    bool dyn;
+    int t, step, end, n;  // static: t advances by step; n = tasks seen (ring position in dynamic mode)
+    uint32_t full0, empty0, ids0;
+    // consumer side: next task id or -1
+    __device__ __forceinline__ int next_consumer(int lane) {
+      if (!dyn) {
+        const int cur = t;
+        t += step;
+        return cur < end ? cur : -1;
+      }
+      const int slot = n % kTaskRing;
+      mbar_wait(full0 + 8 * slot, (n / kTaskRing) & 1, 7);
+      uint32_t id;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(id) : "r"(ids0 + 4 * slot) : "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+      ++n;
+      return static_cast<int>(id) < end ? static_cast<int>(id) : -1;
+    }
+    // producer side (whole warp): fetch the next task from the global counter and publish it to the consumers
+    __device__ __forceinline__ int next_producer(unsigned int* counter) {
+      if (!dyn) {
+        const int cur = t;
+        t += step;
+        return cur < end ? cur : -1;
+      }
+      const int slot = n % kTaskRing;
+      mbar_wait(empty0 + 8 * slot, ((n / kTaskRing) & 1) ^ 1, 8);
+      unsigned int id = 0;
+      if (elect_one()) {
+        id = atomicAdd(counter, 1u);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ids0 + 4 * slot), "r"(id) : "memory");
+        mbar_arrive(full0 + 8 * slot);
+      }
+      id = __shfl_sync(0xffffffffu, id, 0);  // elect.sync picks lane 0 of a converged warp
+      ++n;
+      return static_cast<int>(id) < end ? static_cast<int>(id) : -1;
+    }
+  };
+  TaskIter tasks;
+  tasks.dyn = dyn;
+  tasks.t = static_cast<int>(blockIdx.x);
+  tasks.step = static_cast<int>(gridDim.x);
+  tasks.end = p.num_tasks;
+  tasks.n = 0;
+  tasks.full0 = bar_task_full0;
+  tasks.empty0 = bar_task_empty0;
+  tasks.ids0 = task_ids0;
 
   const int kb = p.kb;
   const int n_apanels = (p.nterm == 1) ? p.msub * kb : 2 * kb;
@@ -237,7 +307,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int it = 0;  // executed tasks (parity of the A barriers)
       if (p.stream_a) {
         const int ksteps = (p.nterm == 1) ? kb : 3 * kb;
-        for (int t = t_begin; t < t_end; t += t_step) {
+        for (int t = tasks.next_producer(p.sched_counter); t >= 0; t = tasks.next_producer(p.sched_counter)) {
           const TaskCoord c = decode_task(p, t);
           for (int nb = c.nb0; nb < c.nb1; ++nb) {
             for (int s = 0; s < ksteps; ++s) {
@@ -259,7 +329,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       } else
-      for (int t = t_begin; t < t_end; t += t_step, ++it) {
+      for (int t = tasks.next_producer(p.sched_counter); t >= 0; t = tasks.next_producer(p.sched_counter), ++it) {
         const TaskCoord c = decode_task(p, t);
         mbar_wait(bar_a_empty, (it & 1) ^ 1, 1);
         if (elect_one()) {
@@ -314,7 +384,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int it = 0;
       if (p.stream_a) {
         const int ksteps = (p.nterm == 1) ? kb : 3 * kb;
-        for (int t = t_begin; t < t_end; t += t_step) {
+        for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane)) {
           const TaskCoord c = decode_task(p, t);
           for (int nb = c.nb0; nb < c.nb1; ++nb) {
             mbar_wait(bar_t_empty(acc_stage), acc_phase ^ 1, 4);
@@ -345,7 +415,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       } else
-      for (int t = t_begin; t < t_end; t += t_step, ++it) {
+      for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane), ++it) {
         const TaskCoord c = decode_task(p, t);
         mbar_wait(bar_a_full, it & 1, 3);
         for (int nb = c.nb0; nb < c.nb1; ++nb) {
@@ -423,7 +493,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     StagedStore ss;
     ss.buf[0] = sStaging + ew * kStagingBytesPerWarp;
     // the LUT region is idle outside the rank epilogue: use it as a second staging buffer per warp
-    ss.buf[1] = (EPI == EPI_RANK_U16) ? ss.buf[0] : sLut + ew * kStagingBytesPerWarp;
+    ss.buf[1] = (EPI == EPI_RANK_U16 || EPI == EPI_RANK_U16_MIRROR) ? ss.buf[0] : sLut + ew * kStagingBytesPerWarp;
     ss.row_off = static_cast<uint32_t>(lane) * 64;
     ss.swz = static_cast<uint32_t>((lane >> 1) & 3);  // 64-byte swizzle: chunk ^= (row >> 1) & 3
     ss.cur = 0;
@@ -433,9 +503,9 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int cur_l = -1;
     float scale = 0.f, bias = 0.f;
 
-    for (int t = t_begin; t < t_end; t += t_step) {
+    for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane)) {
       const TaskCoord c = decode_task(p, t);
-      if (EPI == EPI_RANK_U16 && c.l != cur_l) {
+      if ((EPI == EPI_RANK_U16 || EPI == EPI_RANK_U16_MIRROR) && c.l != cur_l) {
         named_bar_sync(1, NE * 32);  // everyone is done with the previous outcome's LUT
         const uint4* src = reinterpret_cast<const uint4*>(p.lut + static_cast<size_t>(c.l) * kRankLutEntries);
         const int tid = ew * 32 + lane;
@@ -467,23 +537,40 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_32x32(taddr, v);
             if constexpr (EPI != EPI_LINEAR) tmem_ld_wait();  // LINEAR overlaps its global loads with the TMEM load
 
-            if constexpr (EPI == EPI_RANK_U16) {
+            if constexpr (EPI == EPI_RANK_U16 || EPI == EPI_RANK_U16_MIRROR) {
               uint32_t pk[16];
+              // mirror mode (reference normaliser layout, normalize_scores.py:67-70): this chunk holds ranks of
+              // (row > col) pairs; each is also written at [col, row] through a TRANSPOSED staging tile.
+              constexpr bool mirror = (EPI == EPI_RANK_U16_MIRROR);
+              const bool direct = !p.use_tma_store || (mirror && n0 == row0);  // diagonal chunk: masked stores
+              uint32_t tstage = 0;
+              if (mirror && !direct) tstage = ss.acquire(lane) + static_cast<uint32_t>(lane) * 2;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const uint32_t r0 = rank_lookup_smem(sLut, __uint_as_float(v[2 * j]), scale, bias);
                 const uint32_t r1 = rank_lookup_smem(sLut, __uint_as_float(v[2 * j + 1]), scale, bias);
                 pk[j] = __byte_perm(r0, r1, 0x5410);
+                if (mirror && !direct) {  // transposed tile: row = column index, 64-byte pitch, no swizzle
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(tstage + (2 * j) * 64), "h"(static_cast<uint16_t>(r0)) : "memory");
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(tstage + (2 * j + 1) * 64), "h"(static_cast<uint16_t>(r1)) : "memory");
+                }
               }
-              if (p.use_tma_store) {
+              if (!direct) {
+                if (mirror) ss.commit(&tmOut2, row0, n0, c.l, lane);  // [l, n0.., row0..]
                 ss.store(&tmOut, pk, n0, row0, c.l, lane);
               } else if (my_row < p.rows) {
-                uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + c.l * p.out_batch_stride + my_row * p.out_ld + n0;
+                uint16_t* ob = reinterpret_cast<uint16_t*>(p.out) + c.l * p.out_batch_stride;
+                uint16_t* o = ob + static_cast<long long>(my_row) * p.out_ld + n0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  if (n0 + 2 * j < p.cols) o[2 * j] = static_cast<uint16_t>(pk[j] & 0xFFFFu);
-                  if (n0 + 2 * j + 1 < p.cols) o[2 * j + 1] = static_cast<uint16_t>(pk[j] >> 16);
+                for (int j = 0; j < 32; ++j) {
+                  const int col = n0 + j;
+                  const uint16_t r = static_cast<uint16_t>((j & 1) ? (pk[j >> 1] >> 16) : (pk[j >> 1] & 0xFFFFu));
+                  if (col < p.cols && (!mirror || col < my_row)) {
+                    o[j] = r;
+                    if (mirror) ob[static_cast<long long>(col) * p.out_ld + my_row] = r;
+                  }
                 }
+                if (mirror && n0 == row0) o[lane] = 0;  // diagonal (normalize_scores.py:69)
               }
             } else if constexpr (EPI == EPI_TOPK) {
               const float thr = topk_thr;

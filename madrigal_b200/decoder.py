@@ -87,15 +87,20 @@ class RankTable:
 
 def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight: torch.Tensor, *, precision: str = "fp32",
                out: str = "logit", table: Optional[RankTable] = None, table_offset: int = 0,
-               normalize: bool = False, out_tensor: Optional[torch.Tensor] = None) -> torch.Tensor:
+               normalize: bool = False, out_tensor: Optional[torch.Tensor] = None,
+               symmetric: bool = False) -> torch.Tensor:
     """All-pairs bilinear scores  S[l,i,j] = z_rows[i] . W[l] . z_cols[j]  with a fused epilogue.
 
     out='logit' | 'sigmoid' -> float32 [L, Nr, Nc];  out='rank' -> uint16 quantile ranks against `table`
-    (rows table_offset .. table_offset+L of the table).
+    (rows table_offset .. table_offset+L of the table).  symmetric=True (out='rank', z_rows is z_cols): compute only
+    row > col and write each rank at [i,j] and [j,i] with a zero diagonal — the reference normaliser's layout
+    (normalize_scores.py:67-70) at half the MMAs and look-ups.
     """
     zr = _require_cuda_f32(z_rows, "z_rows")
-    zc = _require_cuda_f32(z_cols, "z_cols")
+    zc = zr if z_cols is z_rows else _require_cuda_f32(z_cols, "z_cols")
     W = _require_cuda_f32(weight, "weight")
+    if symmetric and (out != "rank" or zc.data_ptr() != zr.data_ptr() or zc.shape != zr.shape):
+        raise ValueError("symmetric=True needs out='rank' and z_cols is z_rows")
     if zr.dim() != 2 or zc.dim() != 2 or W.dim() != 3:
         raise ValueError("expected z_rows [Nr,D], z_cols [Nc,D], weight [L,D,D]")
     Nr, D = zr.shape
@@ -120,7 +125,8 @@ def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight: torch.Tensor,
     ws = _workspace(zr.device, nbytes)
     with torch.cuda.device(zr.device):
         _lib.check(fn.mdg_pair_score(zr.data_ptr(), zc.data_ptr(), W.data_ptr(), Nr, Nc, D, L, prec, mode,
-                                     _lib.MDG_PAIRS_FULL, int(bool(normalize)),
+                                     _lib.MDG_PAIRS_SYMMETRIC if symmetric else _lib.MDG_PAIRS_FULL,
+                                     int(bool(normalize)),
                                      ctypes.byref(tbl) if tbl is not None else None, out_tensor.data_ptr(),
                                      ws.data_ptr(), ws.numel(), _stream_ptr(zr.device)), "mdg_pair_score")
     return out_tensor

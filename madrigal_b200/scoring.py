@@ -53,16 +53,17 @@ def all_gather_embeddings(z_shard: torch.Tensor, N: int, group=None) -> torch.Te
 
 def score_all_pairs(z: torch.Tensor, weight: torch.Tensor, *, out: str = "rank", table: Optional[RankTable] = None,
                     precision: str = "bf16", label_range: Optional[Tuple[int, int]] = None,
-                    normalize: bool = False, out_tensor: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    normalize: bool = False, out_tensor: Optional[torch.Tensor] = None,
+                    symmetric: bool = False) -> torch.Tensor:
     """Device-resident all-pairs scores for outcomes `label_range` of `weight` (the decoder call of predict.py:428)."""
     l0, l1 = (0, weight.shape[0]) if label_range is None else label_range
     return pair_score(z, z, weight[l0:l1], precision=precision, out=out, table=table, table_offset=l0,
-                      normalize=normalize, out_tensor=out_tensor)
+                      normalize=normalize, out_tensor=out_tensor, symmetric=symmetric)
 
 
 def score_all_pairs_to_host(z: torch.Tensor, weight: torch.Tensor, out_host: torch.Tensor, *, out: str = "rank",
                             table: Optional[RankTable] = None, precision: str = "bf16", chunk: int = 10,
-                            normalize: bool = False) -> torch.Tensor:
+                            normalize: bool = False, symmetric: bool = False) -> torch.Tensor:
     """predict.py:420-429 call pattern: outcomes in chunks of `chunk`, each chunk scored on the GPU and copied into
     `out_host` ([L, N, N], pinned for overlap).  Double-buffered: copy of chunk c overlaps compute of chunk c+1."""
     L, N = weight.shape[0], z.shape[0]
@@ -81,7 +82,7 @@ def score_all_pairs_to_host(z: torch.Tensor, weight: torch.Tensor, out_host: tor
             compute.wait_event(done_copy[b])  # buffer b is free once its previous copy finished
         dst = bufs[b][: l1 - l0]
         pair_score(z, z, weight[l0:l1], precision=precision, out=out, table=table, table_offset=l0,
-                   normalize=normalize, out_tensor=dst)
+                   normalize=normalize, out_tensor=dst, symmetric=symmetric)
         ready = torch.cuda.Event()
         ready.record(compute)
         with torch.cuda.stream(copy):

@@ -242,3 +242,20 @@ def test_topk_matches_dense_logits(mb, cuda_device, N, D, L, k, symmetric, prec)
     lo = gpu(np.full(L, -1e9, np.float32), cuda_device)
     _, _, _, st3 = mb.pair_topk(zt, zt, Wt, lo, k, cap=k, symmetric=symmetric, precision=prec)
     assert st3.cpu().tolist() == [2] * L
+
+
+@pytest.mark.parametrize("N,D,L,Q", [(300, 128, 2, 2048), (513, 256, 3, 16384), (96, 64, 1, 512), (1000, 256, 2, 4096),
+                                     (257, 192, 2, 1000)])
+def test_symmetric_rank_mode_is_the_normaliser_layout(mb, cuda_device, N, D, L, Q):
+    """pairs=SYMMETRIC: rank of S[i,j] for i > j written at [i,j] and [j,i], zero diagonal (normalize_scores.py:67-70),
+    bit-exact vs searchsorted on the lower-triangle logits of the dense path."""
+    z, W = synth.decoder_inputs(N, D, L, seed=N + 1)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    lg = mb.pair_score(zt, zt, Wt, precision="bf16", out="logit").cpu().numpy()
+    table = mb.RankTable(gpu(oracle.reference_quantiles(lg, min(Q, N * (N - 1) // 2)), cuda_device))
+    thr = table.thresholds.cpu().numpy()
+    got = mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, symmetric=True).cpu().numpy()
+    low = np.tril(oracle.quantile_rank(thr, lg, "right").astype(np.int64), -1)   # ranks of the row > col scores
+    expect = (low + low.swapaxes(1, 2)).astype(np.uint16)
+    assert np.array_equal(got, expect)
+    assert (np.diagonal(got, axis1=1, axis2=2) == 0).all() and np.array_equal(got, got.swapaxes(1, 2))

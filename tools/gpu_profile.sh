@@ -2,5 +2,5 @@
 mkdir -p gpurun_out
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $B > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:pair_score_kernel<\(int\)2, \(int\)16>' -s 4 -c 1 -f -o gpurun_out/prof_rank $B > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:pair_score_kernel<\(int\)6" -s 4 -c 1 -f -o gpurun_out/prof_rank $B > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit=$?"; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out/*.ncu-rep

@@ -30,7 +30,7 @@ def timeit(fn, iters=5, warm=2):
     return float(np.median(ts)), float(np.min(ts))
 
 
-def case(N, D, L, precision, mode, Q=16384):
+def case(N, D, L, precision, mode, Q=16384, symmetric=False):
     z, W = decoder_inputs(N, D, L, 0)
     zt, Wt = torch.from_numpy(z).to(dev), torch.from_numpy(W).to(dev)
     table = None
@@ -46,19 +46,23 @@ def case(N, D, L, precision, mode, Q=16384):
             qs.append(v[idx])
         table = mb.RankTable(torch.stack(qs))
     out = torch.empty((L, N, N), dtype=torch.uint16 if mode == "rank" else torch.float32, device=dev)
-    fn = lambda: mb.pair_score(zt, zt, Wt, precision=precision, out=mode, table=table, out_tensor=out)
+    fn = lambda: mb.pair_score(zt, zt, Wt, precision=precision, out=mode, table=table, out_tensor=out,
+                               symmetric=symmetric)
     med, best = timeit(fn)
     triples = L * N * N
     flops = 2.0 * D * triples * (3 if precision == "fp32" else 1)
     obytes = triples * (2 if mode == "rank" else 4)
-    print(f"N={N} D={D} L={L} {precision} {mode}: {med:.3f} ms (best {best:.3f}) -> {triples / med / 1e9:.1f} G triples/s, "
+    print(f"N={N} D={D} L={L} {precision} {mode}{' symmetric' if symmetric else ''}: {med:.3f} ms (best {best:.3f}) -> {triples / med / 1e9:.1f} G triples/s, "
           f"{flops / med / 1e9:.0f} TFLOP/s (incl. split terms), out {obytes / med / 1e6:.0f} GB/s", flush=True)
 
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
     case(4096, 256, 86, "bf16", "rank")
+    case(4096, 256, 86, "bf16", "rank", symmetric=True)
     case(4096, 128, 86, "bf16", "rank")
+    case(4096, 128, 86, "bf16", "rank", symmetric=True)
+    case(8192, 256, 32, "bf16", "rank", symmetric=True)
     case(4096, 256, 86, "bf16", "logit")
     case(4096, 256, 86, "fp32", "logit")
     case(4096, 256, 86, "bf16", "sigmoid")
