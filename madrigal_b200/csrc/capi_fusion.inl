@@ -107,7 +107,7 @@ struct FusionPlan {
   __nv_bfloat16 *w_e2l, *w_l2e, *w_xin, *w_xout;
   __nv_bfloat16 *w_in[MDG_MAX_LAYERS], *w_out[MDG_MAX_LAYERS], *w_l1[MDG_MAX_LAYERS], *w_l2[MDG_MAX_LAYERS];
   __nv_bfloat16 *xb, *nb, *ob, *fb, *pb;
-  float *h, *qkv, *p32, *q_res, *q_proj;
+  float *h, *qkv, *p32, *q_res, *q_proj, *pend;
   size_t ob_bytes, fb_bytes, pb_bytes;
   size_t total, prepared_total;
 };
@@ -158,6 +158,7 @@ int plan_fusion(const MdgFusionCfg* cfg, long long B, int precision, void* ws, v
   }
   pl->q_res = pw.take<float>(Dl);
   pl->q_proj = pw.take<float>(Dl);
+  pl->pend = pw.take<float>(static_cast<size_t>(2 * pl->layers + 1) * Dl);  // fused kernel: biases owed to H per stage
   pl->prepared_total = pw.off;
   // (b) per-call activation workspace
   WsPlanner w;
@@ -176,6 +177,107 @@ int plan_fusion(const MdgFusionCfg* cfg, long long B, int precision, void* ws, v
   pl->p32 = w.take<float>(C * Dl);
   pl->total = w.off;
   return MDG_OK;
+}
+
+
+// ---- fused single-kernel encoder (fused_encoder.cuh): eligibility + launch
+bool fused_encoder_eligible(const MdgFusionCfg* cfg, const FusionPlan& pl) {
+  if (pl.split || !cfg->norm_first) return false;
+  if (pl.Dl % 64 != 0 || pl.Dl > 256) return false;
+  if (pl.hd != 16 && pl.hd != 32 && pl.hd != 64) return false;
+  if (pl.E % 16 != 0 || pl.E > 256) return false;
+  if (pl.T > 32 || pl.T < 1) return false;
+  return true;
+}
+
+template <int HD>
+int launch_fused_instance(const CUtensorMap* tm, const mdg::FusedEncParams& p, int grid, cudaStream_t stream) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  MDG_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    MDG_CUDA(cudaFuncSetAttribute(mdg::fused_encoder_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  mdg::kFeSmemBytes));
+    attr_set[dev] = true;
+  }
+  mdg::fused_encoder_kernel<HD><<<grid, mdg::kFeThreads, mdg::kFeSmemBytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
+                                                                                     tm[5], tm[6], tm[7], p);
+  MDG_CUDA(cudaGetLastError());
+  ++g_last_launches;
+  return MDG_OK;
+}
+
+int run_fused_encoder(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const FusionPlan& pl, const float* tokens,
+                      const uint8_t* key_mask, const uint8_t* src_mask, const uint8_t* pool_key_mask, float* z_out,
+                      long long B, cudaStream_t stream) {
+  const int E = pl.E, Dl = pl.Dl, F = pl.F, hd = pl.hd;
+  const long long ke = kpad_of(E), kd = kpad_of(Dl), kf = kpad_of(F);
+  const int f_pad = static_cast<int>(kf);
+  const int FC = (f_pad % 256 == 0) ? 256 : (f_pad % 128 == 0 ? 128 : 64);
+  const int nl = pl.layers > 0 ? pl.layers : 1;
+  // the per-layer weight blocks are laid out identically, so the layer index is the maps' batch coordinate
+  const long long lstride = pl.layers > 1 ? (pl.w_in[1] - pl.w_in[0]) : 0;
+  CUtensorMap tm[8];
+  int rc;
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  if ((rc = make_map_3d(&tm[0], bf, 2, pl.w_e2l, ke, Dl, 1, ke, Dl * ke, 64, Dl, sw))) return rc;
+  if (pl.layers > 0) {
+    if ((rc = make_map_3d(&tm[1], bf, 2, pl.w_in[0], kd, 3 * Dl, nl, kd, lstride ? lstride : 3 * Dl * kd, 64, hd, sw))) return rc;
+    if ((rc = make_map_3d(&tm[2], bf, 2, pl.w_out[0], kd, Dl, nl, kd, lstride ? lstride : Dl * kd, 64, Dl, sw))) return rc;
+    if ((rc = make_map_3d(&tm[3], bf, 2, pl.w_l1[0], kd, F, nl, kd, lstride ? lstride : F * kd, 64, FC, sw))) return rc;
+    if ((rc = make_map_3d(&tm[4], bf, 2, pl.w_l2[0], kf, Dl, nl, kf, lstride ? lstride : Dl * kf, 64, Dl, sw))) return rc;
+  } else {
+    tm[1] = tm[2] = tm[3] = tm[4] = tm[0];
+  }
+  if ((rc = make_map_3d(&tm[5], bf, 2, pl.w_l2e, kd, E, 1, kd, E * kd, 64, E, sw))) return rc;
+  if (cfg->agg == MDG_AGG_XATTN) {
+    if ((rc = make_map_3d(&tm[6], bf, 2, pl.w_xin, kd, 2 * Dl, 1, kd, 2 * Dl * kd, 64, hd, sw))) return rc;
+    if ((rc = make_map_3d(&tm[7], bf, 2, pl.w_xout, kd, Dl, 1, kd, Dl * kd, 64, Dl, sw))) return rc;
+  } else {
+    tm[6] = tm[7] = tm[0];
+  }
+  mdg::FusedEncParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B;
+  p.T = pl.T; p.E = E; p.Dl = Dl; p.F = F; p.H = pl.H; p.hd = hd; p.layers = pl.layers;
+  p.act = cfg->actn == MDG_ACTN_GELU ? 2 : 1;
+  p.agg = cfg->agg;
+  p.kp_e = static_cast<int>(ke / 64);
+  p.kp_d = static_cast<int>(kd / 64);
+  p.f_pad = f_pad;
+  p.fc = FC;
+  p.tokens = tokens;
+  p.key_mask = key_mask;
+  p.src_mask = src_mask;
+  p.pool_mask = pool_key_mask;
+  p.z_out = z_out;
+  p.pend = pl.pend;
+  for (int i = 0; i < pl.layers; ++i) {
+    const MdgFusionLayer& L = w->layers[i];
+    p.in_bias[i] = L.in_proj_bias;
+    p.l1_bias[i] = L.linear1_bias;
+    p.n1_w[i] = L.norm1_weight; p.n1_b[i] = L.norm1_bias;
+    p.n2_w[i] = L.norm2_weight; p.n2_b[i] = L.norm2_bias;
+  }
+  p.l2e_bias = w->latent2embed_bias;
+  if (cfg->agg == MDG_AGG_XATTN) {
+    p.xkv_nw = w->x_attn_kv_norm_weight; p.xkv_nb = w->x_attn_kv_norm_bias;
+    p.xin_bias = w->x_attn_in_proj_bias;
+    p.xout_bias = w->x_attn_out_proj_bias;
+    p.xq_nw = w->x_attn_query_norm_weight; p.xq_nb = w->x_attn_query_norm_bias;
+    p.q_res = pl.q_res;
+    p.q_proj = pl.q_proj;
+  }
+  p.drugs_per_tile = mdg::kFeRows / pl.T;
+  p.num_tiles = (B + p.drugs_per_tile - 1) / p.drugs_per_tile;
+  const int sms = num_sms();
+  const int grid = static_cast<int>(p.num_tiles < sms ? p.num_tiles : sms);
+  switch (hd) {
+    case 16: return launch_fused_instance<16>(tm, p, grid, stream);
+    case 32: return launch_fused_instance<32>(tm, p, grid, stream);
+    default: return launch_fused_instance<64>(tm, p, grid, stream);
+  }
 }
 
 int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_mask, const uint8_t* src_mask,
@@ -272,6 +374,20 @@ static int fusion_prepare_impl(const MdgFusionWeights* w, const MdgFusionCfg* cf
     if ((rc = convert_rows(L.linear1_weight, F, Dl, Dl, 1, s, pl.w_l1[i], stream))) return rc;
     if ((rc = convert_rows(L.linear2_weight, Dl, F, F, 1, s, pl.w_l2[i], stream))) return rc;
   }
+  if (fused_encoder_eligible(cfg, pl)) {
+    mdg::FusedPendArgs a;
+    memset(&a, 0, sizeof(a));
+    a.e2l_bias = w->embed2latent_bias;
+    for (int i = 0; i < pl.layers; ++i) {
+      a.out_bias[i] = w->layers[i].out_proj_bias;
+      a.l2_bias[i] = w->layers[i].linear2_bias;
+    }
+    a.layers = pl.layers;
+    a.Dl = Dl;
+    mdg::fused_pend_kernel<<<(Dl + 127) / 128, 128, 0, stream>>>(a, pl.pend);
+    MDG_CUDA(cudaGetLastError());
+    ++g_last_launches;
+  }
   if (cfg->agg == MDG_AGG_XATTN) {
     if ((rc = convert_rows(w->x_attn_in_proj_weight + static_cast<size_t>(Dl) * Dl, 2 * Dl, Dl, Dl, 1, s, pl.w_xin, stream))) return rc;
     if ((rc = convert_rows(w->x_attn_out_proj_weight, Dl, Dl, Dl, 1, s, pl.w_xout, stream))) return rc;
@@ -333,6 +449,9 @@ int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
   const int E = pl.E, Dl = pl.Dl, F = pl.F, T = pl.T, s = pl.split;
   const int act = cfg->actn == MDG_ACTN_GELU ? 2 : 1;
   if (!prepared && (rc = fusion_prepare_impl(w, cfg, pl, stream))) return rc;
+  // MDG_FUSION_GENERIC (debug/test knob) forces the multi-kernel path
+  if (fused_encoder_eligible(cfg, pl) && getenv("MDG_FUSION_GENERIC") == nullptr)
+    return run_fused_encoder(w, cfg, pl, tokens, key_mask, src_mask, pool_key_mask, z_out, B, stream);
   // zero the K-padding columns of operand buffers that kernels fill only up to their logical width
   if (kpad_of(Dl) != Dl) {
     MDG_CUDA(cudaMemsetAsync(pl.ob, 0, pl.ob_bytes, stream));

@@ -1,0 +1,708 @@
+// Fused fusion-encoder kernel (reference: TransformerFusion.forward, madrigal/models/models.py:401-455; pre-LN
+// nn.TransformerEncoderLayer semantics as restated in oracle/oracle.py:fusion_forward).
+//
+// ONE persistent kernel runs the whole encoder for a tile of 128 token rows (= floor(128/T) drugs): embed2latent,
+// every transformer layer (LN1 -> per-head QKV -> masked softmax attention -> out-proj -> LN2 -> FFN) and the
+// pooling (cls / mean / max / x-attn) + latent2embed.  Nothing but the tokens, the masks and z touches HBM:
+//
+//   * the residual stream H [128 x Dl] fp32 lives in TMEM columns [0, 256): out-proj and FFN2 are tcgen05.mma's that
+//     ACCUMULATE straight onto it; the biases they would add are carried as per-stage "pending bias" vectors that
+//     are applied whenever H is read (LayerNorm / pooling);
+//   * a second TMEM accumulator (columns [256, 512)) receives the per-head [q|k|v] projections, the FFN1 chunks and
+//     the latent2embed output;
+//   * the A operands (LN output, attention output, GELU output) are produced by the epilogue warps directly in the
+//     128-byte-swizzled K-major shared-memory layout UMMA reads, never leaving the SM;
+//   * weights (bf16, K-major rows, prepared once) stream from L2 through a 2-stage TMA ring.
+//
+// warp 0: TMA weight producer, warp 1: UMMA issuer, warp 2: TMEM allocator, warps 4-7: one thread per token row
+// (tcgen05.ld -> LayerNorm / attention / activation -> swizzled smem).  MMA phases and epilogue phases of a tile
+// alternate strictly (two mbarriers, one arrival protocol), so hazards on the shared buffers are ordered by
+// construction; the weight ring runs ahead independently.
+//
+// Supported: bf16 operands, norm_first, Dl <= 256 (multiple of 64), head_dim in {16, 32, 64}, E <= 256 (multiple of
+// 16), T <= 32, any FFN width.  Everything else takes the generic multi-kernel path in capi_fusion.inl.
+#pragma once
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "../../include/madrigal_b200.h"
+#include "mdg_ptx.cuh"
+
+namespace mdg {
+
+constexpr int kFeRows = 128;
+constexpr int kFeABufBytes = 128 * 256 * 2;      // 64 KB: 4 panels of [128 x 64] bf16
+constexpr int kFeBStageBytes = 256 * 64 * 2;     // 32 KB: [<=256 rows x 64 k] bf16
+constexpr int kFeBStages = 2;
+constexpr int kFeKvBytes = 128 * 2 * 64 * 2;  // k|v rows of one head in bf16 (16-byte chunks XOR-swizzled by row)
+constexpr int kFeSmemA = 0;
+constexpr int kFeSmemO = kFeSmemA + kFeABufBytes;
+constexpr int kFeSmemB = kFeSmemO + kFeABufBytes;
+constexpr int kFeSmemKv = kFeSmemB + kFeBStages * kFeBStageBytes;
+constexpr int kFeSmemBar = kFeSmemKv + kFeKvBytes;
+constexpr int kFeSmemTotal = kFeSmemBar + 128;
+constexpr int kFeSmemBytes = kFeSmemTotal + 1024;
+constexpr int kFeThreads = 256;
+constexpr int kFeTmemH = 0;
+constexpr int kFeTmemAcc = 256;
+static_assert(kFeSmemBytes <= 232448, "fused encoder exceeds 227 KB of shared memory");
+
+struct FusedEncParams {
+  long long B;
+  int T, E, Dl, F, H, hd, layers, act, agg;
+  int kp_e, kp_d;  // 64-wide K panels of E and Dl
+  int f_pad;       // F rounded up to 64
+  int fc;          // FFN chunk width: 256, 128 or 64 (divides f_pad)
+  const float* tokens;        // [B, T, E]
+  const uint8_t* key_mask;    // [B, T]
+  const uint8_t* src_mask;    // [T, T] or NULL
+  const uint8_t* pool_mask;   // [T] or NULL (x-attn)
+  float* z_out;               // [B, E]
+  const float* pend;          // [(2*layers + 1), Dl] cumulative biases folded into reads of H
+  const float* in_bias[MDG_MAX_LAYERS];
+  const float* l1_bias[MDG_MAX_LAYERS];
+  const float* n1_w[MDG_MAX_LAYERS];
+  const float* n1_b[MDG_MAX_LAYERS];
+  const float* n2_w[MDG_MAX_LAYERS];
+  const float* n2_b[MDG_MAX_LAYERS];
+  const float* l2e_bias;
+  // x-attn pooling
+  const float* xkv_nw;   // x_attn_kv_norm
+  const float* xkv_nb;
+  const float* xin_bias;   // x_attn in_proj bias [3*Dl] (k at Dl, v at 2*Dl)
+  const float* xout_bias;  // [Dl]
+  const float* xq_nw;      // x_attn_query_norm (applied after the residual when !norm_first; unused: norm_first only)
+  const float* xq_nb;
+  const float* q_res;      // [Dl]
+  const float* q_proj;     // [Dl] (already scaled)
+  long long num_tiles;
+  int drugs_per_tile;
+};
+
+// element (row, k) of an A buffer: panel k/64, 128-byte rows, 16-byte chunks XOR-swizzled with (row & 7)
+__device__ __forceinline__ uint32_t fe_a_addr(uint32_t buf, int row, int k) {
+  return buf + static_cast<uint32_t>((k >> 6) * 16384 + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + (k & 7) * 2);
+}
+
+__device__ __forceinline__ uint32_t fe_pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// write 32 consecutive k (starting at k0, multiple of 32) of this thread's row as bf16 into a swizzled A buffer
+__device__ __forceinline__ void fe_store_row32(uint32_t buf, int row, int k0, const float (&y)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t addr = fe_a_addr(buf, row, k0 + 8 * c);
+    st_shared_v4(addr, fe_pack2(y[8 * c], y[8 * c + 1]), fe_pack2(y[8 * c + 2], y[8 * c + 3]),
+                 fe_pack2(y[8 * c + 4], y[8 * c + 5]), fe_pack2(y[8 * c + 6], y[8 * c + 7]));
+  }
+}
+
+// Exact-erf GELU (F.gelu default, models.py:366 `activation='gelu'`) without the ~45-instruction erff():
+//   gelu(x) = 0.5 x (1 + erf(x / sqrt2)) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt2),
+//   erfc(u) = (a1 t + ... + a5 t^5) exp(-u^2),  t = 1 / (1 + 0.3275911 u)     (Abramowitz-Stegun 7.1.26,
+//   |error| <= 1.5e-7 in erf) -- two MUFU ops + 9 FMA-pipe instructions; absolute error of gelu < 1e-6.
+__device__ __forceinline__ float fe_gelu(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(ax, 0.3275911f * 0.70710678118654752440f, 1.0f));
+  const float e = exp2f(x * x * (-0.5f * 1.4426950408889634f));
+  float pl = fmaf(t, 1.061405429f, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  pl *= t;
+  return fmaf(-0.5f * ax * pl, e, fmaxf(x, 0.f));
+}
+__device__ __forceinline__ float fe_act(float a, int act) {
+  if (act == 1) return fmaxf(a, 0.f);
+  return fe_gelu(a);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kFeThreads, 1)
+fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_constant__ CUtensorMap tm_in,
+                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_l1,
+                     const __grid_constant__ CUtensorMap tm_l2, const __grid_constant__ CUtensorMap tm_l2e,
+                     const __grid_constant__ CUtensorMap tm_xin, const __grid_constant__ CUtensorMap tm_xout,
+                     const __grid_constant__ FusedEncParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const uint32_t sA = base + kFeSmemA, sO = base + kFeSmemO, sB = base + kFeSmemB, sKv = base + kFeSmemKv,
+                 sBar = base + kFeSmemBar;
+  const uint32_t bar_mma_done = sBar, bar_epi_done = sBar + 8;
+  auto bar_full = [&](int i) { return sBar + 16 + 8 * i; };
+  auto bar_empty = [&](int i) { return sBar + 32 + 8 * i; };
+  const uint32_t tmem_slot = sBar + 64;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = lane_id();
+  if (threadIdx.x == 0) {
+    mbar_init(bar_mma_done, 1);
+    mbar_init(bar_epi_done, 4);  // one arrival per epilogue warp
+    for (int i = 0; i < kFeBStages; ++i) {
+      mbar_init(bar_full(i), 1);
+      mbar_init(bar_empty(i), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_e2l);
+    tma_prefetch_desc(&tm_in);
+    tma_prefetch_desc(&tm_out);
+    tma_prefetch_desc(&tm_l1);
+    tma_prefetch_desc(&tm_l2);
+    tma_prefetch_desc(&tm_l2e);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kFeSmemBar + 64);
+
+  const int Dl = p.Dl, kp_d = p.kp_d, kp_e = p.kp_e;
+  constexpr int hd = HD;
+  const int FC = p.fc;  // FFN chunk width (divides f_pad)
+  const int n_fchunks = p.f_pad / FC;
+  const bool xattn = p.agg == MDG_AGG_XATTN;
+
+  if (warp == 0) {
+    // ======================================================================= weight producer (TMA)
+    int stage = 0;
+    uint32_t phase = 0;
+    // one B k-panel: `nbox` boxes of `rows` rows each (row0[i]) at K offset kc into consecutive row ranges
+    // (`layer` is the tensor map's batch coordinate: per-layer weights share one map)
+    auto load_panel = [&](const CUtensorMap* tm, int layer, int nbox, int rows, int r0, int r1, int r2, int kc) {
+      mbar_wait(bar_empty(stage), phase ^ 1, 21);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_full(stage), static_cast<uint32_t>(nbox * rows * 128));
+        const uint32_t dst = sB + stage * kFeBStageBytes;
+        tma_load_3d(dst, tm, bar_full(stage), kc, r0, layer);
+        if (nbox > 1) tma_load_3d(dst + rows * 128, tm, bar_full(stage), kc, r1, layer);
+        if (nbox > 2) tma_load_3d(dst + 2 * rows * 128, tm, bar_full(stage), kc, r2, layer);
+      }
+      __syncwarp();
+      if (++stage == kFeBStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    };
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int k = 0; k < kp_e; ++k) load_panel(&tm_e2l, 0, 1, Dl, 0, 0, 0, k * 64);  // embed2latent
+      for (int l = 0; l < p.layers; ++l) {
+        for (int h = 0; h < p.H; ++h)  // [Wq_h; Wk_h; Wv_h]
+          for (int k = 0; k < kp_d; ++k) load_panel(&tm_in, l, 3, hd, h * hd, Dl + h * hd, 2 * Dl + h * hd, k * 64);
+        for (int k = 0; k < kp_d; ++k) load_panel(&tm_out, l, 1, Dl, 0, 0, 0, k * 64);  // out-proj
+        for (int c = 0; c < n_fchunks; ++c) {
+          if (c == 0)
+            for (int k = 0; k < kp_d; ++k) load_panel(&tm_l1, l, 1, FC, 0, 0, 0, k * 64);
+          // phase: ffn2(c) then ffn1(c+1)
+          for (int k = 0; k < FC / 64; ++k) load_panel(&tm_l2, l, 1, Dl, 0, 0, 0, c * FC + k * 64);
+          if (c + 1 < n_fchunks)
+            for (int k = 0; k < kp_d; ++k) load_panel(&tm_l1, l, 1, FC, (c + 1) * FC, 0, 0, k * 64);
+        }
+      }
+      if (xattn) {
+        for (int h = 0; h < p.H; ++h)  // [Wk_h; Wv_h] of the pooling MHA (tm_xin holds the k|v rows: 2*Dl)
+          for (int k = 0; k < kp_d; ++k) load_panel(&tm_xin, 0, 2, hd, h * hd, Dl + h * hd, 0, k * 64);
+        for (int k = 0; k < kp_d; ++k) load_panel(&tm_xout, 0, 1, Dl, 0, 0, 0, k * 64);
+      }
+      for (int k = 0; k < kp_d; ++k) load_panel(&tm_l2e, 0, 1, p.E, 0, 0, 0, k * 64);  // latent2embed
+    }
+  } else if (warp == 1) {
+    // ======================================================================= UMMA issuer
+    const uint64_t desc_hi = umma_desc_kmajor_sw128(0) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_kmajor_sw128(0));
+    auto desc_of = [&](uint32_t a) { return desc_hi | static_cast<uint64_t>(desc_lo0 | ((a & 0x3FFFFu) >> 4)); };
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t epi_waits = 0;
+    // D[tmem_col .. +N) (+)= A[abuf panels a_p0 .. a_p0+kp) . B^T, B panels from the ring
+    auto gemm = [&](uint32_t abuf, int a_p0, int kp, int N, uint32_t tmem_col, bool accumulate) {
+      const uint32_t idesc = umma_idesc_bf16_f32(128, N);
+      const uint32_t d = tmem_base + tmem_col;
+      for (int k = 0; k < kp; ++k) {
+        mbar_wait(bar_full(stage), phase, 22);
+        tc_fence_after_sync();
+        const uint64_t adesc = desc_of(abuf + (a_p0 + k) * 16384);
+        const uint64_t bdesc = desc_of(sB + stage * kFeBStageBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            umma_bf16(d, adesc + static_cast<uint64_t>(q * 2), bdesc + static_cast<uint64_t>(q * 2), idesc,
+                      (accumulate || k > 0 || q > 0) ? 1u : 0u);
+          umma_commit(bar_empty(stage));
+        }
+        __syncwarp();
+        if (++stage == kFeBStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    };
+    auto wait_epi = [&]() {
+      mbar_wait(bar_epi_done, epi_waits & 1, 23);
+      ++epi_waits;
+      tc_fence_after_sync();
+    };
+    auto signal = [&]() {
+      if (elect_one()) umma_commit(bar_mma_done);
+      __syncwarp();
+    };
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      wait_epi();  // tokens in A
+      gemm(sA, 0, kp_e, Dl, kFeTmemH, false);
+      signal();
+      for (int l = 0; l < p.layers; ++l) {
+        for (int h = 0; h < p.H; ++h) {
+          wait_epi();  // LN1 in A (h == 0) / previous head consumed
+          gemm(sA, 0, kp_d, 3 * hd, kFeTmemAcc, false);
+          signal();
+        }
+        wait_epi();  // attention output complete in O
+        gemm(sO, 0, kp_d, Dl, kFeTmemH, true);
+        signal();
+        wait_epi();  // LN2 in A
+        gemm(sA, 0, kp_d, FC, kFeTmemAcc, false);
+        signal();
+        for (int c = 0; c < n_fchunks; ++c) {
+          wait_epi();  // activation chunk c in O
+          gemm(sO, 0, FC / 64, Dl, kFeTmemH, true);
+          if (c + 1 < n_fchunks) gemm(sA, 0, kp_d, FC, kFeTmemAcc, false);
+          signal();
+        }
+      }
+      if (xattn) {
+        for (int h = 0; h < p.H; ++h) {
+          wait_epi();  // LN_kv in A (h == 0) / previous head consumed
+          gemm(sA, 0, kp_d, 2 * hd, kFeTmemAcc, false);
+          signal();
+        }
+        wait_epi();  // pooled attention output in O (rows = first token row of each drug)
+        gemm(sO, 0, kp_d, Dl, kFeTmemAcc, false);
+        signal();
+      }
+      wait_epi();  // pooling input in A
+      gemm(sA, 0, kp_d, p.E, kFeTmemAcc, false);
+      signal();
+    }
+  } else if (warp >= 4) {
+    // ======================================================================= epilogue: one thread per token row
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int T = p.T;
+    const int G = p.drugs_per_tile;
+    // k|v exchange rows: k (hd bf16) | v (hd bf16), pitch 4*hd bytes, 16-byte chunk c of row r stored at chunk
+    // c ^ sw(r) so that the 8 lanes of a quarter-warp (consecutive rows, same logical chunk) hit distinct banks
+    constexpr int kv_pitch = 4 * HD;
+    constexpr int kKvShift = (HD == 16) ? 1 : 0;            // rows per 128-byte line = 128 / pitch (hd = 16: 2)
+    constexpr uint32_t kKvMask = (HD == 16) ? 3u : 7u;      // chunks per row - 1, capped at 7
+    auto kv_addr = [&](int r, int chunk) -> uint32_t {
+      return sKv + static_cast<uint32_t>(r * kv_pitch) +
+             ((static_cast<uint32_t>(chunk) ^ ((static_cast<uint32_t>(r) >> kKvShift) & kKvMask)) << 4);
+    };
+    uint32_t mma_waits = 0;
+    auto wait_mma = [&]() {
+      mbar_wait(bar_mma_done, mma_waits & 1, 24);
+      ++mma_waits;
+      tc_fence_after_sync();
+    };
+    auto signal = [&]() {  // smem writes -> async proxy, TMEM reads done
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_epi_done);
+    };
+    // LayerNorm of (H + pend) for this row -> bf16 into `dst` (two passes over TMEM)
+    auto layer_norm_to = [&](uint32_t dst, const float* pend, const float* w, const float* b, bool do_ln) {
+      float mean = 0.f, rstd = 1.f;
+      if (do_ln) {
+        float s = 0.f, ss = 0.f;
+        for (int c = 0; c < Dl; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + kFeTmemH + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]) + __ldg(pend + c + j);
+            s += x;
+            ss = fmaf(x, x, ss);
+          }
+        }
+        mean = s / Dl;
+        const float var = fmaxf(ss / Dl - mean * mean, 0.f);
+        rstd = 1.0f / sqrtf(var + 1e-5f);
+      }
+      for (int c = 0; c < Dl; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(trow + kFeTmemH + c, v);
+        tmem_ld_wait();
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]) + __ldg(pend + c + j);
+          if (do_ln) x = (x - mean) * rstd * __ldg(w + c + j) + __ldg(b + c + j);
+          y[j] = x;
+        }
+        fe_store_row32(dst, row, c, y);
+      }
+    };
+
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int dloc = row / T, tok = row - dloc * T;
+      const long long drug = tile * G + dloc;
+      const bool valid = dloc < G && drug < p.B;
+      // key visibility of this row's drug as a bitmask (bit j set = key j blocked for this query)
+      uint32_t blocked = 0;
+      if (valid) {
+        for (int j = 0; j < T; ++j) {
+          const bool m = p.key_mask[drug * T + j] != 0 || (p.src_mask != nullptr && p.src_mask[tok * T + j] != 0);
+          blocked |= (m ? 1u : 0u) << j;
+        }
+      }
+      const bool my_masked = valid ? (p.key_mask[drug * T + tok] != 0) : true;
+
+      // ---- tokens -> A (bf16, zero padded): each warp copies its 32 rows one at a time, 32 lanes x float4 per
+      //      512-byte piece of the row (coalesced), converted to bf16 and written into the swizzled operand layout
+      {
+        const int kw = kp_e * 64;
+        for (int r = 0; r < 32; ++r) {
+          const int rr = quad * 32 + r;
+          const int dl2 = rr / T;
+          const long long drug2 = tile * G + dl2;
+          const bool ok = dl2 < G && drug2 < p.B;
+          const float* src = p.tokens + (drug2 * T + (rr - dl2 * T)) * static_cast<long long>(p.E);
+          for (int k = lane * 4; k < kw; k += 128) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && k < p.E) x = __ldg(reinterpret_cast<const float4*>(src + k));  // E % 16 == 0
+            const uint32_t addr = fe_a_addr(sA, rr, k);
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(fe_pack2(x.x, x.y)), "r"(fe_pack2(x.z, x.w))
+                         : "memory");
+          }
+        }
+        signal();
+      }
+      for (int l = 0; l < p.layers; ++l) {
+        // ---- LN1
+        wait_mma();
+        layer_norm_to(sA, p.pend + static_cast<long long>(2 * l) * Dl, p.n1_w[l], p.n1_b[l], true);
+        signal();
+        // ---- attention, head by head
+        for (int h = 0; h < p.H; ++h) {
+          wait_mma();
+          const float* ib = p.in_bias[l];
+          const float qscale = 1.0f / sqrtf(static_cast<float>(hd));
+          float q[HD];
+#pragma unroll
+          for (int c = 0; c < 3 * HD; c += 16) {  // columns: [q | k | v] of head h
+            uint32_t v[16];
+            tmem_ld_32x16(trow + kFeTmemAcc + c, v);
+            tmem_ld_wait();
+            constexpr int kChunksPerPart = HD / 16;
+            const int part = (c / 16) / kChunksPerPart, off = c - part * HD;  // compile-time after unrolling
+            const float* bias = ib + part * Dl + h * HD + off;
+            if (part == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) q[off + j] = (__uint_as_float(v[j]) + __ldg(bias + j)) * qscale;
+            } else {
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                w[j] = fe_pack2(__uint_as_float(v[2 * j]) + __ldg(bias + 2 * j),
+                                __uint_as_float(v[2 * j + 1]) + __ldg(bias + 2 * j + 1));
+              const int ch = ((part - 1) * HD + off) / 8;  // 16-byte chunk index within the row
+              st_shared_v4(kv_addr(row, ch), w[0], w[1], w[2], w[3]);
+              st_shared_v4(kv_addr(row, ch + 1), w[4], w[5], w[6], w[7]);
+            }
+          }
+          named_bar_sync(2, 128);  // k/v of every row of the tile are in shared memory
+          float m = -CUDART_INF_F, lsum = 0.f;
+          float acc[HD];
+#pragma unroll
+          for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+          const int r0 = row - tok;  // first row of this drug
+          for (int j = 0; j < T; ++j) {
+            if (!valid || ((blocked >> j) & 1u)) continue;
+            const int rj = r0 + j;
+            float s = 0.f;
+#pragma unroll
+            for (int d8 = 0; d8 < HD / 8; ++d8) {
+              {
+                uint32_t a, b, c2, e;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(rj, d8)));
+                const uint32_t ww[4] = {a, b, c2, e};
+#pragma unroll
+                for (int t2 = 0; t2 < 4; ++t2) {
+                  const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
+                  s = fmaf(q[d8 * 8 + 2 * t2], kk.x, s);
+                  s = fmaf(q[d8 * 8 + 2 * t2 + 1], kk.y, s);
+                }
+              }
+            }
+            const float m_new = fmaxf(m, s);
+            const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first visible key
+            const float pj = expf(s - m_new);
+            lsum = lsum * corr + pj;
+#pragma unroll
+            for (int d8 = 0; d8 < HD / 8; ++d8) {
+              {
+                uint32_t a, b, c2, e;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(rj, HD / 8 + d8)));
+                const uint32_t ww[4] = {a, b, c2, e};
+#pragma unroll
+                for (int t2 = 0; t2 < 4; ++t2) {
+                  const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
+                  acc[d8 * 8 + 2 * t2] = fmaf(pj, vv.x, acc[d8 * 8 + 2 * t2] * corr);
+                  acc[d8 * 8 + 2 * t2 + 1] = fmaf(pj, vv.y, acc[d8 * 8 + 2 * t2 + 1] * corr);
+                }
+              }
+            }
+            m = m_new;
+          }
+          const float inv = valid ? 1.0f / lsum : 0.f;  // all keys masked -> inf/NaN like torch.softmax
+#pragma unroll
+          for (int d8 = 0; d8 < HD / 8; ++d8) {
+            {
+              const float o0 = valid ? acc[d8 * 8] * inv : 0.f, o1 = valid ? acc[d8 * 8 + 1] * inv : 0.f,
+                          o2 = valid ? acc[d8 * 8 + 2] * inv : 0.f, o3 = valid ? acc[d8 * 8 + 3] * inv : 0.f,
+                          o4 = valid ? acc[d8 * 8 + 4] * inv : 0.f, o5 = valid ? acc[d8 * 8 + 5] * inv : 0.f,
+                          o6 = valid ? acc[d8 * 8 + 6] * inv : 0.f, o7 = valid ? acc[d8 * 8 + 7] * inv : 0.f;
+              st_shared_v4(fe_a_addr(sO, row, h * hd + d8 * 8), fe_pack2(o0, o1), fe_pack2(o2, o3), fe_pack2(o4, o5),
+                           fe_pack2(o6, o7));
+            }
+          }
+          named_bar_sync(2, 128);  // everyone is done reading k/v before the next head overwrites them
+          signal();
+        }
+        // ---- LN2
+        wait_mma();
+        layer_norm_to(sA, p.pend + static_cast<long long>(2 * l + 1) * Dl, p.n2_w[l], p.n2_b[l], true);
+        signal();
+        // ---- FFN activation chunks
+        for (int c = 0; c < n_fchunks; ++c) {
+          wait_mma();
+          const float* b1 = p.l1_bias[l] + c * FC;
+          for (int cc = 0; cc < FC; cc += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(trow + kFeTmemAcc + cc, v);
+            tmem_ld_wait();
+            float y[32];
+            if (c * FC + cc + 32 <= p.F) {
+              const float4* b4 = reinterpret_cast<const float4*>(b1 + cc);  // F-chunk offsets are multiples of 32
+              if (p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 bb = __ldg(b4 + (j >> 2));
+                  y[j] = fmaxf(__uint_as_float(v[j]) + bb.x, 0.f);
+                  y[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
+                  y[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f);
+                  y[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 bb = __ldg(b4 + (j >> 2));
+                  y[j] = fe_gelu(__uint_as_float(v[j]) + bb.x);
+                  y[j + 1] = fe_gelu(__uint_as_float(v[j + 1]) + bb.y);
+                  y[j + 2] = fe_gelu(__uint_as_float(v[j + 2]) + bb.z);
+                  y[j + 3] = fe_gelu(__uint_as_float(v[j + 3]) + bb.w);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const bool in = c * FC + cc + j < p.F;  // columns beyond F are K padding: exactly zero
+                y[j] = in ? fe_act(__uint_as_float(v[j]) + __ldg(b1 + cc + j), p.act) : 0.f;
+              }
+            }
+            fe_store_row32(sO, row, cc, y);
+          }
+          signal();
+        }
+      }
+      const float* pend_final = p.pend + static_cast<long long>(2 * p.layers) * Dl;
+      if (xattn) {
+        // ---- x-attn pooling (models.py:422-440): kv = LN_kv(h); one learned query per head; constant key mask
+        wait_mma();
+        layer_norm_to(sA, pend_final, p.xkv_nw, p.xkv_nb, true);
+        signal();
+        uint32_t pblocked = 0;
+        for (int j = 0; j < T; ++j)
+          if (p.pool_mask != nullptr && p.pool_mask[j] != 0) pblocked |= 1u << j;
+        for (int h = 0; h < p.H; ++h) {
+          wait_mma();
+#pragma unroll
+          for (int c = 0; c < 2 * HD; c += 16) {  // columns: [k | v] of head h
+            uint32_t v[16];
+            tmem_ld_32x16(trow + kFeTmemAcc + c, v);
+            tmem_ld_wait();
+            constexpr int kChunksPerPart = HD / 16;
+            const int part = (c / 16) / kChunksPerPart, off = c - part * HD;
+            const float* bias = p.xin_bias + (part + 1) * Dl + h * HD + off;
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              w[j] = fe_pack2(__uint_as_float(v[2 * j]) + __ldg(bias + 2 * j),
+                              __uint_as_float(v[2 * j + 1]) + __ldg(bias + 2 * j + 1));
+            const int ch = (part * HD + off) / 8;
+            st_shared_v4(kv_addr(row, ch), w[0], w[1], w[2], w[3]);
+            st_shared_v4(kv_addr(row, ch + 1), w[4], w[5], w[6], w[7]);
+          }
+          named_bar_sync(2, 128);
+          // the first token row of each drug computes the pooled head output; other rows write zeros
+          float m = -CUDART_INF_F, lsum = 0.f;
+          float acc[HD];
+#pragma unroll
+          for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+          const bool pool_row = valid && tok == 0;
+          if (pool_row) {
+            const float* qp = p.q_proj + h * hd;
+            for (int j = 0; j < T; ++j) {
+              if ((pblocked >> j) & 1u) continue;
+              const int rj = row + j;
+              float s = 0.f;
+#pragma unroll
+              for (int d8 = 0; d8 < HD / 8; ++d8) {
+                uint32_t a, b, c2, e;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(rj, d8)));
+                const uint32_t ww[4] = {a, b, c2, e};
+#pragma unroll
+                for (int t2 = 0; t2 < 4; ++t2) {
+                  const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
+                  s = fmaf(__ldg(qp + d8 * 8 + 2 * t2), kk.x, s);
+                  s = fmaf(__ldg(qp + d8 * 8 + 2 * t2 + 1), kk.y, s);
+                }
+              }
+              const float m_new = fmaxf(m, s);
+              const float corr = expf(m - m_new);
+              const float pj = expf(s - m_new);
+              lsum = lsum * corr + pj;
+#pragma unroll
+              for (int d8 = 0; d8 < HD / 8; ++d8) {
+                {
+                  uint32_t a, b, c2, e;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(rj, HD / 8 + d8)));
+                  const uint32_t ww[4] = {a, b, c2, e};
+#pragma unroll
+                  for (int t2 = 0; t2 < 4; ++t2) {
+                    const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
+                    acc[d8 * 8 + 2 * t2] = fmaf(pj, vv.x, acc[d8 * 8 + 2 * t2] * corr);
+                    acc[d8 * 8 + 2 * t2 + 1] = fmaf(pj, vv.y, acc[d8 * 8 + 2 * t2 + 1] * corr);
+                  }
+                }
+              }
+              m = m_new;
+            }
+          }
+          const float inv = pool_row ? 1.0f / lsum : 0.f;
+#pragma unroll
+          for (int d8 = 0; d8 < HD / 8; ++d8) {
+            {
+              float o[8];
+#pragma unroll
+              for (int t2 = 0; t2 < 8; ++t2) o[t2] = pool_row ? acc[d8 * 8 + t2] * inv : 0.f;
+              st_shared_v4(fe_a_addr(sO, row, h * hd + d8 * 8), fe_pack2(o[0], o[1]), fe_pack2(o[2], o[3]),
+                           fe_pack2(o[4], o[5]), fe_pack2(o[6], o[7]));
+            }
+          }
+          named_bar_sync(2, 128);
+          signal();
+        }
+        // ---- out-proj of the pooled query + residual query (norm_first: no LN here) -> A for latent2embed
+        wait_mma();
+        for (int c = 0; c < Dl; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + kFeTmemAcc + c, v);
+          tmem_ld_wait();
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            y[j] = __uint_as_float(v[j]) + __ldg(p.xout_bias + c + j) + __ldg(p.q_res + c + j);
+          fe_store_row32(sA, row, c, y);
+        }
+        signal();
+      } else {
+        // ---- pooling input: latent2embed is applied to every token row (models.py:415)
+        wait_mma();
+        layer_norm_to(sA, pend_final, nullptr, nullptr, false);
+        signal();
+      }
+      // ---- latent2embed output -> pooled z
+      wait_mma();
+      {
+        float* xbuf = reinterpret_cast<float*>(gbase + kFeSmemKv);  // [128 rows][33] fp32 exchange (16.9 KB)
+        for (int c = 0; c < p.E; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + kFeTmemAcc + c, v);
+          tmem_ld_wait();
+          if (p.agg == MDG_AGG_CLS || xattn) {  // the first token row of each drug IS the result
+            if (valid && tok == 0) {
+              float* zo = p.z_out + drug * p.E + c;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (c + j < p.E)  // E % 16 == 0: whole float4s
+                  *reinterpret_cast<float4*>(zo + j) =
+                      make_float4(__uint_as_float(v[j]) + __ldg(p.l2e_bias + c + j),
+                                  __uint_as_float(v[j + 1]) + __ldg(p.l2e_bias + c + j + 1),
+                                  __uint_as_float(v[j + 2]) + __ldg(p.l2e_bias + c + j + 2),
+                                  __uint_as_float(v[j + 3]) + __ldg(p.l2e_bias + c + j + 3));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xbuf[row * 33 + j] = __uint_as_float(v[j]);
+            named_bar_sync(2, 128);
+            if (valid && tok == 0) {
+              float* zo = p.z_out + drug * p.E + c;
+              // key masks of the drug's tokens: `blocked` of token 0 holds key_mask | src_mask[0]; re-read key_mask
+              for (int j = 0; j < 32; ++j) {
+                if (c + j >= p.E) break;
+                float accv = p.agg == MDG_AGG_MAX ? -CUDART_INF_F : 0.f;
+                int cnt = 0;
+                for (int t2 = 0; t2 < T; ++t2) {
+                  if (p.key_mask[drug * T + t2] != 0) continue;
+                  const float x = xbuf[(row + t2) * 33 + j];
+                  accv = p.agg == MDG_AGG_MAX ? fmaxf(accv, x) : accv + x;
+                  ++cnt;
+                }
+                const float bias = __ldg(p.l2e_bias + c + j);
+                zo[j] = cnt == 0 ? 0.f : (p.agg == MDG_AGG_MAX ? accv + bias : accv / cnt + bias);
+              }
+            }
+            named_bar_sync(2, 128);
+          }
+        }
+        tc_fence_before_sync();
+      }
+      (void)my_masked;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// pend[s][d]: biases already "owed" to the TMEM-resident residual stream at stage s
+//   s = 0: embed2latent bias; s = 2l+1: + out_proj bias of layer l; s = 2l+2: + linear2 bias of layer l
+struct FusedPendArgs {
+  const float* e2l_bias;
+  const float* out_bias[MDG_MAX_LAYERS];
+  const float* l2_bias[MDG_MAX_LAYERS];
+  int layers, Dl;
+};
+__global__ void fused_pend_kernel(FusedPendArgs a, float* __restrict__ pend) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= a.Dl) return;
+  float acc = a.e2l_bias[d];
+  pend[d] = acc;
+  for (int l = 0; l < a.layers; ++l) {
+    acc += a.out_bias[l][d];
+    pend[static_cast<size_t>(2 * l + 1) * a.Dl + d] = acc;
+    acc += a.l2_bias[l][d];
+    pend[static_cast<size_t>(2 * l + 2) * a.Dl + d] = acc;
+  }
+}
+
+}  // namespace mdg

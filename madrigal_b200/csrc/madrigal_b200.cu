@@ -11,6 +11,7 @@
 
 #include "../../include/madrigal_b200.h"
 #include "exact_rank.cuh"
+#include "fused_encoder.cuh"
 #include "fusion_encode.cuh"
 #include "pair_score.cuh"
 #include "rank_table.cuh"

@@ -231,3 +231,59 @@ def test_model_wrapper_end_to_end(mb, cuda_device):
     ref = oracle.bilinear_scores(zn, zn, W, (1, 4), dtype=np.float64)
     assert logits.shape == (3, B, B)
     assert_close(logits.cpu().numpy(), ref, 2e-3, "tokens -> logits")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fused single-kernel encoder (csrc/fused_encoder.cuh): taken for precision='bf16', pre-LN, latent <= 256.
+# Checked against the fp64 oracle (bf16-operand tolerance) and against the multi-kernel bf16 path (same operand
+# rounding points except k/v, which the fused kernel exchanges in bf16).
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("agg,actn,T,nb,B,dims", [
+    ("x-attn", "gelu", 4, 0, 4096, (256, 8, 32, 512)),   # bench.py's encoder (BASELINE config 2)
+    ("mean", "gelu", 4, 0, 1000, (128, 8, 32, 512)),     # BASELINE config 5 shape
+    ("cls", "relu", 5, 0, 257, (128, 4, 64, 256)),       # T does not divide 128; head_dim 64
+    ("max", "relu", 1, 0, 130, (64, 4, 16, 64)),         # one token per drug; head_dim 16
+    ("x-attn", "gelu", 23, 4, 77, (128, 4, 64, 200)),    # production token layout (src_mask, bottlenecks), F % 64 != 0
+    ("mean", "gelu", 32, 0, 9, (48, 2, 32, 1024)),       # T = 32, latent 64, 4 FFN chunks, E % 64 != 0
+    ("cls", "gelu", 19, 0, 50, (256, 3, 64, 128)),       # latent 192
+])
+def test_fused_encoder_kernel(mb, cuda_device, agg, actn, T, nb, B, dims):
+    from madrigal_b200 import _lib
+    E, H, hd, F = dims
+    case = dict(embed_dim=E, num_layers=2, num_heads=H, head_dim=hd, ffn_dim=F, actn=actn, norm_first=True,
+                agg=agg, nb=nb, seed=31 + T)
+    mod, sd = make_module(mb, case, cuda_device, precision="bf16")
+    tokens, mask = synth.fusion_inputs(B, T, E, case["seed"], always_visible=(0,) + tuple(range(3, 3 + nb)))
+    src = None
+    if nb > 0:
+        src = np.zeros((T, T), bool)
+        src[:3, T - 16:] = True
+        src[T - 16:, :3] = True
+    pool = None
+    if agg == "x-attn":
+        pool = np.zeros(T, bool)
+        if nb > 0:
+            pool[:3] = True
+            pool[-16:] = True
+        mod.x_attn_key_padding_mask = torch.from_numpy(pool)[None, :]
+    ref = oracle.fusion_forward(sd, case, tokens, mask, src, pool, dtype=np.float64)
+    args = (gpu(tokens, cuda_device), gpu(mask, cuda_device), None if src is None else gpu(src, cuda_device))
+    with torch.no_grad():
+        z = mod(*args).cpu().numpy()
+        assert mod.last_launch_count == 1, "the fused kernel must be ONE launch"
+        os.environ["MDG_FUSION_GENERIC"] = "1"
+        try:
+            zg = mod(*args).cpu().numpy()
+            assert mod.last_launch_count > 1
+        finally:
+            del os.environ["MDG_FUSION_GENERIC"]
+    rms = np.sqrt(np.mean(ref ** 2))
+    assert np.isfinite(z).all()
+    assert np.abs(z - ref).max() <= 3e-2 * max(rms, np.abs(ref).max() * 0.1), "fused vs fp64 oracle"
+    assert np.abs(z - zg).max() <= 2e-2 * max(rms, np.abs(ref).max() * 0.1), "fused vs multi-kernel bf16 path"
+    # masked-slot contents are don't-care
+    if agg in ("mean", "max") or nb > 0:
+        tok2 = np.where(mask[:, :, None], np.float32(9.0), tokens)
+        with torch.no_grad():
+            z2 = mod(gpu(tok2, cuda_device), *args[1:]).cpu().numpy()
+        assert np.abs(z2 - z).max() <= 1e-5 * max(1.0, np.abs(z).max())

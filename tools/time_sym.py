@@ -1,0 +1,26 @@
+"""Time the symmetric (normaliser-layout) fused rank kernel; prints a checksum so that variants can be compared."""
+import os, sys, ctypes
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import madrigal_b200 as mb
+from madrigal_b200 import normalize, _lib
+from synth import decoder_inputs
+dev = torch.device("cuda:0")
+N, D, L = int(os.environ.get("N", 4096)), int(os.environ.get("D", 256)), int(os.environ.get("L", 86))
+z, W = decoder_inputs(N, D, L, 0)
+zt, Wt = torch.from_numpy(z).to(dev), torch.from_numpy(W).to(dev)
+table = normalize.build_rank_table(zt, Wt, 16384, panel=1024, precision="bf16")
+out = torch.empty((L, N, N), dtype=torch.uint16, device=dev)
+sym = os.environ.get("SYM", "1") == "1"
+fn = lambda: mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, out_tensor=out, symmetric=sym)
+for _ in range(3): fn()
+torch.cuda.synchronize()
+_lib.lib().mdg_profile_enable(20)
+for _ in range(20): fn()
+torch.cuda.synchronize()
+buf = (ctypes.c_float * 256)(); n = _lib.lib().mdg_profile_read(buf, 256)
+ms = np.array(buf[:n])
+chk = int(out.view(torch.int16).to(torch.int64).sum().item())
+print(f"mode={os.environ.get('MDG_MIRROR_MODE','1')} sym={sym} N={N} D={D} L={L}: kernel {ms.mean():.4f} ms (min {ms.min():.4f}) -> "
+      f"{2.0*L*N*N/ms.mean()/1e6:.0f} GB/s out, checksum {chk}")
