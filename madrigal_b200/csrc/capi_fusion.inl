@@ -184,9 +184,26 @@ int plan_fusion(const MdgFusionCfg* cfg, long long B, int precision, void* ws, v
 bool fused_encoder_eligible(const MdgFusionCfg* cfg, const FusionPlan& pl) {
   if (pl.split || !cfg->norm_first) return false;
   if (pl.Dl % 64 != 0 || pl.Dl > 256) return false;
-  if (pl.hd != 16 && pl.hd != 32 && pl.hd != 64) return false;
+  if (pl.hd != 16 && pl.hd != 32) return false;
   if (pl.E % 16 != 0 || pl.E > 256) return false;
   if (pl.T > 32 || pl.T < 1) return false;
+  return true;
+}
+
+// the fused kernel reads bias / LayerNorm vectors with 16-byte loads
+bool fused_encoder_aligned(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const float* tokens, const float* z_out) {
+  auto ok = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  if (!ok(tokens) || !ok(z_out) || !ok(w->latent2embed_bias)) return false;
+  for (int i = 0; i < cfg->num_layers; ++i) {
+    const MdgFusionLayer& L = w->layers[i];
+    if (!ok(L.in_proj_bias) || !ok(L.linear1_bias) || !ok(L.norm1_weight) || !ok(L.norm1_bias) ||
+        !ok(L.norm2_weight) || !ok(L.norm2_bias))
+      return false;
+  }
+  if (cfg->agg == MDG_AGG_XATTN &&
+      (!ok(w->x_attn_kv_norm_weight) || !ok(w->x_attn_kv_norm_bias) || !ok(w->x_attn_in_proj_bias) ||
+       !ok(w->x_attn_out_proj_bias)))
+    return false;
   return true;
 }
 
@@ -273,11 +290,7 @@ int run_fused_encoder(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
   p.num_tiles = (B + p.drugs_per_tile - 1) / p.drugs_per_tile;
   const int sms = num_sms();
   const int grid = static_cast<int>(p.num_tiles < sms ? p.num_tiles : sms);
-  switch (hd) {
-    case 16: return launch_fused_instance<16>(tm, p, grid, stream);
-    case 32: return launch_fused_instance<32>(tm, p, grid, stream);
-    default: return launch_fused_instance<64>(tm, p, grid, stream);
-  }
+  return hd == 16 ? launch_fused_instance<16>(tm, p, grid, stream) : launch_fused_instance<32>(tm, p, grid, stream);
 }
 
 int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_mask, const uint8_t* src_mask,
@@ -450,7 +463,8 @@ int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
   const int act = cfg->actn == MDG_ACTN_GELU ? 2 : 1;
   if (!prepared && (rc = fusion_prepare_impl(w, cfg, pl, stream))) return rc;
   // MDG_FUSION_GENERIC (debug/test knob) forces the multi-kernel path
-  if (fused_encoder_eligible(cfg, pl) && getenv("MDG_FUSION_GENERIC") == nullptr)
+  if (fused_encoder_eligible(cfg, pl) && fused_encoder_aligned(w, cfg, tokens, z_out) &&
+      getenv("MDG_FUSION_GENERIC") == nullptr)
     return run_fused_encoder(w, cfg, pl, tokens, key_mask, src_mask, pool_key_mask, z_out, B, stream);
   // zero the K-padding columns of operand buffers that kernels fill only up to their logical width
   if (kpad_of(Dl) != Dl) {

@@ -14,13 +14,13 @@
 //     128-byte-swizzled K-major shared-memory layout UMMA reads, never leaving the SM;
 //   * weights (bf16, K-major rows, prepared once) stream from L2 through a 2-stage TMA ring.
 //
-// warp 0: TMA weight producer, warp 1: UMMA issuer, warp 2: TMEM allocator, warps 4-7: one thread per token row
-// (tcgen05.ld -> LayerNorm / attention / activation -> swizzled smem).  MMA phases and epilogue phases of a tile
+// warp 0: TMA weight producer, warp 1: UMMA issuer, warp 2: TMEM allocator, warps 4-11: two threads per token row
+// (tcgen05.ld -> LayerNorm / attention / activation -> swizzled smem; the pair splits columns or heads).  MMA phases and epilogue phases of a tile
 // alternate strictly (two mbarriers, one arrival protocol), so hazards on the shared buffers are ordered by
 // construction; the weight ring runs ahead independently.
 //
-// Supported: bf16 operands, norm_first, Dl <= 256 (multiple of 64), head_dim in {16, 32, 64}, E <= 256 (multiple of
-// 16), T <= 32, any FFN width.  Everything else takes the generic multi-kernel path in capi_fusion.inl.
+// Supported: bf16 operands, norm_first, Dl <= 256 (multiple of 64), head_dim in {16, 32}, E <= 256 (multiple of
+// 16), T <= 32, any FFN width, 16-byte aligned bias / LayerNorm vectors.  Everything else takes the generic multi-kernel path in capi_fusion.inl.
 #pragma once
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -42,7 +42,8 @@ constexpr int kFeSmemKv = kFeSmemB + kFeBStages * kFeBStageBytes;
 constexpr int kFeSmemBar = kFeSmemKv + kFeKvBytes;
 constexpr int kFeSmemTotal = kFeSmemBar + 128;
 constexpr int kFeSmemBytes = kFeSmemTotal + 1024;
-constexpr int kFeThreads = 256;
+constexpr int kFeEpiWarps = 8;
+constexpr int kFeThreads = (4 + kFeEpiWarps) * 32;
 constexpr int kFeTmemH = 0;
 constexpr int kFeTmemAcc = 256;
 static_assert(kFeSmemBytes <= 232448, "fused encoder exceeds 227 KB of shared memory");
@@ -119,6 +120,9 @@ __device__ __forceinline__ float fe_act(float a, int act) {
   return fe_gelu(a);
 }
 
+// 16-byte vector load of 4 consecutive fp32 parameters (uniform address across the warp: one L1 wavefront)
+__device__ __forceinline__ float4 fe_ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
 template <int HD>
 __global__ void __launch_bounds__(kFeThreads, 1)
 fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_constant__ CUtensorMap tm_in,
@@ -126,6 +130,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
                      const __grid_constant__ CUtensorMap tm_l2, const __grid_constant__ CUtensorMap tm_l2e,
                      const __grid_constant__ CUtensorMap tm_xin, const __grid_constant__ CUtensorMap tm_xout,
                      const __grid_constant__ FusedEncParams p) {
+  constexpr int HP = 64 / HD;  // heads per attention phase (their q|k|v projections share one accumulator: 192 columns)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -141,7 +146,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
   const int lane = lane_id();
   if (threadIdx.x == 0) {
     mbar_init(bar_mma_done, 1);
-    mbar_init(bar_epi_done, 4);  // one arrival per epilogue warp
+    mbar_init(bar_epi_done, kFeEpiWarps);  // one arrival per epilogue warp
     for (int i = 0; i < kFeBStages; ++i) {
       mbar_init(bar_full(i), 1);
       mbar_init(bar_empty(i), 1);
@@ -167,21 +172,20 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
   const int FC = p.fc;  // FFN chunk width (divides f_pad)
   const int n_fchunks = p.f_pad / FC;
   const bool xattn = p.agg == MDG_AGG_XATTN;
+  const int n_phases = (p.H + HP - 1) / HP;
 
   if (warp == 0) {
     // ======================================================================= weight producer (TMA)
     int stage = 0;
     uint32_t phase = 0;
-    // one B k-panel: `nbox` boxes of `rows` rows each (row0[i]) at K offset kc into consecutive row ranges
-    // (`layer` is the tensor map's batch coordinate: per-layer weights share one map)
-    auto load_panel = [&](const CUtensorMap* tm, int layer, int nbox, int rows, int r0, int r1, int r2, int kc) {
+    // one B k-panel = `nbox` boxes of `rows` rows each (row coordinate row_of(b)), stacked in one ring stage;
+    // `layer` is the tensor map's batch coordinate (per-layer weights share one map)
+    auto load_panel = [&](const CUtensorMap* tm, int layer, int nbox, int rows, int kc, auto row_of) {
       mbar_wait(bar_empty(stage), phase ^ 1, 21);
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_full(stage), static_cast<uint32_t>(nbox * rows * 128));
         const uint32_t dst = sB + stage * kFeBStageBytes;
-        tma_load_3d(dst, tm, bar_full(stage), kc, r0, layer);
-        if (nbox > 1) tma_load_3d(dst + rows * 128, tm, bar_full(stage), kc, r1, layer);
-        if (nbox > 2) tma_load_3d(dst + 2 * rows * 128, tm, bar_full(stage), kc, r2, layer);
+        for (int b = 0; b < nbox; ++b) tma_load_3d(dst + b * rows * 128, tm, bar_full(stage), kc, row_of(b), layer);
       }
       __syncwarp();
       if (++stage == kFeBStages) {
@@ -189,27 +193,34 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         phase ^= 1;
       }
     };
+    auto row0 = [](int) { return 0; };
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      for (int k = 0; k < kp_e; ++k) load_panel(&tm_e2l, 0, 1, Dl, 0, 0, 0, k * 64);  // embed2latent
+      for (int k = 0; k < kp_e; ++k) load_panel(&tm_e2l, 0, 1, Dl, k * 64, row0);  // embed2latent
       for (int l = 0; l < p.layers; ++l) {
-        for (int h = 0; h < p.H; ++h)  // [Wq_h; Wk_h; Wv_h]
-          for (int k = 0; k < kp_d; ++k) load_panel(&tm_in, l, 3, hd, h * hd, Dl + h * hd, 2 * Dl + h * hd, k * 64);
-        for (int k = 0; k < kp_d; ++k) load_panel(&tm_out, l, 1, Dl, 0, 0, 0, k * 64);  // out-proj
+        for (int ph = 0; ph < n_phases; ++ph) {  // [Wq_h; Wk_h; Wv_h] for each head of the phase
+          const int h0 = ph * HP, nh = min(HP, p.H - h0);
+          for (int k = 0; k < kp_d; ++k)
+            load_panel(&tm_in, l, 3 * nh, hd, k * 64, [&](int b) { return (b % 3) * Dl + (h0 + b / 3) * hd; });
+        }
+        for (int k = 0; k < kp_d; ++k) load_panel(&tm_out, l, 1, Dl, k * 64, row0);  // out-proj
         for (int c = 0; c < n_fchunks; ++c) {
           if (c == 0)
-            for (int k = 0; k < kp_d; ++k) load_panel(&tm_l1, l, 1, FC, 0, 0, 0, k * 64);
+            for (int k = 0; k < kp_d; ++k) load_panel(&tm_l1, l, 1, FC, k * 64, row0);
           // phase: ffn2(c) then ffn1(c+1)
-          for (int k = 0; k < FC / 64; ++k) load_panel(&tm_l2, l, 1, Dl, 0, 0, 0, c * FC + k * 64);
+          for (int k = 0; k < FC / 64; ++k) load_panel(&tm_l2, l, 1, Dl, c * FC + k * 64, row0);
           if (c + 1 < n_fchunks)
-            for (int k = 0; k < kp_d; ++k) load_panel(&tm_l1, l, 1, FC, (c + 1) * FC, 0, 0, k * 64);
+            for (int k = 0; k < kp_d; ++k) load_panel(&tm_l1, l, 1, FC, k * 64, [&](int) { return (c + 1) * FC; });
         }
       }
       if (xattn) {
-        for (int h = 0; h < p.H; ++h)  // [Wk_h; Wv_h] of the pooling MHA (tm_xin holds the k|v rows: 2*Dl)
-          for (int k = 0; k < kp_d; ++k) load_panel(&tm_xin, 0, 2, hd, h * hd, Dl + h * hd, 0, k * 64);
-        for (int k = 0; k < kp_d; ++k) load_panel(&tm_xout, 0, 1, Dl, 0, 0, 0, k * 64);
+        for (int ph = 0; ph < n_phases; ++ph) {  // [Wk_h; Wv_h] of the pooling MHA (tm_xin holds the k|v rows: 2*Dl)
+          const int h0 = ph * HP, nh = min(HP, p.H - h0);
+          for (int k = 0; k < kp_d; ++k)
+            load_panel(&tm_xin, 0, 2 * nh, hd, k * 64, [&](int b) { return (b % 2) * Dl + (h0 + b / 2) * hd; });
+        }
+        for (int k = 0; k < kp_d; ++k) load_panel(&tm_xout, 0, 1, Dl, k * 64, row0);
       }
-      for (int k = 0; k < kp_d; ++k) load_panel(&tm_l2e, 0, 1, p.E, 0, 0, 0, k * 64);  // latent2embed
+      for (int k = 0; k < kp_d; ++k) load_panel(&tm_l2e, 0, 1, p.E, k * 64, row0);  // latent2embed
     }
   } else if (warp == 1) {
     // ======================================================================= UMMA issuer
@@ -219,14 +230,14 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
     int stage = 0;
     uint32_t phase = 0;
     uint32_t epi_waits = 0;
-    // D[tmem_col .. +N) (+)= A[abuf panels a_p0 .. a_p0+kp) . B^T, B panels from the ring
-    auto gemm = [&](uint32_t abuf, int a_p0, int kp, int N, uint32_t tmem_col, bool accumulate) {
+    // D[tmem_col .. +N) (+)= A[abuf panels 0 .. kp) . B^T, B panels from the ring
+    auto gemm = [&](uint32_t abuf, int kp, int N, uint32_t tmem_col, bool accumulate) {
       const uint32_t idesc = umma_idesc_bf16_f32(128, N);
       const uint32_t d = tmem_base + tmem_col;
       for (int k = 0; k < kp; ++k) {
         mbar_wait(bar_full(stage), phase, 22);
         tc_fence_after_sync();
-        const uint64_t adesc = desc_of(abuf + (a_p0 + k) * 16384);
+        const uint64_t adesc = desc_of(abuf + k * 16384);
         const uint64_t bdesc = desc_of(sB + stage * kFeBStageBytes);
         if (elect_one()) {
 #pragma unroll
@@ -253,55 +264,60 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
     };
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       wait_epi();  // tokens in A
-      gemm(sA, 0, kp_e, Dl, kFeTmemH, false);
+      gemm(sA, kp_e, Dl, kFeTmemH, false);
       signal();
       for (int l = 0; l < p.layers; ++l) {
-        for (int h = 0; h < p.H; ++h) {
-          wait_epi();  // LN1 in A (h == 0) / previous head consumed
-          gemm(sA, 0, kp_d, 3 * hd, kFeTmemAcc, false);
+        for (int ph = 0; ph < n_phases; ++ph) {
+          wait_epi();  // LN1 in A (ph == 0) / previous heads consumed
+          gemm(sA, kp_d, 3 * hd * min(HP, p.H - ph * HP), kFeTmemAcc, false);
           signal();
         }
         wait_epi();  // attention output complete in O
-        gemm(sO, 0, kp_d, Dl, kFeTmemH, true);
+        gemm(sO, kp_d, Dl, kFeTmemH, true);
         signal();
         wait_epi();  // LN2 in A
-        gemm(sA, 0, kp_d, FC, kFeTmemAcc, false);
+        gemm(sA, kp_d, FC, kFeTmemAcc, false);
         signal();
         for (int c = 0; c < n_fchunks; ++c) {
           wait_epi();  // activation chunk c in O
-          gemm(sO, 0, FC / 64, Dl, kFeTmemH, true);
-          if (c + 1 < n_fchunks) gemm(sA, 0, kp_d, FC, kFeTmemAcc, false);
+          gemm(sO, FC / 64, Dl, kFeTmemH, true);
+          if (c + 1 < n_fchunks) gemm(sA, kp_d, FC, kFeTmemAcc, false);
           signal();
         }
       }
       if (xattn) {
-        for (int h = 0; h < p.H; ++h) {
-          wait_epi();  // LN_kv in A (h == 0) / previous head consumed
-          gemm(sA, 0, kp_d, 2 * hd, kFeTmemAcc, false);
+        for (int ph = 0; ph < n_phases; ++ph) {
+          wait_epi();  // LN_kv in A (ph == 0) / previous heads consumed
+          gemm(sA, kp_d, 2 * hd * min(HP, p.H - ph * HP), kFeTmemAcc, false);
           signal();
         }
         wait_epi();  // pooled attention output in O (rows = first token row of each drug)
-        gemm(sO, 0, kp_d, Dl, kFeTmemAcc, false);
+        gemm(sO, kp_d, Dl, kFeTmemAcc, false);
         signal();
       }
       wait_epi();  // pooling input in A
-      gemm(sA, 0, kp_d, p.E, kFeTmemAcc, false);
+      gemm(sA, kp_d, p.E, kFeTmemAcc, false);
       signal();
     }
   } else if (warp >= 4) {
-    // ======================================================================= epilogue: one thread per token row
+    // ======================================================================= epilogue: TWO threads per token row
+    // warps 4-7 (group 0) and 8-11 (group 1) both map lane -> TMEM lane (warp & 3) * 32 + lane; the groups split the
+    // columns of element-wise stages and the heads of attention stages.
+    const int ew = warp - 4;
     const int quad = warp & 3;
+    const int g = ew >> 2;
     const int row = quad * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int T = p.T;
     const int G = p.drugs_per_tile;
-    // k|v exchange rows: k (hd bf16) | v (hd bf16), pitch 4*hd bytes, 16-byte chunk c of row r stored at chunk
-    // c ^ sw(r) so that the 8 lanes of a quarter-warp (consecutive rows, same logical chunk) hit distinct banks
+    // k|v exchange rows of one head: k (hd bf16) | v (hd bf16), pitch 4*hd bytes, 16-byte chunk c of row r stored at
+    // chunk c ^ sw(r) so that the 8 lanes of a quarter-warp (consecutive rows, same logical chunk) hit distinct banks;
+    // one 128-row region per head of the phase
     constexpr int kv_pitch = 4 * HD;
-    constexpr int kKvShift = (HD == 16) ? 1 : 0;            // rows per 128-byte line = 128 / pitch (hd = 16: 2)
-    constexpr uint32_t kKvMask = (HD == 16) ? 3u : 7u;      // chunks per row - 1, capped at 7
-    auto kv_addr = [&](int r, int chunk) -> uint32_t {
-      return sKv + static_cast<uint32_t>(r * kv_pitch) +
+    constexpr int kKvShift = (HD == 16) ? 1 : 0;        // rows per 128-byte line = 128 / pitch (hd = 16: 2)
+    constexpr uint32_t kKvMask = (HD == 16) ? 3u : 7u;  // chunks per row - 1, capped at 7
+    auto kv_addr = [&](int hh, int r, int chunk) -> uint32_t {
+      return sKv + static_cast<uint32_t>(hh * 128 * kv_pitch + r * kv_pitch) +
              ((static_cast<uint32_t>(chunk) ^ ((static_cast<uint32_t>(r) >> kKvShift) & kKvMask)) << 4);
     };
     uint32_t mma_waits = 0;
@@ -316,38 +332,139 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_epi_done);
     };
-    // LayerNorm of (H + pend) for this row -> bf16 into `dst` (two passes over TMEM)
+    // LayerNorm of (H + pend) for this row -> bf16 into `dst`.  Each of the row's two threads owns half of the
+    // columns; the partial sums meet in shared memory (the k|v exchange region is idle during LN stages).
     auto layer_norm_to = [&](uint32_t dst, const float* pend, const float* w, const float* b, bool do_ln) {
+      const int c0 = g * (Dl >> 1), c1 = c0 + (Dl >> 1);
       float mean = 0.f, rstd = 1.f;
       if (do_ln) {
         float s = 0.f, ss = 0.f;
-        for (int c = 0; c < Dl; c += 32) {
+        for (int c = c0; c < c1; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(trow + kFeTmemH + c, v);
+          float4 pd[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pd[j] = fe_ldg4(pend + c + 4 * j);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = __uint_as_float(v[j]) + __ldg(pend + c + j);
-            s += x;
-            ss = fmaf(x, x, ss);
+          for (int j = 0; j < 8; ++j) {
+            const float x0 = __uint_as_float(v[4 * j]) + pd[j].x, x1 = __uint_as_float(v[4 * j + 1]) + pd[j].y,
+                        x2 = __uint_as_float(v[4 * j + 2]) + pd[j].z, x3 = __uint_as_float(v[4 * j + 3]) + pd[j].w;
+            s += (x0 + x1) + (x2 + x3);
+            ss = fmaf(x0, x0, ss);
+            ss = fmaf(x1, x1, ss);
+            ss = fmaf(x2, x2, ss);
+            ss = fmaf(x3, x3, ss);
           }
         }
+        float2* part = reinterpret_cast<float2*>(gbase + kFeSmemKv);
+        part[g * 128 + row] = make_float2(s, ss);
+        named_bar_sync(1, kFeEpiWarps * 32);
+        const float2 o = part[(g ^ 1) * 128 + row];
+        s += o.x;
+        ss += o.y;
         mean = s / Dl;
         const float var = fmaxf(ss / Dl - mean * mean, 0.f);
         rstd = 1.0f / sqrtf(var + 1e-5f);
       }
-      for (int c = 0; c < Dl; c += 32) {
+      const float shift = -mean * rstd;
+      for (int c = c0; c < c1; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(trow + kFeTmemH + c, v);
-        tmem_ld_wait();
         float y[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) + __ldg(pend + c + j);
-          if (do_ln) x = (x - mean) * rstd * __ldg(w + c + j) + __ldg(b + c + j);
-          y[j] = x;
+        for (int j = 0; j < 8; ++j) {
+          const float4 pd = fe_ldg4(pend + c + 4 * j);
+          y[4 * j] = pd.x; y[4 * j + 1] = pd.y; y[4 * j + 2] = pd.z; y[4 * j + 3] = pd.w;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(v[j]);
+        if (do_ln) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 ww = fe_ldg4(w + c + 4 * j), bb = fe_ldg4(b + c + 4 * j);
+            y[4 * j] = fmaf(fmaf(y[4 * j], rstd, shift), ww.x, bb.x);
+            y[4 * j + 1] = fmaf(fmaf(y[4 * j + 1], rstd, shift), ww.y, bb.y);
+            y[4 * j + 2] = fmaf(fmaf(y[4 * j + 2], rstd, shift), ww.z, bb.z);
+            y[4 * j + 3] = fmaf(fmaf(y[4 * j + 3], rstd, shift), ww.w, bb.w);
+          }
         }
         fe_store_row32(dst, row, c, y);
+      }
+    };
+    // softmax(q . K^T) V over the T keys of this row's drug for head slot hh of the phase (k|v rows start at row r0);
+    // `qv(d)` yields the scaled query.  Result (already normalised) is written to O columns [col0, col0 + HD).
+    auto attend = [&](int hh, int r0, uint32_t key_blocked, bool active, const float (&q)[HD], int col0) {
+      float m = -CUDART_INF_F, lsum = 0.f;
+      float acc[HD];
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+      if (active) {
+        for (int j = 0; j < T; ++j) {
+          if ((key_blocked >> j) & 1u) continue;
+          const int rj = r0 + j;
+          float s = 0.f;
+#pragma unroll
+          for (int d8 = 0; d8 < HD / 8; ++d8) {
+            uint32_t a, b, c2, e;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(hh, rj, d8)));
+            const uint32_t ww[4] = {a, b, c2, e};
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) {
+              const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
+              s = fmaf(q[d8 * 8 + 2 * t2], kk.x, s);
+              s = fmaf(q[d8 * 8 + 2 * t2 + 1], kk.y, s);
+            }
+          }
+          const float m_new = fmaxf(m, s);
+          const float corr = __expf(m - m_new);  // exp(-inf) = 0 on the first visible key
+          const float pj = __expf(s - m_new);
+          lsum = fmaf(lsum, corr, pj);
+#pragma unroll
+          for (int d8 = 0; d8 < HD / 8; ++d8) {
+            uint32_t a, b, c2, e;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(hh, rj, HD / 8 + d8)));
+            const uint32_t ww[4] = {a, b, c2, e};
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) {
+              const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
+              acc[d8 * 8 + 2 * t2] = fmaf(pj, vv.x, acc[d8 * 8 + 2 * t2] * corr);
+              acc[d8 * 8 + 2 * t2 + 1] = fmaf(pj, vv.y, acc[d8 * 8 + 2 * t2 + 1] * corr);
+            }
+          }
+          m = m_new;
+        }
+      }
+      const float inv = active ? 1.0f / lsum : 0.f;  // all keys masked -> inf/NaN like torch.softmax
+#pragma unroll
+      for (int d8 = 0; d8 < HD / 8; ++d8) {
+        float o[8];
+#pragma unroll
+        for (int t2 = 0; t2 < 8; ++t2) o[t2] = active ? acc[d8 * 8 + t2] * inv : 0.f;
+        st_shared_v4(fe_a_addr(sO, row, col0 + d8 * 8), fe_pack2(o[0], o[1]), fe_pack2(o[2], o[3]),
+                     fe_pack2(o[4], o[5]), fe_pack2(o[6], o[7]));
+      }
+    };
+    // accumulator columns [acol, acol + HD) + bias -> bf16 k (part 0) or v (part 1) row of head slot hh
+    auto stash_kv = [&](int hh, int part, uint32_t acol, const float* bias) {
+#pragma unroll
+      for (int c = 0; c < HD; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(trow + kFeTmemAcc + acol + c, v);
+        float4 bb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bb[j] = fe_ldg4(bias + c + 4 * j);
+        tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          w[2 * j] = fe_pack2(__uint_as_float(v[4 * j]) + bb[j].x, __uint_as_float(v[4 * j + 1]) + bb[j].y);
+          w[2 * j + 1] = fe_pack2(__uint_as_float(v[4 * j + 2]) + bb[j].z, __uint_as_float(v[4 * j + 3]) + bb[j].w);
+        }
+        const int ch = (part * HD + c) / 8;  // 16-byte chunk index within the row
+        st_shared_v4(kv_addr(hh, row, ch), w[0], w[1], w[2], w[3]);
+        st_shared_v4(kv_addr(hh, row, ch + 1), w[4], w[5], w[6], w[7]);
       }
     };
 
@@ -363,14 +480,13 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
           blocked |= (m ? 1u : 0u) << j;
         }
       }
-      const bool my_masked = valid ? (p.key_mask[drug * T + tok] != 0) : true;
 
-      // ---- tokens -> A (bf16, zero padded): each warp copies its 32 rows one at a time, 32 lanes x float4 per
+      // ---- tokens -> A (bf16, zero padded): each warp copies its 16 rows one at a time, 32 lanes x float4 per
       //      512-byte piece of the row (coalesced), converted to bf16 and written into the swizzled operand layout
       {
         const int kw = kp_e * 64;
-        for (int r = 0; r < 32; ++r) {
-          const int rr = quad * 32 + r;
+        for (int r = 0; r < 128 / kFeEpiWarps; ++r) {
+          const int rr = ew * (128 / kFeEpiWarps) + r;
           const int dl2 = rr / T;
           const long long drug2 = tile * G + dl2;
           const bool ok = dl2 < G && drug2 < p.B;
@@ -390,128 +506,68 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         wait_mma();
         layer_norm_to(sA, p.pend + static_cast<long long>(2 * l) * Dl, p.n1_w[l], p.n1_b[l], true);
         signal();
-        // ---- attention, head by head
-        for (int h = 0; h < p.H; ++h) {
+        // ---- attention: HP heads per phase, group g takes head slots g, g + 2, ...
+        const float* ib = p.in_bias[l];
+        const float qscale = 1.0f / sqrtf(static_cast<float>(hd));
+        for (int ph = 0; ph < n_phases; ++ph) {
           wait_mma();
-          const float* ib = p.in_bias[l];
-          const float qscale = 1.0f / sqrtf(static_cast<float>(hd));
-          float q[HD];
+          const int h0 = ph * HP, nh = min(HP, p.H - h0);
+          for (int hh = g; hh < nh; hh += 2) {
+            const int h = h0 + hh;
+            const uint32_t acol = static_cast<uint32_t>(hh * 3 * HD);
+            float q[HD];
 #pragma unroll
-          for (int c = 0; c < 3 * HD; c += 16) {  // columns: [q | k | v] of head h
-            uint32_t v[16];
-            tmem_ld_32x16(trow + kFeTmemAcc + c, v);
-            tmem_ld_wait();
-            constexpr int kChunksPerPart = HD / 16;
-            const int part = (c / 16) / kChunksPerPart, off = c - part * HD;  // compile-time after unrolling
-            const float* bias = ib + part * Dl + h * HD + off;
-            if (part == 0) {
+            for (int c = 0; c < HD; c += 16) {
+              uint32_t v[16];
+              tmem_ld_32x16(trow + kFeTmemAcc + acol + c, v);
+              float4 bb[4];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) q[off + j] = (__uint_as_float(v[j]) + __ldg(bias + j)) * qscale;
-            } else {
-              uint32_t w[8];
+              for (int j = 0; j < 4; ++j) bb[j] = fe_ldg4(ib + h * HD + c + 4 * j);
+              tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                w[j] = fe_pack2(__uint_as_float(v[2 * j]) + __ldg(bias + 2 * j),
-                                __uint_as_float(v[2 * j + 1]) + __ldg(bias + 2 * j + 1));
-              const int ch = ((part - 1) * HD + off) / 8;  // 16-byte chunk index within the row
-              st_shared_v4(kv_addr(row, ch), w[0], w[1], w[2], w[3]);
-              st_shared_v4(kv_addr(row, ch + 1), w[4], w[5], w[6], w[7]);
-            }
-          }
-          named_bar_sync(2, 128);  // k/v of every row of the tile are in shared memory
-          float m = -CUDART_INF_F, lsum = 0.f;
-          float acc[HD];
-#pragma unroll
-          for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-          const int r0 = row - tok;  // first row of this drug
-          for (int j = 0; j < T; ++j) {
-            if (!valid || ((blocked >> j) & 1u)) continue;
-            const int rj = r0 + j;
-            float s = 0.f;
-#pragma unroll
-            for (int d8 = 0; d8 < HD / 8; ++d8) {
-              {
-                uint32_t a, b, c2, e;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(rj, d8)));
-                const uint32_t ww[4] = {a, b, c2, e};
-#pragma unroll
-                for (int t2 = 0; t2 < 4; ++t2) {
-                  const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
-                  s = fmaf(q[d8 * 8 + 2 * t2], kk.x, s);
-                  s = fmaf(q[d8 * 8 + 2 * t2 + 1], kk.y, s);
-                }
+              for (int j = 0; j < 4; ++j) {
+                q[c + 4 * j] = (__uint_as_float(v[4 * j]) + bb[j].x) * qscale;
+                q[c + 4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + bb[j].y) * qscale;
+                q[c + 4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + bb[j].z) * qscale;
+                q[c + 4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + bb[j].w) * qscale;
               }
             }
-            const float m_new = fmaxf(m, s);
-            const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first visible key
-            const float pj = expf(s - m_new);
-            lsum = lsum * corr + pj;
-#pragma unroll
-            for (int d8 = 0; d8 < HD / 8; ++d8) {
-              {
-                uint32_t a, b, c2, e;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(rj, HD / 8 + d8)));
-                const uint32_t ww[4] = {a, b, c2, e};
-#pragma unroll
-                for (int t2 = 0; t2 < 4; ++t2) {
-                  const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
-                  acc[d8 * 8 + 2 * t2] = fmaf(pj, vv.x, acc[d8 * 8 + 2 * t2] * corr);
-                  acc[d8 * 8 + 2 * t2 + 1] = fmaf(pj, vv.y, acc[d8 * 8 + 2 * t2 + 1] * corr);
-                }
-              }
-            }
-            m = m_new;
+            stash_kv(hh, 0, acol + HD, ib + Dl + h * HD);
+            stash_kv(hh, 1, acol + 2 * HD, ib + 2 * Dl + h * HD);
+            named_bar_sync(2 + g, 128);  // k/v of head h for every row of the tile are in shared memory
+            attend(hh, row - tok, blocked, valid, q, h * HD);
           }
-          const float inv = valid ? 1.0f / lsum : 0.f;  // all keys masked -> inf/NaN like torch.softmax
-#pragma unroll
-          for (int d8 = 0; d8 < HD / 8; ++d8) {
-            {
-              const float o0 = valid ? acc[d8 * 8] * inv : 0.f, o1 = valid ? acc[d8 * 8 + 1] * inv : 0.f,
-                          o2 = valid ? acc[d8 * 8 + 2] * inv : 0.f, o3 = valid ? acc[d8 * 8 + 3] * inv : 0.f,
-                          o4 = valid ? acc[d8 * 8 + 4] * inv : 0.f, o5 = valid ? acc[d8 * 8 + 5] * inv : 0.f,
-                          o6 = valid ? acc[d8 * 8 + 6] * inv : 0.f, o7 = valid ? acc[d8 * 8 + 7] * inv : 0.f;
-              st_shared_v4(fe_a_addr(sO, row, h * hd + d8 * 8), fe_pack2(o0, o1), fe_pack2(o2, o3), fe_pack2(o4, o5),
-                           fe_pack2(o6, o7));
-            }
-          }
-          named_bar_sync(2, 128);  // everyone is done reading k/v before the next head overwrites them
           signal();
         }
         // ---- LN2
         wait_mma();
         layer_norm_to(sA, p.pend + static_cast<long long>(2 * l + 1) * Dl, p.n2_w[l], p.n2_b[l], true);
         signal();
-        // ---- FFN activation chunks
+        // ---- FFN activation chunks (each group takes half of the chunk's columns)
         for (int c = 0; c < n_fchunks; ++c) {
           wait_mma();
           const float* b1 = p.l1_bias[l] + c * FC;
-          for (int cc = 0; cc < FC; cc += 32) {
+          const int half = FC >> 1;
+          for (int cc = g * half; cc < (g + 1) * half; cc += 32) {
             uint32_t v[32];
             tmem_ld_32x32(trow + kFeTmemAcc + cc, v);
-            tmem_ld_wait();
             float y[32];
             if (c * FC + cc + 32 <= p.F) {
-              const float4* b4 = reinterpret_cast<const float4*>(b1 + cc);  // F-chunk offsets are multiples of 32
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = fe_ldg4(b1 + cc + 4 * j);
+                y[4 * j] = bb.x; y[4 * j + 1] = bb.y; y[4 * j + 2] = bb.z; y[4 * j + 3] = bb.w;
+              }
+              tmem_ld_wait();
               if (p.act == 1) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 bb = __ldg(b4 + (j >> 2));
-                  y[j] = fmaxf(__uint_as_float(v[j]) + bb.x, 0.f);
-                  y[j + 1] = fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
-                  y[j + 2] = fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f);
-                  y[j + 3] = fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
-                }
+                for (int j = 0; j < 32; ++j) y[j] = fmaxf(__uint_as_float(v[j]) + y[j], 0.f);
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 bb = __ldg(b4 + (j >> 2));
-                  y[j] = fe_gelu(__uint_as_float(v[j]) + bb.x);
-                  y[j + 1] = fe_gelu(__uint_as_float(v[j + 1]) + bb.y);
-                  y[j + 2] = fe_gelu(__uint_as_float(v[j + 2]) + bb.z);
-                  y[j + 3] = fe_gelu(__uint_as_float(v[j + 3]) + bb.w);
-                }
+                for (int j = 0; j < 32; ++j) y[j] = fe_gelu(__uint_as_float(v[j]) + y[j]);
               }
             } else {
+              tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const bool in = c * FC + cc + j < p.F;  // columns beyond F are K padding: exactly zero
@@ -532,95 +588,40 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         uint32_t pblocked = 0;
         for (int j = 0; j < T; ++j)
           if (p.pool_mask != nullptr && p.pool_mask[j] != 0) pblocked |= 1u << j;
-        for (int h = 0; h < p.H; ++h) {
+        const bool pool_row = valid && tok == 0;  // the first token row of each drug computes the pooled output
+        for (int ph = 0; ph < n_phases; ++ph) {
           wait_mma();
+          const int h0 = ph * HP, nh = min(HP, p.H - h0);
+          for (int hh = g; hh < nh; hh += 2) {
+            const int h = h0 + hh;
+            const uint32_t acol = static_cast<uint32_t>(hh * 2 * HD);
+            stash_kv(hh, 0, acol, p.xin_bias + Dl + h * HD);
+            stash_kv(hh, 1, acol + HD, p.xin_bias + 2 * Dl + h * HD);
+            float q[HD];
 #pragma unroll
-          for (int c = 0; c < 2 * HD; c += 16) {  // columns: [k | v] of head h
-            uint32_t v[16];
-            tmem_ld_32x16(trow + kFeTmemAcc + c, v);
-            tmem_ld_wait();
-            constexpr int kChunksPerPart = HD / 16;
-            const int part = (c / 16) / kChunksPerPart, off = c - part * HD;
-            const float* bias = p.xin_bias + (part + 1) * Dl + h * HD + off;
-            uint32_t w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              w[j] = fe_pack2(__uint_as_float(v[2 * j]) + __ldg(bias + 2 * j),
-                              __uint_as_float(v[2 * j + 1]) + __ldg(bias + 2 * j + 1));
-            const int ch = (part * HD + off) / 8;
-            st_shared_v4(kv_addr(row, ch), w[0], w[1], w[2], w[3]);
-            st_shared_v4(kv_addr(row, ch + 1), w[4], w[5], w[6], w[7]);
-          }
-          named_bar_sync(2, 128);
-          // the first token row of each drug computes the pooled head output; other rows write zeros
-          float m = -CUDART_INF_F, lsum = 0.f;
-          float acc[HD];
-#pragma unroll
-          for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-          const bool pool_row = valid && tok == 0;
-          if (pool_row) {
-            const float* qp = p.q_proj + h * hd;
-            for (int j = 0; j < T; ++j) {
-              if ((pblocked >> j) & 1u) continue;
-              const int rj = row + j;
-              float s = 0.f;
-#pragma unroll
-              for (int d8 = 0; d8 < HD / 8; ++d8) {
-                uint32_t a, b, c2, e;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(rj, d8)));
-                const uint32_t ww[4] = {a, b, c2, e};
-#pragma unroll
-                for (int t2 = 0; t2 < 4; ++t2) {
-                  const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
-                  s = fmaf(__ldg(qp + d8 * 8 + 2 * t2), kk.x, s);
-                  s = fmaf(__ldg(qp + d8 * 8 + 2 * t2 + 1), kk.y, s);
-                }
-              }
-              const float m_new = fmaxf(m, s);
-              const float corr = expf(m - m_new);
-              const float pj = expf(s - m_new);
-              lsum = lsum * corr + pj;
-#pragma unroll
-              for (int d8 = 0; d8 < HD / 8; ++d8) {
-                {
-                  uint32_t a, b, c2, e;
-                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(rj, HD / 8 + d8)));
-                  const uint32_t ww[4] = {a, b, c2, e};
-#pragma unroll
-                  for (int t2 = 0; t2 < 4; ++t2) {
-                    const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
-                    acc[d8 * 8 + 2 * t2] = fmaf(pj, vv.x, acc[d8 * 8 + 2 * t2] * corr);
-                    acc[d8 * 8 + 2 * t2 + 1] = fmaf(pj, vv.y, acc[d8 * 8 + 2 * t2 + 1] * corr);
-                  }
-                }
-              }
-              m = m_new;
+            for (int c = 0; c < HD; c += 4) {
+              const float4 qq = fe_ldg4(p.q_proj + h * HD + c);
+              q[c] = qq.x; q[c + 1] = qq.y; q[c + 2] = qq.z; q[c + 3] = qq.w;
             }
+            named_bar_sync(2 + g, 128);
+            attend(hh, row, pblocked, pool_row, q, h * HD);
           }
-          const float inv = pool_row ? 1.0f / lsum : 0.f;
-#pragma unroll
-          for (int d8 = 0; d8 < HD / 8; ++d8) {
-            {
-              float o[8];
-#pragma unroll
-              for (int t2 = 0; t2 < 8; ++t2) o[t2] = pool_row ? acc[d8 * 8 + t2] * inv : 0.f;
-              st_shared_v4(fe_a_addr(sO, row, h * hd + d8 * 8), fe_pack2(o[0], o[1]), fe_pack2(o[2], o[3]),
-                           fe_pack2(o[4], o[5]), fe_pack2(o[6], o[7]));
-            }
-          }
-          named_bar_sync(2, 128);
           signal();
         }
         // ---- out-proj of the pooled query + residual query (norm_first: no LN here) -> A for latent2embed
         wait_mma();
-        for (int c = 0; c < Dl; c += 32) {
+        for (int c = g * (Dl >> 1); c < (g + 1) * (Dl >> 1); c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(trow + kFeTmemAcc + c, v);
-          tmem_ld_wait();
           float y[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            y[j] = __uint_as_float(v[j]) + __ldg(p.xout_bias + c + j) + __ldg(p.q_res + c + j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = fe_ldg4(p.xout_bias + c + 4 * j), b = fe_ldg4(p.q_res + c + 4 * j);
+            y[4 * j] = a.x + b.x; y[4 * j + 1] = a.y + b.y; y[4 * j + 2] = a.z + b.z; y[4 * j + 3] = a.w + b.w;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(v[j]);
           fe_store_row32(sA, row, c, y);
         }
         signal();
@@ -630,11 +631,11 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         layer_norm_to(sA, pend_final, nullptr, nullptr, false);
         signal();
       }
-      // ---- latent2embed output -> pooled z
+      // ---- latent2embed output -> pooled z (32-column chunks alternate between the two groups)
       wait_mma();
       {
-        float* xbuf = reinterpret_cast<float*>(gbase + kFeSmemKv);  // [128 rows][33] fp32 exchange (16.9 KB)
-        for (int c = 0; c < p.E; c += 32) {
+        float* xbuf = reinterpret_cast<float*>(gbase + kFeSmemO) + g * (128 * 33);  // per-group [128][33] fp32 exchange
+        for (int c = g * 32; c < p.E; c += 64) {
           uint32_t v[32];
           tmem_ld_32x32(trow + kFeTmemAcc + c, v);
           tmem_ld_wait();
@@ -643,20 +644,19 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
               float* zo = p.z_out + drug * p.E + c;
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
-                if (c + j < p.E)  // E % 16 == 0: whole float4s
+                if (c + j < p.E) {  // E % 16 == 0: whole float4s
+                  const float4 bb = fe_ldg4(p.l2e_bias + c + j);
                   *reinterpret_cast<float4*>(zo + j) =
-                      make_float4(__uint_as_float(v[j]) + __ldg(p.l2e_bias + c + j),
-                                  __uint_as_float(v[j + 1]) + __ldg(p.l2e_bias + c + j + 1),
-                                  __uint_as_float(v[j + 2]) + __ldg(p.l2e_bias + c + j + 2),
-                                  __uint_as_float(v[j + 3]) + __ldg(p.l2e_bias + c + j + 3));
+                      make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y,
+                                  __uint_as_float(v[j + 2]) + bb.z, __uint_as_float(v[j + 3]) + bb.w);
+                }
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) xbuf[row * 33 + j] = __uint_as_float(v[j]);
-            named_bar_sync(2, 128);
+            named_bar_sync(2 + g, 128);
             if (valid && tok == 0) {
               float* zo = p.z_out + drug * p.E + c;
-              // key masks of the drug's tokens: `blocked` of token 0 holds key_mask | src_mask[0]; re-read key_mask
               for (int j = 0; j < 32; ++j) {
                 if (c + j >= p.E) break;
                 float accv = p.agg == MDG_AGG_MAX ? -CUDART_INF_F : 0.f;
@@ -671,12 +671,11 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
                 zo[j] = cnt == 0 ? 0.f : (p.agg == MDG_AGG_MAX ? accv + bias : accv / cnt + bias);
               }
             }
-            named_bar_sync(2, 128);
+            named_bar_sync(2 + g, 128);
           }
         }
         tc_fence_before_sync();
       }
-      (void)my_masked;
     }
   }
   tc_fence_before_sync();

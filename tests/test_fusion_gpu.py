@@ -241,11 +241,11 @@ def test_model_wrapper_end_to_end(mb, cuda_device):
 @pytest.mark.parametrize("agg,actn,T,nb,B,dims", [
     ("x-attn", "gelu", 4, 0, 4096, (256, 8, 32, 512)),   # bench.py's encoder (BASELINE config 2)
     ("mean", "gelu", 4, 0, 1000, (128, 8, 32, 512)),     # BASELINE config 5 shape
-    ("cls", "relu", 5, 0, 257, (128, 4, 64, 256)),       # T does not divide 128; head_dim 64
+    ("cls", "relu", 5, 0, 257, (128, 8, 16, 256)),       # T does not divide 128; head_dim 16, two attention phases
     ("max", "relu", 1, 0, 130, (64, 4, 16, 64)),         # one token per drug; head_dim 16
-    ("x-attn", "gelu", 23, 4, 77, (128, 4, 64, 200)),    # production token layout (src_mask, bottlenecks), F % 64 != 0
+    ("x-attn", "gelu", 23, 4, 77, (128, 4, 32, 200)),    # production token layout (src_mask, bottlenecks), F % 64 != 0
     ("mean", "gelu", 32, 0, 9, (48, 2, 32, 1024)),       # T = 32, latent 64, 4 FFN chunks, E % 64 != 0
-    ("cls", "gelu", 19, 0, 50, (256, 3, 64, 128)),       # latent 192
+    ("cls", "gelu", 19, 0, 50, (256, 6, 32, 128)),       # latent 192, three attention phases
 ])
 def test_fused_encoder_kernel(mb, cuda_device, agg, actn, T, nb, B, dims):
     from madrigal_b200 import _lib
