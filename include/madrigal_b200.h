@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 1
+#define MDG_ABI_VERSION 2
 
 typedef enum MdgStatus {
   MDG_OK = 0,
@@ -83,12 +83,19 @@ typedef enum MdgPairs {
 #define MDG_RANK_LUT_ENTRIES (1 << MDG_RANK_BUCKET_BITS) /* uint32 entries per outcome (32 KB) */
 #define MDG_RANK_MAX_Q 65535
 
+typedef enum MdgRankKind {
+  MDG_RANK_LUT = 0, /* exact bucket LUT: every threshold moves by <= ~3 grid cells (mdg_rank_table_build)          */
+  MDG_RANK_PWL = 1  /* 256-bin histogram CDF, linear inside a bin, exact at the bin edges; bank-conflict-free in
+                       shared memory (mdg_rank_table_build_pwl).  Thresholds move by up to max_dev ranks.          */
+} MdgRankKind;
+
 typedef struct MdgRankTable {
   const float* thresholds; /* [L, Q] ascending, snapped to the lookup grid (what np.searchsorted is run against) */
   const uint32_t* lut;     /* [L, MDG_RANK_LUT_ENTRIES]                                                          */
   const float* affine;     /* [L, 2]  (scale, bias) of the logit -> grid map                                     */
   int32_t L;
   int32_t Q;
+  int32_t kind;            /* MdgRankKind of `lut`                                                               */
 } MdgRankTable;
 
 /*
@@ -103,6 +110,19 @@ typedef struct MdgRankTable {
  */
 int mdg_rank_table_build(const float* quantiles, int32_t L, int32_t Q, float* thresholds_out, uint32_t* lut_out,
                          float* affine_out, void* stream);
+
+/*
+ * Histogram-CDF variant (MDG_RANK_PWL).  Same inputs / outputs / contract as mdg_rank_table_build (the fused epilogue
+ * equals np.searchsorted(thresholds_out[l], x, side='right') bit for bit), but the lookup structure is a 256-bin
+ * piecewise-linear CDF on the same grid: exact at the 257 bin edges, interpolated inside a bin.  Because the 256
+ * entries are replicated once per shared-memory bank, the epilogue's lookups are conflict-free (the exact LUT costs
+ * ~4.9 shared-memory wavefronts per warp lookup).  The price: thresholds_out[i] may sit up to max_dev ranks away from
+ * quantiles[i]; max_dev_out [L] (optional, device) reports max_i |table_rank(quantiles[i]) - (i + 1)| per outcome
+ * (about 1 for smooth score distributions at Q = 16384).  thresholds_out[i] = +inf where no finite score reaches
+ * rank i + 1.
+ */
+int mdg_rank_table_build_pwl(const float* quantiles, int32_t L, int32_t Q, float* thresholds_out, uint32_t* lut_out,
+                             float* affine_out, float* max_dev_out, void* stream);
 
 /* Stand-alone lookup of already materialised logits through a prepared table (same device function as the fused
  * epilogue).  logits [L, n] -> ranks [L, n] uint16. */

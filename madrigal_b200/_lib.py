@@ -17,12 +17,14 @@ MDG_RANK_MAX_Q = 65535
 MDG_PREC_BF16, MDG_PREC_FP32 = 0, 1
 MDG_OUT_LOGIT_F32, MDG_OUT_SIGMOID_F32, MDG_OUT_RANK_U16 = 0, 1, 2
 MDG_PAIRS_FULL, MDG_PAIRS_SYMMETRIC = 0, 1
+MDG_RANK_KIND = {"lut": 0, "pwl": 1}
 MDG_AGG = {"cls": 0, "x-attn": 1, "mean": 2, "max": 3}
 MDG_ACTN = {"relu": 0, "gelu": 1}
 
 
 class MdgRankTable(Structure):
-    _fields_ = [("thresholds", c_void_p), ("lut", c_void_p), ("affine", c_void_p), ("L", c_int32), ("Q", c_int32)]
+    _fields_ = [("thresholds", c_void_p), ("lut", c_void_p), ("affine", c_void_p), ("L", c_int32), ("Q", c_int32),
+                ("kind", c_int32)]
 
 
 class MdgFusionLayer(Structure):
@@ -58,6 +60,7 @@ SIGNATURES = {
     "mdg_abi_version": (c_int, []),
     "mdg_check_device": (c_int, [c_int]),
     "mdg_rank_table_build": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mdg_rank_table_build_pwl": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mdg_rank_lookup": (c_int, [c_void_p, c_int64, POINTER(MdgRankTable), c_void_p, c_void_p]),
     "mdg_pair_score_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "mdg_pair_score": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int,

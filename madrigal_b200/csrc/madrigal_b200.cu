@@ -193,6 +193,12 @@ int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     case mdg::EPI_RANK_U16_MIRROR:
       rc = launch_pair_instance<mdg::EPI_RANK_U16_MIRROR, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
       break;
+    case mdg::EPI_RANK_U16_PWL:
+      rc = launch_pair_instance<mdg::EPI_RANK_U16_PWL, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
+      break;
+    case mdg::EPI_RANK_U16_MIRROR_PWL:
+      rc = launch_pair_instance<mdg::EPI_RANK_U16_MIRROR_PWL, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
+      break;
     case mdg::EPI_TOPK: rc = launch_pair_instance<mdg::EPI_TOPK, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
     case mdg::EPI_LINEAR:
       rc = (linear_warps == 8) ? launch_pair_instance<mdg::EPI_LINEAR, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream)
@@ -241,6 +247,20 @@ int mdg_rank_table_build(const float* quantiles, int32_t L, int32_t Q, float* th
   return MDG_OK;
 }
 
+int mdg_rank_table_build_pwl(const float* quantiles, int32_t L, int32_t Q, float* thresholds_out, uint32_t* lut_out,
+                             float* affine_out, float* max_dev_out, void* stream) {
+  if (!quantiles || !thresholds_out || !lut_out || !affine_out)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_rank_table_build_pwl: NULL pointer");
+  if (L <= 0 || Q <= 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_rank_table_build_pwl: L=%d Q=%d", L, Q);
+  if (Q > MDG_RANK_MAX_Q) return fail(MDG_ERR_UNSUPPORTED, "Q=%d exceeds %d (uint16 ranks)", Q, MDG_RANK_MAX_Q);
+  if (static_cast<const void*>(quantiles) == static_cast<const void*>(thresholds_out))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_rank_table_build_pwl: quantiles and thresholds_out must not alias");
+  mdg::rank_table_build_pwl_kernel<<<L, 256, 0, static_cast<cudaStream_t>(stream)>>>(quantiles, Q, thresholds_out,
+                                                                                      lut_out, affine_out, max_dev_out);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
+}
+
 int mdg_rank_lookup(const float* logits, int64_t n_per_outcome, const MdgRankTable* table, uint16_t* ranks,
                     void* stream) {
   if (!logits || !table || !ranks || !table->lut || !table->affine)
@@ -250,8 +270,14 @@ int mdg_rank_lookup(const float* logits, int64_t n_per_outcome, const MdgRankTab
   int64_t blocks = (n_per_outcome + 255) / 256;
   if (blocks > 4 * 148) blocks = 4 * 148;
   dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(table->L));
-  mdg::rank_lookup_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, n_per_outcome, table->lut,
-                                                                                table->affine, ranks);
+  if (table->kind != MDG_RANK_LUT && table->kind != MDG_RANK_PWL)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_rank_lookup: table kind %d", table->kind);
+  if (table->kind == MDG_RANK_PWL)
+    mdg::rank_lookup_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, n_per_outcome, table->lut,
+                                                                                        table->affine, ranks);
+  else
+    mdg::rank_lookup_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, n_per_outcome, table->lut,
+                                                                                         table->affine, ranks);
   MDG_CUDA(cudaGetLastError());
   return MDG_OK;
 }
@@ -295,6 +321,8 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     if (!table || !table->lut || !table->affine)
       return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: MDG_OUT_RANK_U16 needs a rank table");
     if (table->L < L) return fail(MDG_ERR_INVALID_ARGUMENT, "rank table has %d outcomes, need %lld", table->L, (long long)L);
+    if (table->kind != MDG_RANK_LUT && table->kind != MDG_RANK_PWL)
+      return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: rank table kind %d", table->kind);
   }
   if (Nr == 0 || Nc == 0 || L == 0) return MDG_OK;
   if (!workspace) return fail(MDG_ERR_WORKSPACE, "mdg_pair_score: NULL workspace");
@@ -395,17 +423,19 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
       p.topk_count = topk->counts;
       p.topk_cand = topk->cand;
       p.topk_cap = topk->cap;
+      if (getenv("MDG_DEBUG_MAINLOOP_ONLY")) p.topk_cap = -1;  // debug: time the TMA/MMA mainloop without the epilogue
       p.lower_only = pairs == MDG_PAIRS_SYMMETRIC;
     } else if (out_mode == MDG_OUT_SIGMOID_F32) {
       epi = mdg::EPI_SIGMOID;
     } else if (out_mode == MDG_OUT_RANK_U16) {
-      epi = mdg::EPI_RANK_U16;
+      const bool pwl = table->kind == MDG_RANK_PWL;
+      epi = pwl ? mdg::EPI_RANK_U16_PWL : mdg::EPI_RANK_U16;
       p.lut = table->lut;
       p.affine = table->affine;
       elem = 2;
       dt = CU_TENSOR_MAP_DATA_TYPE_UINT16;
       if (pairs == MDG_PAIRS_SYMMETRIC) {
-        epi = mdg::EPI_RANK_U16_MIRROR;
+        epi = pwl ? mdg::EPI_RANK_U16_MIRROR_PWL : mdg::EPI_RANK_U16_MIRROR;
         p.lower_only = 1;
         p.mirror = 1;
       }

@@ -38,8 +38,15 @@ constexpr int kTaskRing = 4;  // dynamic-scheduler ring depth
 
 enum EpiMode : int {
   EPI_F32 = 0, EPI_SIGMOID = 1, EPI_RANK_U16 = 2, EPI_BF16_SPLIT = 3, EPI_LINEAR = 4, EPI_TOPK = 5,
-  EPI_RANK_U16_MIRROR = 6  // rank of row > col pairs, written at [row, col] and [col, row]
+  EPI_RANK_U16_MIRROR = 6,  // rank of row > col pairs, written at [row, col] and [col, row]
+  EPI_RANK_U16_PWL = 7,         // the two rank modes with the histogram-CDF table (MDG_RANK_PWL): conflict-free lookups
+  EPI_RANK_U16_MIRROR_PWL = 8
 };
+__host__ __device__ constexpr bool epi_is_rank(int e) {
+  return e == EPI_RANK_U16 || e == EPI_RANK_U16_MIRROR || e == EPI_RANK_U16_PWL || e == EPI_RANK_U16_MIRROR_PWL;
+}
+__host__ __device__ constexpr bool epi_is_mirror(int e) { return e == EPI_RANK_U16_MIRROR || e == EPI_RANK_U16_MIRROR_PWL; }
+__host__ __device__ constexpr bool epi_is_pwl(int e) { return e == EPI_RANK_U16_PWL || e == EPI_RANK_U16_MIRROR_PWL; }
 
 // Shared-memory plan for a kernel instance with NE epilogue warps (staging is per warp, so more epilogue warps
 // trade one B stage for staging space).
@@ -115,6 +122,27 @@ __device__ __forceinline__ uint32_t rank_lookup_smem(uint32_t lut_smem, float x,
   uint32_t bucket;
   asm("mul.hi.u32 %0, %1, %2;" : "=r"(bucket) : "r"(kb), "r"(1u << 28));  // kb >> 4
   return rank_finish(lds_u32(lut_smem + bucket * 4), kb);
+}
+
+// Histogram-CDF table (rank_pwl_raw): lane c reads copy c of the 256-entry table, i.e. always bank c.
+// `lut_lane` = table base + 4 * lane.  Piece extraction and addressing stay on the FMA pipe (mul.hi / mad).
+__device__ __forceinline__ uint32_t rank_lookup_pwl_smem(uint32_t lut_lane, float x, float scale, float bias) {
+  const uint32_t kb = rank_key_bits(x, scale, bias);
+  uint32_t addr;
+  asm("{\n\t"
+      ".reg .u32 pc;\n\t"
+      "mul.hi.u32 pc, %1, %2;\n\t"       // kb >> 9
+      "mad.lo.u32 %0, pc, 128, %3;\n\t"  // 32 copies x 4 B per piece
+      "}\n"
+      : "=r"(addr)
+      : "r"(kb), "r"(1u << (32 - kRankPwlSubBits)), "r"(lut_lane));
+  return rank_pwl_finish(lds_u32(addr), kb);
+}
+template <bool PWL>
+__device__ __forceinline__ uint32_t rank_lookup_epi(uint32_t lut_smem, uint32_t lut_lane, float x, float scale,
+                                                    float bias) {
+  if constexpr (PWL) return rank_lookup_pwl_smem(lut_lane, x, scale, bias);
+  else return rank_lookup_smem(lut_smem, x, scale, bias);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -493,7 +521,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     StagedStore ss;
     ss.buf[0] = sStaging + ew * kStagingBytesPerWarp;
     // the LUT region is idle outside the rank epilogue: use it as a second staging buffer per warp
-    ss.buf[1] = (EPI == EPI_RANK_U16 || EPI == EPI_RANK_U16_MIRROR) ? ss.buf[0] : sLut + ew * kStagingBytesPerWarp;
+    ss.buf[1] = epi_is_rank(EPI) ? ss.buf[0] : sLut + ew * kStagingBytesPerWarp;
     ss.row_off = static_cast<uint32_t>(lane) * 64;
     ss.swz = static_cast<uint32_t>((lane >> 1) & 3);  // 64-byte swizzle: chunk ^= (row >> 1) & 3
     ss.cur = 0;
@@ -505,7 +533,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane)) {
       const TaskCoord c = decode_task(p, t);
-      if ((EPI == EPI_RANK_U16 || EPI == EPI_RANK_U16_MIRROR) && c.l != cur_l) {
+      if (epi_is_rank(EPI) && c.l != cur_l) {
         named_bar_sync(1, NE * 32);  // everyone is done with the previous outcome's LUT
         const uint4* src = reinterpret_cast<const uint4*>(p.lut + static_cast<size_t>(c.l) * kRankLutEntries);
         const int tid = ew * 32 + lane;
@@ -526,7 +554,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int nb = c.nb0; nb < c.nb1; ++nb) {
         mbar_wait(bar_t_full(acc_stage), acc_phase, 6);
         tc_fence_after_sync();
-        if (row0 < p.rows) {
+        if (row0 < p.rows && !(EPI == EPI_TOPK && p.topk_cap < 0)) {  // topk_cap < 0: mainloop-only timing (debug)
           for (int cc = col_begin; cc < col_end; cc += 32) {
             const int n0 = nb * kBN + cc;
             if (n0 >= p.cols) break;
@@ -537,18 +565,19 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_32x32(taddr, v);
             if constexpr (EPI != EPI_LINEAR) tmem_ld_wait();  // LINEAR overlaps its global loads with the TMEM load
 
-            if constexpr (EPI == EPI_RANK_U16 || EPI == EPI_RANK_U16_MIRROR) {
+            if constexpr (epi_is_rank(EPI)) {
               uint32_t pk[16];
+              const uint32_t sLutLane = sLut + static_cast<uint32_t>(lane) * 4;
               // mirror mode (reference normaliser layout, normalize_scores.py:67-70): this chunk holds ranks of
               // (row > col) pairs; each is also written at [col, row] through a TRANSPOSED staging tile.
-              constexpr bool mirror = (EPI == EPI_RANK_U16_MIRROR);
+              constexpr bool mirror = epi_is_mirror(EPI);
               const bool direct = !p.use_tma_store || (mirror && n0 == row0);  // diagonal chunk: masked stores
               uint32_t tstage = 0;
               if (mirror && !direct) tstage = ss.acquire(lane) + static_cast<uint32_t>(lane) * 2;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const uint32_t r0 = rank_lookup_smem(sLut, __uint_as_float(v[2 * j]), scale, bias);
-                const uint32_t r1 = rank_lookup_smem(sLut, __uint_as_float(v[2 * j + 1]), scale, bias);
+                const uint32_t r0 = rank_lookup_epi<epi_is_pwl(EPI)>(sLut, sLutLane, __uint_as_float(v[2 * j]), scale, bias);
+                const uint32_t r1 = rank_lookup_epi<epi_is_pwl(EPI)>(sLut, sLutLane, __uint_as_float(v[2 * j + 1]), scale, bias);
                 pk[j] = __byte_perm(r0, r1, 0x5410);
                 if (mirror && !direct) {  // transposed tile: row = column index, 64-byte pitch, no swizzle
                   asm volatile("st.shared.u16 [%0], %1;" ::"r"(tstage + (2 * j) * 64), "h"(static_cast<uint16_t>(r0)) : "memory");

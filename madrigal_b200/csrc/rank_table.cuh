@@ -55,6 +55,27 @@ __device__ __forceinline__ uint32_t rank_lookup_raw(const uint32_t* lut, float x
   return rank_finish(lut[kb >> kRankSubBits], kb);
 }
 
+// ---- MDG_RANK_PWL: the same 17-bit cell grid, but the table is a 256-bin histogram CDF with linear interpolation:
+//   piece = cell >> 9, sub = cell & 511,   rank = base[piece] + (((sub + 1) * slope[piece]) >> 16)
+// with base[piece] = #{thresholds whose cell < 512*piece} (exact at the 257 knots) and slope = floor(128 * (base[p+1]
+// - base[p])) capped at 65535, so the function is monotone non-decreasing in the cell and hence in x.  One entry is
+// base << 16 | slope; the 256 entries are REPLICATED 32x (entry p of copy c at word 32*p + c) so that lane c always
+// reads bank c: the shared-memory lookup is conflict-free (1 wavefront per warp instead of ~4.9 for the exact LUT).
+// The table the ranks are bit-exact against (np.searchsorted) is thresholds_out[i] = min{x : rank(x) >= i + 1}.
+constexpr int kRankPwlPieceBits = 8;
+constexpr int kRankPwlPieces = 1 << kRankPwlPieceBits;                 // 256
+constexpr int kRankPwlSubBits = kRankCellBits - kRankPwlPieceBits;      // 9
+static_assert(kRankPwlPieces * 32 == kRankLutEntries, "the replicated PWL table fills the LUT storage exactly");
+__device__ __forceinline__ uint32_t rank_pwl_finish(uint32_t entry, uint32_t key_bits) {
+  const uint32_t sub = key_bits & ((1u << kRankPwlSubBits) - 1u);
+  const uint32_t m = entry & 0xFFFFu;
+  return (entry >> 16) + ((sub * m + m) >> 16);  // (sub + 1) * slope: reaches base[p + 1] in the last cell of a full bin
+}
+__device__ __forceinline__ uint32_t rank_pwl_raw(const uint32_t* lut, float x, float scale, float bias) {
+  const uint32_t kb = rank_key_bits(x, scale, bias);
+  return rank_pwl_finish(lut[(kb >> kRankPwlSubBits) * 32], kb);
+}
+
 // ------------------------------------------------------------------------------------------------ builder
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
   uint32_t u = __float_as_uint(f);
@@ -156,6 +177,87 @@ __global__ void __launch_bounds__(256) rank_table_build_kernel(const float* __re
   }
 }
 
+// One block per outcome: histogram-CDF (MDG_RANK_PWL) table from ascending quantiles.  max_dev_out[l] (optional) =
+// max over the quantiles of |table rank at q_i - exact rank (i + 1)|: how far the interpolated CDF is from the
+// order statistics it was built from, in rank units.
+__global__ void __launch_bounds__(256) rank_table_build_pwl_kernel(const float* __restrict__ quantiles, int Q,
+                                                                   float* __restrict__ thresholds_out,
+                                                                   uint32_t* __restrict__ lut_out,
+                                                                   float* __restrict__ affine_out,
+                                                                   float* __restrict__ max_dev_out) {
+  const int l = blockIdx.x;
+  const float* q = quantiles + static_cast<size_t>(l) * Q;
+  float* thr = thresholds_out + static_cast<size_t>(l) * Q;
+  uint32_t* lut = lut_out + static_cast<size_t>(l) * kRankLutEntries;
+  __shared__ float s_scale, s_bias;
+  __shared__ uint32_t s_base[kRankPwlPieces + 1];
+  __shared__ uint32_t s_entry[kRankPwlPieces];
+  __shared__ int s_dev;
+  if (threadIdx.x == 0) {
+    float lo = q[0], hi = q[Q - 1];
+    float r = hi - lo;
+    if (!(r > 0.f)) r = fmaxf(fabsf(lo), 1.0f) * 1e-3f;
+    float lo2 = lo - 0.01f * r, hi2 = hi + 0.01f * r;
+    float scale = 1.0f / (hi2 - lo2);
+    s_scale = scale;
+    s_bias = -lo2 * scale;
+    affine_out[2 * l + 0] = s_scale;
+    affine_out[2 * l + 1] = s_bias;
+    s_dev = 0;
+  }
+  __syncthreads();
+  const float scale = s_scale, bias = s_bias;
+  // base[p] = #{i : cell(q_i) < 512 p}: the quantiles ascend, so do their cells -> binary search per knot
+  for (int pce = threadIdx.x; pce <= kRankPwlPieces; pce += blockDim.x) {
+    const uint32_t edge = static_cast<uint32_t>(pce) << kRankPwlSubBits;
+    int lo = 0, hi = Q;  // first index with cell >= edge
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (rank_cell(q[mid], scale, bias) >= edge) hi = mid; else lo = mid + 1;
+    }
+    s_base[pce] = static_cast<uint32_t>(lo);
+  }
+  __syncthreads();
+  for (int pce = threadIdx.x; pce < kRankPwlPieces; pce += blockDim.x) {
+    const uint32_t d = s_base[pce + 1] - s_base[pce];
+    uint32_t m = d << (16 - kRankPwlSubBits);  // floor(d * 65536 / 512)
+    if (m > 0xFFFFu) m = 0xFFFFu;
+    s_entry[pce] = (s_base[pce] << 16) | m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kRankLutEntries; i += blockDim.x) lut[i] = s_entry[i >> 5];
+  auto f = [&](float x) -> uint32_t {
+    const uint32_t kb = rank_key_bits(x, scale, bias);
+    return rank_pwl_finish(s_entry[kb >> kRankPwlSubBits], kb);
+  };
+  // snapped thresholds: t_i = min fp32 x with f(x) >= i + 1 (bisection over the ordered-uint image of fp32)
+  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+    const uint32_t want = static_cast<uint32_t>(i) + 1u;
+    uint32_t lo_o = float_to_ordered(-3.0e38f), hi_o = float_to_ordered(3.0e38f);
+    float t;
+    if (f(ordered_to_float(lo_o)) >= want) {
+      t = ordered_to_float(lo_o);
+    } else if (f(ordered_to_float(hi_o)) < want) {
+      t = __uint_as_float(0x7f800000u);  // +inf: no finite score reaches this rank
+    } else {
+      while (hi_o - lo_o > 1u) {
+        const uint32_t mid = lo_o + ((hi_o - lo_o) >> 1);
+        if (f(ordered_to_float(mid)) >= want) hi_o = mid; else lo_o = mid;
+      }
+      t = ordered_to_float(hi_o);
+    }
+    // deviation from the order statistic the table was built from (last of a run of equal quantiles only)
+    if (i + 1 == Q || q[i + 1] != q[i]) {
+      const int d = static_cast<int>(f(q[i])) - (i + 1);
+      atomicMax(&s_dev, d < 0 ? -d : d);
+    }
+    thr[i] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && max_dev_out != nullptr) max_dev_out[l] = static_cast<float>(s_dev);
+}
+
+template <bool PWL>
 __global__ void __launch_bounds__(256) rank_lookup_kernel(const float* __restrict__ logits, int64_t n,
                                                           const uint32_t* __restrict__ lut_all,
                                                           const float* __restrict__ affine,
@@ -167,7 +269,8 @@ __global__ void __launch_bounds__(256) rank_lookup_kernel(const float* __restric
   uint16_t* r = ranks + static_cast<size_t>(l) * n;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    r[i] = static_cast<uint16_t>(rank_lookup_raw(lut, x[i], scale, bias) & 0xFFFFu);
+    r[i] = static_cast<uint16_t>((PWL ? rank_pwl_raw(lut, x[i], scale, bias) : rank_lookup_raw(lut, x[i], scale, bias)) &
+                                 0xFFFFu);
 }
 
 }  // namespace mdg

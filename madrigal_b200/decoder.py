@@ -51,26 +51,39 @@ class RankTable:
     `thresholds[l]` is what `np.searchsorted(..., side='right')` must be run against to reproduce the ranks.
     """
 
-    def __init__(self, quantiles: torch.Tensor):
+    def __init__(self, quantiles: torch.Tensor, kind: str = "lut"):
+        """kind='lut': exact bucket LUT (thresholds move by <= ~3 grid cells).  kind='pwl': 256-bin histogram CDF with
+        linear interpolation, conflict-free in shared memory (faster epilogue); `max_rank_deviation[l]` then reports how
+        many ranks the table is away from the supplied quantiles at worst."""
         q = _require_cuda_f32(quantiles, "quantiles")
         if q.dim() != 2:
             raise ValueError("quantiles must be [L, Q]")
+        if kind not in _lib.MDG_RANK_KIND:
+            raise ValueError(f"kind={kind!r} (supported: {sorted(_lib.MDG_RANK_KIND)})")
         L, Q = q.shape
         if Q > _lib.MDG_RANK_MAX_Q:
             raise ValueError(f"Q={Q} exceeds {_lib.MDG_RANK_MAX_Q}")
-        self.L, self.Q = L, Q
+        self.L, self.Q, self.kind = L, Q, kind
         self.thresholds = torch.empty_like(q)
         self.lut = torch.empty((L, _lib.MDG_RANK_LUT_ENTRIES), dtype=torch.int32, device=q.device)
         self.affine = torch.empty((L, 2), dtype=torch.float32, device=q.device)
+        self.max_rank_deviation = None
         with torch.cuda.device(q.device):
-            _lib.check(_lib.lib().mdg_rank_table_build(q.data_ptr(), L, Q, self.thresholds.data_ptr(),
-                                                       self.lut.data_ptr(), self.affine.data_ptr(),
-                                                       _stream_ptr(q.device)), "mdg_rank_table_build")
+            if kind == "pwl":
+                self.max_rank_deviation = torch.empty((L,), dtype=torch.float32, device=q.device)
+                _lib.check(_lib.lib().mdg_rank_table_build_pwl(q.data_ptr(), L, Q, self.thresholds.data_ptr(),
+                                                               self.lut.data_ptr(), self.affine.data_ptr(),
+                                                               self.max_rank_deviation.data_ptr(),
+                                                               _stream_ptr(q.device)), "mdg_rank_table_build_pwl")
+            else:
+                _lib.check(_lib.lib().mdg_rank_table_build(q.data_ptr(), L, Q, self.thresholds.data_ptr(),
+                                                           self.lut.data_ptr(), self.affine.data_ptr(),
+                                                           _stream_ptr(q.device)), "mdg_rank_table_build")
 
     def struct(self, l0: int = 0, l1: Optional[int] = None) -> MdgRankTable:
         l1 = self.L if l1 is None else l1
         return MdgRankTable(self.thresholds[l0:l1].data_ptr(), self.lut[l0:l1].data_ptr(),
-                            self.affine[l0:l1].data_ptr(), l1 - l0, self.Q)
+                            self.affine[l0:l1].data_ptr(), l1 - l0, self.Q, _lib.MDG_RANK_KIND[self.kind])
 
     def lookup(self, logits: torch.Tensor) -> torch.Tensor:
         """ranks[l, ...] = searchsorted(thresholds[l], logits[l, ...], 'right') for materialised logits."""

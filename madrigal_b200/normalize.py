@@ -73,8 +73,8 @@ def build_reference_quantiles(z: torch.Tensor, weight: torch.Tensor, Q: int, *, 
     return out
 
 
-def build_rank_table(z: torch.Tensor, weight: torch.Tensor, Q: int = 16384, **kw) -> RankTable:
-    return RankTable(build_reference_quantiles(z, weight, Q, **kw))
+def build_rank_table(z: torch.Tensor, weight: torch.Tensor, Q: int = 16384, kind: str = "lut", **kw) -> RankTable:
+    return RankTable(build_reference_quantiles(z, weight, Q, **kw), kind=kind)
 
 
 def ranks_to_normalized(ranks_u16: torch.Tensor, Q: int) -> torch.Tensor:

@@ -259,3 +259,48 @@ def test_symmetric_rank_mode_is_the_normaliser_layout(mb, cuda_device, N, D, L, 
     expect = (low + low.swapaxes(1, 2)).astype(np.uint16)
     assert np.array_equal(got, expect)
     assert (np.diagonal(got, axis1=1, axis2=2) == 0).all() and np.array_equal(got, got.swapaxes(1, 2))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Histogram-CDF rank table (MDG_RANK_PWL): same contract as the exact LUT — the fused epilogue, the stand-alone lookup
+# and np.searchsorted(table.thresholds) agree bit for bit — plus a bound on how far the table sits from the quantiles
+# it was built from.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,D,L,Q,prec,symmetric", [(192, 128, 2, 1024, "bf16", False), (513, 256, 3, 16384, "bf16", True),
+                                                    (64, 64, 2, 2016, "fp32", False), (1000, 256, 2, 16384, "bf16", True),
+                                                    (150, 128, 1, 65535 // 8, "bf16", False)])
+def test_pwl_rank_table_is_bit_exact_searchsorted(mb, cuda_device, N, D, L, Q, prec, symmetric):
+    z, W = synth.decoder_inputs(N, D, L, seed=N + 3)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    logits = mb.pair_score(zt, zt, Wt, precision=prec, out="logit")
+    lg = logits.cpu().numpy()
+    M = N * (N - 1) // 2
+    quant = oracle.reference_quantiles(lg, min(Q, M))
+    table = mb.RankTable(gpu(quant, cuda_device), kind="pwl")
+    thr = table.thresholds.cpu().numpy()
+    assert (np.diff(thr, axis=1) >= 0).all()
+    ref = oracle.quantile_rank(thr, lg, "right")
+    assert np.array_equal(table.lookup(logits).cpu().numpy(), ref)
+    fused = mb.pair_score(zt, zt, Wt, precision=prec, out="rank", table=table, symmetric=symmetric).cpu().numpy()
+    if symmetric:
+        low = np.tril(ref.astype(np.int64), -1)
+        ref = (low + low.swapaxes(1, 2)).astype(np.uint16)
+    assert fused.dtype == np.uint16 and np.array_equal(fused, ref)
+    # distance from the supplied order statistics, in ranks: reported by the builder, and checked independently
+    dev = table.max_rank_deviation.cpu().numpy()
+    exact = oracle.quantile_rank(quant, quant, "right").astype(np.int64)      # rank of each quantile in its own table
+    got = oracle.quantile_rank(thr, quant, "right").astype(np.int64)
+    assert np.abs(got - exact).max(axis=1).tolist() == dev.tolist()
+    # a 256-bin histogram resolves the CDF to (bin mass) / 2 at worst; for these near-Gaussian scores far less
+    assert dev.max() <= max(4.0, 0.004 * quant.shape[1])
+
+
+def test_pwl_rank_edge_values(mb, cuda_device):
+    q = torch.linspace(-1, 1, 1000, device=cuda_device)[None, :].contiguous()
+    table = mb.RankTable(q, kind="pwl")
+    x = torch.tensor([[-1e30, -1.5, -1.0, 0.0, 1.0, 1.5, 1e30, 3.4e38, -3.4e38]], device=cuda_device)
+    got = table.lookup(x).cpu().numpy()
+    ref = oracle.quantile_rank(table.thresholds.cpu().numpy(), x.cpu().numpy(), "right")
+    assert np.array_equal(got, ref)
+    assert got[0, 0] == 0 and got[0, 6] == 1000
+    assert table.max_rank_deviation.item() <= 2.0   # uniform quantiles: the CDF IS piecewise linear (+ integer floors)

@@ -10,7 +10,9 @@ dev = torch.device("cuda:0")
 N, D, L = int(os.environ.get("N", 4096)), int(os.environ.get("D", 256)), int(os.environ.get("L", 86))
 z, W = decoder_inputs(N, D, L, 0)
 zt, Wt = torch.from_numpy(z).to(dev), torch.from_numpy(W).to(dev)
-table = normalize.build_rank_table(zt, Wt, 16384, panel=1024, precision="bf16")
+kind = os.environ.get("KIND", "lut")
+table = normalize.build_rank_table(zt, Wt, 16384, kind=kind, panel=2048, precision="bf16")
+if kind == "pwl": print("max rank deviation per outcome: max", table.max_rank_deviation.max().item(), "mean", table.max_rank_deviation.mean().item())
 out = torch.empty((L, N, N), dtype=torch.uint16, device=dev)
 sym = os.environ.get("SYM", "1") == "1"
 fn = lambda: mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, out_tensor=out, symmetric=sym)
@@ -22,5 +24,5 @@ torch.cuda.synchronize()
 buf = (ctypes.c_float * 256)(); n = _lib.lib().mdg_profile_read(buf, 256)
 ms = np.array(buf[:n])
 chk = int(out.view(torch.int16).to(torch.int64).sum().item())
-print(f"mode={os.environ.get('MDG_MIRROR_MODE','1')} sym={sym} N={N} D={D} L={L}: kernel {ms.mean():.4f} ms (min {ms.min():.4f}) -> "
+print(f"kind={kind} sym={sym} N={N} D={D} L={L}: kernel {ms.mean():.4f} ms (min {ms.min():.4f}) -> "
       f"{2.0*L*N*N/ms.mean()/1e6:.0f} GB/s out, checksum {chk}")
