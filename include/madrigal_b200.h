@@ -160,6 +160,36 @@ int mdg_pair_topk(const float* z_rows, const float* z_cols, const float* W, int6
                   int32_t cap, float* scores_out, int32_t* rows_out, int32_t* cols_out, int32_t* status_out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Scores of a LIST of triples without the dense tensor  (reference: `pred = sigmoid(model(...))` followed by
+ * `pred[ddi_labels, head_idx, tail_idx]`, train_ddi_batch.py:285-286 and evaluate.py:191-195 — the reference
+ * materialises all of [L, Nh, Nt] and then gathers; data.py:938 explains why).
+ *   out[t] = z_rows[heads[t]] . W[labels[t]] . z_cols[tails[t]]      t < n     (sigmoid applied for MDG_OUT_SIGMOID_F32)
+ * GEMM 1 (z_rows . W_l for every outcome) runs on the tensor cores exactly as in mdg_pair_score; the N^2 GEMM is
+ * replaced by one dot product per listed triple.  labels/heads/tails: int32 device arrays; an out-of-range index
+ * yields NaN in out[t].  Workspace: mdg_pair_score_workspace_bytes(Nr, Nc, D, L, precision).
+ */
+int mdg_pair_score_gather(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
+                          int64_t L, int precision, int normalize_rows, const int32_t* labels, const int32_t* heads,
+                          const int32_t* tails, int64_t n, int out_mode, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/*
+ * Ensemble reductions over K same-shaped device tensors of n elements (K <= MDG_MAX_ENSEMBLE):
+ *   MDG_ENS_MEAN_F32        out = mean_k x_k                   (mean over checkpoints of sigmoid scores,
+ *                                                               madrigal/evaluate/predict.py:493, 612)
+ *   MDG_ENS_GMEAN_F32       out = exp(mean_k log x_k), fp32    (geometric mean of the checkpoints' normalised ranks,
+ *                                                               notebooks/generate_embeddings.ipynb cell 18:
+ *                                                               scipy.stats.mstats.gmean on float32)
+ *   MDG_ENS_GMEAN_RANK_U16  the same on uint16 quantile ranks scaled by rank_scale (= 1/Q); 0 stays 0.
+ * members_host: HOST array of K device pointers.  The reference then re-ranks the result with the same normaliser
+ * (ipynb cell 20): feed `out` to mdg_exact_rank.
+ */
+#define MDG_MAX_ENSEMBLE 16
+typedef enum MdgEnsembleMode { MDG_ENS_MEAN_F32 = 0, MDG_ENS_GMEAN_F32 = 1, MDG_ENS_GMEAN_RANK_U16 = 2 } MdgEnsembleMode;
+int mdg_ensemble_reduce(const void* const* members_host, int32_t K, int64_t n, int mode, float rank_scale, float* out,
+                        void* stream);
+
 /* Number of kernel launches the last successful mdg_pair_score call on this thread enqueued (for bench accounting). */
 int mdg_last_launch_count(void);
 

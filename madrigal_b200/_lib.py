@@ -18,6 +18,8 @@ MDG_PREC_BF16, MDG_PREC_FP32 = 0, 1
 MDG_OUT_LOGIT_F32, MDG_OUT_SIGMOID_F32, MDG_OUT_RANK_U16 = 0, 1, 2
 MDG_PAIRS_FULL, MDG_PAIRS_SYMMETRIC = 0, 1
 MDG_RANK_KIND = {"lut": 0, "pwl": 1}
+MDG_ENS_MEAN_F32, MDG_ENS_GMEAN_F32, MDG_ENS_GMEAN_RANK_U16 = 0, 1, 2
+MDG_MAX_ENSEMBLE = 16
 MDG_AGG = {"cls": 0, "x-attn": 1, "mean": 2, "max": 3}
 MDG_ACTN = {"relu": 0, "gelu": 1}
 
@@ -69,6 +71,10 @@ SIGNATURES = {
     "mdg_pair_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                               c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                               c_void_p]),
+    "mdg_pair_score_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
+    "mdg_ensemble_reduce": (c_int, [POINTER(c_void_p), c_int32, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "mdg_last_launch_count": (c_int, []),
     "mdg_profile_enable": (c_int, [c_int]),
     "mdg_profile_read": (c_int, [POINTER(c_float), c_int]),

@@ -294,12 +294,18 @@ struct TopkArgs {
   unsigned long long* cand;
   int cap;
 };
-constexpr int kOutTopk = 100;  // internal out_mode of mdg_pair_topk
+constexpr int kOutTopk = 100;    // internal out_mode of mdg_pair_topk
+constexpr int kOutGather = 101;  // internal out_mode of mdg_pair_score_gather
+struct GatherArgs {
+  const int32_t *labels, *heads, *tails;
+  int64_t n;
+  int sigmoid;
+};
 
 static int pair_score_impl(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
                            int64_t L, int precision, int out_mode, int pairs, int normalize_rows,
                            const MdgRankTable* table, void* out, void* workspace, size_t workspace_bytes,
-                           cudaStream_t stream, const TopkArgs* topk) {
+                           cudaStream_t stream, const TopkArgs* topk, const GatherArgs* gather = nullptr) {
   if (!z_rows || !z_cols || !W || (!out && out_mode != kOutTopk))
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: NULL pointer");
   if (Nr < 0 || Nc < 0 || L < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: negative size");
@@ -307,7 +313,7 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: D=%lld (supported: 64, 128, 192, 256)", (long long)D);
   if (precision != MDG_PREC_BF16 && precision != MDG_PREC_FP32)
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: precision=%d", precision);
-  if (out_mode != kOutTopk && (out_mode < MDG_OUT_LOGIT_F32 || out_mode > MDG_OUT_RANK_U16))
+  if (out_mode != kOutTopk && out_mode != kOutGather && (out_mode < MDG_OUT_LOGIT_F32 || out_mode > MDG_OUT_RANK_U16))
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: out_mode=%d", out_mode);
   if (pairs != MDG_PAIRS_FULL && out_mode != kOutTopk && out_mode != MDG_OUT_RANK_U16)
     return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: pairs=%d is implemented for the rank and top-k outputs only", pairs);
@@ -387,6 +393,16 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     p.out_batch_stride = ws.nr_pad * ka;
     rc = launch_pair_kernel(tmA, tmB, tmOut, p, mdg::EPI_BF16_SPLIT, stream);
     if (rc) return rc;
+  }
+  if (out_mode == kOutGather) {  // listed triples only: out[t] = Y[l_t, h_t, :] . zc[t_t, :]
+    const long long blocks = (gather->n + 7) / 8;
+    mdg::gather_dot_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        ws.y, ws.zc, ws.nr_pad, static_cast<int>(ka), static_cast<int>(D), split, static_cast<int>(L),
+        static_cast<int>(Nr), static_cast<int>(Nc), gather->labels, gather->heads, gather->tails, gather->n,
+        gather->sigmoid, static_cast<float*>(out));
+    MDG_CUDA(cudaGetLastError());
+    ++g_last_launches;
+    return MDG_OK;
   }
   // ---- GEMM 2:  S[l] = Y[l] . z_cols^T    A = y [L, nr_pad, ka], B = zc [1, nc_pad, ka], out [L, Nr, Nc]
   {
@@ -475,6 +491,49 @@ int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int
   if (out_mode == kOutTopk) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: out_mode=%d", out_mode);
   return pair_score_impl(z_rows, z_cols, W, Nr, Nc, D, L, precision, out_mode, pairs, normalize_rows, table, out,
                          workspace, workspace_bytes, static_cast<cudaStream_t>(stream_v), nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------ triple gather
+int mdg_pair_score_gather(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
+                          int64_t L, int precision, int normalize_rows, const int32_t* labels, const int32_t* heads,
+                          const int32_t* tails, int64_t n, int out_mode, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream_v) {
+  g_last_launches = 0;
+  if (n < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score_gather: n=%lld", (long long)n);
+  if (out_mode != MDG_OUT_LOGIT_F32 && out_mode != MDG_OUT_SIGMOID_F32)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score_gather: out_mode=%d (logit or sigmoid)", out_mode);
+  if (n == 0) return MDG_OK;
+  if (!labels || !heads || !tails || !out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score_gather: NULL pointer");
+  if (n > (1LL << 34)) return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score_gather: too many triples");
+  if (Nr == 0 || Nc == 0 || L == 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score_gather: triples over an empty tensor");
+  GatherArgs g{labels, heads, tails, n, out_mode == MDG_OUT_SIGMOID_F32};
+  return pair_score_impl(z_rows, z_cols, W, Nr, Nc, D, L, precision, kOutGather, MDG_PAIRS_FULL, normalize_rows, nullptr,
+                         out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream_v), nullptr, &g);
+}
+
+// ------------------------------------------------------------------------------------------------ ensembles
+int mdg_ensemble_reduce(const void* const* members_host, int32_t K, int64_t n, int mode, float rank_scale, float* out,
+                        void* stream_v) {
+  if (!members_host || !out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_ensemble_reduce: NULL pointer");
+  if (K < 1 || K > MDG_MAX_ENSEMBLE) return fail(MDG_ERR_UNSUPPORTED, "mdg_ensemble_reduce: K=%d (1..%d)", K, MDG_MAX_ENSEMBLE);
+  if (n < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_ensemble_reduce: n < 0");
+  if (mode < MDG_ENS_MEAN_F32 || mode > MDG_ENS_GMEAN_RANK_U16)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_ensemble_reduce: mode=%d", mode);
+  if (n == 0) return MDG_OK;
+  mdg::EnsemblePtrs ptrs;
+  for (int k = 0; k < 16; ++k) ptrs.p[k] = k < K ? members_host[k] : nullptr;
+  for (int k = 0; k < K; ++k)
+    if (!ptrs.p[k]) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_ensemble_reduce: member %d is NULL", k);
+  long long blocks = (n + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const unsigned g = static_cast<unsigned>(blocks);
+  if (mode == MDG_ENS_MEAN_F32) mdg::ensemble_reduce_kernel<0><<<g, 256, 0, stream>>>(ptrs, K, n, rank_scale, out);
+  else if (mode == MDG_ENS_GMEAN_F32) mdg::ensemble_reduce_kernel<1><<<g, 256, 0, stream>>>(ptrs, K, n, rank_scale, out);
+  else mdg::ensemble_reduce_kernel<2><<<g, 256, 0, stream>>>(ptrs, K, n, rank_scale, out);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ top-k output

@@ -780,6 +780,78 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------ triple gather
+// Scores of a LIST of (outcome, head, tail) triples without the dense [L, Nh, Nt] tensor (reference: the full forward
+// followed by pred[labels, heads, tails], train_ddi_batch.py:285-286, evaluate.py:191-195):
+//   out[t] = Y[l_t, h_t, :] . z_cols[t_t, :]   with Y = z_rows . W_l from GEMM 1 (bf16 operand rows, [hi | lo] in the
+// fp32-parity mode) and z_cols in the same operand format.  One warp per triple, 16-byte loads, shuffle reduction.
+__global__ void __launch_bounds__(256) gather_dot_kernel(const __nv_bfloat16* __restrict__ y,
+                                                         const __nv_bfloat16* __restrict__ zc, long long nr_pad,
+                                                         int ka, int D, int split, int L, int Nr, int Nc,
+                                                         const int* __restrict__ labels, const int* __restrict__ heads,
+                                                         const int* __restrict__ tails, long long n, int sigmoid,
+                                                         float* __restrict__ out) {
+  const long long t = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= n) return;
+  const int lane = threadIdx.x & 31;
+  const int l = labels[t], h = heads[t], c = tails[t];
+  if (l < 0 || l >= L || h < 0 || h >= Nr || c < 0 || c >= Nc) {  // out-of-range index: poison, do not touch memory
+    if (lane == 0) out[t] = __uint_as_float(0x7fc00000u);
+    return;
+  }
+  const uint4* yr = reinterpret_cast<const uint4*>(y + (static_cast<long long>(l) * nr_pad + h) * ka);
+  const uint4* zr = reinterpret_cast<const uint4*>(zc + static_cast<long long>(c) * ka);
+  float acc = 0.f;
+  for (int k8 = lane; k8 < D / 8; k8 += 32) {  // 8 bf16 per 16-byte load; D is a multiple of 64
+    const uint4 a = yr[k8], b = zr[k8];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    float alo[8] = {0, 0, 0, 0, 0, 0, 0, 0}, blo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (split) {
+      const uint4 a2 = yr[D / 8 + k8], b2 = zr[D / 8 + k8];
+      const uint32_t aw2[4] = {a2.x, a2.y, a2.z, a2.w}, bw2[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw2[i]));
+        const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw2[i]));
+        alo[2 * i] = p.x; alo[2 * i + 1] = p.y; blo[2 * i] = q.x; blo[2 * i + 1] = q.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
+      const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[i]));
+      acc = fmaf(p.x + alo[2 * i], q.x + blo[2 * i], acc);
+      acc = fmaf(p.y + alo[2 * i + 1], q.y + blo[2 * i + 1], acc);
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) out[t] = sigmoid ? 1.0f / (1.0f + expf(-acc)) : acc;
+}
+
+// Ensemble reductions over K same-shaped tensors (reference: mean over checkpoints of sigmoid scores,
+// predict.py:493, 612; geometric mean of the checkpoints' normalised ranks, generate_embeddings.ipynb cell 18 =
+// scipy.stats.mstats.gmean = exp(mean(log x)) in the input's float32).
+struct EnsemblePtrs {
+  const void* p[16];
+};
+template <int MODE>  // 0: mean of fp32, 1: gmean of fp32, 2: gmean of uint16 ranks * scale
+__global__ void __launch_bounds__(256) ensemble_reduce_kernel(EnsemblePtrs in, int K, long long n, float scale,
+                                                              float* __restrict__ out) {
+  const float invk = 1.0f / static_cast<float>(K);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      float x;
+      if (MODE == 2) x = static_cast<float>(static_cast<const uint16_t*>(in.p[k])[i]) * scale;
+      else x = static_cast<const float*>(in.p[k])[i];
+      acc += (MODE == 0) ? x : logf(x);
+    }
+    out[i] = (MODE == 0) ? acc * invk : expf(acc * invk);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ operand prep
 // z [N, D] fp32 -> bf16 [Npad, Ka]  with Ka = D (hi only) or 2D ([hi | lo]); rows >= N are zero.
 // Optional row L2 normalisation (F.normalize: x / max(||x||_2, 1e-12), models.py:947-949).  One warp per row.

@@ -145,6 +145,66 @@ def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight: torch.Tensor,
     return out_tensor
 
 
+def pair_score_gather(z_rows: torch.Tensor, z_cols: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor,
+                      heads: torch.Tensor, tails: torch.Tensor, *, precision: str = "fp32", out: str = "logit",
+                      normalize: bool = False) -> torch.Tensor:
+    """Scores of the listed (label, head, tail) triples only:  out[t] = z_rows[heads[t]] . W[labels[t]] . z_cols[tails[t]].
+
+    What the reference computes as `model(...)[ddi_labels, head_idx, tail_idx]` (train_ddi_batch.py:285-286,
+    evaluate.py:191-195) after materialising the whole [L, Nh, Nt] tensor; here the N^2 GEMM never runs
+    (mdg_pair_score_gather).  out='logit' | 'sigmoid'."""
+    zr = _require_cuda_f32(z_rows, "z_rows")
+    zc = zr if z_cols is z_rows else _require_cuda_f32(z_cols, "z_cols")
+    W = _require_cuda_f32(weight, "weight")
+    if out not in ("logit", "sigmoid"):
+        raise ValueError("out must be 'logit' or 'sigmoid'")
+    idx = []
+    for name, t in (("labels", labels), ("heads", heads), ("tails", tails)):
+        if not t.is_cuda:
+            raise RuntimeError(f"madrigal_b200: `{name}` must be a CUDA tensor (no CPU path exists)")
+        idx.append(t.to(torch.int32).contiguous().reshape(-1))
+    n = idx[0].numel()
+    if idx[1].numel() != n or idx[2].numel() != n:
+        raise ValueError("labels, heads and tails must have the same length")
+    Nr, D = zr.shape
+    Nc, L = zc.shape[0], W.shape[0]
+    res = torch.empty((n,), dtype=torch.float32, device=zr.device)
+    prec = _PRECISION[precision]
+    fn = _lib.lib()
+    ws = _workspace(zr.device, fn.mdg_pair_score_workspace_bytes(Nr, Nc, D, L, prec))
+    with torch.cuda.device(zr.device):
+        _lib.check(fn.mdg_pair_score_gather(zr.data_ptr(), zc.data_ptr(), W.data_ptr(), Nr, Nc, D, L, prec,
+                                            int(bool(normalize)), idx[0].data_ptr(), idx[1].data_ptr(),
+                                            idx[2].data_ptr(), n, _OUT[out][0], res.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), _stream_ptr(zr.device)), "mdg_pair_score_gather")
+    return res
+
+
+def ensemble_reduce(members, mode: str = "mean", rank_scale: float = 1.0) -> torch.Tensor:
+    """mean / geometric mean over K same-shaped CUDA tensors (mdg_ensemble_reduce).  mode: 'mean' (fp32),
+    'gmean' (fp32, scipy.stats.mstats.gmean semantics), 'gmean_rank' (uint16 quantile ranks * rank_scale)."""
+    modes = {"mean": (_lib.MDG_ENS_MEAN_F32, torch.float32), "gmean": (_lib.MDG_ENS_GMEAN_F32, torch.float32),
+             "gmean_rank": (_lib.MDG_ENS_GMEAN_RANK_U16, torch.uint16)}
+    if mode not in modes:
+        raise ValueError(f"mode={mode!r}")
+    code, dtype = modes[mode]
+    members = list(members)
+    if not 1 <= len(members) <= _lib.MDG_MAX_ENSEMBLE:
+        raise ValueError(f"need 1..{_lib.MDG_MAX_ENSEMBLE} members")
+    first = members[0]
+    ms = []
+    for m in members:
+        if not m.is_cuda or m.dtype != dtype or m.shape != first.shape or m.device != first.device:
+            raise RuntimeError(f"madrigal_b200: ensemble members must be same-shape {dtype} CUDA tensors on one device")
+        ms.append(m.contiguous())
+    out = torch.empty(first.shape, dtype=torch.float32, device=first.device)
+    ptrs = (ctypes.c_void_p * len(ms))(*[m.data_ptr() for m in ms])
+    with torch.cuda.device(first.device):
+        _lib.check(_lib.lib().mdg_ensemble_reduce(ptrs, len(ms), first.numel(), code, float(rank_scale),
+                                                  out.data_ptr(), _stream_ptr(first.device)), "mdg_ensemble_reduce")
+    return out
+
+
 class Symmetric(nn.Module):
     """Parametrisation making each W_l exactly symmetric from its upper triangle (models.py:522-524)."""
 

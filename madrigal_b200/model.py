@@ -4,7 +4,7 @@ from typing import Optional, Tuple
 import torch
 import torch.nn as nn
 
-from .decoder import BilinearDDIScorer, Symmetric, pair_score
+from .decoder import BilinearDDIScorer, Symmetric, pair_score, pair_score_gather
 
 
 class NovelDDIMultilabel(nn.Module):
@@ -39,6 +39,19 @@ class NovelDDIMultilabel(nn.Module):
         # F.normalize of both embedding tables (models.py:947-949) is fused into the decoder's operand preparation
         return pair_score(z_head, z_tail, weight, precision=self.decoder.precision, out="logit",
                           normalize=bool(self.normalize))
+
+
+    def forward_triples(self, batch_head, batch_tail, batch_head_mod_masks, batch_tail_mod_masks, batch_kg, ddi_labels,
+                        head_idx, tail_idx, sigmoid: bool = True):
+        """`sigmoid(model(...))[ddi_labels, head_idx, tail_idx]` (train_ddi_batch.py:285-286, evaluate.py:191-195)
+        without the dense [L, Nh, Nt] tensor the reference materialises first."""
+        z_head = self.encoder(batch_head['drugs'], batch_head_mod_masks, batch_head['strs'], batch_kg,
+                              batch_head['cv'], batch_head['tx'])
+        z_tail = self.encoder(batch_tail['drugs'], batch_tail_mod_masks, batch_tail['strs'], batch_kg,
+                              batch_tail['cv'], batch_tail['tx'])
+        return pair_score_gather(z_head, z_tail, self.decoder.weight, ddi_labels, head_idx, tail_idx,
+                                 precision=self.decoder.precision, out="sigmoid" if sigmoid else "logit",
+                                 normalize=bool(self.normalize))
 
 
 class PrecomputedEmbeddingEncoder(nn.Module):

@@ -16,7 +16,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .decoder import RankTable, _require_cuda_f32, _stream_ptr, _workspace, pair_score
+from .decoder import RankTable, _require_cuda_f32, _stream_ptr, _workspace, ensemble_reduce, pair_score
 
 
 def exact_normalized_ranks(scores: torch.Tensor) -> torch.Tensor:
@@ -80,3 +80,21 @@ def build_rank_table(z: torch.Tensor, weight: torch.Tensor, Q: int = 16384, kind
 def ranks_to_normalized(ranks_u16: torch.Tensor, Q: int) -> torch.Tensor:
     """uint16 quantile ranks -> the reference's (0, 1] normalised-rank scale (|error| <= 1/Q + snapping)."""
     return ranks_u16.to(torch.float32) / float(Q)
+
+
+def gmean_normalized_ranks(members, Q: Optional[int] = None) -> torch.Tensor:
+    """Geometric mean over checkpoints of their normalised-rank tensors (generate_embeddings.ipynb cell 18:
+    scipy.stats.mstats.gmean over the stacked float32 tensors).  members: K fp32 [L, N, N] tensors, or K uint16
+    fused-rank tensors with their table size Q (ranks are scaled by 1/Q first)."""
+    members = list(members)
+    if members[0].dtype == torch.uint16:
+        if not Q:
+            raise ValueError("uint16 rank members need Q")
+        return ensemble_reduce(members, "gmean_rank", 1.0 / float(Q))
+    return ensemble_reduce(members, "gmean")
+
+
+def ensemble_normalized_ranks(members, Q: Optional[int] = None) -> torch.Tensor:
+    """The reference's final ensemble tensor (ipynb cells 18 + 20): gmean of the checkpoints' normalised ranks,
+    re-normalised with the same in-sample rank (`run_slice` again)."""
+    return exact_normalized_ranks(gmean_normalized_ranks(members, Q))

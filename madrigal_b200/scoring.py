@@ -108,8 +108,7 @@ def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
 def ensemble_mean_sigmoid(z_list, weight_list, *, precision: str = "bf16",
                           label_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """predict.py:493, 612: mean over checkpoints of sigmoid(raw scores), per checkpoint's (z, W)."""
-    acc = None
-    for z, W in zip(z_list, weight_list):
-        s = score_all_pairs(z, W, out="sigmoid", precision=precision, label_range=label_range)
-        acc = s if acc is None else acc.add_(s)
-    return acc.div_(len(z_list))
+    from .decoder import ensemble_reduce
+    members = [score_all_pairs(z, W, out="sigmoid", precision=precision, label_range=label_range)
+               for z, W in zip(z_list, weight_list)]
+    return ensemble_reduce(members, "mean")

@@ -137,6 +137,26 @@ def ensemble_mean_sigmoid(logits_per_ckpt: Sequence[np.ndarray]) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------------- fusion transformer (a-1)
+def gmean_normalized_ranks(members: Sequence[np.ndarray]) -> np.ndarray:
+    """Geometric mean of the checkpoints' normalised-rank tensors (notebooks/generate_embeddings.ipynb cell 18:
+    `gmean(np.stack([...], axis=-1), axis=-1)` with scipy.stats.mstats.gmean = exp(mean(log a)) in the input's
+    float32; zeros (the diagonal) give log = -inf and a result of 0)."""
+    a = np.stack([np.asarray(m, F32) for m in members], axis=-1)
+    with np.errstate(divide="ignore"):
+        log_a = np.log(a)
+    return np.exp(log_a.mean(axis=-1)).astype(F32)
+
+
+def ensemble_normalized_ranks(members: Sequence[np.ndarray], kind: Optional[str] = None) -> np.ndarray:
+    """ipynb cells 18 + 20: gmean of the normalised ranks, then the same run_slice re-normalisation."""
+    return normalize_scores(gmean_normalized_ranks(members), kind=kind)
+
+
+def gather_triples(scores: np.ndarray, labels: np.ndarray, heads: np.ndarray, tails: np.ndarray) -> np.ndarray:
+    """`pred[ddi_labels, head_idx, tail_idx]` (train_ddi_batch.py:286, evaluate.py:195) on a dense [L, Nh, Nt] array."""
+    return scores[labels, heads, tails]
+
+
 def _layer_norm(x, w, b, eps=1e-5):
     """F.layer_norm over the last dim (biased variance, eps 1e-5 = nn.LayerNorm default; models.py:366, 372-373)."""
     mu = x.mean(axis=-1, keepdims=True)

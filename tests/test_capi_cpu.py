@@ -32,7 +32,7 @@ def test_header_symbols_all_exported(handle):
 
 
 def test_abi_version_and_error_string(handle):
-    assert handle.mdg_abi_version() == 1
+    assert handle.mdg_abi_version() == 2
     assert isinstance(handle.mdg_last_error(), bytes)
 
 

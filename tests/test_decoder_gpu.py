@@ -304,3 +304,30 @@ def test_pwl_rank_edge_values(mb, cuda_device):
     assert np.array_equal(got, ref)
     assert got[0, 0] == 0 and got[0, 6] == 1000
     assert table.max_rank_deviation.item() <= 2.0   # uniform quantiles: the CDF IS piecewise linear (+ integer floors)
+
+
+@pytest.mark.parametrize("N1,N2,D,L,n,prec", [(200, 150, 128, 7, 5000, "fp32"), (513, 513, 256, 3, 20000, "bf16"),
+                                              (64, 64, 64, 2, 1, "fp32")])
+def test_triple_gather_matches_dense_then_index(mb, cuda_device, N1, N2, D, L, n, prec):
+    """mdg_pair_score_gather == the reference's model(...)[labels, heads, tails] (train_ddi_batch.py:285-286)."""
+    z1, W = synth.decoder_inputs(N1, D, L, seed=5)
+    z2, _ = synth.decoder_inputs(N2, D, 1, seed=6)
+    rng = np.random.default_rng(n)
+    lab, hd, tl = rng.integers(0, L, n), rng.integers(0, N1, n), rng.integers(0, N2, n)
+    dev = lambda a: torch.from_numpy(a.astype(np.int64)).to(cuda_device)   # the reference indexes with int64 tensors
+    z1t, z2t, Wt = gpu(z1, cuda_device), gpu(z2, cuda_device), gpu(W, cuda_device)
+    got = mb.pair_score_gather(z1t, z2t, Wt, dev(lab), dev(hd), dev(tl), precision=prec).cpu().numpy()
+    ref = oracle.gather_triples(oracle.bilinear_scores(z1, z2, W, dtype=np.float64), lab, hd, tl)
+    tol = 1e-3 if prec == "fp32" else 1e-2
+    scale = np.maximum(np.abs(ref), np.sqrt(np.mean(ref ** 2))) if prec == "fp32" else np.abs(ref).max()
+    assert (np.abs(got - ref) <= tol * scale).all()
+    # same operand rounding as the dense path: differs from it only by summation order
+    dense = mb.pair_score(z1t, z2t, Wt, precision=prec, out="logit").cpu().numpy()[lab, hd, tl]
+    assert np.abs(got - dense).max() <= 2e-5 * np.abs(ref).max() + (0 if prec == "bf16" else 1e-4 * np.abs(ref).max())
+    sg = mb.pair_score_gather(z1t, z2t, Wt, dev(lab), dev(hd), dev(tl), precision=prec, out="sigmoid").cpu().numpy()
+    assert np.abs(sg - oracle.sigmoid(got.astype(np.float64))).max() <= 1e-6
+    # out-of-range indices poison the entry instead of reading out of bounds
+    bad = mb.pair_score_gather(z1t, z2t, Wt, dev(np.array([L])), dev(np.array([0])), dev(np.array([0])), precision=prec)
+    assert torch.isnan(bad).all()
+    empty = mb.pair_score_gather(z1t, z2t, Wt, dev(lab[:0]), dev(hd[:0]), dev(tl[:0]), precision=prec)
+    assert empty.shape == (0,)

@@ -77,3 +77,41 @@ def test_fused_quantile_rank_tracks_exact_rank_within_one_over_q(norm, cuda_devi
     i, j = np.tril_indices(N, -1)
     for l in range(L):
         assert np.abs(fused[l][i, j] - exact[l][i, j]).max() <= 1.0 / Q + 4.0 / 131072 + 1e-7
+
+
+def test_gmean_ensemble_and_rerank_vs_oracle(norm, cuda_device):
+    """generate_embeddings.ipynb cells 18 + 20: geometric mean of 5 checkpoints' normalised ranks, then run_slice again."""
+    rng = np.random.default_rng(9)
+    K, L, N = 5, 2, 120
+    members = [oracle.normalize_scores(rng.standard_normal((L, N, N)).astype(np.float32)) for _ in range(K)]
+    g_ref = oracle.gmean_normalized_ranks(members)
+    dev_members = [torch.from_numpy(m).to(cuda_device) for m in members]
+    g = norm.gmean_normalized_ranks(dev_members).cpu().numpy()
+    assert (np.diagonal(g, axis1=1, axis2=2) == 0).all()                       # log(0) = -inf -> exp = 0, as scipy
+    assert np.abs(g - g_ref).max() <= 4e-6 * g_ref.max()                        # logf/expf vs numpy's float32 log/exp
+    # re-normalisation: bit-identical to the reference normaliser applied to the SAME gmean values (stable ties)
+    final = norm.ensemble_normalized_ranks(dev_members).cpu().numpy()
+    assert np.array_equal(final, oracle.normalize_scores(g, kind="stable"))
+    # and within one rank step of the all-numpy chain wherever its gmean values are not nearly tied
+    ref_final = oracle.ensemble_normalized_ranks(members, kind="stable")
+    M = N * (N - 1) // 2
+    assert np.abs(final - ref_final).max() <= 3.0 / M
+    # uint16 fused-rank members: gmean of rank / Q
+    Q = 4096
+    ranks = [torch.from_numpy(rng.integers(0, Q + 1, size=(L, N, N)).astype(np.uint16)).to(cuda_device) for _ in range(3)]
+    gu = norm.gmean_normalized_ranks(ranks, Q).cpu().numpy()
+    ref_u = oracle.gmean_normalized_ranks([r.cpu().numpy().astype(np.float32) * np.float32(1.0 / Q) for r in ranks])
+    assert np.abs(gu - ref_u).max() <= 4e-6
+
+
+def test_mean_sigmoid_ensemble_vs_oracle(norm, cuda_device):
+    import madrigal_b200 as mb
+    from madrigal_b200 import scoring
+    import synth
+    zs, Ws, lgs = [], [], []
+    for k in range(3):
+        z, W = synth.decoder_inputs(96, 64, 4, seed=40 + k)
+        zs.append(torch.from_numpy(z).to(cuda_device)); Ws.append(torch.from_numpy(W).to(cuda_device))
+        lgs.append(oracle.bilinear_scores(z, z, W, (1, 3)))
+    got = scoring.ensemble_mean_sigmoid(zs, Ws, precision="fp32", label_range=(1, 3)).cpu().numpy()
+    assert np.abs(got - oracle.ensemble_mean_sigmoid(lgs)).max() <= 2e-4
