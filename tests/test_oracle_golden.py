@@ -218,3 +218,16 @@ def test_encode_assembly_matches_reference(case):
         uni = embeds[~multi][np.arange((~multi).sum()), uni_idx]
         z[~multi] = oracle.mlp_adaptor(ops, uni)
     _close(z, ref, 3e-5)
+
+
+def test_gmean_restatement_matches_scipy_mstats():
+    """generate_embeddings.ipynb cell 18 calls scipy.stats.mstats.gmean on the stacked float32 rank tensors; the
+    oracle restates it as exp(mean(log a)).  scipy is importable here, so pin the restatement against the real call."""
+    from scipy.stats.mstats import gmean
+    rng = np.random.default_rng(3)
+    members = [oracle.normalize_scores(rng.standard_normal((2, 40, 40)).astype(np.float32)) for _ in range(5)]
+    with np.errstate(divide="ignore"):
+        ref = np.asarray(gmean(np.stack(members, axis=-1), axis=-1))
+    got = oracle.gmean_normalized_ranks(members)
+    assert got.dtype == np.float32 and np.allclose(got, ref, rtol=1e-6, atol=0)
+    assert (np.diagonal(got, axis1=1, axis2=2) == 0).all()

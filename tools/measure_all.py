@@ -1,0 +1,158 @@
+"""Round measurements beyond bench.py's single line: every output mode of the pair kernel, both rank-table kinds, the
+fused encoder at BASELINE config-5 shapes, and one GPU's slice of config 4 (20,000 drugs x 119 of 953 outcomes) with
+size-independent property checks.  Writes gpurun_out/measurements.json (copied to profiles/ by hand)."""
+import ctypes, json, os, sys, time
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import madrigal_b200 as mb
+from madrigal_b200 import normalize, _lib
+import synth
+from synth import decoder_inputs
+
+dev = torch.device("cuda:0")
+PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) \
+    else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+res = {"device": torch.cuda.get_device_name(0), "peaks": {k: PEAKS[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained")},
+       "pair_kernel": [], "encoder": [], "config4_slice": None}
+
+
+def kernel_ms(fn, iters=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    _lib.lib().mdg_profile_enable(iters)
+    for _ in range(iters): fn()
+    torch.cuda.synchronize()
+    buf = (ctypes.c_float * 256)(); n = _lib.lib().mdg_profile_read(buf, 256); _lib.lib().mdg_profile_enable(0)
+    return float(np.mean(buf[:n])), float(np.min(buf[:n]))
+
+
+def pair_case(N, D, L, mode, kind="lut", symmetric=False, precision="bf16"):
+    z, W = decoder_inputs(N, D, L, 0)
+    zt, Wt = torch.from_numpy(z).to(dev), torch.from_numpy(W).to(dev)
+    table = normalize.build_rank_table(zt, Wt, 16384, kind=kind, panel=2048, precision=precision) if mode in ("rank", "topk") else None
+    if mode == "topk":
+        k = 1000
+        M = N * (N - 1) // 2 if symmetric else N * N
+        qi = min(16383, max(0, int(16384 * (1.0 - 3.0 * k / M)) - 1))
+        thr = table.thresholds[:, qi].contiguous()
+        fn = lambda: mb.pair_topk(zt, zt, Wt, thr, k, cap=8192, symmetric=symmetric, precision=precision)
+        elem = 0
+    else:
+        out = torch.empty((L, N, N), dtype=torch.uint16 if mode == "rank" else torch.float32, device=dev)
+        fn = lambda: mb.pair_score(zt, zt, Wt, precision=precision, out=mode, table=table, out_tensor=out, symmetric=symmetric)
+        elem = 2 if mode == "rank" else 4
+    ms, best = kernel_ms(fn)
+    triples = L * N * N
+    flops = 2.0 * D * triples * (0.5 if symmetric else 1.0) * (3 if precision == "fp32" else 1)
+    rec = {"N": N, "D": D, "L": L, "mode": mode, "table": kind if table is not None else None, "symmetric": symmetric,
+           "precision": precision, "kernel_ms": ms, "kernel_ms_min": best, "triples_per_s": triples / ms * 1e3,
+           "tflops": flops / ms / 1e9, "out_gbs": elem * triples / ms / 1e6,
+           "frac_hbm": elem * triples / ms / 1e6 / PEAKS["hbm_gbs"], "frac_tensor_sustained": flops / ms / 1e9 / PEAKS["bf16_tflops_sustained"]}
+    if kind == "pwl" and table is not None:
+        rec["max_rank_deviation"] = float(table.max_rank_deviation.max().item())
+    res["pair_kernel"].append(rec)
+    print(rec, flush=True)
+    del table
+
+
+def enc_case(B, T, E, H, hd, F, agg, precision="bf16", iters=5):
+    cfg = dict(embed_dim=E, num_layers=2, num_heads=H, head_dim=hd, ffn_dim=F, actn="gelu", norm_first=True, agg=agg, nb=0)
+    enc = mb.TransformerFusion(E, 0, 2, H, hd, F, transformer_actn="gelu", transformer_norm_first=True,
+                               transformer_batch_first=False, transformer_agg=agg, precision=precision)
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in synth.fusion_state_dict(cfg, 1).items()})
+    if agg == "x-attn":
+        enc.x_attn_key_padding_mask = torch.zeros(1, T, dtype=torch.bool)
+    enc = enc.to(dev).eval()
+    tokens = torch.randn(B, T, E, device=dev)
+    mask = torch.rand(B, T, device=dev) < 0.5
+    mask[:, 0] = False
+    ts = []
+    with torch.no_grad():
+        for _ in range(2): enc(tokens, mask)
+        torch.cuda.synchronize()
+        for _ in range(iters):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); enc(tokens, mask); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
+    ms = float(np.median(ts))
+    Dl = H * hd
+    per_tok = 2 * (8 * Dl * Dl + 4 * Dl * F) + 2 * E * Dl
+    pool = 4 * Dl * Dl * T + 2 * Dl * Dl + 2 * Dl * E if agg == "x-attn" else 2 * Dl * E * T
+    fl = (T * per_tok + pool) * B
+    hbm = (T * E * 4 + E * 4 + T) * B
+    rec = {"B": B, "T": T, "E": E, "Dl": Dl, "F": F, "agg": agg, "precision": precision, "ms": ms, "launches": enc.last_launch_count,
+           "drugs_per_s": B / ms * 1e3, "tflops": fl / ms / 1e9, "frac_tensor_sustained": fl / ms / 1e9 / PEAKS["bf16_tflops_sustained"],
+           "hbm_gbs": hbm / ms / 1e6, "frac_hbm": hbm / ms / 1e6 / PEAKS["hbm_gbs"]}
+    res["encoder"].append(rec)
+    print(rec, flush=True)
+
+
+def config4_slice():
+    """One GPU's share of BASELINE config 4: 20,000 drugs x 119 outcomes (953 / 8), uint16 ranks in the normaliser layout
+    (95 GB) + per-outcome top-1000.  Properties: symmetry, zero diagonal, rank histogram ~ uniform, top-k consistent."""
+    N, D, L, Q = 20000, 256, 119, 16384
+    z, W = decoder_inputs(N, D, L, 3)
+    zt, Wt = torch.from_numpy(z).to(dev), torch.from_numpy(W).to(dev)
+    table = normalize.build_rank_table(zt, Wt, Q, panel=2048, precision="bf16")
+    out = torch.empty((L, N, N), dtype=torch.uint16, device=dev)
+    fn = lambda: mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, out_tensor=out, symmetric=True)
+    ms, best = kernel_ms(fn, iters=3, warm=1)
+    rec = {"N": N, "D": D, "L": L, "rank_kernel_ms": ms, "triples_per_s": L * N * N / ms * 1e3, "out_gbs": 2.0 * L * N * N / ms / 1e6,
+           "out_bytes": 2 * L * N * N}
+    # properties on a few outcomes (whole-tensor transposes would double the footprint)
+    ok_sym, ok_diag = True, True
+    for l in (0, 57, L - 1):
+        a = out[l]
+        ok_sym &= bool(torch.equal(a[:4096, :4096], a[:4096, :4096].T)) and bool(torch.equal(a[15000:, :3000], a[:3000, 15000:].T))
+        ok_diag &= bool((torch.diagonal(a) == 0).all())
+    rec["symmetric"], rec["zero_diagonal"] = ok_sym, ok_diag
+    # ranks against the panel's quantiles should be ~uniform over [0, Q] for the whole catalogue (same distribution)
+    sample = out[3][1000:3000, :1000].to(torch.int32).flatten().float()
+    rec["rank_mean_over_Q"] = float(sample.mean().item() / Q)
+    # spot parity: a block of the dense fp32-logit path looked up through the same table
+    blk = mb.pair_score(zt[8000:8256], zt[100:356], Wt[5:6], precision="bf16", out="logit")
+    rec["block_matches_lookup"] = bool(torch.equal(table_lookup(table, blk, 5), out[5, 8000:8256, 100:356]))
+    del out
+    torch.cuda.empty_cache()
+    thr = table.thresholds[:, Q - 2].contiguous()   # ~1.2e-4 of 2e8 pairs = 24k candidates per outcome
+    t0 = time.perf_counter()
+    scores, rows, cols, status = mb.pair_topk(zt, zt, Wt, thr, 1000, cap=65536, symmetric=True, precision="bf16")
+    torch.cuda.synchronize()
+    tk_ms, _ = kernel_ms(lambda: mb.pair_topk(zt, zt, Wt, thr, 1000, cap=65536, symmetric=True, precision="bf16"), iters=3, warm=1)
+    rec["topk_kernel_ms"] = tk_ms
+    rec["topk_status_ok"] = int((status == 0).sum().item())
+    rec["topk_sorted_desc"] = bool((scores[:, 1:] <= scores[:, :-1]).all().item())
+    rec["topk_rows_gt_cols"] = bool((rows > cols).all().item())
+    res["config4_slice"] = rec
+    print(rec, flush=True)
+
+
+def table_lookup(table, logits, l):
+    sub = mb.RankTable.__new__(mb.RankTable)
+    sub.L, sub.Q, sub.kind = 1, table.Q, table.kind
+    sub.thresholds, sub.lut, sub.affine = table.thresholds[l:l + 1], table.lut[l:l + 1], table.affine[l:l + 1]
+    return sub.lookup(logits)[0]
+
+
+if __name__ == "__main__":
+    for kind in ("lut", "pwl"):
+        for sym in (True, False):
+            pair_case(4096, 256, 86, "rank", kind, sym)
+    pair_case(4096, 128, 86, "rank", "lut", True)
+    pair_case(4096, 128, 86, "rank", "pwl", True)
+    pair_case(8192, 256, 32, "rank", "lut", True)
+    pair_case(4096, 256, 86, "logit")
+    pair_case(4096, 256, 86, "sigmoid")
+    pair_case(4096, 256, 86, "logit", precision="fp32")
+    pair_case(4096, 256, 86, "topk", symmetric=False)
+    pair_case(4096, 256, 86, "topk", symmetric=True)
+    enc_case(4096, 4, 256, 8, 32, 512, "x-attn")
+    enc_case(1 << 20, 4, 128, 8, 32, 512, "mean", iters=3)
+    enc_case(1 << 20, 4, 256, 8, 32, 512, "x-attn", iters=3)
+    enc_case(1 << 18, 4, 128, 8, 64, 1024, "mean", iters=3)       # latent 512: multi-kernel path
+    enc_case(16384, 23, 128, 8, 64, 256, "x-attn", iters=3)        # production DrugBank shape: multi-kernel path
+    if "--no-config4" not in sys.argv:
+        config4_slice()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "measurements.json"), "w"), indent=1)
+    print("wrote gpurun_out/measurements.json")

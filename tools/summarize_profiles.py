@@ -29,10 +29,15 @@ def launch_list():
             pass
     # the last DEVICE-RESIDENT bench step: it ends with the full-size rank launch (the e2e steps that follow score the
     # outcomes in chunks of 10, so their rank launches are ~9x shorter) and starts with the encoder's token conversion
-    rank = [(i, d[1]) for i, d in enumerate(data) if "pair_score_kernel<2" in d[0].replace("(int)", "")]
+    def is_rank(name):
+        n = name.replace("(int)", "")
+        return any(f"pair_score_kernel<{e}," in n for e in (2, 6, 7, 8))
+    rank = [(i, d[1]) for i, d in enumerate(data) if is_rank(d[0])]
     longest = max(v for _, v in rank)
     rank_idx = max(i for i, v in rank if v > 0.5 * longest)
-    step_start = max(i for i, d in enumerate(data[:rank_idx]) if "convert_rows_kernel" in d[0])
+    starts = [i for i, d in enumerate(data[:rank_idx]) if "fused_encoder_kernel" in d[0]] or \
+             [i for i, d in enumerate(data[:rank_idx]) if "convert_rows_kernel" in d[0]]
+    step_start = max(starts)
     step = data[step_start:rank_idx + 1]
     total = sum(d[1] for d in step)
     with open(os.path.join(OUT, f"{ROUND}_bench_step_launches.csv"), "w") as f:
@@ -46,7 +51,7 @@ def launch_list():
     agg = collections.OrderedDict()
     for k, v, g, b in step:
         name = k.split("(")[0].replace("void ", "")
-        if "pair_score_kernel" in k:
+        if "pair_score_kernel" in k or "fused_encoder_kernel" in k:
             name = k.split("(CUtensorMap")[0].replace("void ", "").replace("(int)", "")
         agg.setdefault(name, [0, 0.0])
         agg[name][0] += 1
@@ -101,8 +106,12 @@ if __name__ == "__main__":
     shares = launch_list()
     if shares:
         summary["bench_step_shares"] = shares
-    cap = full_capture("prof_rank.ncu-rep", "pair_score_rank", "pair_score_kernel<EPI_RANK_U16, 16>")
-    if cap:
-        summary["pair_score_kernel"] = cap
-        print("rank kernel:", cap)
+    for rep, tag, key, name in (
+            ("prof_rank.ncu-rep", "pair_score_rank", "pair_score_kernel", "pair_score_kernel<EPI_RANK_U16_MIRROR, 16> (exact LUT table)"),
+            ("prof_pwl.ncu-rep", "pair_score_rank_pwl", "pair_score_kernel_pwl", "pair_score_kernel<EPI_RANK_U16_MIRROR_PWL, 16> (histogram-CDF table)"),
+            ("prof_fenc2.ncu-rep", "fused_encoder", "fused_encoder_kernel", "fused_encoder_kernel<32> (4096 drugs x 4 tokens, one launch)")):
+        cap = full_capture(rep, tag, name)
+        if cap:
+            summary[key] = cap
+            print(tag, cap)
     json.dump(summary, open(os.path.join(OUT, "ncu_summary.json"), "w"), indent=1)
