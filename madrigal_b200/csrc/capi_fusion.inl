@@ -313,6 +313,32 @@ int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_
     ++g_last_launches;
     return MDG_OK;
   }
+  if ((pl.hd == 32 || pl.hd == 64) && getenv("MDG_ATTENTION_GENERIC") == nullptr) {
+    // 8 < T <= 32: K rows / V columns in registers (the production shapes T = 21 / 23, head_dim 64)
+    const int warps = 4;
+    const size_t smem = static_cast<size_t>(warps) * pl.T * (2 * pl.hd + 4) * sizeof(float);
+    static bool attr_rows[64] = {false};
+    int dev = 0;
+    MDG_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_rows[dev]) {
+      MDG_CUDA(cudaFuncSetAttribute(mdg::attention_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      MDG_CUDA(cudaFuncSetAttribute(mdg::attention_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_rows[dev] = true;
+    }
+    const long long items = Bc * pl.H;
+    long long blocks = (items + warps - 1) / warps;
+    const long long cap = static_cast<long long>(num_sms()) * 12;
+    if (blocks > cap) blocks = cap;
+    if (pl.hd == 32)
+      mdg::attention_rows_kernel<32><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
+          qkv, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl), pl.split);
+    else
+      mdg::attention_rows_kernel<64><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
+          qkv, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl), pl.split);
+    MDG_CUDA(cudaGetLastError());
+    ++g_last_launches;
+    return MDG_OK;
+  }
   int TP = 1;
   while (TP < pl.T) TP <<= 1;
   const int G = 32 / TP;

@@ -148,6 +148,96 @@ __global__ void attention_kernel(const float* __restrict__ qkv, const uint8_t* _
   }
 }
 
+// Register-resident variant for 8 < T <= 32 and head_dim 32 / 64 (the shipped production shapes: T = 21 / 23, 8 heads of
+// 64).  One (drug, head) per warp.  Scores use lane = key with that key's K ROW in registers (HD floats); the
+// P.V product uses lane = head dimension with the V COLUMNS in registers; the query rows are broadcast from shared
+// memory with 16-byte loads.  Per query: HD/4 LDS.128 + HD FMA + two 5-step shuffle reductions + T shuffle-FMA pairs,
+// against 2*HD + 2*T scalar shared-memory loads per lane in the generic kernel above.
+template <int HD>
+__global__ void __launch_bounds__(128) attention_rows_kernel(const float* __restrict__ qkv,
+                                                             const uint8_t* __restrict__ key_mask,
+                                                             const uint8_t* __restrict__ src_mask, long long B, int T,
+                                                             int H, __nv_bfloat16* __restrict__ out, int k_pad,
+                                                             int split) {
+  constexpr int NV = HD / 32;        // head dimensions per lane in the P.V stage
+  constexpr int KP = HD + 4;         // K staging pitch (floats): 16-byte loads of 8 consecutive rows hit distinct banks
+  extern __shared__ float att_smem[];
+  const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* Ks = att_smem + static_cast<size_t>(wid) * T * (KP + HD);
+  float* Qs = Ks + T * KP;
+  const int Dl = H * HD;
+  const float qscale = 1.0f / sqrtf(static_cast<float>(HD));
+  // src_mask is the same for every item: lane j keeps, as a bit set over queries i, "query i may not attend key j"
+  uint32_t blocked_q = 0;
+  if (src_mask != nullptr && lane < T)
+    for (int i = 0; i < T; ++i) blocked_q |= (src_mask[i * T + lane] != 0 ? 1u : 0u) << i;
+  const long long total = B * H;
+  for (long long item = static_cast<long long>(blockIdx.x) * warps + wid; item < total;
+       item += static_cast<long long>(gridDim.x) * warps) {
+    const long long b = item / H;
+    const int h = static_cast<int>(item - b * H);
+    const float* base = qkv + (b * T) * 3LL * Dl + h * HD;
+    __syncwarp();
+    // coalesced loads: row r of q / k (lane = dimension) -> shared memory; V columns straight into registers
+    float v[NV][32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      if (r < T) {
+        const float* row = base + static_cast<long long>(r) * 3 * Dl;
+#pragma unroll
+        for (int e = 0; e < NV; ++e) {
+          Qs[r * HD + lane + 32 * e] = row[lane + 32 * e] * qscale;
+          Ks[r * KP + lane + 32 * e] = row[Dl + lane + 32 * e];
+          v[e][r] = row[2 * Dl + lane + 32 * e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < NV; ++e) v[e][r] = 0.f;
+      }
+    }
+    __syncwarp();
+    float kreg[HD];  // this lane's key row
+    const int jr = lane < T ? lane : 0;
+#pragma unroll
+    for (int c = 0; c < HD; c += 4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(Ks + jr * KP + c);
+      kreg[c] = k4.x; kreg[c + 1] = k4.y; kreg[c + 2] = k4.z; kreg[c + 3] = k4.w;
+    }
+    const bool key_ok = lane < T && key_mask[b * T + lane] == 0;
+    const long long out_pitch = split ? 2 * k_pad : k_pad;
+    for (int i = 0; i < T; ++i) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent FMA chains
+#pragma unroll
+      for (int c = 0; c < HD; c += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(Qs + i * HD + c);  // broadcast
+        s0 = fmaf(q4.x, kreg[c], s0);
+        s1 = fmaf(q4.y, kreg[c + 1], s1);
+        s2 = fmaf(q4.z, kreg[c + 2], s2);
+        s3 = fmaf(q4.w, kreg[c + 3], s3);
+      }
+      float sc = (s0 + s1) + (s2 + s3);
+      if (!key_ok || ((blocked_q >> i) & 1u)) sc = -CUDART_INF_F;
+      const float m = warp_max(sc);
+      const float pexp = (sc == -CUDART_INF_F) ? 0.f : expf(sc - m);
+      const float pj = pexp / warp_sum(pexp);  // NaN if every key is masked, like torch.softmax over all -inf
+      float acc[NV][2];  // even / odd keys: independent chains
+#pragma unroll
+      for (int e = 0; e < NV; ++e) acc[e][0] = acc[e][1] = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        if (jj < T) {
+          const float pb = __shfl_sync(0xffffffffu, pj, jj);
+#pragma unroll
+          for (int e = 0; e < NV; ++e) acc[e][jj & 1] = fmaf(pb, v[e][jj], acc[e][jj & 1]);
+        }
+      }
+      __nv_bfloat16* orow = out + (b * T + i) * out_pitch + h * HD;
+#pragma unroll
+      for (int e = 0; e < NV; ++e) store_bf16_split(orow, lane + 32 * e, k_pad, split, acc[e][0] + acc[e][1]);
+    }
+  }
+}
+
 // Few-token variant (T <= TT <= 8, hd <= 32*DPT): one (drug, head) per warp with the HEAD DIMENSION on lanes.  q/k/v
 // rows are read straight from global memory as coalesced 128-byte rows into registers (no shared memory), the T*T
 // scores are warp-shuffle reductions, softmax and the P.V product are lane-local.  This is the shape of BASELINE
