@@ -300,6 +300,12 @@ int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
                       const uint8_t* key_mask, const uint8_t* src_mask, const uint8_t* pool_key_mask, float* z_out,
                       int64_t B, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement hook for the fused encoder kernel: with the environment variable MDG_FUSION_TRACE set, CTA 0 of every
+ * fused launch records clock64() at each phase boundary (records [0,512): first epilogue warp — after each wait for
+ * the MMA warp and before each hand-over; [512,1024): MMA warp — after each wait for the epilogue and after each
+ * commit).  Synchronises the device, copies up to max_records values to a HOST array, returns the count (-1: error). */
+int mdg_fusion_trace_read(uint64_t* clocks_out_host, int max_records);
+
 /* Token assembly feeding mdg_fusion_encode  (reference: NovelDDIEncoder.encode, models.py:772-852).
  *   embeds [B, M, E] stacked modality embeddings in the order [non-TX..., TX...] (models.py:772), masks [B, M] uint8
  *   (non-zero = modality missing).  Sequence: [cls?][non-TX][bottleneck tokens][TX]; bottleneck / CLS tokens are

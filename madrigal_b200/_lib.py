@@ -88,6 +88,7 @@ SIGNATURES = {
                                    c_void_p]),
     "mdg_fusion_encode": (c_int, [POINTER(MdgFusionWeights), POINTER(MdgFusionCfg), c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "mdg_fusion_trace_read": (c_int, [c_void_p, c_int]),
     "mdg_assemble_tokens": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                     c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "mdg_masked_pool": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

@@ -286,6 +286,7 @@ int run_fused_encoder(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
     p.q_res = pl.q_res;
     p.q_proj = pl.q_proj;
   }
+  p.trace = getenv("MDG_FUSION_TRACE") != nullptr;  // measurement hook: phase timeline of CTA 0 (mdg_fusion_trace_read)
   p.drugs_per_tile = mdg::kFeRows / pl.T;
   p.num_tiles = (B + p.drugs_per_tile - 1) / p.drugs_per_tile;
   const int sms = num_sms();
@@ -563,6 +564,16 @@ int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
     }
   }
   return MDG_OK;
+}
+
+int mdg_fusion_trace_read(uint64_t* clocks_out_host, int max_records) {
+  if (!clocks_out_host || max_records < 0) return -1;
+  static unsigned long long buf[2 * mdg::kFeTraceLen];
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(buf, mdg::g_fe_trace, sizeof(buf)) != cudaSuccess) return -1;
+  const int n = max_records < 2 * mdg::kFeTraceLen ? max_records : 2 * mdg::kFeTraceLen;
+  for (int i = 0; i < n; ++i) clocks_out_host[i] = buf[i];
+  return n;
 }
 
 // ------------------------------------------------------------------------------------------------ unimodal MLP

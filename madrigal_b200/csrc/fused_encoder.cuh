@@ -14,8 +14,9 @@
 //     128-byte-swizzled K-major shared-memory layout UMMA reads, never leaving the SM;
 //   * weights (bf16, K-major rows, prepared once) stream from L2 through a 2-stage TMA ring.
 //
-// warp 0: TMA weight producer, warp 1: UMMA issuer, warp 2: TMEM allocator, warps 4-11: two threads per token row
-// (tcgen05.ld -> LayerNorm / attention / activation -> swizzled smem; the pair splits columns or heads).  MMA phases and epilogue phases of a tile
+// warp 0: TMA weight producer, warp 1: UMMA issuer, warp 2: TMEM allocator, warps 4-19: FOUR threads per token row
+// (tcgen05.ld -> LayerNorm / attention / activation -> swizzled smem; the four split 32-column chunks in element-wise
+// stages and (head, 16-dimension slice) in attention stages).  MMA phases and epilogue phases of a tile
 // alternate strictly (two mbarriers, one arrival protocol), so hazards on the shared buffers are ordered by
 // construction; the weight ring runs ahead independently.
 //
@@ -42,13 +43,19 @@ constexpr int kFeSmemKv = kFeSmemB + kFeBStages * kFeBStageBytes;
 constexpr int kFeSmemBar = kFeSmemKv + kFeKvBytes;
 constexpr int kFeSmemTotal = kFeSmemBar + 128;
 constexpr int kFeSmemBytes = kFeSmemTotal + 1024;
-constexpr int kFeEpiWarps = 8;
+constexpr int kFeEpiWarps = 16;
 constexpr int kFeThreads = (4 + kFeEpiWarps) * 32;
 constexpr int kFeTmemH = 0;
 constexpr int kFeTmemAcc = 256;
 static_assert(kFeSmemBytes <= 232448, "fused encoder exceeds 227 KB of shared memory");
 
+// Phase trace of CTA 0 (measurement hook, enabled per launch by FusedEncParams::trace): clock64 at every epilogue
+// `wait_mma` return / `signal` and every MMA-warp `wait_epi` return / commit.  Read back with mdg_fusion_trace_read.
+constexpr int kFeTraceLen = 512;
+__device__ unsigned long long g_fe_trace[2 * kFeTraceLen];  // [0, 512): epilogue warp 4, [512, 1024): MMA warp
+
 struct FusedEncParams {
+  int trace;  // non-zero: CTA 0 records its phase timeline into g_fe_trace
   long long B;
   int T, E, Dl, F, H, hd, layers, act, agg;
   int kp_e, kp_d;  // 64-wide K panels of E and Dl
@@ -253,14 +260,18 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         }
       }
     };
+    int tr_n = 0;
+    const bool tracing = p.trace != 0 && blockIdx.x == 0 && lane == 0;
     auto wait_epi = [&]() {
       mbar_wait(bar_epi_done, epi_waits & 1, 23);
       ++epi_waits;
       tc_fence_after_sync();
+      if (tracing && tr_n < kFeTraceLen) g_fe_trace[kFeTraceLen + tr_n++] = clock64();
     };
     auto signal = [&]() {
       if (elect_one()) umma_commit(bar_mma_done);
       __syncwarp();
+      if (tracing && tr_n < kFeTraceLen) g_fe_trace[kFeTraceLen + tr_n++] = clock64();
     };
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       wait_epi();  // tokens in A
@@ -300,9 +311,14 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       signal();
     }
   } else if (warp >= 4) {
-    // ======================================================================= epilogue: TWO threads per token row
-    // warps 4-7 (group 0) and 8-11 (group 1) both map lane -> TMEM lane (warp & 3) * 32 + lane; the groups split the
-    // columns of element-wise stages and the heads of attention stages.
+    // ======================================================================= epilogue: FOUR threads per token row
+    // warps 4-7 (group 0) .. 16-19 (group 3) all map lane -> TMEM lane (warp & 3) * 32 + lane.  The four threads of a
+    // row split element-wise stages by 32-column chunk (chunk ci belongs to group ci % 4) and attention stages by
+    // (head of the phase, 16-dimension slice of the head's output): a thread always accumulates 16 output dimensions.
+    constexpr int TPR = kFeEpiWarps / 4;  // threads per row
+    constexpr int TPH = TPR / HP;         // threads per head of a phase (hd 32: 2, hd 16: 1)
+    constexpr int DPT = HD / TPH;         // output dimensions per thread (16)
+    static_assert(TPR == 4 && DPT == 16, "epilogue mapping assumes 4 threads per row and 16 dimensions per thread");
     const int ew = warp - 4;
     const int quad = warp & 3;
     const int g = ew >> 2;
@@ -321,25 +337,32 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
              ((static_cast<uint32_t>(chunk) ^ ((static_cast<uint32_t>(r) >> kKvShift) & kKvMask)) << 4);
     };
     uint32_t mma_waits = 0;
+    int tr_n = 0;
+    const bool tracing = p.trace != 0 && blockIdx.x == 0 && warp == 4 && lane == 0;
     auto wait_mma = [&]() {
       mbar_wait(bar_mma_done, mma_waits & 1, 24);
       ++mma_waits;
       tc_fence_after_sync();
+      if (tracing && tr_n < kFeTraceLen) g_fe_trace[tr_n++] = (1ull << 56) | (clock64() & 0xFFFFFFFFFFFFull);
+    };
+    auto mark = [&](unsigned long long tag) {  // sub-phase marker (trace only)
+      if (tracing && tr_n < kFeTraceLen) g_fe_trace[tr_n++] = (tag << 56) | (clock64() & 0xFFFFFFFFFFFFull);
     };
     auto signal = [&]() {  // smem writes -> async proxy, TMEM reads done
+      mark(3);
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
+      if (tracing && tr_n < kFeTraceLen) g_fe_trace[tr_n++] = (2ull << 56) | (clock64() & 0xFFFFFFFFFFFFull);
       if (lane == 0) mbar_arrive(bar_epi_done);
     };
-    // LayerNorm of (H + pend) for this row -> bf16 into `dst`.  Each of the row's two threads owns half of the
-    // columns; the partial sums meet in shared memory (the k|v exchange region is idle during LN stages).
+    // LayerNorm of (H + pend) for this row -> bf16 into `dst`.  Each of the row's threads owns every 4th 32-column
+    // chunk; the partial sums meet in shared memory (the k|v exchange region is idle during LN stages).
     auto layer_norm_to = [&](uint32_t dst, const float* pend, const float* w, const float* b, bool do_ln) {
-      const int c0 = g * (Dl >> 1), c1 = c0 + (Dl >> 1);
       float mean = 0.f, rstd = 1.f;
       if (do_ln) {
         float s = 0.f, ss = 0.f;
-        for (int c = c0; c < c1; c += 32) {
+        for (int c = g * 32; c < Dl; c += 32 * TPR) {
           uint32_t v[32];
           tmem_ld_32x32(trow + kFeTmemH + c, v);
           float4 pd[8];
@@ -359,16 +382,23 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         }
         float2* part = reinterpret_cast<float2*>(gbase + kFeSmemKv);
         part[g * 128 + row] = make_float2(s, ss);
+        mark(4);
         named_bar_sync(1, kFeEpiWarps * 32);
-        const float2 o = part[(g ^ 1) * 128 + row];
-        s += o.x;
-        ss += o.y;
+        mark(5);
+        s = 0.f;
+        ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < TPR; ++k) {  // same order in all four threads: identical statistics
+          const float2 o = part[k * 128 + row];
+          s += o.x;
+          ss += o.y;
+        }
         mean = s / Dl;
         const float var = fmaxf(ss / Dl - mean * mean, 0.f);
         rstd = 1.0f / sqrtf(var + 1e-5f);
       }
       const float shift = -mean * rstd;
-      for (int c = c0; c < c1; c += 32) {
+      for (int c = g * 32; c < Dl; c += 32 * TPR) {
         uint32_t v[32];
         tmem_ld_32x32(trow + kFeTmemH + c, v);
         float y[32];
@@ -393,13 +423,14 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         fe_store_row32(dst, row, c, y);
       }
     };
-    // softmax(q . K^T) V over the T keys of this row's drug for head slot hh of the phase (k|v rows start at row r0);
-    // `qv(d)` yields the scaled query.  Result (already normalised) is written to O columns [col0, col0 + HD).
-    auto attend = [&](int hh, int r0, uint32_t key_blocked, bool active, const float (&q)[HD], int col0) {
+    // softmax(q . K^T) V over the T keys of this row's drug for head slot hh of the phase (k|v rows start at row r0),
+    // output dimensions [d0, d0 + DPT) of the head; q is the full scaled query.  The (already normalised) result
+    // goes to O columns [col0 + d0, col0 + d0 + DPT).
+    auto attend = [&](int hh, int r0, uint32_t key_blocked, bool active, const float (&q)[HD], int d0, int col0) {
       float m = -CUDART_INF_F, lsum = 0.f;
-      float acc[HD];
+      float acc[DPT];
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+      for (int d = 0; d < DPT; ++d) acc[d] = 0.f;
       if (active) {
         for (int j = 0; j < T; ++j) {
           if ((key_blocked >> j) & 1u) continue;
@@ -422,9 +453,9 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
           const float pj = __expf(s - m_new);
           lsum = fmaf(lsum, corr, pj);
 #pragma unroll
-          for (int d8 = 0; d8 < HD / 8; ++d8) {
+          for (int d8 = 0; d8 < DPT / 8; ++d8) {
             uint32_t a, b, c2, e;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(hh, rj, HD / 8 + d8)));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(hh, rj, HD / 8 + d0 / 8 + d8)));
             const uint32_t ww[4] = {a, b, c2, e};
 #pragma unroll
             for (int t2 = 0; t2 < 4; ++t2) {
@@ -438,35 +469,35 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       }
       const float inv = active ? 1.0f / lsum : 0.f;  // all keys masked -> inf/NaN like torch.softmax
 #pragma unroll
-      for (int d8 = 0; d8 < HD / 8; ++d8) {
+      for (int d8 = 0; d8 < DPT / 8; ++d8) {
         float o[8];
 #pragma unroll
         for (int t2 = 0; t2 < 8; ++t2) o[t2] = active ? acc[d8 * 8 + t2] * inv : 0.f;
-        st_shared_v4(fe_a_addr(sO, row, col0 + d8 * 8), fe_pack2(o[0], o[1]), fe_pack2(o[2], o[3]),
+        st_shared_v4(fe_a_addr(sO, row, col0 + d0 + d8 * 8), fe_pack2(o[0], o[1]), fe_pack2(o[2], o[3]),
                      fe_pack2(o[4], o[5]), fe_pack2(o[6], o[7]));
       }
     };
-    // accumulator columns [acol, acol + HD) + bias -> bf16 k (part 0) or v (part 1) row of head slot hh
-    auto stash_kv = [&](int hh, int part, uint32_t acol, const float* bias) {
+    // 16 accumulator columns [acol, acol + 16) + bias -> bf16 into the k (part 0) / v (part 1) row of head slot hh at
+    // dimension offset d0
+    auto stash_kv16 = [&](int hh, int part, int d0, uint32_t acol, const float* bias) {
+      uint32_t v[16];
+      tmem_ld_32x16(trow + kFeTmemAcc + acol, v);
+      float4 bb[4];
 #pragma unroll
-      for (int c = 0; c < HD; c += 16) {
-        uint32_t v[16];
-        tmem_ld_32x16(trow + kFeTmemAcc + acol + c, v);
-        float4 bb[4];
+      for (int j = 0; j < 4; ++j) bb[j] = fe_ldg4(bias + 4 * j);
+      tmem_ld_wait();
+      uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bb[j] = fe_ldg4(bias + c + 4 * j);
-        tmem_ld_wait();
-        uint32_t w[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          w[2 * j] = fe_pack2(__uint_as_float(v[4 * j]) + bb[j].x, __uint_as_float(v[4 * j + 1]) + bb[j].y);
-          w[2 * j + 1] = fe_pack2(__uint_as_float(v[4 * j + 2]) + bb[j].z, __uint_as_float(v[4 * j + 3]) + bb[j].w);
-        }
-        const int ch = (part * HD + c) / 8;  // 16-byte chunk index within the row
-        st_shared_v4(kv_addr(hh, row, ch), w[0], w[1], w[2], w[3]);
-        st_shared_v4(kv_addr(hh, row, ch + 1), w[4], w[5], w[6], w[7]);
+      for (int j = 0; j < 4; ++j) {
+        w[2 * j] = fe_pack2(__uint_as_float(v[4 * j]) + bb[j].x, __uint_as_float(v[4 * j + 1]) + bb[j].y);
+        w[2 * j + 1] = fe_pack2(__uint_as_float(v[4 * j + 2]) + bb[j].z, __uint_as_float(v[4 * j + 3]) + bb[j].w);
       }
+      const int ch = (part * HD + d0) / 8;  // 16-byte chunk index within the row
+      st_shared_v4(kv_addr(hh, row, ch), w[0], w[1], w[2], w[3]);
+      st_shared_v4(kv_addr(hh, row, ch + 1), w[4], w[5], w[6], w[7]);
     };
+    const int hh_mine = g % HP;          // head slot of a phase this thread works on
+    const int d0_mine = (g / HP) * DPT;  // its slice of that head's dimensions
 
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int dloc = row / T, tok = row - dloc * T;
@@ -481,7 +512,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         }
       }
 
-      // ---- tokens -> A (bf16, zero padded): each warp copies its 16 rows one at a time, 32 lanes x float4 per
+      // ---- tokens -> A (bf16, zero padded): each warp copies its 8 rows one at a time, 32 lanes x float4 per
       //      512-byte piece of the row (coalesced), converted to bf16 and written into the swizzled operand layout
       {
         const int kw = kp_e * 64;
@@ -506,14 +537,14 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         wait_mma();
         layer_norm_to(sA, p.pend + static_cast<long long>(2 * l) * Dl, p.n1_w[l], p.n1_b[l], true);
         signal();
-        // ---- attention: HP heads per phase, group g takes head slots g, g + 2, ...
+        // ---- attention: HP heads per phase; a thread takes (head slot, 16-dimension slice)
         const float* ib = p.in_bias[l];
         const float qscale = 1.0f / sqrtf(static_cast<float>(hd));
         for (int ph = 0; ph < n_phases; ++ph) {
           wait_mma();
           const int h0 = ph * HP, nh = min(HP, p.H - h0);
-          for (int hh = g; hh < nh; hh += 2) {
-            const int h = h0 + hh;
+          if (hh_mine < nh) {
+            const int hh = hh_mine, h = h0 + hh;
             const uint32_t acol = static_cast<uint32_t>(hh * 3 * HD);
             float q[HD];
 #pragma unroll
@@ -532,10 +563,13 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
                 q[c + 4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + bb[j].w) * qscale;
               }
             }
-            stash_kv(hh, 0, acol + HD, ib + Dl + h * HD);
-            stash_kv(hh, 1, acol + 2 * HD, ib + 2 * Dl + h * HD);
-            named_bar_sync(2 + g, 128);  // k/v of head h for every row of the tile are in shared memory
-            attend(hh, row - tok, blocked, valid, q, h * HD);
+            mark(6);
+            stash_kv16(hh, 0, d0_mine, acol + HD + d0_mine, ib + Dl + h * HD + d0_mine);
+            stash_kv16(hh, 1, d0_mine, acol + 2 * HD + d0_mine, ib + 2 * Dl + h * HD + d0_mine);
+            mark(7);
+            named_bar_sync(2 + hh, TPH * 128);  // k/v of head h for every row of the tile are in shared memory
+            mark(8);
+            attend(hh, row - tok, blocked, valid, q, d0_mine, h * HD);
           }
           signal();
         }
@@ -543,12 +577,11 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         wait_mma();
         layer_norm_to(sA, p.pend + static_cast<long long>(2 * l + 1) * Dl, p.n2_w[l], p.n2_b[l], true);
         signal();
-        // ---- FFN activation chunks (each group takes half of the chunk's columns)
+        // ---- FFN activation chunks (32-column pieces of the chunk alternate between the row's threads)
         for (int c = 0; c < n_fchunks; ++c) {
           wait_mma();
           const float* b1 = p.l1_bias[l] + c * FC;
-          const int half = FC >> 1;
-          for (int cc = g * half; cc < (g + 1) * half; cc += 32) {
+          for (int cc = g * 32; cc < FC; cc += 32 * TPR) {
             uint32_t v[32];
             tmem_ld_32x32(trow + kFeTmemAcc + cc, v);
             float y[32];
@@ -592,25 +625,25 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         for (int ph = 0; ph < n_phases; ++ph) {
           wait_mma();
           const int h0 = ph * HP, nh = min(HP, p.H - h0);
-          for (int hh = g; hh < nh; hh += 2) {
-            const int h = h0 + hh;
+          if (hh_mine < nh) {
+            const int hh = hh_mine, h = h0 + hh;
             const uint32_t acol = static_cast<uint32_t>(hh * 2 * HD);
-            stash_kv(hh, 0, acol, p.xin_bias + Dl + h * HD);
-            stash_kv(hh, 1, acol + HD, p.xin_bias + 2 * Dl + h * HD);
+            stash_kv16(hh, 0, d0_mine, acol + d0_mine, p.xin_bias + Dl + h * HD + d0_mine);
+            stash_kv16(hh, 1, d0_mine, acol + HD + d0_mine, p.xin_bias + 2 * Dl + h * HD + d0_mine);
             float q[HD];
 #pragma unroll
             for (int c = 0; c < HD; c += 4) {
               const float4 qq = fe_ldg4(p.q_proj + h * HD + c);
               q[c] = qq.x; q[c + 1] = qq.y; q[c + 2] = qq.z; q[c + 3] = qq.w;
             }
-            named_bar_sync(2 + g, 128);
-            attend(hh, row, pblocked, pool_row, q, h * HD);
+            named_bar_sync(2 + hh, TPH * 128);
+            attend(hh, row, pblocked, pool_row, q, d0_mine, h * HD);
           }
           signal();
         }
         // ---- out-proj of the pooled query + residual query (norm_first: no LN here) -> A for latent2embed
         wait_mma();
-        for (int c = g * (Dl >> 1); c < (g + 1) * (Dl >> 1); c += 32) {
+        for (int c = g * 32; c < Dl; c += 32 * TPR) {
           uint32_t v[32];
           tmem_ld_32x32(trow + kFeTmemAcc + c, v);
           float y[32];
@@ -631,11 +664,14 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         layer_norm_to(sA, pend_final, nullptr, nullptr, false);
         signal();
       }
-      // ---- latent2embed output -> pooled z (32-column chunks alternate between the two groups)
+      // ---- latent2embed output -> pooled z (32-column chunks rotate over the row's threads)
       wait_mma();
       {
-        float* xbuf = reinterpret_cast<float*>(gbase + kFeSmemO) + g * (128 * 33);  // per-group [128][33] fp32 exchange
-        for (int c = g * 32; c < p.E; c += 64) {
+        // per-group [128][33] fp32 exchange for mean / max pooling: groups 0-2 in the (idle) O buffer, group 3 in the
+        // k|v exchange region
+        float* xbuf = (g < 3) ? reinterpret_cast<float*>(gbase + kFeSmemO) + g * (128 * 33)
+                              : reinterpret_cast<float*>(gbase + kFeSmemKv);
+        for (int c = g * 32; c < p.E; c += 32 * TPR) {
           uint32_t v[32];
           tmem_ld_32x32(trow + kFeTmemAcc + c, v);
           tmem_ld_wait();
