@@ -261,6 +261,23 @@ def run_gpu_arm(args):
     kern_ms = float(np.mean(buf[:n_rec])) if n_rec > 0 else None
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- context (untimed region): what a plain write of the same tensor costs on this GPU (the kernel's traffic is
+    #      ~all writes; a copy, the contract's HBM denominator, moves half its bytes as reads)
+    memset_ms = None
+    if rank == 0:
+        flat = out.view(torch.uint8).reshape(-1)
+        for _ in range(3):
+            flat.zero_()
+        ms_list = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            flat.zero_()
+            b.record()
+            torch.cuda.synchronize()
+            ms_list.append(a.elapsed_time(b))
+        memset_ms = float(np.median(ms_list))
+
     # ---- secondary measurement (untimed region): the same kernel with the histogram-CDF rank table (MDG_RANK_PWL)
     pwl_ms = None
     if rank == 0:
@@ -341,6 +358,12 @@ def run_gpu_arm(args):
                         "tensor_view": {"achieved_tflops": flops / (kern_ms * 1e-3) / 1e12,
                                         "peak_tflops": peaks["tf_sustained"],
                                         "frac": flops / (kern_ms * 1e-3) / 1e12 / peaks["tf_sustained"]}}
+            if memset_ms:
+                roofline["write_only_context"] = {
+                    "memset_ms": memset_ms, "memset_gbs": out_bytes / (memset_ms * 1e-3) / 1e9,
+                    "kernel_over_memset": kern_ms / memset_ms,
+                    "note": "cudaMemset of the same uint16 rank tensor: the write-only bandwidth this GPU delivers; "
+                            "`peak` above is the copy (read+write) bandwidth the contract prescribes"}
             if pwl_ms:
                 roofline["histogram_cdf_table_variant"] = {
                     "kernel_ms": pwl_ms, "achieved": out_bytes / (pwl_ms * 1e-3) / 1e9,

@@ -331,3 +331,24 @@ def test_triple_gather_matches_dense_then_index(mb, cuda_device, N1, N2, D, L, n
     assert torch.isnan(bad).all()
     empty = mb.pair_score_gather(z1t, z2t, Wt, dev(lab[:0]), dev(hd[:0]), dev(tl[:0]), precision=prec)
     assert empty.shape == (0,)
+
+
+def test_outcome_sharding_is_bit_identical_to_one_pass(mb, cuda_device):
+    """scoring outcome shards separately (label_range + the matching rows of the rank table, as each GPU does)
+    gives exactly the bytes of the single-pass result — sharding must not change any arithmetic."""
+    from madrigal_b200 import scoring
+    N, D, L, Q = 384, 256, 11, 4096
+    z, W = synth.decoder_inputs(N, D, L, seed=77)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    lg = mb.pair_score(zt, zt, Wt, precision="bf16", out="logit").cpu().numpy()
+    table = mb.RankTable(gpu(oracle.reference_quantiles(lg, Q), cuda_device))
+    for symmetric in (False, True):
+        full = scoring.score_all_pairs(zt, Wt, out="rank", table=table, precision="bf16", symmetric=symmetric)
+        for world in (2, 3, 8):
+            parts = [scoring.score_all_pairs(zt, Wt, out="rank", table=table, precision="bf16", symmetric=symmetric,
+                                             label_range=scoring.outcome_shard(L, r, world)) for r in range(world)]
+            assert torch.equal(torch.cat(parts, dim=0), full)
+    logits = scoring.score_all_pairs(zt, Wt, out="logit", precision="fp32")
+    parts = [scoring.score_all_pairs(zt, Wt, out="logit", precision="fp32", label_range=scoring.outcome_shard(L, r, 4))
+             for r in range(4)]
+    assert torch.equal(torch.cat(parts, dim=0), logits)
