@@ -5,10 +5,11 @@ calls the C ABI in include/madrigal_b200.h through ctypes; nothing falls back to
 """
 from .decoder import (BilinearDDIScorer, RankTable, Symmetric, ensemble_reduce, pair_score,  # noqa: F401
                       pair_score_gather, pair_topk)
-from .fusion import (FusionEncoder, MLPAdaptor, PositionEncodingLearnable, PositionEncodingSinusoidal,  # noqa: F401
+from .fusion import (FusionEncoder, MLPAdaptor, MLPEncoder, PositionEncodingLearnable, PositionEncodingSinusoidal,  # noqa: F401
                      TransformerFusion, masked_pool)
 from .model import NovelDDIMultilabel, PrecomputedEmbeddingEncoder  # noqa: F401
+from . import ops  # noqa: F401  (registers torch.ops.madrigal_b200.*)
 
-__all__ = ["BilinearDDIScorer", "RankTable", "Symmetric", "pair_score", "pair_topk", "pair_score_gather", "ensemble_reduce", "TransformerFusion", "MLPAdaptor",
+__all__ = ["BilinearDDIScorer", "RankTable", "Symmetric", "pair_score", "pair_topk", "pair_score_gather", "ensemble_reduce", "TransformerFusion", "MLPAdaptor", "MLPEncoder",
            "FusionEncoder", "PositionEncodingSinusoidal", "PositionEncodingLearnable", "masked_pool",
            "NovelDDIMultilabel", "PrecomputedEmbeddingEncoder"]

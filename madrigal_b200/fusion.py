@@ -256,6 +256,13 @@ class PositionEncodingLearnable(nn.Module):
         self.pe = nn.Parameter(torch.randn(1, max_len, d_model))
 
 
+class MLPEncoder(MLPAdaptor):
+    """Drop-in for the reference `MLPEncoder` (models.py:121-180), the tabular modality encoder used for the
+    cell-viability (`cv_encoder: mlp`, get_tabular_mod_encoder :250-259) and `tx_encoder: mlp` modalities.  The
+    reference class is line-for-line the same module as `MLPAdaptor` (same ctor, same `fc.*` keys), so it runs on the
+    same kernel chain (mdg_mlp_forward); pretrained `cv_model_ae.pt` state_dicts load unchanged."""
+
+
 def masked_pool(tokens: torch.Tensor, masks: torch.Tensor, mode: str) -> torch.Tensor:
     """fusion='mean' / 'add' (models.py:870-878): masked mean / sum over visible modality tokens."""
     x = _require_cuda_f32(tokens, "tokens")

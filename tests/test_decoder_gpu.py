@@ -352,3 +352,18 @@ def test_outcome_sharding_is_bit_identical_to_one_pass(mb, cuda_device):
     parts = [scoring.score_all_pairs(zt, Wt, out="logit", precision="fp32", label_range=scoring.outcome_shard(L, r, 4))
              for r in range(4)]
     assert torch.equal(torch.cat(parts, dim=0), logits)
+
+
+def test_torch_ops_registration(mb, cuda_device):
+    """torch.ops.madrigal_b200.* (torch.library shims over the C ABI): same results as the Python API; CUDA only."""
+    z, W = synth.decoder_inputs(130, 128, 3, seed=8)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    a = torch.ops.madrigal_b200.pair_score(zt, zt, Wt, "fp32", "logit", False)
+    assert torch.equal(a, mb.pair_score(zt, zt, Wt, precision="fp32", out="logit"))
+    idx = torch.arange(50, device=cuda_device)
+    g = torch.ops.madrigal_b200.pair_score_gather(zt, zt, Wt, idx % 3, idx, (idx * 7) % 130, "fp32", False, False)
+    assert torch.allclose(g, a[idx % 3, idx, (idx * 7) % 130], rtol=0, atol=2e-4 * a.abs().max().item())
+    r = torch.ops.madrigal_b200.exact_normalized_ranks(a)
+    assert np.array_equal(r.cpu().numpy(), oracle.normalize_scores(a.cpu().numpy(), kind="stable"))
+    with pytest.raises(NotImplementedError):   # no CPU kernel is registered: there is no fallback
+        torch.ops.madrigal_b200.pair_score(zt.cpu(), zt.cpu(), Wt.cpu(), "fp32", "logit", False)

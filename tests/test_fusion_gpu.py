@@ -287,3 +287,22 @@ def test_fused_encoder_kernel(mb, cuda_device, agg, actn, T, nb, B, dims):
         with torch.no_grad():
             z2 = mod(gpu(tok2, cuda_device), *args[1:]).cpu().numpy()
         assert np.abs(z2 - z).max() <= 1e-5 * max(1.0, np.abs(z).max())
+
+
+def test_mlp_encoder_is_the_tabular_modality_encoder(mb, cuda_device):
+    """reference MLPEncoder (models.py:121-180, the cv / tx 'mlp' modality encoder) == MLPAdaptor line for line: same
+    kernel chain, same `fc.*` keys; checked against the oracle's restatement with norm=None (the cv default) and 'ln'."""
+    for norm in (None, "ln"):
+        mod = mb.MLPEncoder(96, [64, 48], 128, 0.1, norm, "relu", "nd")
+        ops = []
+        for m in mod.fc:
+            if isinstance(m, torch.nn.Linear):
+                ops.append({"op": "linear", "w": m.weight.detach().numpy().copy(), "b": m.bias.detach().numpy().copy()})
+            elif isinstance(m, torch.nn.LayerNorm):
+                ops.append({"op": "ln", "w": m.weight.detach().numpy().copy(), "b": m.bias.detach().numpy().copy()})
+            elif isinstance(m, (torch.nn.ReLU, torch.nn.GELU)):
+                ops.append({"op": "act", "actn": "relu"})
+        x = np.random.default_rng(4).standard_normal((33, 96)).astype(np.float32)
+        ref = oracle.mlp_adaptor(ops, x, dtype=np.float64)
+        y = mod.to(cuda_device)(gpu(x, cuda_device)).detach().cpu().numpy()
+        assert_close(y, ref, 1e-3, f"MLPEncoder norm={norm}")
