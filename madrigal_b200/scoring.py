@@ -61,6 +61,16 @@ def score_all_pairs(z: torch.Tensor, weight: torch.Tensor, *, out: str = "rank",
                       normalize=normalize, out_tensor=out_tensor, symmetric=symmetric)
 
 
+def score_row_block(z: torch.Tensor, weight: torch.Tensor, rank: int, world_size: int, *, out: str = "rank",
+                    table: Optional[RankTable] = None, precision: str = "bf16", normalize: bool = False) -> torch.Tensor:
+    """The other axis of the SURVEY 8e partition, for L < number of GPUs or for load balance: this rank scores its block
+    of head-drug ROWS (`row_shard`) against the whole catalogue for every outcome -> [L, rows_of_rank, N].  Concatenating
+    the ranks' blocks along dim 1 gives the single-GPU tensor bit for bit (full N x N layout; the normaliser layout
+    needs whole outcomes and shards by outcome instead)."""
+    r0, r1 = row_shard(z.shape[0], rank, world_size)
+    return pair_score(z[r0:r1].contiguous(), z, weight, precision=precision, out=out, table=table, normalize=normalize)
+
+
 def score_all_pairs_to_host(z: torch.Tensor, weight: torch.Tensor, out_host: torch.Tensor, *, out: str = "rank",
                             table: Optional[RankTable] = None, precision: str = "bf16", chunk: int = 10,
                             normalize: bool = False, symmetric: bool = False) -> torch.Tensor:

@@ -367,3 +367,19 @@ def test_torch_ops_registration(mb, cuda_device):
     assert np.array_equal(r.cpu().numpy(), oracle.normalize_scores(a.cpu().numpy(), kind="stable"))
     with pytest.raises(NotImplementedError):   # no CPU kernel is registered: there is no fallback
         torch.ops.madrigal_b200.pair_score(zt.cpu(), zt.cpu(), Wt.cpu(), "fp32", "logit", False)
+
+
+def test_row_block_sharding_is_bit_identical(mb, cuda_device):
+    """Drug-row-block partition (used when outcomes < GPUs): blocks concatenate to the one-pass tensor."""
+    from madrigal_b200 import scoring
+    N, D, L, Q = 333, 128, 2, 2048
+    z, W = synth.decoder_inputs(N, D, L, seed=78)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    lg = mb.pair_score(zt, zt, Wt, precision="bf16", out="logit")
+    table = mb.RankTable(gpu(oracle.reference_quantiles(lg.cpu().numpy(), Q), cuda_device))
+    full = mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table)
+    for world in (2, 8):
+        blocks = [scoring.score_row_block(zt, Wt, r, world, out="rank", table=table) for r in range(world)]
+        assert torch.equal(torch.cat(blocks, dim=1), full)
+    blocks = [scoring.score_row_block(zt, Wt, r, 4, out="logit") for r in range(4)]
+    assert torch.equal(torch.cat(blocks, dim=1), lg)
