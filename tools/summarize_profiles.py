@@ -31,7 +31,8 @@ def launch_list():
     # outcomes in chunks of 10, so their rank launches are ~9x shorter) and starts with the encoder's token conversion
     def is_rank(name):
         n = name.replace("(int)", "")
-        return any(f"pair_score_kernel<{e}," in n for e in (2, 6, 7, 8))
+        return any(f"pair_score_kernel<{e}," in n for e in (2, 6))  # the headline (exact-LUT) rank kernels; the PWL
+        # variant (<7 / <8) is launched by bench.py AFTER the timed steps as a secondary measurement
     rank = [(i, d[1]) for i, d in enumerate(data) if is_rank(d[0])]
     longest = max(v for _, v in rank)
     rank_idx = max(i for i, v in rank if v > 0.5 * longest)
