@@ -107,7 +107,7 @@ struct FusionPlan {
   __nv_bfloat16 *w_e2l, *w_l2e, *w_xin, *w_xout;
   __nv_bfloat16 *w_in[MDG_MAX_LAYERS], *w_out[MDG_MAX_LAYERS], *w_l1[MDG_MAX_LAYERS], *w_l2[MDG_MAX_LAYERS];
   __nv_bfloat16 *xb, *nb, *ob, *fb, *pb;
-  float *h, *qkv, *p32, *q_res, *q_proj, *pend;
+  float *h, *qkv, *p32, *q_res, *q_proj, *pend, *xo_qres;
   size_t ob_bytes, fb_bytes, pb_bytes;
   size_t total, prepared_total;
 };
@@ -159,6 +159,7 @@ int plan_fusion(const MdgFusionCfg* cfg, long long B, int precision, void* ws, v
   pl->q_res = pw.take<float>(Dl);
   pl->q_proj = pw.take<float>(Dl);
   pl->pend = pw.take<float>(static_cast<size_t>(2 * pl->layers + 1) * Dl);  // fused kernel: biases owed to H per stage
+  pl->xo_qres = pw.take<float>(Dl);  // fused kernel: x_attn out_proj bias + residual query
   pl->prepared_total = pw.off;
   // (b) per-call activation workspace
   WsPlanner w;
@@ -187,6 +188,7 @@ bool fused_encoder_eligible(const MdgFusionCfg* cfg, const FusionPlan& pl) {
   if (pl.hd != 16 && pl.hd != 32) return false;
   if (pl.E % 16 != 0 || pl.E > 256) return false;
   if (pl.T > 32 || pl.T < 1) return false;
+  if (pl.F % 4 != 0) return false;  // bias vectors are staged in 16-byte pieces
   return true;
 }
 
@@ -285,6 +287,7 @@ int run_fused_encoder(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
     p.xq_nw = w->x_attn_query_norm_weight; p.xq_nb = w->x_attn_query_norm_bias;
     p.q_res = pl.q_res;
     p.q_proj = pl.q_proj;
+    p.xo_qres = pl.xo_qres;
   }
   p.trace = getenv("MDG_FUSION_TRACE") != nullptr;  // measurement hook: phase timeline of CTA 0 (mdg_fusion_trace_read)
   p.drugs_per_tile = mdg::kFeRows / pl.T;
@@ -435,6 +438,9 @@ static int fusion_prepare_impl(const MdgFusionWeights* w, const MdgFusionCfg* cf
                                                    w->x_attn_query_norm_bias, cfg->norm_first,
                                                    w->x_attn_in_proj_weight, w->x_attn_in_proj_bias, Dl, pl.hd,
                                                    pl.q_res, pl.q_proj);
+    MDG_CUDA(cudaGetLastError());
+    ++g_last_launches;
+    mdg::vec_add_kernel<<<(Dl + 127) / 128, 128, 0, stream>>>(w->x_attn_out_proj_bias, pl.q_res, pl.xo_qres, Dl);
     MDG_CUDA(cudaGetLastError());
     ++g_last_launches;
   }

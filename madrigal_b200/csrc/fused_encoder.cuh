@@ -41,8 +41,10 @@ constexpr int kFeSmemO = kFeSmemA + kFeABufBytes;
 constexpr int kFeSmemB = kFeSmemO + kFeABufBytes;
 constexpr int kFeSmemKv = kFeSmemB + kFeBStages * kFeBStageBytes;
 constexpr int kFeSmemBar = kFeSmemKv + kFeKvBytes;
-constexpr int kFeSmemTotal = kFeSmemBar + 128;
-constexpr int kFeSmemBytes = kFeSmemTotal + 1024;
+constexpr int kFeSmemPar = kFeSmemBar + 128;          // 2 x 1 KB: the parameter vector of the current / next phase
+constexpr int kFeParBytes = 1024;
+constexpr int kFeSmemTotal = kFeSmemPar + 2 * kFeParBytes;
+constexpr int kFeSmemBytes = kFeSmemTotal;  // the dynamic shared-memory base is 1024-byte aligned (checked in the kernel)
 constexpr int kFeEpiWarps = 16;
 constexpr int kFeThreads = (4 + kFeEpiWarps) * 32;
 constexpr int kFeTmemH = 0;
@@ -82,6 +84,7 @@ struct FusedEncParams {
   const float* xq_nw;      // x_attn_query_norm (applied after the residual when !norm_first; unused: norm_first only)
   const float* xq_nb;
   const float* q_res;      // [Dl]
+  const float* xo_qres;    // [Dl] x_attn out_proj bias + q_res (what is added to the pooled out-proj output)
   const float* q_proj;     // [Dl] (already scaled)
   long long num_tiles;
   int drugs_per_tile;
@@ -130,6 +133,12 @@ __device__ __forceinline__ float fe_act(float a, int act) {
 // 16-byte vector load of 4 consecutive fp32 parameters (uniform address across the warp: one L1 wavefront)
 __device__ __forceinline__ float4 fe_ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+__device__ __forceinline__ float4 fe_lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(kFeThreads, 1)
 fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_constant__ CUtensorMap tm_in,
@@ -138,12 +147,15 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
                      const __grid_constant__ CUtensorMap tm_xin, const __grid_constant__ CUtensorMap tm_xout,
                      const __grid_constant__ FusedEncParams p) {
   constexpr int HP = 64 / HD;  // heads per attention phase (their q|k|v projections share one accumulator: 192 columns)
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* gbase = smem_raw + (base - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) {  // the swizzled operand layouts need 1024-byte alignment; there is no slack to realign
+    g_hang_code = 0x40000000u;
+    asm volatile("trap;");
+  }
+  uint8_t* gbase = smem_raw;
   const uint32_t sA = base + kFeSmemA, sO = base + kFeSmemO, sB = base + kFeSmemB, sKv = base + kFeSmemKv,
-                 sBar = base + kFeSmemBar;
+                 sBar = base + kFeSmemBar, sPar = base + kFeSmemPar;
   const uint32_t bar_mma_done = sBar, bar_epi_done = sBar + 8;
   auto bar_full = [&](int i) { return sBar + 16 + 8 * i; };
   auto bar_empty = [&](int i) { return sBar + 32 + 8 * i; };
@@ -356,9 +368,45 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       if (tracing && tr_n < kFeTraceLen) g_fe_trace[tr_n++] = (2ull << 56) | (clock64() & 0xFFFFFFFFFFFFull);
       if (lane == 0) mbar_arrive(bar_epi_done);
     };
+    // Per-phase parameter vectors (pending bias, q|k|v biases of the phase's heads, FFN bias chunk, ...) are read by
+    // every thread; with ~225 KB of shared memory the L1 cache is gone, so a global load is an L2 round trip.  They
+    // are therefore STAGED: right after handing a phase to the MMA warp, the first threads copy the NEXT phase's
+    // vector (<= 256 floats) into one of two 1 KB buffers (the copy overlaps the MMA phase); after the wait a
+    // 512-thread barrier publishes it.  Buffer k&1 was last read two phases ago, which every warp has left.
+    uint32_t par_n = 0;
+    const int etid = ew * 32 + lane;
+    auto stage = [&](int n4, auto src_of) {  // src_of(i) -> address of the i-th float4 of the vector
+      if (etid < n4) {
+        const float4 v = fe_ldg4(src_of(etid));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sPar + (par_n & 1u) * kFeParBytes + etid * 16),
+                     "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+      }
+      ++par_n;
+    };
+    auto publish = [&]() -> uint32_t {  // after wait_mma: the vector staged last is now readable; returns its address
+      named_bar_sync(6, kFeEpiWarps * 32);
+      return sPar + ((par_n - 1u) & 1u) * kFeParBytes;
+    };
+    auto stage_vec = [&](const float* v, int n) { stage((n + 3) >> 2, [&](int i) { return v + 4 * i; }); };
+    // q|k|v biases of the heads of attention phase ph, layout [head slot][q | k | v][HD]
+    auto stage_qkv = [&](const float* ib, int ph) {
+      const int h0 = ph * HP, nh = min(HP, p.H - h0);
+      stage(nh * 3 * (HD / 4), [&](int i) {
+        const int seg = i / (HD / 4), off = i - seg * (HD / 4);
+        return ib + (seg % 3) * Dl + (h0 + seg / 3) * HD + 4 * off;
+      });
+    };
+    // pooling phase: [head slot][k bias | v bias | projected query][HD]
+    auto stage_pool = [&](int ph) {
+      const int h0 = ph * HP, nh = min(HP, p.H - h0);
+      stage(nh * 3 * (HD / 4), [&](int i) {
+        const int seg = i / (HD / 4), off = i - seg * (HD / 4), part = seg % 3, h = h0 + seg / 3;
+        return (part == 2 ? p.q_proj + h * HD : p.xin_bias + (part + 1) * Dl + h * HD) + 4 * off;
+      });
+    };
     // LayerNorm of (H + pend) for this row -> bf16 into `dst`.  Each of the row's threads owns every 4th 32-column
     // chunk; the partial sums meet in shared memory (the k|v exchange region is idle during LN stages).
-    auto layer_norm_to = [&](uint32_t dst, const float* pend, const float* w, const float* b, bool do_ln) {
+    auto layer_norm_to = [&](uint32_t dst, uint32_t pend, const float* w, const float* b, bool do_ln) {
       float mean = 0.f, rstd = 1.f;
       if (do_ln) {
         float s = 0.f, ss = 0.f;
@@ -367,7 +415,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
           tmem_ld_32x32(trow + kFeTmemH + c, v);
           float4 pd[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) pd[j] = fe_ldg4(pend + c + 4 * j);
+          for (int j = 0; j < 8; ++j) pd[j] = fe_lds4(pend + (c + 4 * j) * 4);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -404,7 +452,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         float y[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 pd = fe_ldg4(pend + c + 4 * j);
+          const float4 pd = fe_lds4(pend + (c + 4 * j) * 4);
           y[4 * j] = pd.x; y[4 * j + 1] = pd.y; y[4 * j + 2] = pd.z; y[4 * j + 3] = pd.w;
         }
         tmem_ld_wait();
@@ -479,12 +527,12 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
     };
     // 16 accumulator columns [acol, acol + 16) + bias -> bf16 into the k (part 0) / v (part 1) row of head slot hh at
     // dimension offset d0
-    auto stash_kv16 = [&](int hh, int part, int d0, uint32_t acol, const float* bias) {
+    auto stash_kv16 = [&](int hh, int part, int d0, uint32_t acol, uint32_t bias) {
       uint32_t v[16];
       tmem_ld_32x16(trow + kFeTmemAcc + acol, v);
       float4 bb[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = fe_ldg4(bias + 4 * j);
+      for (int j = 0; j < 4; ++j) bb[j] = fe_lds4(bias + 16 * j);
       tmem_ld_wait();
       uint32_t w[8];
 #pragma unroll
@@ -514,6 +562,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
 
       // ---- tokens -> A (bf16, zero padded): each warp copies its 8 rows one at a time, 32 lanes x float4 per
       //      512-byte piece of the row (coalesced), converted to bf16 and written into the swizzled operand layout
+      const float* pend_final = p.pend + static_cast<long long>(2 * p.layers) * Dl;
       {
         const int kw = kp_e * 64;
         for (int r = 0; r < 128 / kFeEpiWarps; ++r) {
@@ -531,21 +580,25 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
           }
         }
         signal();
+        stage_vec(p.layers > 0 ? p.pend : pend_final, Dl);  // next phase: LN1 of layer 0 (or the pooling input)
       }
       for (int l = 0; l < p.layers; ++l) {
+        const float* ib = p.in_bias[l];
         // ---- LN1
         wait_mma();
-        layer_norm_to(sA, p.pend + static_cast<long long>(2 * l) * Dl, p.n1_w[l], p.n1_b[l], true);
+        layer_norm_to(sA, publish(), p.n1_w[l], p.n1_b[l], true);
         signal();
+        stage_qkv(ib, 0);
         // ---- attention: HP heads per phase; a thread takes (head slot, 16-dimension slice)
-        const float* ib = p.in_bias[l];
         const float qscale = 1.0f / sqrtf(static_cast<float>(hd));
         for (int ph = 0; ph < n_phases; ++ph) {
           wait_mma();
+          const uint32_t par = publish();
           const int h0 = ph * HP, nh = min(HP, p.H - h0);
           if (hh_mine < nh) {
             const int hh = hh_mine, h = h0 + hh;
             const uint32_t acol = static_cast<uint32_t>(hh * 3 * HD);
+            const uint32_t bq = par + static_cast<uint32_t>(hh * 3 * HD) * 4;  // [q | k | v] biases of this head
             float q[HD];
 #pragma unroll
             for (int c = 0; c < HD; c += 16) {
@@ -553,7 +606,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
               tmem_ld_32x16(trow + kFeTmemAcc + acol + c, v);
               float4 bb[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) bb[j] = fe_ldg4(ib + h * HD + c + 4 * j);
+              for (int j = 0; j < 4; ++j) bb[j] = fe_lds4(bq + (c + 4 * j) * 4);
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -563,24 +616,24 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
                 q[c + 4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + bb[j].w) * qscale;
               }
             }
-            mark(6);
-            stash_kv16(hh, 0, d0_mine, acol + HD + d0_mine, ib + Dl + h * HD + d0_mine);
-            stash_kv16(hh, 1, d0_mine, acol + 2 * HD + d0_mine, ib + 2 * Dl + h * HD + d0_mine);
-            mark(7);
+            stash_kv16(hh, 0, d0_mine, acol + HD + d0_mine, bq + (HD + d0_mine) * 4);
+            stash_kv16(hh, 1, d0_mine, acol + 2 * HD + d0_mine, bq + (2 * HD + d0_mine) * 4);
             named_bar_sync(2 + hh, TPH * 128);  // k/v of head h for every row of the tile are in shared memory
-            mark(8);
             attend(hh, row - tok, blocked, valid, q, d0_mine, h * HD);
           }
           signal();
+          if (ph + 1 < n_phases) stage_qkv(ib, ph + 1);
+          else stage_vec(p.pend + static_cast<long long>(2 * l + 1) * Dl, Dl);  // next: LN2
         }
         // ---- LN2
         wait_mma();
-        layer_norm_to(sA, p.pend + static_cast<long long>(2 * l + 1) * Dl, p.n2_w[l], p.n2_b[l], true);
+        layer_norm_to(sA, publish(), p.n2_w[l], p.n2_b[l], true);
         signal();
+        stage_vec(p.l1_bias[l], min(FC, p.F));
         // ---- FFN activation chunks (32-column pieces of the chunk alternate between the row's threads)
         for (int c = 0; c < n_fchunks; ++c) {
           wait_mma();
-          const float* b1 = p.l1_bias[l] + c * FC;
+          const uint32_t b1 = publish();  // linear1 bias of columns [c * FC, c * FC + FC)
           for (int cc = g * 32; cc < FC; cc += 32 * TPR) {
             uint32_t v[32];
             tmem_ld_32x32(trow + kFeTmemAcc + cc, v);
@@ -588,7 +641,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
             if (c * FC + cc + 32 <= p.F) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 bb = fe_ldg4(b1 + cc + 4 * j);
+                const float4 bb = fe_lds4(b1 + (cc + 4 * j) * 4);
                 y[4 * j] = bb.x; y[4 * j + 1] = bb.y; y[4 * j + 2] = bb.z; y[4 * j + 3] = bb.w;
               }
               tmem_ld_wait();
@@ -601,56 +654,64 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
               }
             } else {
               tmem_ld_wait();
+              const float* b1g = p.l1_bias[l] + c * FC;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const bool in = c * FC + cc + j < p.F;  // columns beyond F are K padding: exactly zero
-                y[j] = in ? fe_act(__uint_as_float(v[j]) + __ldg(b1 + cc + j), p.act) : 0.f;
+                y[j] = in ? fe_act(__uint_as_float(v[j]) + __ldg(b1g + cc + j), p.act) : 0.f;
               }
             }
             fe_store_row32(sO, row, cc, y);
           }
           signal();
+          if (c + 1 < n_fchunks) stage_vec(p.l1_bias[l] + (c + 1) * FC, min(FC, p.F - (c + 1) * FC));
+          else stage_vec(l + 1 < p.layers ? p.pend + static_cast<long long>(2 * l + 2) * Dl : pend_final, Dl);
         }
       }
-      const float* pend_final = p.pend + static_cast<long long>(2 * p.layers) * Dl;
       if (xattn) {
         // ---- x-attn pooling (models.py:422-440): kv = LN_kv(h); one learned query per head; constant key mask
         wait_mma();
-        layer_norm_to(sA, pend_final, p.xkv_nw, p.xkv_nb, true);
+        layer_norm_to(sA, publish(), p.xkv_nw, p.xkv_nb, true);
         signal();
+        stage_pool(0);
         uint32_t pblocked = 0;
         for (int j = 0; j < T; ++j)
           if (p.pool_mask != nullptr && p.pool_mask[j] != 0) pblocked |= 1u << j;
         const bool pool_row = valid && tok == 0;  // the first token row of each drug computes the pooled output
         for (int ph = 0; ph < n_phases; ++ph) {
           wait_mma();
+          const uint32_t par = publish();
           const int h0 = ph * HP, nh = min(HP, p.H - h0);
           if (hh_mine < nh) {
             const int hh = hh_mine, h = h0 + hh;
             const uint32_t acol = static_cast<uint32_t>(hh * 2 * HD);
-            stash_kv16(hh, 0, d0_mine, acol + d0_mine, p.xin_bias + Dl + h * HD + d0_mine);
-            stash_kv16(hh, 1, d0_mine, acol + HD + d0_mine, p.xin_bias + 2 * Dl + h * HD + d0_mine);
+            const uint32_t bk = par + static_cast<uint32_t>(hh * 3 * HD) * 4;  // [k bias | v bias | query] of this head
+            stash_kv16(hh, 0, d0_mine, acol + d0_mine, bk + d0_mine * 4);
+            stash_kv16(hh, 1, d0_mine, acol + HD + d0_mine, bk + (HD + d0_mine) * 4);
             float q[HD];
 #pragma unroll
             for (int c = 0; c < HD; c += 4) {
-              const float4 qq = fe_ldg4(p.q_proj + h * HD + c);
+              const float4 qq = fe_lds4(bk + (2 * HD + c) * 4);
               q[c] = qq.x; q[c + 1] = qq.y; q[c + 2] = qq.z; q[c + 3] = qq.w;
             }
             named_bar_sync(2 + hh, TPH * 128);
             attend(hh, row, pblocked, pool_row, q, d0_mine, h * HD);
           }
           signal();
+          if (ph + 1 < n_phases) stage_pool(ph + 1);
+          else stage_vec(p.xo_qres, Dl);  // next: out-proj bias + residual query
         }
         // ---- out-proj of the pooled query + residual query (norm_first: no LN here) -> A for latent2embed
         wait_mma();
+        const uint32_t xo = publish();
         for (int c = g * 32; c < Dl; c += 32 * TPR) {
           uint32_t v[32];
           tmem_ld_32x32(trow + kFeTmemAcc + c, v);
           float y[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 a = fe_ldg4(p.xout_bias + c + 4 * j), b = fe_ldg4(p.q_res + c + 4 * j);
-            y[4 * j] = a.x + b.x; y[4 * j + 1] = a.y + b.y; y[4 * j + 2] = a.z + b.z; y[4 * j + 3] = a.w + b.w;
+            const float4 a = fe_lds4(xo + (c + 4 * j) * 4);
+            y[4 * j] = a.x; y[4 * j + 1] = a.y; y[4 * j + 2] = a.z; y[4 * j + 3] = a.w;
           }
           tmem_ld_wait();
 #pragma unroll
@@ -661,12 +722,14 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       } else {
         // ---- pooling input: latent2embed is applied to every token row (models.py:415)
         wait_mma();
-        layer_norm_to(sA, pend_final, nullptr, nullptr, false);
+        layer_norm_to(sA, publish(), nullptr, nullptr, false);
         signal();
       }
+      stage_vec(p.l2e_bias, p.E);
       // ---- latent2embed output -> pooled z (32-column chunks rotate over the row's threads)
       wait_mma();
       {
+        const uint32_t l2b = publish();
         // per-group [128][33] fp32 exchange for mean / max pooling: groups 0-2 in the (idle) O buffer, group 3 in the
         // k|v exchange region
         float* xbuf = (g < 3) ? reinterpret_cast<float*>(gbase + kFeSmemO) + g * (128 * 33)
@@ -681,7 +744,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 if (c + j < p.E) {  // E % 16 == 0: whole float4s
-                  const float4 bb = fe_ldg4(p.l2e_bias + c + j);
+                  const float4 bb = fe_lds4(l2b + (c + j) * 4);
                   *reinterpret_cast<float4*>(zo + j) =
                       make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y,
                                   __uint_as_float(v[j + 2]) + bb.z, __uint_as_float(v[j + 3]) + bb.w);
@@ -717,6 +780,11 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void vec_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
 }
 
 // pend[s][d]: biases already "owed" to the TMEM-resident residual stream at stage s
