@@ -19,6 +19,7 @@
 // [hi | lo] along K and the K loop runs hi*hi + lo*hi + hi*lo into one accumulator (msub = 1).
 #pragma once
 #include <cuda_bf16.h>
+#include <math_constants.h>
 
 #include "mdg_ptx.cuh"
 #include "rank_table.cuh"
@@ -554,7 +555,87 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int nb = c.nb0; nb < c.nb1; ++nb) {
         mbar_wait(bar_t_full(acc_stage), acc_phase, 6);
         tc_fence_after_sync();
-        if (row0 < p.rows && !(EPI == EPI_TOPK && p.topk_cap < 0)) {  // topk_cap < 0: mainloop-only timing (debug)
+        if constexpr (EPI == EPI_TOPK) {
+          // Top-k epilogue.  (1) A tcgen05.ld issued while MMAs are queued only completes once the queue drains, so the
+          // warp's whole slice of the tile (up to 4 chunks) is fetched with ALL loads in flight and ONE wait, and the
+          // accumulator stage goes back to the MMA warp before anything is examined.  (2) Candidates are ~1e-4 of the
+          // scores but ~20 % of the 1024-score chunks hold one, so the scan is a warp vote per column (uniform, almost
+          // never taken branch) and the rare append is warp-aggregated: one atomicAdd per vote, not one scan loop
+          // plus one atomic round trip per chunk.
+          if (row0 < p.rows && p.topk_cap >= 0) {  // topk_cap < 0: mainloop-only timing (debug)
+            uint32_t a[4][32];
+            bool want[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int cc = col_begin + 32 * q, n0 = nb * kBN + cc;
+              want[q] = cc < col_end && n0 < p.cols && !(p.lower_only && n0 > row0 + 31);
+              if (want[q])
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                  static_cast<uint32_t>((acc_stage * 2 + ms) * kBN + cc), a[q]);
+            }
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_t_empty(acc_stage));
+            const float thr = my_row < p.rows ? topk_thr : CUDART_INF_F;  // rows beyond the matrix never qualify
+            // per-lane hit masks of the (up to) 4 chunks: 2 instructions per score, no branches
+            uint32_t hm[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              hm[q] = 0;
+              if (!want[q]) continue;
+              const int n0 = nb * kBN + col_begin + 32 * q;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (__uint_as_float(a[q][j]) >= thr) hm[q] |= 1u << j;
+              // columns this lane may report: inside the matrix and, for unordered pairs, strictly left of its row
+              int jlim = p.cols - n0;
+              if (p.lower_only) jlim = min(jlim, my_row - n0);
+              if (jlim < 32) hm[q] &= jlim > 0 ? (1u << jlim) - 1u : 0u;
+            }
+            // Append loop: ONE copy of the code for the whole tile (128 inlined copies of an append block, or four
+            // unrolled per-chunk loops, thrash the 32 KB instruction cache: 3-4x slower kernel).  Every pass takes
+            // each lane's next hit; hits are ~1 per warp per tile, so this almost always runs once or not at all.
+            while (__any_sync(0xffffffffu, (hm[0] | hm[1] | hm[2] | hm[3]) != 0)) {
+              int idx = -1;
+#pragma unroll
+              for (int q = 3; q >= 0; --q)
+                if (hm[q] != 0) idx = q * 32 + (__ffs(hm[q]) - 1);  // lowest chunk wins
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if ((idx >> 5) == q) hm[q] &= hm[q] - 1u;  // clear the bit just taken (idx = -1 matches no q)
+              uint32_t bits = 0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (idx == q * 32 + j) bits = a[q][j];               // 128-way register select
+              const bool h = idx >= 0;
+              const uint32_t bal = __ballot_sync(0xffffffffu, h);
+              const int leader = __ffs(bal) - 1;
+              unsigned int base_slot = 0;
+              if (lane == leader) base_slot = atomicAdd(p.topk_count + c.l, static_cast<unsigned int>(__popc(bal)));
+              base_slot = __shfl_sync(0xffffffffu, base_slot, leader);
+              if (h) {
+                const unsigned int slot = base_slot + static_cast<unsigned int>(__popc(bal & ((1u << lane) - 1u)));
+                const int col = nb * kBN + col_begin + idx;
+                if (slot < static_cast<unsigned int>(p.topk_cap))
+                  p.topk_cand[static_cast<size_t>(c.l) * p.topk_cap + slot] =
+                      (static_cast<unsigned long long>(bits) << 32) |
+                      static_cast<unsigned long long>(static_cast<unsigned int>(my_row) *
+                                                      static_cast<unsigned int>(p.cols) + col);
+              }
+            }
+          } else {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_t_empty(acc_stage));
+          }
+          acc_stage ^= 1;
+          if (acc_stage == 0) acc_phase ^= 1;
+          continue;
+        }
+        if (row0 < p.rows) {
           for (int cc = col_begin; cc < col_end; cc += 32) {
             const int n0 = nb * kBN + cc;
             if (n0 >= p.cols) break;
@@ -600,25 +681,6 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   }
                 }
                 if (mirror && n0 == row0) o[lane] = 0;  // diagonal (normalize_scores.py:69)
-              }
-            } else if constexpr (EPI == EPI_TOPK) {
-              const float thr = topk_thr;
-              bool hit = false;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) hit |= __uint_as_float(v[j]) >= thr;
-              if (__any_sync(0xffffffffu, hit) && hit && my_row < p.rows) {  // rare: candidates are ~k of N^2 scores
-                for (int j = 0; j < 32; ++j) {
-                  const int col = n0 + j;
-                  const float x = __uint_as_float(v[j]);
-                  if (x >= thr && col < p.cols && !(p.lower_only && col >= my_row)) {
-                    const unsigned int slot = atomicAdd(p.topk_count + c.l, 1u);
-                    if (slot < static_cast<unsigned int>(p.topk_cap))
-                      p.topk_cand[static_cast<size_t>(c.l) * p.topk_cap + slot] =
-                          (static_cast<unsigned long long>(v[j]) << 32) |
-                          static_cast<unsigned long long>(static_cast<unsigned int>(my_row) *
-                                                          static_cast<unsigned int>(p.cols) + col);
-                  }
-                }
               }
             } else if constexpr (EPI == EPI_LINEAR) {
               // y = act(acc + bias) (+ residual); fp32 and/or bf16 (hi | lo) outputs, guarded direct stores

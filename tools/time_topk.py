@@ -14,8 +14,8 @@ def case(N, D, L, symmetric, k=1000, Q=16384):
     quant = normalize.build_reference_quantiles(zt, Wt, Q, panel=2048, precision="bf16")
     M = N * (N - 1) // 2 if symmetric else N * N
     qi = min(Q - 1, max(0, int(Q * (1.0 - 3.0 * k / M)) - 1))    # ~3k candidates per outcome
-    thr = quant[:, qi].contiguous()
-    cap = 8192
+    thr = (quant[:, qi] + float(os.environ.get('THR_SHIFT', '0'))).contiguous()
+    cap = int(os.environ.get('CAP', 8192))
     import ctypes
     from madrigal_b200 import _lib
     fn = lambda: mb.pair_topk(zt, zt, Wt, thr, k, cap=cap, symmetric=symmetric, precision="bf16")
