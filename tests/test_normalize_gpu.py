@@ -115,3 +115,54 @@ def test_mean_sigmoid_ensemble_vs_oracle(norm, cuda_device):
         lgs.append(oracle.bilinear_scores(z, z, W, (1, 3)))
     got = scoring.ensemble_mean_sigmoid(zs, Ws, precision="fp32", label_range=(1, 3)).cpu().numpy()
     assert np.abs(got - oracle.ensemble_mean_sigmoid(lgs)).max() <= 2e-4
+
+
+def test_config1_end_to_end_vs_oracle_chain(norm, cuda_device):
+    """SURVEY 4, integration: BASELINE config 1 (1,024 drugs, 4 modality tokens, 86 outcomes) through the whole path —
+    fusion encoder -> bilinear decoder -> normalised ranks — against the CPU oracle chain on the same seeded weights.
+    Outcomes are sub-sampled (the CPU normaliser takes ~0.2 s per outcome at this size)."""
+    import madrigal_b200 as mb
+    import synth
+    N, T, E, L = 1024, 4, 128, 86
+    cfg = dict(embed_dim=E, num_layers=2, num_heads=8, head_dim=32, ffn_dim=512, actn="gelu", norm_first=True,
+               agg="mean", nb=0)
+    sd = synth.fusion_state_dict(cfg, seed=11)
+    tokens, masks = synth.fusion_inputs(N, T, E, seed=11)
+    _, W = synth.decoder_inputs(1, E, L, seed=12)
+    pick = [0, 17, 42, 85]
+    # CPU oracle chain (float64 encoder/decoder so that only the GPU's own error is measured, fp32 normaliser as the reference)
+    z_ref = oracle.fusion_forward(sd, cfg, tokens, masks, dtype=np.float64)
+    lg_ref = np.stack([oracle.bilinear_scores(z_ref, z_ref, W, (l, l + 1), dtype=np.float64)[0] for l in pick]).astype(np.float32)
+    rk_ref = oracle.normalize_scores(lg_ref, kind="stable")
+    M = N * (N - 1) // 2
+    i, j = np.tril_indices(N, -1)
+    for precision, tol_logit, tol_rank in (("fp32", 1e-3, 2e-3), ("bf16", 3e-2, 3e-2)):
+        enc = mb.TransformerFusion(E, 0, 2, 8, 32, 512, transformer_actn="gelu", transformer_norm_first=True,
+                                   transformer_batch_first=False, transformer_agg="mean", precision=precision)
+        enc.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        enc = enc.to(cuda_device).eval()
+        with torch.no_grad():
+            z = enc(torch.from_numpy(tokens).to(cuda_device), torch.from_numpy(masks).to(cuda_device))
+        Wt = torch.from_numpy(W[pick]).to(cuda_device)
+        logits = mb.pair_score(z, z, Wt, precision=precision, out="logit")
+        ranks = norm.exact_normalized_ranks(logits).cpu().numpy()
+        lg = logits.cpu().numpy()
+        rms = np.sqrt(np.mean(lg_ref.astype(np.float64) ** 2))
+        if precision == "fp32":   # 1e-3 bar against max(|ref|, rms) element-wise, loosened to the scale of the tensor
+            assert np.abs(lg - lg_ref).max() <= tol_logit * max(rms, np.abs(lg_ref).max() * 0.1), precision
+        else:                     # bf16 operands through 2 transformer layers AND the quadratic form: 1e-2 of max|ref|
+            assert np.abs(lg - lg_ref).max() <= 1e-2 * np.abs(lg_ref).max(), precision
+            assert np.abs(lg - lg_ref).mean() <= 1e-2 * rms, precision
+        # the normaliser output has the reference's structure exactly ...
+        assert np.array_equal(ranks, ranks.swapaxes(1, 2)) and (np.diagonal(ranks, axis1=1, axis2=2) == 0).all()
+        for a in range(len(pick)):
+            assert np.array_equal(np.sort(ranks[a][i, j]), (np.arange(1, M + 1) / M).astype(np.float32))  # a permutation of 1..M
+            # ... and its values track the reference chain: a logit error e moves a rank by ~ density * e
+            d = np.abs(ranks[a][i, j].astype(np.float64) - rk_ref[a][i, j])
+            assert d.max() <= tol_rank and d.mean() <= tol_rank / 10, (precision, pick[a], d.max(), d.mean())
+        # fused quantile ranks from the same logits: within (1 + snapping)/Q of the exact in-sample ranks
+        if precision == "bf16":
+            table = norm.build_rank_table(z, Wt, 16384, precision="bf16")
+            fused = mb.pair_score(z, z, Wt, precision="bf16", out="rank", table=table, symmetric=True).cpu().numpy()
+            for a in range(len(pick)):
+                assert np.abs(fused[a][i, j] / 16384.0 - ranks[a][i, j]).max() <= 1.0 / 16384 + 4.0 / 131072 + 1e-7
