@@ -156,7 +156,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
   uint8_t* gbase = smem_raw;
   const uint32_t sA = base + kFeSmemA, sO = base + kFeSmemO, sB = base + kFeSmemB, sKv = base + kFeSmemKv,
                  sBar = base + kFeSmemBar, sPar = base + kFeSmemPar;
-  const uint32_t bar_mma_done = sBar, bar_epi_done = sBar + 8;
+  const uint32_t bar_mma_done = sBar, bar_epi_done = sBar + 8, bar_acc_free = sBar + 48;
   auto bar_full = [&](int i) { return sBar + 16 + 8 * i; };
   auto bar_empty = [&](int i) { return sBar + 32 + 8 * i; };
   const uint32_t tmem_slot = sBar + 64;
@@ -166,6 +166,8 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
   if (threadIdx.x == 0) {
     mbar_init(bar_mma_done, 1);
     mbar_init(bar_epi_done, kFeEpiWarps);  // one arrival per epilogue warp
+    mbar_init(bar_acc_free, kFeEpiWarps);  // "the q|k|v accumulator has been read out": lets the next head pair's
+                                           // projection run under the current pair's softmax
     for (int i = 0; i < kFeBStages; ++i) {
       mbar_init(bar_full(i), 1);
       mbar_init(bar_empty(i), 1);
@@ -285,13 +287,20 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       __syncwarp();
       if (tracing && tr_n < kFeTraceLen) g_fe_trace[kFeTraceLen + tr_n++] = clock64();
     };
+    uint32_t acc_waits = 0;
+    auto wait_acc = [&]() {
+      mbar_wait(bar_acc_free, acc_waits & 1, 25);
+      ++acc_waits;
+      tc_fence_after_sync();
+    };
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       wait_epi();  // tokens in A
       gemm(sA, kp_e, Dl, kFeTmemH, false);
       signal();
       for (int l = 0; l < p.layers; ++l) {
         for (int ph = 0; ph < n_phases; ++ph) {
-          wait_epi();  // LN1 in A (ph == 0) / previous heads consumed
+          if (ph == 0) wait_epi();  // LN1 in A
+          else wait_acc();          // the previous head pair's q|k|v have left the accumulator (their softmax still runs)
           gemm(sA, kp_d, 3 * hd * min(HP, p.H - ph * HP), kFeTmemAcc, false);
           signal();
         }
@@ -310,7 +319,8 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       }
       if (xattn) {
         for (int ph = 0; ph < n_phases; ++ph) {
-          wait_epi();  // LN_kv in A (ph == 0) / previous heads consumed
+          if (ph == 0) wait_epi();  // LN_kv in A
+          else wait_acc();
           gemm(sA, kp_d, 2 * hd * min(HP, p.H - ph * HP), kFeTmemAcc, false);
           signal();
         }
@@ -367,6 +377,11 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       __syncwarp();
       if (tracing && tr_n < kFeTraceLen) g_fe_trace[tr_n++] = (2ull << 56) | (clock64() & 0xFFFFFFFFFFFFull);
       if (lane == 0) mbar_arrive(bar_epi_done);
+    };
+    auto release_acc = [&]() {  // this warp's tcgen05.ld of the q|k|v accumulator are complete
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_free);
     };
     // Per-phase parameter vectors (pending bias, q|k|v biases of the phase's heads, FFN bias chunk, ...) are read by
     // every thread; with ~225 KB of shared memory the L1 cache is gone, so a global load is an L2 round trip.  They
@@ -618,12 +633,21 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
             }
             stash_kv16(hh, 0, d0_mine, acol + HD + d0_mine, bq + (HD + d0_mine) * 4);
             stash_kv16(hh, 1, d0_mine, acol + 2 * HD + d0_mine, bq + (2 * HD + d0_mine) * 4);
+            if (ph + 1 < n_phases) release_acc();  // the next head pair's projection may overwrite the accumulator
             named_bar_sync(2 + hh, TPH * 128);  // k/v of head h for every row of the tile are in shared memory
             attend(hh, row - tok, blocked, valid, q, d0_mine, h * HD);
+          } else if (ph + 1 < n_phases) {
+            release_acc();
           }
-          signal();
-          if (ph + 1 < n_phases) stage_qkv(ib, ph + 1);
-          else stage_vec(p.pend + static_cast<long long>(2 * l + 1) * Dl, Dl);  // next: LN2
+          // the hand-over to the MMA warp happens once, after the last head pair (the attention output is complete);
+          // between head pairs the MMA warp only waits for the accumulator (release_acc) and the publish() barrier of
+          // the next phase keeps the k|v exchange region from being overwritten under a slower warp's softmax
+          if (ph + 1 < n_phases) {
+            stage_qkv(ib, ph + 1);
+          } else {
+            signal();
+            stage_vec(p.pend + static_cast<long long>(2 * l + 1) * Dl, Dl);  // next: LN2
+          }
         }
         // ---- LN2
         wait_mma();
@@ -694,12 +718,18 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
               const float4 qq = fe_lds4(bk + (2 * HD + c) * 4);
               q[c] = qq.x; q[c + 1] = qq.y; q[c + 2] = qq.z; q[c + 3] = qq.w;
             }
+            if (ph + 1 < n_phases) release_acc();
             named_bar_sync(2 + hh, TPH * 128);
             attend(hh, row, pblocked, pool_row, q, d0_mine, h * HD);
+          } else if (ph + 1 < n_phases) {
+            release_acc();
           }
-          signal();
-          if (ph + 1 < n_phases) stage_pool(ph + 1);
-          else stage_vec(p.xo_qres, Dl);  // next: out-proj bias + residual query
+          if (ph + 1 < n_phases) {
+            stage_pool(ph + 1);
+          } else {
+            signal();
+            stage_vec(p.xo_qres, Dl);  // next: out-proj bias + residual query
+          }
         }
         // ---- out-proj of the pooled query + residual query (norm_first: no LN here) -> A for latent2embed
         wait_mma();
