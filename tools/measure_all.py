@@ -97,7 +97,12 @@ def config4_slice():
     out = torch.empty((L, N, N), dtype=torch.uint16, device=dev)
     fn = lambda: mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, out_tensor=out, symmetric=True)
     ms, best = kernel_ms(fn, iters=3, warm=1)
-    rec = {"N": N, "D": D, "L": L, "rank_kernel_ms": ms, "triples_per_s": L * N * N / ms * 1e3, "out_gbs": 2.0 * L * N * N / ms / 1e6,
+    table_pwl = normalize.build_rank_table(zt, Wt, Q, kind="pwl", panel=2048, precision="bf16")
+    ms_pwl, _ = kernel_ms(lambda: mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table_pwl, out_tensor=out,
+                                                symmetric=True), iters=3, warm=1)
+    fn()  # leave the exact-LUT ranks in `out` for the checks below
+    rec = {"N": N, "D": D, "L": L, "rank_kernel_ms": ms, "rank_kernel_ms_pwl_table": ms_pwl,
+           "frac_hbm": 2.0 * L * N * N / ms / 1e6 / PEAKS["hbm_gbs"], "frac_hbm_pwl_table": 2.0 * L * N * N / ms_pwl / 1e6 / PEAKS["hbm_gbs"], "triples_per_s": L * N * N / ms * 1e3, "out_gbs": 2.0 * L * N * N / ms / 1e6,
            "out_bytes": 2 * L * N * N}
     # properties on a few outcomes (whole-tensor transposes would double the footprint)
     ok_sym, ok_diag = True, True
@@ -160,6 +165,9 @@ def table_lookup(table, logits, l):
 
 
 if __name__ == "__main__":
+    if "--config4-only" in sys.argv:
+        config4_slice()
+        sys.exit(0)
     for kind in ("lut", "pwl"):
         for sym in (True, False):
             pair_case(4096, 256, 86, "rank", kind, sym)
