@@ -171,6 +171,7 @@ if __name__ == "__main__":
     for kind in ("lut", "pwl"):
         for sym in (True, False):
             pair_case(4096, 256, 86, "rank", kind, sym)
+    pair_case(4096, 256, 121, "rank", "lut", True)   # BASELINE config 3, one of 8 GPUs' share of the 963 outcomes
     pair_case(4096, 128, 86, "rank", "lut", True)
     pair_case(4096, 128, 86, "rank", "pwl", True)
     pair_case(8192, 256, 32, "rank", "lut", True)
