@@ -460,12 +460,12 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     const bool tma_ok = out_mode != kOutTopk && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
                         ((Nc * elem) % 16 == 0) && (getenv("MDG_FORCE_DIRECT_STORE") == nullptr);
     p.use_tma_store = tma_ok ? 1 : 0;
-    CUtensorMap tmOutT = tmA;  // mirror mode: same tensor, un-swizzled 32 x 32 boxes for the transposed tiles
+    CUtensorMap tmOutT = tmA;  // mirror mode: the same tensor and box shape, used for the transposed tiles
     if (tma_ok) {
       rc = make_map_3d(&tmOut, dt, elem, out, Nc, Nr, L, Nc, Nr * Nc, 64 / elem, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
       if (p.mirror) {
-        rc = make_map_3d(&tmOutT, dt, elem, out, Nc, Nr, L, Nc, Nr * Nc, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+        rc = make_map_3d(&tmOutT, dt, elem, out, Nc, Nr, L, Nc, Nr * Nc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
         p.use_tma_store2 = 1;
       }

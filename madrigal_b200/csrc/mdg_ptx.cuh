@@ -151,6 +151,29 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x (4 x 256 bits = 32 columns) in the mma accumulator-fragment layout: thread t receives, for column group
+// i = 0..3, registers 4i+0,1 = (lane base + t/4, columns 8i + 2(t%4), +1) and 4i+2,3 = (lane base + 8 + t/4, same
+// columns)  [verified on B200 with tools/probe/tmem_layout.cu].  `taddr`'s lane field selects one 16-lane half of the
+// warp's quadrant.  This is the layout stmatrix consumes, so 8x8 b16 blocks can be stored plain or TRANSPOSED.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// Four 8x8 b16 matrices, fragment layout (thread t: row t/4, columns 2(t%4), +1 of each matrix); thread t supplies the
+// shared-memory address of row t%8 of matrix t/8 (16 bytes per row).  trans: the matrices are stored transposed.
+__device__ __forceinline__ void stmatrix_x4(uint32_t row_addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(row_addr), "r"(r0), "r"(r1),
+               "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t row_addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(row_addr), "r"(r0),
+               "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA (tcgen05.mma, kind::f16, operands in smem)

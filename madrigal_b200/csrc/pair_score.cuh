@@ -555,6 +555,95 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int nb = c.nb0; nb < c.nb1; ++nb) {
         mbar_wait(bar_t_full(acc_stage), acc_phase, 6);
         tc_fence_after_sync();
+        if constexpr (epi_is_mirror(EPI)) {
+          // Normaliser-layout epilogue (normalize_scores.py:67-70).  Each 32x32 chunk with row > col is ranked once and
+          // written twice: at [row, col] and, transposed, at [col, row].  The accumulator is read in the mma fragment
+          // layout (tcgen05.ld.16x256b), because that is what stmatrix stores: four stmatrix.x4 put the chunk into the
+          // 64B-swizzled staging tile of the plain TMA store and four stmatrix.x4.trans build the transposed tile —
+          // 32 conflict-free shared-memory wavefronts per chunk instead of 16 + 64 for st.shared.v4 + 32 sub-word
+          // st.shared.u16 from the row-per-lane layout (the shared-memory pipe is this kernel's bound).
+          const uint32_t sLutLane = sLut + static_cast<uint32_t>(lane) * 4;
+          const int fr = lane >> 2, fc = (lane & 3) * 2;  // fragment row / first column of this thread
+          if (row0 < p.rows) {
+            for (int cc = col_begin; cc < col_end; cc += 32) {
+              const int n0 = nb * kBN + cc;
+              if (n0 >= p.cols) break;
+              if (n0 > row0 + 31) break;  // every (row, col) of this chunk has col > row
+              uint32_t v[2][16];
+              const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                     static_cast<uint32_t>((acc_stage * 2 + ms) * kBN + cc);
+              tmem_ld_16x256b_x4(taddr, v[0]);
+              tmem_ld_16x256b_x4(taddr + (16u << 16), v[1]);
+              tmem_ld_wait();
+              // P[hf][i][s]: ranks of (row 16hf + 8s + fr, cols 8i + fc, +1) packed as b16x2
+              uint32_t P[2][4][2];
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                  for (int s = 0; s < 2; ++s) {
+                    const uint32_t ra = rank_lookup_epi<epi_is_pwl(EPI)>(sLut, sLutLane, __uint_as_float(v[hf][4 * i + 2 * s]), scale, bias);
+                    const uint32_t rb = rank_lookup_epi<epi_is_pwl(EPI)>(sLut, sLutLane, __uint_as_float(v[hf][4 * i + 2 * s + 1]), scale, bias);
+                    P[hf][i][s] = __byte_perm(ra, rb, 0x5410);
+                  }
+              const bool direct = !p.use_tma_store || n0 == row0;  // diagonal chunk (or unaligned output): masked stores
+              if (!direct) {
+                // transposed tile: staging row = chunk column c, 16-byte piece m = rows 8m .. 8m+7, piece position
+                // swizzled like the plain tile (64B swizzle: piece ^ ((row >> 1) & 3))
+                {
+                  const uint32_t tb = ss.acquire(lane);
+                  const int m = lane >> 3, k = lane & 7;  // this thread addresses stored-row k of matrix m
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const int c = 8 * i + k;
+                    stmatrix_x4_trans(tb + c * 64 + ((m ^ ((c >> 1) & 3)) << 4), P[0][i][0], P[0][i][1], P[1][i][0], P[1][i][1]);
+                  }
+                  ss.commit(&tmOut2, row0, n0, c.l, lane);  // [l, n0.., row0..]
+                }
+                {
+                  const uint32_t nbuf = ss.acquire(lane);
+                  const int i = lane >> 3, k = lane & 7;  // matrix i = column group, row k
+#pragma unroll
+                  for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                      const int R = 16 * hf + 8 * s + k;
+                      stmatrix_x4(nbuf + R * 64 + ((i ^ ((R >> 1) & 3)) << 4), P[hf][0][s], P[hf][1][s], P[hf][2][s], P[hf][3][s]);
+                    }
+                  ss.commit(&tmOut, n0, row0, c.l, lane);
+                }
+              } else {
+                uint16_t* ob = reinterpret_cast<uint16_t*>(p.out) + c.l * p.out_batch_stride;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int s = 0; s < 2; ++s)
+#pragma unroll
+                      for (int e = 0; e < 2; ++e) {
+                        const int row = row0 + 16 * hf + 8 * s + fr, col = n0 + 8 * i + fc + e;
+                        const uint16_t r = static_cast<uint16_t>(e ? (P[hf][i][s] >> 16) : (P[hf][i][s] & 0xFFFFu));
+                        if (row < p.rows && col < p.cols) {
+                          if (col < row) {
+                            ob[static_cast<long long>(row) * p.out_ld + col] = r;
+                            ob[static_cast<long long>(col) * p.out_ld + row] = r;
+                          } else if (col == row) {
+                            ob[static_cast<long long>(row) * p.out_ld + col] = 0;  // diagonal (normalize_scores.py:69)
+                          }
+                        }
+                      }
+              }
+            }
+          }
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_t_empty(acc_stage));
+          acc_stage ^= 1;
+          if (acc_stage == 0) acc_phase ^= 1;
+          continue;
+        }
         if constexpr (EPI == EPI_TOPK) {
           // Top-k epilogue.  (1) A tcgen05.ld issued while MMAs are queued only completes once the queue drains, so the
           // warp's whole slice of the tile (up to 4 chunks) is fetched with ALL loads in flight and ONE wait, and the
