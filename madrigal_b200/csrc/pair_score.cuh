@@ -735,41 +735,23 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_32x32(taddr, v);
             if constexpr (EPI != EPI_LINEAR) tmem_ld_wait();  // LINEAR overlaps its global loads with the TMEM load
 
-            if constexpr (epi_is_rank(EPI)) {
+            if constexpr (epi_is_rank(EPI)) {  // full layout (the normaliser layout has its own branch above)
               uint32_t pk[16];
               const uint32_t sLutLane = sLut + static_cast<uint32_t>(lane) * 4;
-              // mirror mode (reference normaliser layout, normalize_scores.py:67-70): this chunk holds ranks of
-              // (row > col) pairs; each is also written at [col, row] through a TRANSPOSED staging tile.
-              constexpr bool mirror = epi_is_mirror(EPI);
-              const bool direct = !p.use_tma_store || (mirror && n0 == row0);  // diagonal chunk: masked stores
-              uint32_t tstage = 0;
-              if (mirror && !direct) tstage = ss.acquire(lane) + static_cast<uint32_t>(lane) * 2;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const uint32_t r0 = rank_lookup_epi<epi_is_pwl(EPI)>(sLut, sLutLane, __uint_as_float(v[2 * j]), scale, bias);
                 const uint32_t r1 = rank_lookup_epi<epi_is_pwl(EPI)>(sLut, sLutLane, __uint_as_float(v[2 * j + 1]), scale, bias);
                 pk[j] = __byte_perm(r0, r1, 0x5410);
-                if (mirror && !direct) {  // transposed tile: row = column index, 64-byte pitch, no swizzle
-                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(tstage + (2 * j) * 64), "h"(static_cast<uint16_t>(r0)) : "memory");
-                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(tstage + (2 * j + 1) * 64), "h"(static_cast<uint16_t>(r1)) : "memory");
-                }
               }
-              if (!direct) {
-                if (mirror) ss.commit(&tmOut2, row0, n0, c.l, lane);  // [l, n0.., row0..]
+              if (p.use_tma_store) {
                 ss.store(&tmOut, pk, n0, row0, c.l, lane);
               } else if (my_row < p.rows) {
-                uint16_t* ob = reinterpret_cast<uint16_t*>(p.out) + c.l * p.out_batch_stride;
-                uint16_t* o = ob + static_cast<long long>(my_row) * p.out_ld + n0;
+                uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + c.l * p.out_batch_stride +
+                              static_cast<long long>(my_row) * p.out_ld + n0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int col = n0 + j;
-                  const uint16_t r = static_cast<uint16_t>((j & 1) ? (pk[j >> 1] >> 16) : (pk[j >> 1] & 0xFFFFu));
-                  if (col < p.cols && (!mirror || col < my_row)) {
-                    o[j] = r;
-                    if (mirror) ob[static_cast<long long>(col) * p.out_ld + my_row] = r;
-                  }
-                }
-                if (mirror && n0 == row0) o[lane] = 0;  // diagonal (normalize_scores.py:69)
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < p.cols) o[j] = static_cast<uint16_t>((j & 1) ? (pk[j >> 1] >> 16) : (pk[j >> 1] & 0xFFFFu));
               }
             } else if constexpr (EPI == EPI_LINEAR) {
               // y = act(acc + bias) (+ residual); fp32 and/or bf16 (hi | lo) outputs, guarded direct stores
