@@ -388,6 +388,7 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     p.use_tma_store = 1;
     p.lo_col_offset = static_cast<int>(D);
     p.write_lo = split;
+    p.a_reuse = getenv("MDG_GEMM1_NO_REUSE") ? 0 : 1;  // z row blocks stay resident across outcomes
     p.out = ws.y;
     p.out_ld = ka;
     p.out_batch_stride = ws.nr_pad * ka;

@@ -108,6 +108,8 @@ struct PairScoreParams {
   unsigned int* sched_counter;  // zeroed by the host before the launch: dynamic task scheduler (NULL: static deal)
   int mirror;      // EPI_RANK_U16 with lower_only: also write each rank at [col, row]; diagonal = 0
   int lower_only;  // keep only row > col (unordered pairs of one catalogue) and skip column blocks above the diagonal
+  int a_reuse;     // A is shared by all outcomes (GEMM 1: z . W_l): tasks are ordered row-block-major and dealt in
+                   // contiguous per-CTA ranges so that the resident A panels are loaded once per row block, not per task
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
@@ -156,11 +158,20 @@ struct TaskCoord {
 };
 __device__ __forceinline__ TaskCoord decode_task(const PairScoreParams& p, int t) {
   TaskCoord c;
-  int per_l = p.m_blocks * p.chunks_per_row;
-  c.l = t / per_l;
-  int rem = t - c.l * per_l;
-  int mb = rem / p.chunks_per_row;
-  int ch = rem - mb * p.chunks_per_row;
+  int mb, ch;
+  if (p.a_reuse) {  // row-block-major: consecutive tasks share the A operand
+    const int per_mb = p.L * p.chunks_per_row;
+    mb = t / per_mb;
+    const int rem = t - mb * per_mb;
+    c.l = rem / p.chunks_per_row;
+    ch = rem - c.l * p.chunks_per_row;
+  } else {
+    const int per_l = p.m_blocks * p.chunks_per_row;
+    c.l = t / per_l;
+    const int rem = t - c.l * per_l;
+    mb = rem / p.chunks_per_row;
+    ch = rem - mb * p.chunks_per_row;
+  }
   if (p.lower_only) mb = p.m_blocks - 1 - mb;  // largest row blocks (most tiles below the diagonal) first
   c.m0 = mb * kBM * p.msub;
   c.nb0 = ch * p.nchunk;
@@ -319,6 +330,12 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tasks.t = static_cast<int>(blockIdx.x);
   tasks.step = static_cast<int>(gridDim.x);
   tasks.end = p.num_tasks;
+  if (p.a_reuse && !dyn) {  // contiguous range per CTA
+    const int per = (p.num_tasks + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    tasks.t = static_cast<int>(blockIdx.x) * per;
+    tasks.step = 1;
+    tasks.end = min(tasks.t + per, p.num_tasks);
+  }
   tasks.n = 0;
   tasks.full0 = bar_task_full0;
   tasks.empty0 = bar_task_empty0;
@@ -334,6 +351,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t b_phase = 0;
       int it = 0;  // executed tasks (parity of the A barriers)
+      int last_m0 = -1;
       if (p.stream_a) {
         const int ksteps = (p.nterm == 1) ? kb : 3 * kb;
         for (int t = tasks.next_producer(p.sched_counter); t >= 0; t = tasks.next_producer(p.sched_counter)) {
@@ -361,7 +379,11 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int t = tasks.next_producer(p.sched_counter); t >= 0; t = tasks.next_producer(p.sched_counter), ++it) {
         const TaskCoord c = decode_task(p, t);
         mbar_wait(bar_a_empty, (it & 1) ^ 1, 1);
-        if (elect_one()) {
+        const bool a_resident = p.a_reuse && !p.a_batched && it > 0 && c.m0 == last_m0;  // same panels as the last task
+        last_m0 = c.m0;
+        if (a_resident) {
+          if (elect_one()) mbar_arrive(bar_a_full);
+        } else if (elect_one()) {
           mbar_arrive_expect_tx(bar_a_full, n_apanels * kPanelBytes);
           for (int pn = 0; pn < n_apanels; ++pn) {
             int row, kc;
