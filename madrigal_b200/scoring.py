@@ -105,6 +105,64 @@ def score_all_pairs_to_host(z: torch.Tensor, weight: torch.Tensor, out_host: tor
     return out_host
 
 
+def raw_scores_path(checkpoint_dir: str, eval_type: str, drug_group_str: str, epoch, all_outcomes: bool = True) -> str:
+    """The `.npy` file name the reference's drivers write and its notebooks read back (predict.py:412-436, 460-462)."""
+    which = "all" if all_outcomes else "selected"
+    return f"{checkpoint_dir}/{eval_type}_{which}_outcomes_{drug_group_str}_drugs_raw_scores_{epoch}.npy"
+
+
+def score_all_pairs_to_npy(z: torch.Tensor, weight: torch.Tensor, path: str, *, out: str = "logit",
+                           outcome_inds=None, table: Optional[RankTable] = None, precision: str = "fp32",
+                           chunk: int = 10, normalize: bool = False, symmetric: bool = False):
+    """predict.py:412-436 / 439-462: all-pairs scores of the selected drugs written to a `.npy` memmap, outcomes in chunks
+    of `chunk` (or only `outcome_inds`, predict.py:447-452), returned as `np.load(path, mmap_mode='r')`.
+
+    The reference fills a `.raw` memmap and then copies it into a `.npy` with `np.save`; here the `.npy` is created
+    directly (`np.lib.format.open_memmap`) and each chunk goes GPU -> pinned staging buffer -> file, the device-to-host
+    copy of chunk c overlapping the kernel of chunk c+1."""
+    import numpy as np
+    W = weight if outcome_inds is None else weight[torch.as_tensor(outcome_inds, device=weight.device)].contiguous()
+    L, N = W.shape[0], z.shape[0]
+    np_dtype = {"logit": np.float32, "sigmoid": np.float32, "rank": np.uint16}[out]
+    fp = np.lib.format.open_memmap(path, mode="w+", dtype=np_dtype, shape=(L, N, N))
+    dev = z.device
+    compute = torch.cuda.current_stream(dev)
+    copy = _copy_stream(dev)
+    n = min(chunk, L) if L > 0 else 1
+    dbufs = [torch.empty((n, N, N), dtype=_OUT_DTYPE[out], device=dev) for _ in range(2)]
+    hbufs = [torch.empty((n, N, N), dtype=_OUT_DTYPE[out]).pin_memory() for _ in range(2)]
+    pending = [None, None]  # (event, l0, l1) of the copy in flight per buffer
+
+    def drain(b):
+        if pending[b] is not None:
+            ev, a0, a1 = pending[b]
+            ev.synchronize()
+            fp[a0:a1] = hbufs[b][: a1 - a0].numpy()
+            pending[b] = None
+
+    for ci, l0 in enumerate(range(0, L, chunk)):
+        l1 = min(l0 + chunk, L)
+        b = ci & 1
+        drain(b)  # the previous use of this buffer pair has reached the file
+        dst = dbufs[b][: l1 - l0]
+        pair_score(z, z, W[l0:l1], precision=precision, out=out, table=table, table_offset=l0 if outcome_inds is None else 0,
+                   normalize=normalize, out_tensor=dst, symmetric=symmetric)
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        with torch.cuda.stream(copy):
+            copy.wait_event(ready)
+            hbufs[b][: l1 - l0].copy_(dst, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        pending[b] = (ev, l0, l1)
+    drain(0)
+    drain(1)
+    compute.wait_stream(copy)
+    fp.flush()
+    del fp
+    return np.load(path, mmap_mode="r")
+
+
 _copy_streams = {}
 
 

@@ -383,3 +383,23 @@ def test_row_block_sharding_is_bit_identical(mb, cuda_device):
         assert torch.equal(torch.cat(blocks, dim=1), full)
     blocks = [scoring.score_row_block(zt, Wt, r, 4, out="logit") for r in range(4)]
     assert torch.equal(torch.cat(blocks, dim=1), lg)
+
+
+def test_scores_to_npy_file_like_the_reference_driver(mb, cuda_device, tmp_path):
+    """predict.py:412-436: chunked all-pairs raw scores written to the reference's `.npy` file name and read back with
+    np.load(mmap_mode='r'); also the selected-outcomes variant (predict.py:439-462)."""
+    from madrigal_b200 import scoring
+    N, D, L = 150, 128, 23
+    z, W = synth.decoder_inputs(N, D, L, seed=91)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    path = scoring.raw_scores_path(str(tmp_path), "full_full", "selected", 700)
+    assert path.endswith("full_full_all_outcomes_selected_drugs_raw_scores_700.npy")
+    got = scoring.score_all_pairs_to_npy(zt, Wt, path, out="logit", precision="fp32", chunk=10)
+    assert isinstance(got, np.memmap) and got.shape == (L, N, N) and got.dtype == np.float32
+    dense = mb.pair_score(zt, zt, Wt, precision="fp32").cpu().numpy()
+    assert np.array_equal(np.asarray(got), dense)
+    sel = [3, 17, 4]
+    path2 = scoring.raw_scores_path(str(tmp_path), "full_full", "selected", 700, all_outcomes=False)
+    got2 = scoring.score_all_pairs_to_npy(zt, Wt, path2, out="sigmoid", outcome_inds=sel, precision="fp32", chunk=2)
+    ref2 = oracle.sigmoid(oracle.bilinear_scores(z, z, W, dtype=np.float64)[sel])
+    assert got2.shape == (3, N, N) and np.abs(np.asarray(got2) - ref2).max() <= 1e-4
