@@ -227,10 +227,10 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         for (int c = 0; c < n_fchunks; ++c) {
           if (c == 0)
             for (int k = 0; k < kp_d; ++k) load_panel(&tm_l1, l, 1, FC, k * 64, row0);
-          // phase: ffn2(c) then ffn1(c+1)
-          for (int k = 0; k < FC / 64; ++k) load_panel(&tm_l2, l, 1, Dl, c * FC + k * 64, row0);
+          // phase: ffn1(c+1) (runs under the tail of chunk c's activation) then ffn2(c)
           if (c + 1 < n_fchunks)
             for (int k = 0; k < kp_d; ++k) load_panel(&tm_l1, l, 1, FC, k * 64, [&](int) { return (c + 1) * FC; });
+          for (int k = 0; k < FC / 64; ++k) load_panel(&tm_l2, l, 1, Dl, c * FC + k * 64, row0);
         }
       }
       if (xattn) {
@@ -311,9 +311,12 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         gemm(sA, kp_d, FC, kFeTmemAcc, false);
         signal();
         for (int c = 0; c < n_fchunks; ++c) {
+          if (c + 1 < n_fchunks) {
+            wait_acc();  // every thread has its pieces of chunk c in registers: the accumulator can take chunk c + 1
+            gemm(sA, kp_d, FC, kFeTmemAcc, false);
+          }
           wait_epi();  // activation chunk c in O
           gemm(sO, FC / 64, Dl, kFeTmemH, true);
-          if (c + 1 < n_fchunks) gemm(sA, kp_d, FC, kFeTmemAcc, false);
           signal();
         }
       }
@@ -658,9 +661,12 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         for (int c = 0; c < n_fchunks; ++c) {
           wait_mma();
           const uint32_t b1 = publish();  // linear1 bias of columns [c * FC, c * FC + FC)
+          const bool more_chunks = c + 1 < n_fchunks;
+          if (more_chunks && g * 32 >= FC) release_acc();  // this thread reads nothing of the chunk
           for (int cc = g * 32; cc < FC; cc += 32 * TPR) {
             uint32_t v[32];
             tmem_ld_32x32(trow + kFeTmemAcc + cc, v);
+            const bool last_piece = cc + 32 * TPR >= FC;
             float y[32];
             if (c * FC + cc + 32 <= p.F) {
 #pragma unroll
@@ -669,6 +675,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
                 y[4 * j] = bb.x; y[4 * j + 1] = bb.y; y[4 * j + 2] = bb.z; y[4 * j + 3] = bb.w;
               }
               tmem_ld_wait();
+              if (more_chunks && last_piece) release_acc();  // FFN1 of the next chunk runs under this piece's GELU
               if (p.act == 1) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) y[j] = fmaxf(__uint_as_float(v[j]) + y[j], 0.f);
@@ -678,6 +685,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
               }
             } else {
               tmem_ld_wait();
+              if (more_chunks && last_piece) release_acc();
               const float* b1g = p.l1_bias[l] + c * FC;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
