@@ -106,6 +106,9 @@ struct FusionPlan {
   // workspace pieces
   __nv_bfloat16 *w_e2l, *w_l2e, *w_xin, *w_xout;
   __nv_bfloat16 *w_in[MDG_MAX_LAYERS], *w_out[MDG_MAX_LAYERS], *w_l1[MDG_MAX_LAYERS], *w_l2[MDG_MAX_LAYERS];
+  // fused kernel only: LayerNorm weight/bias folded into the linear that consumes the normalised rows
+  __nv_bfloat16 *w_in_f[MDG_MAX_LAYERS], *w_l1_f[MDG_MAX_LAYERS], *w_xin_f;
+  float *in_bias_f[MDG_MAX_LAYERS], *l1_bias_f[MDG_MAX_LAYERS], *xin_bias_f;
   __nv_bfloat16 *xb, *nb, *ob, *fb, *pb;
   float *h, *qkv, *p32, *q_res, *q_proj, *pend, *xo_qres;
   size_t ob_bytes, fb_bytes, pb_bytes;
@@ -155,7 +158,15 @@ int plan_fusion(const MdgFusionCfg* cfg, long long B, int precision, void* ws, v
     pl->w_out[i] = pw.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(Dl, s));
     pl->w_l1[i] = pw.take<__nv_bfloat16>(static_cast<size_t>(F) * ka_of(Dl, s));
     pl->w_l2[i] = pw.take<__nv_bfloat16>(static_cast<size_t>(Dl) * ka_of(F, s));
+    pl->w_in_f[i] = pw.take<__nv_bfloat16>(static_cast<size_t>(3 * Dl) * ka_of(Dl, 0));
+    pl->w_l1_f[i] = pw.take<__nv_bfloat16>(static_cast<size_t>(F) * ka_of(Dl, 0));
   }
+  pl->w_xin_f = pw.take<__nv_bfloat16>(static_cast<size_t>(2 * Dl) * ka_of(Dl, 0));
+  for (int i = 0; i < pl->layers; ++i) {
+    pl->in_bias_f[i] = pw.take<float>(static_cast<size_t>(3 * Dl));
+    pl->l1_bias_f[i] = pw.take<float>(static_cast<size_t>(F));
+  }
+  pl->xin_bias_f = pw.take<float>(static_cast<size_t>(3 * Dl));
   pl->q_res = pw.take<float>(Dl);
   pl->q_proj = pw.take<float>(Dl);
   pl->pend = pw.take<float>(static_cast<size_t>(2 * pl->layers + 1) * Dl);  // fused kernel: biases owed to H per stage
@@ -196,16 +207,7 @@ bool fused_encoder_eligible(const MdgFusionCfg* cfg, const FusionPlan& pl) {
 bool fused_encoder_aligned(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const float* tokens, const float* z_out) {
   auto ok = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   if (!ok(tokens) || !ok(z_out) || !ok(w->latent2embed_bias)) return false;
-  for (int i = 0; i < cfg->num_layers; ++i) {
-    const MdgFusionLayer& L = w->layers[i];
-    if (!ok(L.in_proj_bias) || !ok(L.linear1_bias) || !ok(L.norm1_weight) || !ok(L.norm1_bias) ||
-        !ok(L.norm2_weight) || !ok(L.norm2_bias))
-      return false;
-  }
-  if (cfg->agg == MDG_AGG_XATTN &&
-      (!ok(w->x_attn_kv_norm_weight) || !ok(w->x_attn_kv_norm_bias) || !ok(w->x_attn_in_proj_bias) ||
-       !ok(w->x_attn_out_proj_bias)))
-    return false;
+  if (cfg->agg == MDG_AGG_XATTN && !ok(w->x_attn_out_proj_bias)) return false;
   return true;
 }
 
@@ -242,16 +244,16 @@ int run_fused_encoder(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   if ((rc = make_map_3d(&tm[0], bf, 2, pl.w_e2l, ke, Dl, 1, ke, Dl * ke, 64, Dl, sw))) return rc;
   if (pl.layers > 0) {
-    if ((rc = make_map_3d(&tm[1], bf, 2, pl.w_in[0], kd, 3 * Dl, nl, kd, lstride ? lstride : 3 * Dl * kd, 64, hd, sw))) return rc;
+    if ((rc = make_map_3d(&tm[1], bf, 2, pl.w_in_f[0], kd, 3 * Dl, nl, kd, lstride ? lstride : 3 * Dl * kd, 64, hd, sw))) return rc;
     if ((rc = make_map_3d(&tm[2], bf, 2, pl.w_out[0], kd, Dl, nl, kd, lstride ? lstride : Dl * kd, 64, Dl, sw))) return rc;
-    if ((rc = make_map_3d(&tm[3], bf, 2, pl.w_l1[0], kd, F, nl, kd, lstride ? lstride : F * kd, 64, FC, sw))) return rc;
+    if ((rc = make_map_3d(&tm[3], bf, 2, pl.w_l1_f[0], kd, F, nl, kd, lstride ? lstride : F * kd, 64, FC, sw))) return rc;
     if ((rc = make_map_3d(&tm[4], bf, 2, pl.w_l2[0], kf, Dl, nl, kf, lstride ? lstride : Dl * kf, 64, Dl, sw))) return rc;
   } else {
     tm[1] = tm[2] = tm[3] = tm[4] = tm[0];
   }
   if ((rc = make_map_3d(&tm[5], bf, 2, pl.w_l2e, kd, E, 1, kd, E * kd, 64, E, sw))) return rc;
   if (cfg->agg == MDG_AGG_XATTN) {
-    if ((rc = make_map_3d(&tm[6], bf, 2, pl.w_xin, kd, 2 * Dl, 1, kd, 2 * Dl * kd, 64, hd, sw))) return rc;
+    if ((rc = make_map_3d(&tm[6], bf, 2, pl.w_xin_f, kd, 2 * Dl, 1, kd, 2 * Dl * kd, 64, hd, sw))) return rc;
     if ((rc = make_map_3d(&tm[7], bf, 2, pl.w_xout, kd, Dl, 1, kd, Dl * kd, 64, Dl, sw))) return rc;
   } else {
     tm[6] = tm[7] = tm[0];
@@ -274,15 +276,13 @@ int run_fused_encoder(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
   p.pend = pl.pend;
   for (int i = 0; i < pl.layers; ++i) {
     const MdgFusionLayer& L = w->layers[i];
-    p.in_bias[i] = L.in_proj_bias;
-    p.l1_bias[i] = L.linear1_bias;
-    p.n1_w[i] = L.norm1_weight; p.n1_b[i] = L.norm1_bias;
-    p.n2_w[i] = L.norm2_weight; p.n2_b[i] = L.norm2_bias;
+    (void)L;
+    p.in_bias[i] = pl.in_bias_f[i];  // LayerNorm-folded biases (fusion_prepare_impl)
+    p.l1_bias[i] = pl.l1_bias_f[i];
   }
   p.l2e_bias = w->latent2embed_bias;
   if (cfg->agg == MDG_AGG_XATTN) {
-    p.xkv_nw = w->x_attn_kv_norm_weight; p.xkv_nb = w->x_attn_kv_norm_bias;
-    p.xin_bias = w->x_attn_in_proj_bias;
+    p.xin_bias = pl.xin_bias_f;
     p.xout_bias = w->x_attn_out_proj_bias;
     p.xq_nw = w->x_attn_query_norm_weight; p.xq_nb = w->x_attn_query_norm_bias;
     p.q_res = pl.q_res;
@@ -430,6 +430,23 @@ static int fusion_prepare_impl(const MdgFusionWeights* w, const MdgFusionCfg* cf
     mdg::fused_pend_kernel<<<(Dl + 127) / 128, 128, 0, stream>>>(a, pl.pend);
     MDG_CUDA(cudaGetLastError());
     ++g_last_launches;
+    // LayerNorm affine folded into the next linear:  LN(x) . W^T + b  =  xhat . (W * ln_w)^T + (b + W . ln_b)
+    auto fold = [&](const float* W, const float* bias, const float* lnw, const float* lnb, int N, __nv_bfloat16* wout,
+                    float* bout) -> int {
+      mdg::fold_ln_linear_kernel<<<(N + 7) / 8, 256, 0, stream>>>(W, bias, lnw, lnb, N, Dl, kpad_of(Dl), wout, bout);
+      MDG_CUDA(cudaGetLastError());
+      ++g_last_launches;
+      return MDG_OK;
+    };
+    for (int i = 0; i < pl.layers; ++i) {
+      const MdgFusionLayer& L = w->layers[i];
+      if ((rc = fold(L.in_proj_weight, L.in_proj_bias, L.norm1_weight, L.norm1_bias, 3 * Dl, pl.w_in_f[i], pl.in_bias_f[i]))) return rc;
+      if ((rc = fold(L.linear1_weight, L.linear1_bias, L.norm2_weight, L.norm2_bias, F, pl.w_l1_f[i], pl.l1_bias_f[i]))) return rc;
+    }
+    if (cfg->agg == MDG_AGG_XATTN) {  // k | v rows of the pooling MHA, LN = x_attn_kv_norm; biases keep the [3 Dl] indexing
+      if ((rc = fold(w->x_attn_in_proj_weight + static_cast<size_t>(Dl) * Dl, w->x_attn_in_proj_bias + Dl,
+                     w->x_attn_kv_norm_weight, w->x_attn_kv_norm_bias, 2 * Dl, pl.w_xin_f, pl.xin_bias_f + Dl))) return rc;
+    }
   }
   if (cfg->agg == MDG_AGG_XATTN) {
     if ((rc = convert_rows(w->x_attn_in_proj_weight + static_cast<size_t>(Dl) * Dl, 2 * Dl, Dl, Dl, 1, s, pl.w_xin, stream))) return rc;

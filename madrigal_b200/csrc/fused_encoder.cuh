@@ -71,14 +71,8 @@ struct FusedEncParams {
   const float* pend;          // [(2*layers + 1), Dl] cumulative biases folded into reads of H
   const float* in_bias[MDG_MAX_LAYERS];
   const float* l1_bias[MDG_MAX_LAYERS];
-  const float* n1_w[MDG_MAX_LAYERS];
-  const float* n1_b[MDG_MAX_LAYERS];
-  const float* n2_w[MDG_MAX_LAYERS];
-  const float* n2_b[MDG_MAX_LAYERS];
   const float* l2e_bias;
   // x-attn pooling
-  const float* xkv_nw;   // x_attn_kv_norm
-  const float* xkv_nb;
   const float* xin_bias;   // x_attn in_proj bias [3*Dl] (k at Dl, v at 2*Dl)
   const float* xout_bias;  // [Dl]
   const float* xq_nw;      // x_attn_query_norm (applied after the residual when !norm_first; unused: norm_first only)
@@ -424,7 +418,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
     };
     // LayerNorm of (H + pend) for this row -> bf16 into `dst`.  Each of the row's threads owns every 4th 32-column
     // chunk; the partial sums meet in shared memory (the k|v exchange region is idle during LN stages).
-    auto layer_norm_to = [&](uint32_t dst, uint32_t pend, const float* w, const float* b, bool do_ln) {
+    auto layer_norm_to = [&](uint32_t dst, uint32_t pend, bool do_ln) {
       float mean = 0.f, rstd = 1.f;
       if (do_ln) {
         float s = 0.f, ss = 0.f;
@@ -476,15 +470,9 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(v[j]);
-        if (do_ln) {
+        if (do_ln) {  // the LayerNorm weight / bias live in the next linear's weights (folded at prepare time)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 ww = fe_ldg4(w + c + 4 * j), bb = fe_ldg4(b + c + 4 * j);
-            y[4 * j] = fmaf(fmaf(y[4 * j], rstd, shift), ww.x, bb.x);
-            y[4 * j + 1] = fmaf(fmaf(y[4 * j + 1], rstd, shift), ww.y, bb.y);
-            y[4 * j + 2] = fmaf(fmaf(y[4 * j + 2], rstd, shift), ww.z, bb.z);
-            y[4 * j + 3] = fmaf(fmaf(y[4 * j + 3], rstd, shift), ww.w, bb.w);
-          }
+          for (int j = 0; j < 32; ++j) y[j] = fmaf(y[j], rstd, shift);
         }
         fe_store_row32(dst, row, c, y);
       }
@@ -604,7 +592,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         const float* ib = p.in_bias[l];
         // ---- LN1
         wait_mma();
-        layer_norm_to(sA, publish(), p.n1_w[l], p.n1_b[l], true);
+        layer_norm_to(sA, publish(), true);
         signal();
         stage_qkv(ib, 0);
         // ---- attention: HP heads per phase; a thread takes (head slot, 16-dimension slice)
@@ -654,7 +642,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         }
         // ---- LN2
         wait_mma();
-        layer_norm_to(sA, publish(), p.n2_w[l], p.n2_b[l], true);
+        layer_norm_to(sA, publish(), true);
         signal();
         stage_vec(p.l1_bias[l], min(FC, p.F));
         // ---- FFN activation chunks (32-column pieces of the chunk alternate between the row's threads)
@@ -703,7 +691,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       if (xattn) {
         // ---- x-attn pooling (models.py:422-440): kv = LN_kv(h); one learned query per head; constant key mask
         wait_mma();
-        layer_norm_to(sA, publish(), p.xkv_nw, p.xkv_nb, true);
+        layer_norm_to(sA, publish(), true);
         signal();
         stage_pool(0);
         uint32_t pblocked = 0;
@@ -760,7 +748,7 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       } else {
         // ---- pooling input: latent2embed is applied to every token row (models.py:415)
         wait_mma();
-        layer_norm_to(sA, publish(), nullptr, nullptr, false);
+        layer_norm_to(sA, publish(), false);
         signal();
       }
       stage_vec(p.l2e_bias, p.E);
@@ -818,6 +806,33 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// W' = W * diag(ln_w) as bf16 operand rows [N, k_pad] (zero padded) and b' = b + W . ln_b: the LayerNorm affine of the
+// rows feeding a linear, folded into that linear.  One warp per output row.
+__global__ void __launch_bounds__(256) fold_ln_linear_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                             const float* __restrict__ ln_w,
+                                                             const float* __restrict__ ln_b, int N, int K, int k_pad,
+                                                             __nv_bfloat16* __restrict__ w_out,
+                                                             float* __restrict__ b_out) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  const float* wr = W + static_cast<size_t>(n) * K;
+  __nv_bfloat16* o = w_out + static_cast<size_t>(n) * k_pad;
+  float acc = 0.f;
+  for (int k = lane; k < k_pad; k += 32) {
+    float x = 0.f;
+    if (k < K) {
+      const float wv = wr[k];
+      x = wv * ln_w[k];
+      acc = fmaf(wv, ln_b[k], acc);
+    }
+    o[k] = __float2bfloat16_rn(x);
+  }
+#pragma unroll
+  for (int s2 = 16; s2 > 0; s2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s2);
+  if (lane == 0) b_out[n] = bias[n] + acc;
 }
 
 __global__ void vec_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
