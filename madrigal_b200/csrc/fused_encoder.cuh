@@ -485,7 +485,50 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
       float acc[DPT];
 #pragma unroll
       for (int d = 0; d < DPT; ++d) acc[d] = 0.f;
-      if (active) {
+      if (active && T <= 4) {
+        // few-token case (BASELINE's 4 modality tokens): all scores first, ONE max / normaliser, then P.V without the
+        // running rescale of the online form below
+        float sc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sc[j] = -CUDART_INF_F;
+          if (j < T && !((key_blocked >> j) & 1u)) {
+            float s0 = 0.f, s1 = 0.f;  // two independent FMA chains
+#pragma unroll
+            for (int d8 = 0; d8 < HD / 8; ++d8) {
+              uint32_t a, b, c2, e;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(hh, r0 + j, d8)));
+              const uint32_t ww[4] = {a, b, c2, e};
+#pragma unroll
+              for (int t2 = 0; t2 < 4; ++t2) {
+                const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
+                s0 = fmaf(q[d8 * 8 + 2 * t2], kk.x, s0);
+                s1 = fmaf(q[d8 * 8 + 2 * t2 + 1], kk.y, s1);
+              }
+            }
+            sc[j] = s0 + s1;
+          }
+        }
+        m = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (sc[j] == -CUDART_INF_F) continue;  // masked (or beyond T): contributes exactly 0
+          const float pj = __expf(sc[j] - m);
+          lsum += pj;
+#pragma unroll
+          for (int d8 = 0; d8 < DPT / 8; ++d8) {
+            uint32_t a, b, c2, e;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(hh, r0 + j, HD / 8 + d0 / 8 + d8)));
+            const uint32_t ww[4] = {a, b, c2, e};
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) {
+              const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
+              acc[d8 * 8 + 2 * t2] = fmaf(pj, vv.x, acc[d8 * 8 + 2 * t2]);
+              acc[d8 * 8 + 2 * t2 + 1] = fmaf(pj, vv.y, acc[d8 * 8 + 2 * t2 + 1]);
+            }
+          }
+        }
+      } else if (active) {
         for (int j = 0; j < T; ++j) {
           if ((key_blocked >> j) & 1u) continue;
           const int rj = r0 + j;
