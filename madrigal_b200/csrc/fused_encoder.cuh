@@ -119,6 +119,24 @@ __device__ __forceinline__ float fe_gelu(float x) {
   pl *= t;
   return fmaf(-0.5f * ax * pl, e, fmaxf(x, 0.f));
 }
+// The same GELU for two values at once on the packed fp32x2 pipe (fma.rn.f32x2 / mul.f32x2 / add.f32x2, sm_100):
+// every polynomial step is ONE instruction for the pair; only |x|, max(x, 0) and the two MUFU ops stay scalar.
+__device__ __forceinline__ float2 fe_gelu2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 den = __ffma2_rn(ax, make_float2(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f),
+                                make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
+  const float2 xx = __fmul2_rn(x, x);
+  const float2 ea = __fmul2_rn(xx, make_float2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+  const float2 e = make_float2(exp2f(ea.x), exp2f(ea.y));
+  float2 pl = __ffma2_rn(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
+  pl = __ffma2_rn(pl, t, make_float2(1.421413741f, 1.421413741f));
+  pl = __ffma2_rn(pl, t, make_float2(-0.284496736f, -0.284496736f));
+  pl = __ffma2_rn(pl, t, make_float2(0.254829592f, 0.254829592f));
+  pl = __fmul2_rn(pl, t);
+  const float2 w = __fmul2_rn(__fmul2_rn(ax, make_float2(-0.5f, -0.5f)), pl);
+  return __ffma2_rn(w, e, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
 __device__ __forceinline__ float fe_act(float a, int act) {
   if (act == 1) return fmaxf(a, 0.f);
   return fe_gelu(a);
@@ -712,7 +730,12 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
                 for (int j = 0; j < 32; ++j) y[j] = fmaxf(__uint_as_float(v[j]) + y[j], 0.f);
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) y[j] = fe_gelu(__uint_as_float(v[j]) + y[j]);
+                for (int j = 0; j < 32; j += 2) {
+                  const float2 r = fe_gelu2(__fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                                       make_float2(y[j], y[j + 1])));
+                  y[j] = r.x;
+                  y[j + 1] = r.y;
+                }
               }
             } else {
               tmem_ld_wait();
