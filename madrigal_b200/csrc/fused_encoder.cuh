@@ -511,20 +511,21 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
         for (int j = 0; j < 4; ++j) {
           sc[j] = -CUDART_INF_F;
           if (j < T && !((key_blocked >> j) & 1u)) {
-            float s0 = 0.f, s1 = 0.f;  // two independent FMA chains
+            float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);  // packed fp32x2 FMA chains
 #pragma unroll
             for (int d8 = 0; d8 < HD / 8; ++d8) {
               uint32_t a, b, c2, e;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c2), "=r"(e) : "r"(kv_addr(hh, r0 + j, d8)));
               const uint32_t ww[4] = {a, b, c2, e};
 #pragma unroll
-              for (int t2 = 0; t2 < 4; ++t2) {
-                const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
-                s0 = fmaf(q[d8 * 8 + 2 * t2], kk.x, s0);
-                s1 = fmaf(q[d8 * 8 + 2 * t2 + 1], kk.y, s1);
+              for (int t2 = 0; t2 < 4; t2 += 2) {
+                const float2 k0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
+                const float2 k1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2 + 1]));
+                s01 = __ffma2_rn(make_float2(q[d8 * 8 + 2 * t2], q[d8 * 8 + 2 * t2 + 1]), k0, s01);
+                s23 = __ffma2_rn(make_float2(q[d8 * 8 + 2 * t2 + 2], q[d8 * 8 + 2 * t2 + 3]), k1, s23);
               }
             }
-            sc[j] = s0 + s1;
+            sc[j] = (s01.x + s01.y) + (s23.x + s23.y);
           }
         }
         m = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
@@ -541,8 +542,9 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
 #pragma unroll
             for (int t2 = 0; t2 < 4; ++t2) {
               const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t2]));
-              acc[d8 * 8 + 2 * t2] = fmaf(pj, vv.x, acc[d8 * 8 + 2 * t2]);
-              acc[d8 * 8 + 2 * t2 + 1] = fmaf(pj, vv.y, acc[d8 * 8 + 2 * t2 + 1]);
+              const float2 r = __ffma2_rn(make_float2(pj, pj), vv, make_float2(acc[d8 * 8 + 2 * t2], acc[d8 * 8 + 2 * t2 + 1]));
+              acc[d8 * 8 + 2 * t2] = r.x;
+              acc[d8 * 8 + 2 * t2 + 1] = r.y;
             }
           }
         }
