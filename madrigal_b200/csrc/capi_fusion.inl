@@ -297,8 +297,10 @@ int run_fused_encoder(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
   return hd == 16 ? launch_fused_instance<16>(tm, p, grid, stream) : launch_fused_instance<32>(tm, p, grid, stream);
 }
 
-int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_mask, const uint8_t* src_mask,
-                     long long Bc, cudaStream_t stream) {
+// qkv rows: fp32 [R, 3 Dl] (fp32-parity mode) or bf16 [R, kpad(3 Dl)] (bf16 mode)
+template <typename TIn>
+int launch_attention_t(const FusionPlan& pl, const TIn* qkv, long long ld, const uint8_t* key_mask,
+                       const uint8_t* src_mask, long long Bc, cudaStream_t stream) {
   if (pl.T <= 8 && pl.hd <= 64) {  // few tokens: head dimension on lanes, registers only
     const long long items = Bc * pl.H;
     long long blocks = (items + 7) / 8;
@@ -306,8 +308,8 @@ int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_
     if (blocks > cap) blocks = cap;
     const int kp = kpad_of(pl.Dl);
 #define MDG_ATT_SMALL(TT, DPT)                                                                              \
-  mdg::attention_small_kernel<TT, DPT><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(                  \
-      qkv, key_mask, src_mask, Bc, pl.T, pl.H, pl.hd, pl.ob, kp, pl.split)
+  mdg::attention_small_kernel<TT, DPT, TIn><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(             \
+      qkv, ld, key_mask, src_mask, Bc, pl.T, pl.H, pl.hd, pl.ob, kp, pl.split)
     if (pl.T <= 4 && pl.hd <= 32) MDG_ATT_SMALL(4, 1);
     else if (pl.T <= 4) MDG_ATT_SMALL(4, 2);
     else if (pl.hd <= 32) MDG_ATT_SMALL(8, 1);
@@ -325,8 +327,8 @@ int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_
     int dev = 0;
     MDG_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_rows[dev]) {
-      MDG_CUDA(cudaFuncSetAttribute(mdg::attention_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      MDG_CUDA(cudaFuncSetAttribute(mdg::attention_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      MDG_CUDA(cudaFuncSetAttribute(mdg::attention_rows_kernel<32, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      MDG_CUDA(cudaFuncSetAttribute(mdg::attention_rows_kernel<64, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       attr_rows[dev] = true;
     }
     const long long items = Bc * pl.H;
@@ -334,11 +336,11 @@ int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_
     const long long cap = static_cast<long long>(num_sms()) * 12;
     if (blocks > cap) blocks = cap;
     if (pl.hd == 32)
-      mdg::attention_rows_kernel<32><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
-          qkv, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl), pl.split);
+      mdg::attention_rows_kernel<32, TIn><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
+          qkv, ld, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl), pl.split);
     else
-      mdg::attention_rows_kernel<64><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
-          qkv, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl), pl.split);
+      mdg::attention_rows_kernel<64, TIn><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
+          qkv, ld, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl), pl.split);
     MDG_CUDA(cudaGetLastError());
     ++g_last_launches;
     return MDG_OK;
@@ -355,15 +357,15 @@ int launch_attention(const FusionPlan& pl, const float* qkv, const uint8_t* key_
   int dev = 0;
   MDG_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    MDG_CUDA(cudaFuncSetAttribute(mdg::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MDG_CUDA(cudaFuncSetAttribute(mdg::attention_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set[dev] = true;
   }
   const long long groups = (Bc * pl.H + G - 1) / G;
   long long blocks = (groups + warps - 1) / warps;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
-  mdg::attention_kernel<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
-      qkv, key_mask, src_mask, Bc, pl.T, TP, pl.H, pl.hd, pl.ob, kpad_of(pl.Dl), pl.split);
+  mdg::attention_kernel<TIn><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
+      qkv, ld, key_mask, src_mask, Bc, pl.T, TP, pl.H, pl.hd, pl.ob, kpad_of(pl.Dl), pl.split);
   MDG_CUDA(cudaGetLastError());
   ++g_last_launches;
   return MDG_OK;
@@ -539,8 +541,14 @@ int mdg_fusion_encode(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
       } else {
         if ((rc = ln_convert(pl.h, R, Dl, nullptr, nullptr, nullptr, 0, nullptr, pl.nb, s, stream))) return rc;
       }
-      if ((rc = run_linear(pl.nb, R, pl.w_in[i], 3 * Dl, Dl, s, L.in_proj_bias, 0, nullptr, 0, pl.qkv, 3 * Dl, nullptr, 0, stream))) return rc;
-      if ((rc = launch_attention(pl, pl.qkv, km, src_mask, Bc, stream))) return rc;
+      if (s) {  // fp32-parity mode: fp32 q|k|v rows
+        if ((rc = run_linear(pl.nb, R, pl.w_in[i], 3 * Dl, Dl, s, L.in_proj_bias, 0, nullptr, 0, pl.qkv, 3 * Dl, nullptr, 0, stream))) return rc;
+        if ((rc = launch_attention_t<float>(pl, pl.qkv, 3LL * Dl, km, src_mask, Bc, stream))) return rc;
+      } else {  // bf16 mode: the in_proj epilogue writes bf16 rows (pitch kpad(3 Dl)) into the same buffer
+        __nv_bfloat16* qkv16 = reinterpret_cast<__nv_bfloat16*>(pl.qkv);
+        if ((rc = run_linear(pl.nb, R, pl.w_in[i], 3 * Dl, Dl, 0, L.in_proj_bias, 0, nullptr, 0, nullptr, 0, qkv16, 3 * Dl, stream))) return rc;
+        if ((rc = launch_attention_t<__nv_bfloat16>(pl, qkv16, kpad_of(3 * Dl), km, src_mask, Bc, stream))) return rc;
+      }
       if ((rc = run_linear(pl.ob, R, pl.w_out[i], Dl, Dl, s, L.out_proj_bias, 0, pl.h, Dl, pl.h, Dl, nullptr, 0, stream))) return rc;
       if (cfg->norm_first) {
         if ((rc = ln_convert(pl.h, R, Dl, nullptr, L.norm2_weight, L.norm2_bias, 1, nullptr, pl.nb, s, stream))) return rc;

@@ -21,6 +21,11 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// attention inputs: the packed q|k|v rows are fp32 in the fp32-parity mode and bf16 in the bf16 mode (half the traffic
+// of the in_proj GEMM's output and of the attention kernels' input)
+__device__ __forceinline__ float ld_in(const float* p) { return *p; }
+__device__ __forceinline__ float ld_in(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
 __device__ __forceinline__ void store_bf16_split(__nv_bfloat16* row, int k, int k_pad, int split, float x) {
   const __nv_bfloat16 hi = __float2bfloat16_rn(x);
   row[k] = hi;
@@ -84,7 +89,8 @@ __global__ void __launch_bounds__(256) ln_convert_kernel(const float* __restrict
 // K/V tiles are staged in shared memory (row pitch hd+1), the query row is broadcast from shared memory, softmax is
 // a segmented warp-shuffle max/sum over the TP lanes of an item.  Scores use q * (1/sqrt(hd)) as
 // nn.MultiheadAttention does; masked scores are -inf.
-__global__ void attention_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ key_mask,
+template <typename TIn>
+__global__ void attention_kernel(const TIn* __restrict__ qkv, long long ld, const uint8_t* __restrict__ key_mask,
                                  const uint8_t* __restrict__ src_mask, long long B, int T, int TP, int H, int hd,
                                  __nv_bfloat16* __restrict__ out, int k_pad, int split) {
   extern __shared__ float att_smem[];
@@ -107,20 +113,20 @@ __global__ void attention_kernel(const float* __restrict__ qkv, const uint8_t* _
     const bool live = item < total;
     const long long b = live ? item / H : 0;
     const int h = live ? static_cast<int>(item - b * H) : 0;
-    const float* base = qkv + (b * T) * 3LL * Dl + h * hd;
+    const TIn* base = qkv + (b * T) * ld + h * hd;
     __syncwarp();
     if (live) {
       for (int idx = j; idx < T * hd; idx += TP) {
         const int r = idx / hd, d = idx - r * hd;
-        Ks[r * pitch + d] = base[static_cast<long long>(r) * 3 * Dl + Dl + d];
-        Vs[r * pitch + d] = base[static_cast<long long>(r) * 3 * Dl + 2 * Dl + d];
+        Ks[r * pitch + d] = ld_in(base + static_cast<long long>(r) * ld + Dl + d);
+        Vs[r * pitch + d] = ld_in(base + static_cast<long long>(r) * ld + 2 * Dl + d);
       }
     }
     const bool key_ok = live && j < T && key_mask[b * T + j] == 0;
     for (int i = 0; i < T; ++i) {
       __syncwarp();
       if (live)
-        for (int d = j; d < hd; d += TP) Qs[d] = base[static_cast<long long>(i) * 3 * Dl + d] * qscale;
+        for (int d = j; d < hd; d += TP) Qs[d] = ld_in(base + static_cast<long long>(i) * ld + d) * qscale;
       __syncwarp();
       float sc = -CUDART_INF_F;
       if (key_ok && !(src_mask != nullptr && src_mask[i * T + j] != 0)) {
@@ -153,8 +159,8 @@ __global__ void attention_kernel(const float* __restrict__ qkv, const uint8_t* _
 // P.V product uses lane = head dimension with the V COLUMNS in registers; the query rows are broadcast from shared
 // memory with 16-byte loads.  Per query: HD/4 LDS.128 + HD FMA + two 5-step shuffle reductions + T shuffle-FMA pairs,
 // against 2*HD + 2*T scalar shared-memory loads per lane in the generic kernel above.
-template <int HD>
-__global__ void __launch_bounds__(128) attention_rows_kernel(const float* __restrict__ qkv,
+template <int HD, typename TIn>
+__global__ void __launch_bounds__(128) attention_rows_kernel(const TIn* __restrict__ qkv, long long ld,
                                                              const uint8_t* __restrict__ key_mask,
                                                              const uint8_t* __restrict__ src_mask, long long B, int T,
                                                              int H, __nv_bfloat16* __restrict__ out, int k_pad,
@@ -176,19 +182,19 @@ __global__ void __launch_bounds__(128) attention_rows_kernel(const float* __rest
        item += static_cast<long long>(gridDim.x) * warps) {
     const long long b = item / H;
     const int h = static_cast<int>(item - b * H);
-    const float* base = qkv + (b * T) * 3LL * Dl + h * HD;
+    const TIn* base = qkv + (b * T) * ld + h * HD;
     __syncwarp();
     // coalesced loads: row r of q / k (lane = dimension) -> shared memory; V columns straight into registers
     float v[NV][32];
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
       if (r < T) {
-        const float* row = base + static_cast<long long>(r) * 3 * Dl;
+        const TIn* row = base + static_cast<long long>(r) * ld;
 #pragma unroll
         for (int e = 0; e < NV; ++e) {
-          Qs[r * HD + lane + 32 * e] = row[lane + 32 * e] * qscale;
-          Ks[r * KP + lane + 32 * e] = row[Dl + lane + 32 * e];
-          v[e][r] = row[2 * Dl + lane + 32 * e];
+          Qs[r * HD + lane + 32 * e] = ld_in(row + lane + 32 * e) * qscale;
+          Ks[r * KP + lane + 32 * e] = ld_in(row + Dl + lane + 32 * e);
+          v[e][r] = ld_in(row + 2 * Dl + lane + 32 * e);
         }
       } else {
 #pragma unroll
@@ -242,8 +248,8 @@ __global__ void __launch_bounds__(128) attention_rows_kernel(const float* __rest
 // rows are read straight from global memory as coalesced 128-byte rows into registers (no shared memory), the T*T
 // scores are warp-shuffle reductions, softmax and the P.V product are lane-local.  This is the shape of BASELINE
 // config 5 (4 modality tokens) where the keys-on-lanes kernel above would leave 28 of 32 lanes idle.
-template <int TT, int DPT>
-__global__ void __launch_bounds__(256) attention_small_kernel(const float* __restrict__ qkv,
+template <int TT, int DPT, typename TIn>
+__global__ void __launch_bounds__(256) attention_small_kernel(const TIn* __restrict__ qkv, long long ld,
                                                               const uint8_t* __restrict__ key_mask,
                                                               const uint8_t* __restrict__ src_mask, long long B,
                                                               int T, int H, int hd, __nv_bfloat16* __restrict__ out,
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(256) attention_small_kernel(const float* __res
        item += static_cast<long long>(gridDim.x) * warps) {
     const long long b = item / H;
     const int h = static_cast<int>(item - b * H);
-    const float* base = qkv + (b * T) * 3LL * Dl + h * hd;
+    const TIn* base = qkv + (b * T) * ld + h * hd;
     float q[TT][DPT], k[TT][DPT], v[TT][DPT];
     bool kok[TT];
 #pragma unroll
@@ -266,10 +272,10 @@ __global__ void __launch_bounds__(256) attention_small_kernel(const float* __res
       for (int e = 0; e < DPT; ++e) {
         const int d = lane + 32 * e;
         const bool ok = t < T && d < hd;
-        const float* r = base + static_cast<long long>(t) * 3 * Dl + d;
-        q[t][e] = ok ? r[0] * qscale : 0.f;
-        k[t][e] = ok ? r[Dl] : 0.f;
-        v[t][e] = ok ? r[2 * Dl] : 0.f;
+        const TIn* r = base + static_cast<long long>(t) * ld + d;
+        q[t][e] = ok ? ld_in(r) * qscale : 0.f;
+        k[t][e] = ok ? ld_in(r + Dl) : 0.f;
+        v[t][e] = ok ? ld_in(r + 2 * Dl) : 0.f;
       }
     }
 #pragma unroll

@@ -14,3 +14,9 @@ tokens = torch.randn(B, T, E, device=dev); mask = torch.rand(B, T, device=dev) <
 with torch.no_grad():
     for _ in range(3): enc(tokens, mask)
 torch.cuda.synchronize(); print("ok", enc.last_launch_count)
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+with torch.no_grad():
+    e0.record()
+    for _ in range(10): enc(tokens, mask)
+    e1.record()
+torch.cuda.synchronize(); print("ms_per_forward", e0.elapsed_time(e1) / 10)
