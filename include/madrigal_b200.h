@@ -343,6 +343,21 @@ size_t mdg_mlp_workspace_bytes(const MdgMlp* mlp, int64_t B, int precision);
 int mdg_mlp_forward(const MdgMlp* mlp, const float* x, float* y, int64_t B, int precision, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * chemCPA transcriptomic token  (reference: TxAdaptingComPert.predict, madrigal/chemcpa/chemCPA/model.py:678-697, the
+ * `tx` modality encoder NovelDDIEncoder.encode calls at models.py:761-769).  The encoder MLP itself (Linear ->
+ * BatchNorm1d(eval) -> ReLU chains, model.py:161-231) runs through mdg_mlp_forward with the batch-norm statistics
+ * folded into the preceding linear; this call finishes the token:
+ *   out[b,:] = (basal[b,:] + scale_b * drug_latent[b,:]) + cov_table[cov_idx[b],:]
+ *   doser: 0 scale_b = dosage[b]; 1 'sigm', 2 'logsigm' (GeneralizedSigmoid, model.py:259-271, parameters
+ *          doser_beta / doser_bias [num_drugs] indexed by drug_idx[b]); 3 scale_b = dosage[b] holds a precomputed
+ *          scale (the 'amortized' doser MLP's output).
+ *   drug_latent [B, dim] or NULL (use_drugs=False); cov_table [C, dim] + cov_idx [B] (int64) or both NULL
+ *   (latent_basal + drug only).  All device pointers, fp32; out may alias basal. */
+int mdg_tx_latent_combine(const float* basal, const float* drug_latent, const float* dosage, const int64_t* drug_idx,
+                          const float* doser_beta, const float* doser_bias, int32_t doser, const float* cov_table,
+                          const int64_t* cov_idx, int64_t B, int32_t dim, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

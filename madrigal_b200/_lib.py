@@ -94,6 +94,8 @@ SIGNATURES = {
     "mdg_masked_pool": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "mdg_mlp_workspace_bytes": (c_size_t, [POINTER(MdgMlp), c_int64, c_int]),
     "mdg_mlp_forward": (c_int, [POINTER(MdgMlp), c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "mdg_tx_latent_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                      c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
 }
 
 _LIB = None

@@ -672,6 +672,27 @@ int mdg_mlp_forward(const MdgMlp* mlp, const float* x, float* y, int64_t B, int 
   return MDG_OK;
 }
 
+// ------------------------------------------------------------------------------------ chemCPA transcriptomic token
+int mdg_tx_latent_combine(const float* basal, const float* drug_latent, const float* dosage, const int64_t* drug_idx,
+                          const float* doser_beta, const float* doser_bias, int32_t doser, const float* cov_table,
+                          const int64_t* cov_idx, int64_t B, int32_t dim, float* out, void* stream_v) {
+  if (!basal || !out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_tx_latent_combine: NULL pointer");
+  if (B < 0 || dim <= 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_tx_latent_combine: bad sizes");
+  if (doser < 0 || doser > 3) return fail(MDG_ERR_UNSUPPORTED, "mdg_tx_latent_combine: doser %d", doser);
+  if (drug_latent && !dosage) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_tx_latent_combine: NULL dose scale");
+  if (drug_latent && (doser == 1 || doser == 2) && (!drug_idx || !doser_beta || !doser_bias))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_tx_latent_combine: sigmoid doser needs drug_idx, beta, bias");
+  if ((cov_table == nullptr) != (cov_idx == nullptr))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_tx_latent_combine: cov_table and cov_idx go together");
+  if (B == 0) return MDG_OK;
+  const long long n = static_cast<long long>(B) * dim;
+  mdg::tx_latent_combine_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      basal, drug_latent, dosage, reinterpret_cast<const long long*>(drug_idx), doser_beta, doser_bias, doser, cov_table,
+      reinterpret_cast<const long long*>(cov_idx), B, dim, out);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ token assembly
 int mdg_assemble_tokens(const float* embeds, const uint8_t* masks, int64_t B, int32_t M, int32_t E, int32_t n_non_tx,
                         int32_t num_bottlenecks, const float* bottleneck_tokens, const float* cls_token,

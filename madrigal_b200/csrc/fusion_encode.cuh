@@ -413,6 +413,36 @@ __global__ void __launch_bounds__(256) masked_pool_kernel(const float* __restric
   z[idx] = cnt == 0 ? 0.f : (is_max == 0 ? acc / cnt : acc);
 }
 
+// chemCPA transcriptomic token (reference: TxAdaptingComPert.predict, chemcpa/chemCPA/model.py:678-697):
+//   latent_treated = (latent_basal + dose_scale * drug_latent) + covariate_embedding[cell_line]
+// dose_scale: doser 0 = the dosage itself (GeneralizedSigmoid nonlin=None, :272), 1 = 'sigm', 2 = 'logsigm'
+// (:259-271: sigmoid(f(d) * beta[i] + bias[i]) - sigmoid(bias[i]), i = the row's drug index), 3 = precomputed per row
+// (the 'amortized' doser MLP's output, :622-627).  drug_latent NULL = model built with use_drugs=False.
+__device__ __forceinline__ float tx_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+__global__ void __launch_bounds__(256) tx_latent_combine_kernel(
+    const float* __restrict__ basal, const float* __restrict__ drug_latent, const float* __restrict__ dosage,
+    const long long* __restrict__ drug_idx, const float* __restrict__ beta, const float* __restrict__ bias, int doser,
+    const float* __restrict__ cov_table, const long long* __restrict__ cov_idx, long long B, int dim,
+    float* __restrict__ out) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= B * dim) return;
+  const long long b = idx / dim;
+  const int d = static_cast<int>(idx - b * dim);
+  float v = basal[idx];
+  if (drug_latent != nullptr) {
+    float sc = dosage[b];
+    if (doser == 1 || doser == 2) {
+      const long long i = drug_idx[b];
+      const float bi = bias[i];
+      const float x = doser == 2 ? log1pf(sc) : sc;
+      sc = tx_sigmoid(x * beta[i] + bi) - tx_sigmoid(bi);
+    }
+    v = v + sc * drug_latent[idx];
+  }
+  if (cov_table != nullptr) v = v + cov_table[cov_idx[b] * dim + d];
+  out[idx] = v;
+}
+
 // Token assembly (reference: NovelDDIEncoder.encode, models.py:772-852): builds the position-encoded fusion sequence
 // and its key mask from the stacked modality embeddings.
 //   embeds [B, M, E] (order [non-TX..., TX...], models.py:772), masks [B, M] (non-zero = missing)

@@ -290,6 +290,66 @@ def mlp_adaptor(layers: Sequence[dict], x: np.ndarray, dtype=F32) -> np.ndarray:
     return h.astype(dtype)
 
 
+# ------------------------------------------------------------------------------ chemCPA transcriptomic token (f-4)
+def chemcpa_mlp(sd: dict, prefix: str, x: np.ndarray, dtype=F32) -> np.ndarray:
+    """chemCPA `MLP.forward` in eval mode with last_layer_act='linear' (chemcpa/chemCPA/model.py:161-231), driven by
+    the module's own state_dict: entries `{prefix}network.<name>.*` in registration order.  A 2-D `weight` is a
+    Linear; `running_mean` marks a BatchNorm1d (eval: (x - mean) / sqrt(var + 1e-5) * weight + bias); a ReLU follows
+    every Linear (after its BatchNorm1d when present) except the last Linear of the chain (model.py:178-187,
+    199-218)."""
+    names = []
+    for k in sd:
+        if k.startswith(prefix + "network."):
+            n = k[len(prefix + "network."):].rsplit(".", 1)[0]
+            if n not in names:
+                names.append(n)
+    get = lambda n, f: np.asarray(sd[f"{prefix}network.{n}.{f}"]).astype(dtype)
+    linears = [n for n in names if np.asarray(sd[f"{prefix}network.{n}.weight"]).ndim == 2]
+    h = x.astype(dtype)
+    for pos, n in enumerate(names):
+        if n in linears:
+            h = _linear(h, get(n, "weight"), get(n, "bias"))
+            nxt = names[pos + 1] if pos + 1 < len(names) else None
+            has_bn = nxt is not None and f"{prefix}network.{nxt}.running_mean" in sd
+            if not has_bn and n != linears[-1]:
+                h = np.maximum(h, 0)
+        else:  # BatchNorm1d, always followed by a ReLU
+            h = (h - get(n, "running_mean")) / np.sqrt(get(n, "running_var") + dtype(1e-5)) * get(n, "weight") \
+                + get(n, "bias")
+            h = np.maximum(h, 0)
+    return h.astype(dtype)
+
+
+def chemcpa_tx_latents(sd: dict, genes: np.ndarray, cov_idx: Sequence[np.ndarray], *, use_drugs: bool,
+                       doser_type: Optional[str] = None, drug_table: Optional[np.ndarray] = None,
+                       drugs_idx: Optional[np.ndarray] = None, dosages: Optional[np.ndarray] = None, dtype=F32):
+    """`TxAdaptingComPert.predict` restricted to its latents (model.py:678-697) -> (latent_basal, latent_treated).
+    Dose scale per compute_drug_embeddings_ (:601-653) with the dosers of :259-271 ('sigm'/'logsigm'), :622-627
+    ('amortized') or the dosage itself (nonlin None)."""
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+    basal = chemcpa_mlp(sd, "encoder.", genes, dtype)
+    treated = basal
+    if use_drugs:
+        emb = drug_table.astype(dtype)[drugs_idx]
+        d = dosages.astype(dtype)
+        if doser_type in ("sigm", "logsigm"):
+            beta = np.asarray(sd["dosers.beta"]).astype(dtype)[0][drugs_idx]
+            bias = np.asarray(sd["dosers.bias"]).astype(dtype)[0][drugs_idx]
+            xx = np.log1p(d) if doser_type == "logsigm" else d
+            scale = sig(xx * beta + bias) - sig(bias)
+        elif doser_type == "amortized":
+            scale = chemcpa_mlp(sd, "dosers.", np.concatenate([emb, d[:, None]], axis=1), dtype).reshape(-1)
+        elif doser_type is None:
+            scale = d
+        else:
+            raise NotImplementedError(doser_type)
+        lat = chemcpa_mlp(sd, "drug_embedding_encoder.", emb, dtype)
+        treated = treated + scale.astype(dtype)[:, None] * lat
+    for c, idx in enumerate(cov_idx):
+        treated = treated + np.asarray(sd[f"covariates_embeddings.{c}.weight"]).astype(dtype)[idx]
+    return basal.astype(dtype), treated.astype(dtype)
+
+
 # ----------------------------------------------------------------------------------------------- token assembly (a-2)
 def assemble_fusion_inputs(all_embeds: np.ndarray, batch_masks: np.ndarray, *, n_non_tx: int, num_tx_bottlenecks: int,
                            agg: str, tx_bottleneck_tokens: Optional[np.ndarray] = None,

@@ -108,3 +108,63 @@ def params_checksum(arrays) -> float:
         a = np.asarray(a, dtype=np.float64).reshape(-1)
         tot += float((a * np.cos(np.arange(a.size) * 0.37 + k)).sum())
     return tot
+
+
+# ------------------------------------------------------------------------------------- chemCPA tx encoder (f-4)
+CHEMCPA_CASES = [
+    dict(name="no_drugs_production_shape", num_genes=978, num_drugs=7, n_cell=18, use_drugs=False, doser_type="amortized",
+         hparams=dict(dim=32, autoencoder_width=64, autoencoder_depth=2, dosers_width=8, dosers_depth=2,
+                      embedding_encoder_width=16, embedding_encoder_depth=0), emb_dim=24, B=11, seed=3),
+    dict(name="drugs_logsigm", num_genes=120, num_drugs=9, n_cell=5, use_drugs=True, doser_type="logsigm",
+         hparams=dict(dim=48, autoencoder_width=96, autoencoder_depth=3, dosers_width=8, dosers_depth=2,
+                      embedding_encoder_width=16, embedding_encoder_depth=0), emb_dim=24, B=13, seed=4),
+    dict(name="drugs_amortized_enc1", num_genes=64, num_drugs=6, n_cell=4, use_drugs=True, doser_type="amortized",
+         hparams=dict(dim=32, autoencoder_width=48, autoencoder_depth=1, dosers_width=16, dosers_depth=2,
+                      embedding_encoder_width=40, embedding_encoder_depth=1), emb_dim=20, B=9, seed=5),
+    dict(name="drugs_sigm_depth0", num_genes=50, num_drugs=5, n_cell=3, use_drugs=True, doser_type="sigm",
+         hparams=dict(dim=16, autoencoder_width=48, autoencoder_depth=0, dosers_width=16, dosers_depth=2,
+                      embedding_encoder_width=40, embedding_encoder_depth=0), emb_dim=12, B=8, seed=6),
+]
+
+
+def _chemcpa_mlp_state(rng, prefix, sizes, batch_norm=True):
+    """state_dict entries of chemCPA's MLP(sizes) (model.py:176-224) with non-trivial BatchNorm1d statistics."""
+    sd, pos = {}, 0
+    n = len(sizes) - 1
+    for s in range(n):
+        sd[f"{prefix}network.{pos}.weight"] = _uniform(rng, (sizes[s + 1], sizes[s]), sizes[s])
+        sd[f"{prefix}network.{pos}.bias"] = _uniform(rng, (sizes[s + 1],), sizes[s])
+        pos += 1
+        if batch_norm and s < n - 1:
+            w = sizes[s + 1]
+            sd[f"{prefix}network.{pos}.weight"] = (1.0 + 0.2 * rng.standard_normal(w)).astype(F32)
+            sd[f"{prefix}network.{pos}.bias"] = (0.1 * rng.standard_normal(w)).astype(F32)
+            sd[f"{prefix}network.{pos}.running_mean"] = (0.2 * rng.standard_normal(w)).astype(F32)
+            sd[f"{prefix}network.{pos}.running_var"] = (0.5 + rng.random(w)).astype(F32)
+            sd[f"{prefix}network.{pos}.num_batches_tracked"] = np.asarray(7, dtype=np.int64)
+            pos += 1
+        pos += 1  # ReLU (dropped after the last Linear)
+    return sd
+
+
+def chemcpa_case(case):
+    """(state_dict of numpy arrays in the reference's key names, drug embedding table, inputs) for one CHEMCPA_CASES
+    entry; the same arrays are loaded into the reference module (golden generator), the oracle and the CUDA path."""
+    rng = np.random.default_rng(case["seed"] + 7000)
+    hp = case["hparams"]
+    sd = _chemcpa_mlp_state(rng, "encoder.", [case["num_genes"]] + [hp["autoencoder_width"]] * hp["autoencoder_depth"] + [hp["dim"]])
+    table = rng.standard_normal((case["num_drugs"], case["emb_dim"])).astype(F32)
+    if case["use_drugs"]:
+        sd.update(_chemcpa_mlp_state(rng, "drug_embedding_encoder.", [case["emb_dim"]] + [hp["embedding_encoder_width"]] * hp["embedding_encoder_depth"] + [hp["dim"]]))
+        if case["doser_type"] == "amortized":
+            sd.update(_chemcpa_mlp_state(rng, "dosers.", [case["emb_dim"] + 1] + [hp["dosers_width"]] * hp["dosers_depth"] + [1]))
+        else:
+            sd["dosers.beta"] = (1.0 + 0.3 * rng.standard_normal((1, case["num_drugs"]))).astype(F32)
+            sd["dosers.bias"] = (0.3 * rng.standard_normal((1, case["num_drugs"]))).astype(F32)
+    sd["covariates_embeddings.0.weight"] = rng.standard_normal((case["n_cell"], hp["dim"])).astype(F32)
+    B = case["B"]
+    inputs = dict(genes=rng.standard_normal((B, case["num_genes"])).astype(F32),
+                  drugs_idx=rng.integers(0, case["num_drugs"], B).astype(np.int64),
+                  dosages=(rng.random(B) * 3.0).astype(F32),
+                  cov_idx=rng.integers(0, case["n_cell"], B).astype(np.int64))
+    return sd, table, inputs

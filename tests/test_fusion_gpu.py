@@ -308,3 +308,54 @@ def test_mlp_encoder_is_the_tabular_modality_encoder(mb, cuda_device):
         ref = oracle.mlp_adaptor(ops, x, dtype=np.float64)
         y = mod.to(cuda_device)(gpu(x, cuda_device)).detach().cpu().numpy()
         assert_close(y, ref, 1e-3, f"MLPEncoder norm={norm}")
+
+
+def _chemcpa_module(mb, case, sd, table, dev, precision):
+    emb = torch.nn.Embedding.from_pretrained(torch.from_numpy(table), freeze=True)
+    mod = mb.chemcpa.TxAdaptingComPert(num_genes=case["num_genes"], num_drugs=case["num_drugs"],
+                                       covariate_names_unique={"cell_iname": [f"C{i}" for i in range(case["n_cell"])]},
+                                       doser_type=case["doser_type"], hparams=dict(case["hparams"]),
+                                       drug_embeddings=emb, append_layer_width=None, use_drugs=case["use_drugs"],
+                                       disable_adv=True, precision=precision)
+    res = mod.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
+    assert not res.unexpected_keys and [k for k in res.missing_keys if k != "drug_embeddings.weight"] == []
+    return mod.to(dev).eval()
+
+
+@pytest.mark.parametrize("case", synth.CHEMCPA_CASES, ids=lambda c: c["name"])
+def test_chemcpa_tx_encoder_vs_reference_golden(mb, cuda_device, case):
+    """chemcpa.TxAdaptingComPert.predict (mdg_mlp_forward with folded batch-norm + mdg_tx_latent_combine) vs the
+    reference module's latents (golden) and the oracle; same state_dict keys as the reference."""
+    g = np.load(os.path.join(HERE, "golden", "golden_chemcpa.npz"))
+    sd, table, inp = synth.chemcpa_case(case)
+    ref_b, ref_t = oracle.chemcpa_tx_latents(sd, inp["genes"], [inp["cov_idx"]], use_drugs=case["use_drugs"],
+                                             doser_type=case["doser_type"], drug_table=table,
+                                             drugs_idx=inp["drugs_idx"], dosages=inp["dosages"], dtype=np.float64)
+    onehot = torch.nn.functional.one_hot(torch.from_numpy(inp["cov_idx"]), case["n_cell"]).long()
+    for precision, tol in (("fp32", 1e-3), ("bf16", 3e-2)):
+        mod = _chemcpa_module(mb, case, sd, table, cuda_device, precision)
+        out = mod.predict(genes=gpu(inp["genes"], cuda_device), drugs_idx=gpu(inp["drugs_idx"], cuda_device),
+                          dosages=gpu(inp["dosages"], cuda_device), covariates=[onehot.to(cuda_device)],
+                          return_latent_basal=True, return_latent_treated=True)
+        assert out[0] is None and out[1] is None and len(out) == 4
+        basal, treated = out[2].cpu().numpy(), out[3].cpu().numpy()
+        assert_close(basal, ref_b, tol, f"{case['name']} basal {precision}")
+        assert_close(treated, ref_t, tol, f"{case['name']} treated {precision}")
+        if precision == "fp32":
+            assert_close(basal, g[f"{case['name']}.basal"], tol, "basal vs golden")
+            assert_close(treated, g[f"{case['name']}.treated"], tol, "treated vs golden")
+    # the way NovelDDIEncoder.encode takes its tx tokens (models.py:761-769): one latent, split per cell line
+    only = mod.predict(genes=gpu(inp["genes"], cuda_device), drugs_idx=gpu(inp["drugs_idx"], cuda_device),
+                       dosages=gpu(inp["dosages"], cuda_device), covariates=[onehot.to(cuda_device)],
+                       return_latent_basal=False, return_latent_treated=True)
+    assert len(only) == 3 and torch.equal(only[2], out[3])
+
+
+def test_chemcpa_mlp_rejects_training_mode_and_cpu(mb, cuda_device):
+    m = mb.chemcpa.MLP([16, 32, 8])
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 16, device=cuda_device))  # training mode: batch statistics are not an inference path
+    with pytest.raises((RuntimeError, ValueError, TypeError)):
+        m.eval()(torch.zeros(2, 16))  # CPU tensor: no fallback
+    assert list(mb.chemcpa.MLP([4, 5, 6], append_layer_width=3, append_layer_position="first").state_dict())[:2] == \
+        ["network.append_linear.weight", "network.append_linear.bias"]

@@ -231,3 +231,17 @@ def test_gmean_restatement_matches_scipy_mstats():
     got = oracle.gmean_normalized_ranks(members)
     assert got.dtype == np.float32 and np.allclose(got, ref, rtol=1e-6, atol=0)
     assert (np.diagonal(got, axis1=1, axis2=2) == 0).all()
+
+
+@pytest.mark.parametrize("case", synth.CHEMCPA_CASES, ids=lambda c: c["name"])
+def test_chemcpa_tx_latents_match_reference(case):
+    """oracle.chemcpa_tx_latents vs the reference TxAdaptingComPert.predict latents (golden_chemcpa.npz, generated by
+    tests/golden/make_golden_chemcpa.py from chemcpa/chemCPA/model.py)."""
+    g = np.load(os.path.join(G, "golden_chemcpa.npz"))
+    sd, table, inp = synth.chemcpa_case(case)
+    assert abs(synth.params_checksum([sd[k] for k in sd] + [table]) - float(g[f"{case['name']}.checksum"])) < 1e-6
+    basal, treated = oracle.chemcpa_tx_latents(sd, inp["genes"], [inp["cov_idx"]], use_drugs=case["use_drugs"],
+                                               doser_type=case["doser_type"], drug_table=table,
+                                               drugs_idx=inp["drugs_idx"], dosages=inp["dosages"])
+    np.testing.assert_allclose(basal, g[f"{case['name']}.basal"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(treated, g[f"{case['name']}.treated"], rtol=2e-5, atol=2e-5)
