@@ -92,7 +92,7 @@ def cpu_reference_pass(n_outcomes, cores):
 
 def cpu_baseline(cores=None):
     cores = cores or os.cpu_count() or 1
-    n_out = max(1, min(2 * cores, N_OUTCOMES))  # two outcomes per worker: ~10 s of CPU work on the box's 16 cores
+    n_out = max(1, min(4 * cores, N_OUTCOMES))  # four outcomes per worker: ~10 s wall on the box's 16 cores
     dt = cpu_reference_pass(n_out, cores)
     return {"value": n_out * N_DRUGS * N_DRUGS / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n_out} of {N_OUTCOMES} outcomes x {N_DRUGS}^2 pairs: fp32 fusion encoder for all {N_DRUGS} drugs "
