@@ -180,3 +180,23 @@ def ensemble_mean_sigmoid(z_list, weight_list, *, precision: str = "bf16",
     members = [score_all_pairs(z, W, out="sigmoid", precision=precision, label_range=label_range)
                for z, W in zip(z_list, weight_list)]
     return ensemble_reduce(members, "mean")
+
+
+def ensemble_normalized_ranks_chunks(z_list, weight_list, *, precision: str = "fp32", chunk: int = 2,
+                                     normalize: bool = False):
+    """The reference's whole ensemble normalisation (generate_embeddings.ipynb cells 13-20) streamed by outcome chunk,
+    nothing but one chunk ever materialised: for each checkpoint k, raw scores (models.py:537-547) -> in-sample
+    normalised ranks (normalize_scores.py:62-74); geometric mean over checkpoints (cell 18); `run_slice` again on the
+    gmean (cell 20).  Yields (l0, l1, ranks[l1-l0, N, N] fp32); the yielded tensor is reused by the next iteration."""
+    from .normalize import exact_normalized_ranks, gmean_normalized_ranks
+    L = weight_list[0].shape[0]
+    for l0 in range(0, L, chunk):
+        l1 = min(l0 + chunk, L)
+        members = []
+        for z, W in zip(z_list, weight_list):
+            raw = pair_score(z, z, W[l0:l1], precision=precision, out="logit", normalize=normalize)
+            members.append(exact_normalized_ranks(raw))
+            del raw
+        g = gmean_normalized_ranks(members)
+        del members
+        yield l0, l1, exact_normalized_ranks(g)

@@ -117,6 +117,34 @@ def test_mean_sigmoid_ensemble_vs_oracle(norm, cuda_device):
     assert np.abs(got - oracle.ensemble_mean_sigmoid(lgs)).max() <= 2e-4
 
 
+def test_streamed_ensemble_normalisation_vs_oracle_chain(norm, cuda_device):
+    """scoring.ensemble_normalized_ranks_chunks == per-checkpoint scores -> normaliser -> gmean -> normaliser, against
+    the all-numpy chain (within rank steps where logits / gmeans are nearly tied) and bit-identical to the library's
+    own materialised chain."""
+    from madrigal_b200 import scoring
+    import synth
+    K, N, D, L = 3, 150, 64, 5
+    zs, Ws, members = [], [], []
+    for k in range(K):
+        z, W = synth.decoder_inputs(N, D, L, seed=70 + k)
+        zs.append(torch.from_numpy(z).to(cuda_device)); Ws.append(torch.from_numpy(W).to(cuda_device))
+        members.append(oracle.normalize_scores(oracle.bilinear_scores(z, z, W), kind="stable"))
+    ref = oracle.ensemble_normalized_ranks(members, kind="stable")
+    got = np.zeros_like(ref)
+    seen = []
+    for l0, l1, r in scoring.ensemble_normalized_ranks_chunks(zs, Ws, precision="fp32", chunk=2):
+        got[l0:l1] = r.cpu().numpy()
+        seen.append((l0, l1))
+    assert seen == [(0, 2), (2, 4), (4, 5)]
+    M = N * (N - 1) // 2
+    assert np.array_equal(got, got.transpose(0, 2, 1)) and (np.diagonal(got, axis1=1, axis2=2) == 0).all()
+    # 1e-3-accurate logits can swap near-tied neighbours in a member's ranking: a few rank steps after the gmean
+    assert np.abs(got - ref).max() <= 12.0 / M and np.abs(got - ref).mean() <= 0.5 / M
+    import madrigal_b200 as mb
+    mats = [norm.exact_normalized_ranks(mb.pair_score(z, z, W, precision="fp32", out="logit")) for z, W in zip(zs, Ws)]
+    assert np.array_equal(got, norm.ensemble_normalized_ranks(mats).cpu().numpy())
+
+
 def test_config1_end_to_end_vs_oracle_chain(norm, cuda_device):
     """SURVEY 4, integration: BASELINE config 1 (1,024 drugs, 4 modality tokens, 86 outcomes) through the whole path —
     fusion encoder -> bilinear decoder -> normalised ranks — against the CPU oracle chain on the same seeded weights.
