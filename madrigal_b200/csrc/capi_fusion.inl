@@ -1,3 +1,4 @@
+#include <type_traits>
 // C-ABI entry points of the fusion encoder, the unimodal MLP bypass and token assembly (host orchestration).
 // Every nn.Linear is one launch of the tcgen05 GEMM kernel (EPI_LINEAR); see fusion_encode.cuh for the glue kernels.
 
@@ -301,7 +302,9 @@ int run_fused_encoder(const MdgFusionWeights* w, const MdgFusionCfg* cfg, const 
 template <typename TIn>
 int launch_attention_t(const FusionPlan& pl, const TIn* qkv, long long ld, const uint8_t* key_mask,
                        const uint8_t* src_mask, long long Bc, cudaStream_t stream) {
-  if (pl.T <= 8 && pl.hd <= 64) {  // few tokens: head dimension on lanes, registers only
+  const char* mma_knob = getenv("MDG_ATTENTION_MMA");
+  const bool mma_all = std::is_same<TIn, __nv_bfloat16>::value && mma_knob != nullptr && mma_knob[0] == 'a' && pl.hd == 64 && !pl.split;
+  if (pl.T <= 8 && pl.hd <= 64 && !mma_all) {  // few tokens: head dimension on lanes, registers only
     const long long items = Bc * pl.H;
     long long blocks = (items + 7) / 8;
     const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -318,6 +321,25 @@ int launch_attention_t(const FusionPlan& pl, const TIn* qkv, long long ld, const
     MDG_CUDA(cudaGetLastError());
     ++g_last_launches;
     return MDG_OK;
+  }
+  if constexpr (std::is_same<TIn, __nv_bfloat16>::value) {
+    // bf16 rows, head_dim 64, T <= 32: warp-level tensor-core attention (one (drug, head) per warp)
+    const char* knob = getenv("MDG_ATTENTION_MMA");  // "0": FMA kernels; "all": also for T <= 8
+    const bool off = knob != nullptr && knob[0] == '0';
+    const bool all = knob != nullptr && knob[0] == 'a';
+    if (pl.hd == 64 && pl.T <= 32 && !pl.split && !off && (pl.T > 8 || all) && ld % 8 == 0) {
+      const int warps = 4;
+      const size_t smem = static_cast<size_t>(warps) * 3 * 4096;
+      const long long items = Bc * pl.H;
+      long long blocks = (items + warps - 1) / warps;
+      const long long cap = static_cast<long long>(num_sms()) * 16;
+      if (blocks > cap) blocks = cap;
+      mdg::attention_mma_kernel<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
+          qkv, ld, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl));
+      MDG_CUDA(cudaGetLastError());
+      ++g_last_launches;
+      return MDG_OK;
+    }
   }
   if ((pl.hd == 32 || pl.hd == 64) && getenv("MDG_ATTENTION_GENERIC") == nullptr) {
     // 8 < T <= 32: K rows / V columns in registers (the production shapes T = 21 / 23, head_dim 64)
