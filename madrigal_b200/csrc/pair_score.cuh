@@ -823,7 +823,11 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
               } else if (p.act == 2) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) y[j] = 0.5f * y[j] * (1.0f + erff(y[j] * 0.70710678118654752440f));
+                for (int j = 0; j < 32; j += 2) {  // exact-erf GELU on the packed fp32x2 pipe (|error| < 1e-6, fused_encoder.cuh)
+                  const float2 r = fe_gelu2(make_float2(y[j], y[j + 1]));
+                  y[j] = r.x;
+                  y[j + 1] = r.y;
+                }
               }
 #pragma unroll
               for (int j = 0; j < 32; ++j) y[j] += rs[j];
