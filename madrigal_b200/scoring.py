@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from .decoder import RankTable, pair_score
+from .decoder import RankTable, pair_score, pair_topk
 
 _OUT_DTYPE = {"logit": torch.float32, "sigmoid": torch.float32, "rank": torch.uint16}
 
@@ -200,3 +200,50 @@ def ensemble_normalized_ranks_chunks(z_list, weight_list, *, precision: str = "f
         g = gmean_normalized_ranks(members)
         del members
         yield l0, l1, exact_normalized_ranks(g)
+
+
+def top_pairs_per_outcome(z: torch.Tensor, weight: torch.Tensor, k: int, table: RankTable, *, precision: str = "bf16",
+                          cap: int = 65536, max_rounds: int = 20, normalize: bool = False):
+    """Per-outcome top-k unordered pairs of one catalogue (BASELINE "top-1000 per outcome") with the candidate
+    threshold taken from the rank table and adjusted per outcome until every list is complete.
+
+    The fused top-k kernel keeps the scores >= a per-outcome threshold (mdg_pair_topk).  The starting threshold is the
+    table quantile that leaves ~3k candidates if the table's panel represents the catalogue.  An outcome that came
+    back short (status 1) needs a lower quantile, one that overflowed `cap` (status 2) a higher one: the quantile
+    index is moved in growing steps until the outcome is bracketed, then bisected; only the failed outcomes are
+    re-run each round.  An overflow at the table's last quantile grows the candidate list 4x instead.  Any threshold
+    with status 0 yields the exact top-k.  Returns (scores [L,k], rows, cols, status, rounds); status is all-zero
+    unless the table cannot bracket an outcome within max_rounds."""
+    N, L, Q = z.shape[0], weight.shape[0], table.Q
+    M = N * (N - 1) // 2
+    if k > M:
+        raise ValueError("k exceeds the number of unordered pairs")
+    dev = z.device
+    q0 = min(Q - 2, max(0, int(Q * (1.0 - 3.0 * k / M)) - 1))
+    qidx = torch.full((L,), q0, dtype=torch.int64, device=dev)
+    lo = torch.full((L,), -1, dtype=torch.int64, device=dev)   # highest index known to overflow
+    hi = torch.full((L,), Q, dtype=torch.int64, device=dev)    # lowest index known to come back short
+    thr = table.thresholds.gather(1, qidx[:, None]).reshape(-1).contiguous()
+    scores, rows, cols, status = pair_topk(z, z, weight, thr, k, cap=cap, symmetric=True, precision=precision,
+                                           normalize=normalize)
+    rounds, step, caps = 1, 1, cap
+    while rounds < max_rounds:
+        bad = torch.nonzero(status != 0).reshape(-1)
+        if bad.numel() == 0:
+            break
+        st, q = status[bad], qidx[bad]
+        lo[bad] = torch.where(st == 2, torch.maximum(lo[bad], q), lo[bad])
+        hi[bad] = torch.where(st == 1, torch.minimum(hi[bad], q), hi[bad])
+        if bool(((st == 2) & (q >= Q - 1)).any()):
+            caps *= 4
+        step *= 4
+        bracketed = (lo[bad] >= 0) & (hi[bad] < Q)
+        walk = torch.where(st == 1, q - step, q + step)
+        new_q = torch.where(bracketed, (lo[bad] + hi[bad]) // 2, walk).clamp_(0, Q - 1)
+        qidx[bad] = new_q
+        thr_b = table.thresholds[bad].gather(1, new_q[:, None]).reshape(-1).contiguous()
+        s_b, r_b, c_b, st_b = pair_topk(z, z, weight[bad].contiguous(), thr_b, k, cap=caps, symmetric=True,
+                                        precision=precision, normalize=normalize)
+        scores[bad], rows[bad], cols[bad], status[bad] = s_b, r_b, c_b, st_b
+        rounds += 1
+    return scores, rows, cols, status, rounds

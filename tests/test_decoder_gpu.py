@@ -244,6 +244,30 @@ def test_topk_matches_dense_logits(mb, cuda_device, N, D, L, k, symmetric, prec)
     assert st3.cpu().tolist() == [2] * L
 
 
+@pytest.mark.parametrize("shift", [0.0, 0.6, -0.6])
+def test_top_pairs_per_outcome_recovers_from_a_misplaced_table(mb, cuda_device, shift):
+    """scoring.top_pairs_per_outcome: thresholds come from the rank table; a table whose panel does not represent the
+    catalogue (here: quantiles shifted up / down, so the first pass comes back short / overflows) is handled by
+    re-running the failed outcomes with adjusted quantiles.  Result == exact top-k of the dense logits."""
+    from madrigal_b200 import scoring
+    N, D, L, k, Q = 700, 128, 3, 50, 4096
+    z, W = synth.decoder_inputs(N, D, L, seed=77)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    lg = mb.pair_score(zt, zt, Wt, precision="bf16", out="logit").cpu().numpy()
+    q = oracle.reference_quantiles(lg, Q)
+    spread = (q[:, -1] - q[:, 0])[:, None]
+    table = mb.RankTable(gpu((q + shift * spread).astype(np.float32), cuda_device))
+    scores, rows, cols, status, rounds = scoring.top_pairs_per_outcome(zt, Wt, k, table, cap=1024)
+    assert status.cpu().tolist() == [0] * L
+    assert rounds == 1 if shift == 0.0 else rounds > 1
+    i, j = np.tril_indices(N, -1)
+    for l in range(L):
+        v = lg[l][i, j]
+        order = np.lexsort((i * N + j, -v))[:k]
+        assert np.array_equal(scores[l].cpu().numpy(), v[order])
+        assert np.array_equal(rows[l].cpu().numpy(), i[order]) and np.array_equal(cols[l].cpu().numpy(), j[order])
+
+
 @pytest.mark.parametrize("N,D,L,Q", [(300, 128, 2, 2048), (513, 256, 3, 16384), (96, 64, 1, 512), (1000, 256, 2, 4096),
                                      (257, 192, 2, 1000)])
 def test_symmetric_rank_mode_is_the_normaliser_layout(mb, cuda_device, N, D, L, Q):
