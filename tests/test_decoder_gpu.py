@@ -211,6 +211,46 @@ def test_config1_full_size_properties(mb, cuda_device):
     assert np.abs(total - expect).max() <= 1e-3 * np.abs(expect).max() + 1e-2
 
 
+def test_config2_full_size_every_triple(mb, cuda_device):
+    """BASELINE config 2 at full size (4,096 drugs x 86 outcomes, D=256, the bench workload): all 1.44e9 uint16 ranks of
+    the fused kernel in the normaliser layout, checked element by element against torch.searchsorted over the dense
+    fp32 logits of the same GEMM arithmetic (a checker independent of the fused epilogue), plus symmetry, zero
+    diagonal, the checksum of checksums of the logits and the oracle's numpy searchsorted on sampled rows."""
+    from madrigal_b200 import normalize
+    N, D, L, Q = 4096, 256, 86, 16384
+    z, W = synth.decoder_inputs(N, D, L, seed=2)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    table = normalize.build_rank_table(zt, Wt, Q, panel=2048, precision="bf16")
+    ranks = mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, symmetric=True)
+    assert ranks.shape == (L, N, N) and ranks.dtype == torch.uint16
+    thr = table.thresholds
+    lower = torch.tril(torch.ones(N, N, dtype=torch.bool, device=cuda_device), -1)
+    zs = z.astype(np.float64).sum(0)
+    zb = zt.to(torch.bfloat16).double().sum(0).cpu().numpy()     # the kernel's operands are bf16-rounded rows
+    mismatches, total = 0, 0
+    for l0 in range(0, L, 8):
+        l1 = min(l0 + 8, L)
+        lg = mb.pair_score(zt, zt, Wt[l0:l1], precision="bf16", out="logit")
+        for l in range(l0, l1):
+            want = torch.searchsorted(thr[l], lg[l - l0].reshape(-1), right=True).reshape(N, N)
+            want = torch.where(lower, want, torch.zeros_like(want))
+            want = want + want.T                                  # normalize_scores.py:67-70: mirror, zero diagonal
+            got = ranks[l].to(torch.int64)
+            mismatches += int((got != want).sum().item())
+            total += N * N
+            if l in (0, 43, 85):  # the oracle's numpy lookup on sampled rows (strict lower triangle)
+                rows = np.asarray([1, 2047, 4095])
+                ref = oracle.quantile_rank(thr[l:l + 1].cpu().numpy(), lg[l - l0][rows][None].cpu().numpy(), "right")[0]
+                keep = np.arange(N)[None, :] < rows[:, None]
+                assert np.array_equal(np.where(keep, got[rows].cpu().numpy(), 0), np.where(keep, ref, 0))
+        sums = lg.double().sum(dim=(1, 2)).cpu().numpy()
+        expect = np.einsum("a,lab,b->l", zs, W[l0:l1].astype(np.float64), zs)
+        assert np.abs(sums - expect).max() <= 2e-2 * np.abs(expect).max() + 1.0, (sums, expect, zb[:2])
+        del lg
+    assert total == L * N * N and mismatches == 0
+    assert int(ranks.to(torch.int32).max().item()) <= Q
+
+
 @pytest.mark.parametrize("N,D,L,k,symmetric,prec", [(300, 128, 3, 50, True, "fp32"), (513, 256, 2, 1000, True, "bf16"),
                                                    (200, 64, 2, 100, False, "bf16")])
 def test_topk_matches_dense_logits(mb, cuda_device, N, D, L, k, symmetric, prec):
