@@ -788,11 +788,29 @@ int mdg_exact_rank(const float* scores, int64_t L, int64_t N, float* out, void* 
   long long blocks = static_cast<long long>((M + 255) / 256);
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
+  // small inputs: direct scatter; otherwise group the pairs by the top 8 bits of their index first (exact_rank.cuh)
+  const bool direct = M < (1ull << 22) || getenv("MDG_EXACT_RANK_DIRECT") != nullptr;
+  int bits = 1;
+  while ((1ull << bits) < M) ++bits;
+  const int tiles = static_cast<int>((N + 31) / 32);
   for (int64_t l = 0; l < L; ++l) {
     int rc = exact_rank_sort(scores + static_cast<size_t>(l) * N * N, N, w, stream);
     if (rc) return rc;
-    mdg::tri_scatter_rank_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-        w.idx_out, static_cast<int>(N), M, out + static_cast<size_t>(l) * N * N);
+    float* out_l = out + static_cast<size_t>(l) * N * N;
+    if (direct) {
+      mdg::tri_scatter_rank_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(w.idx_out, static_cast<int>(N), M, out_l);
+      MDG_CUDA(cudaGetLastError());
+      continue;
+    }
+    // keys = sorted pair indices (position = rank), values = positions (idx_in still holds 0..M-1: SortPairs keeps
+    // its inputs); outputs reuse the two key buffers, which the rank path no longer needs
+    size_t tb = w.cub_bytes;
+    MDG_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.idx_out, w.keys_in, w.idx_in, w.keys_out,
+                                             static_cast<long long>(M), bits - 8, bits, stream));
+    mdg::tri_place_rank_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(w.keys_in, w.keys_out, static_cast<int>(N), M, out_l);
+    MDG_CUDA(cudaGetLastError());
+    mdg::tri_mirror_kernel<<<static_cast<unsigned>(static_cast<long long>(tiles) * (tiles + 1) / 2), dim3(32, 8), 0, stream>>>(
+        out_l, static_cast<int>(N));
     MDG_CUDA(cudaGetLastError());
   }
   return MDG_OK;

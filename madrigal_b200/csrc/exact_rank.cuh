@@ -52,6 +52,48 @@ __global__ void __launch_bounds__(256) tri_scatter_rank_kernel(const uint32_t* _
     out[d * N + d] = 0.f;  // normalize_scores.py:69
 }
 
+// The scatter above writes 4 bytes to two random places per pair: at the reference's size (67 M pairs per outcome)
+// that is 4.2 GB of partial-sector read-modify-write traffic and 70 % of the exact-rank time.  The placement below
+// replaces it: one more radix PASS groups the (pair index, rank) pairs by the top 8 bits of the pair index, so that
+// consecutive threads write into a few-MB window of the output (L2-resident: sectors are completed before they are
+// written back), then only the strict lower triangle is placed, and a tiled transpose mirrors it (coalesced both ways).
+__global__ void __launch_bounds__(256) tri_place_rank_kernel(const uint32_t* __restrict__ part_idx,
+                                                             const uint32_t* __restrict__ part_rank, int N,
+                                                             unsigned long long M, float* __restrict__ out) {
+  for (unsigned long long t = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; t < M;
+       t += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    unsigned int i, j;
+    tri_unflatten(part_idx[t], &i, &j);
+    // normalize_scores.py:57: rank / (N*(N-1)/2) in float64, stored into a float32 memmap (:72)
+    out[static_cast<size_t>(i) * N + j] =
+        static_cast<float>(static_cast<double>(part_rank[t] + 1u) / static_cast<double>(M));
+  }
+}
+
+// out[j, i] = out[i, j] for i > j, diagonal 0 (normalize_scores.py:69-70); one 32x32 tile pair per block of (32, 8)
+__global__ void __launch_bounds__(256) tri_mirror_kernel(float* __restrict__ out, int N) {
+  __shared__ float tile[32][33];
+  unsigned int bi, bj;  // blockIdx.x = bi (bi + 1) / 2 + bj, bj <= bi
+  {
+    const unsigned long long t = blockIdx.x;
+    unsigned long long b = static_cast<unsigned long long>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
+    while (b * (b + 1) / 2 > t) --b;
+    while ((b + 1) * (b + 2) / 2 <= t) ++b;
+    bi = static_cast<unsigned int>(b);
+    bj = static_cast<unsigned int>(t - b * (b + 1) / 2);
+  }
+  const int x = threadIdx.x;
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int r = bi * 32 + y, c = bj * 32 + x;
+    tile[y][x] = (r < N && c < N && c < r) ? out[static_cast<size_t>(r) * N + c] : 0.f;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int r = bj * 32 + y, c = bi * 32 + x;  // transposed position: value of (row c, col r)
+    if (r < N && c < N && c >= r) out[static_cast<size_t>(r) * N + c] = tile[x][y];  // c == r: tile value is 0
+  }
+}
+
 // Q order statistics (ranks ceil(i*M/Q), i = 1..Q) of the sorted keys -> ascending fp32 quantiles
 __global__ void __launch_bounds__(256) pick_quantiles_kernel(const uint32_t* __restrict__ sorted_keys,
                                                              unsigned long long M, int Q, float* __restrict__ out) {

@@ -43,7 +43,7 @@ def test_exact_rank_vs_reference_golden(norm, cuda_device, case):
             assert (r <= np.searchsorted(v, raw[l][i, j], "right")).all()
 
 
-@pytest.mark.parametrize("L,N", [(2, 257), (1, 2), (3, 1), (1, 700)])
+@pytest.mark.parametrize("L,N", [(2, 257), (1, 2), (3, 1), (1, 700), (2, 3001)])  # 3001: grouped-placement path
 def test_exact_rank_vs_oracle(norm, cuda_device, L, N):
     rng = np.random.default_rng(N)
     raw = rng.standard_normal((L, N, N)).astype(np.float32)
