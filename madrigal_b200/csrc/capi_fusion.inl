@@ -788,7 +788,7 @@ int mdg_exact_rank(const float* scores, int64_t L, int64_t N, float* out, void* 
   long long blocks = static_cast<long long>((M + 255) / 256);
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  // small inputs: direct scatter; otherwise group the pairs by the top 8 bits of their index first (exact_rank.cuh)
+  // small inputs: direct scatter; otherwise order the pairs by the high bits of their index first (exact_rank.cuh)
   const bool direct = M < (1ull << 22) || getenv("MDG_EXACT_RANK_DIRECT") != nullptr;
   int bits = 1;
   while ((1ull << bits) < M) ++bits;
@@ -806,8 +806,9 @@ int mdg_exact_rank(const float* scores, int64_t L, int64_t N, float* out, void* 
     // its inputs); outputs reuse the two key buffers, which the rank path no longer needs
     size_t tb = w.cub_bytes;
     MDG_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.idx_out, w.keys_in, w.idx_in, w.keys_out,
-                                             static_cast<long long>(M), bits - 8, bits, stream));
-    mdg::tri_place_rank_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(w.keys_in, w.keys_out, static_cast<int>(N), M, out_l);
+                                             static_cast<long long>(M), mdg::kRankSliceBits, bits, stream));
+    mdg::tri_place_rank_kernel<<<static_cast<unsigned>((M + mdg::kRankSlice - 1) / mdg::kRankSlice), 256, 0, stream>>>(
+        w.keys_in, w.keys_out, static_cast<int>(N), M, out_l);
     MDG_CUDA(cudaGetLastError());
     mdg::tri_mirror_kernel<<<static_cast<unsigned>(static_cast<long long>(tiles) * (tiles + 1) / 2), dim3(32, 8), 0, stream>>>(
         out_l, static_cast<int>(N));

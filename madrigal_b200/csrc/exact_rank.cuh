@@ -54,19 +54,27 @@ __global__ void __launch_bounds__(256) tri_scatter_rank_kernel(const uint32_t* _
 
 // The scatter above writes 4 bytes to two random places per pair: at the reference's size (67 M pairs per outcome)
 // that is 4.2 GB of partial-sector read-modify-write traffic and 70 % of the exact-rank time.  The placement below
-// replaces it: one more radix PASS groups the (pair index, rank) pairs by the top 8 bits of the pair index, so that
-// consecutive threads write into a few-MB window of the output (L2-resident: sectors are completed before they are
-// written back), then only the strict lower triangle is placed, and a tiled transpose mirrors it (coalesced both ways).
+// replaces it.  Two more radix passes order the (pair index, rank) pairs by the pair index's bits >= 13; since every
+// pair index 0..M-1 occurs exactly once, slice b of 8192 consecutive array elements then holds exactly the pair
+// indices [8192 b, 8192 (b+1)).  One block per slice drops the ranks into shared memory at (index - 8192 b) and writes
+// the slice out in index order = row-major order of the strict lower triangle: coalesced, every sector written once.
+// A tiled transpose then mirrors the triangle (coalesced both ways).
+constexpr int kRankSliceBits = 13;
+constexpr int kRankSlice = 1 << kRankSliceBits;
 __global__ void __launch_bounds__(256) tri_place_rank_kernel(const uint32_t* __restrict__ part_idx,
                                                              const uint32_t* __restrict__ part_rank, int N,
                                                              unsigned long long M, float* __restrict__ out) {
-  for (unsigned long long t = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; t < M;
-       t += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+  __shared__ uint32_t ranks[kRankSlice];
+  const unsigned long long base = static_cast<unsigned long long>(blockIdx.x) * kRankSlice;
+  const int n = static_cast<int>(min(static_cast<unsigned long long>(kRankSlice), M - base));
+  for (int k = threadIdx.x; k < n; k += 256) ranks[part_idx[base + k] - static_cast<uint32_t>(base)] = part_rank[base + k];
+  __syncthreads();
+  const double inv_den = static_cast<double>(M);
+  for (int k = threadIdx.x; k < n; k += 256) {
     unsigned int i, j;
-    tri_unflatten(part_idx[t], &i, &j);
+    tri_unflatten(base + k, &i, &j);
     // normalize_scores.py:57: rank / (N*(N-1)/2) in float64, stored into a float32 memmap (:72)
-    out[static_cast<size_t>(i) * N + j] =
-        static_cast<float>(static_cast<double>(part_rank[t] + 1u) / static_cast<double>(M));
+    out[static_cast<size_t>(i) * N + j] = static_cast<float>(static_cast<double>(ranks[k] + 1u) / inv_den);
   }
 }
 
