@@ -195,6 +195,8 @@ def run_gpu_arm(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    # one process per GPU: run on the cores local to this GPU so that pinned buffers land on its NUMA node
+    numa = scoring.bind_host_thread_to_gpu(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -379,6 +381,8 @@ def run_gpu_arm(args):
                     "ms_per_step": te.item()},
             "gpu_launches": launches_per_step * args.steps,
         }
+        if numa is not None:
+            line["host_affinity"] = {"cores_before": len(numa[0]), "cores_gpu_local": len(numa[1])}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)

@@ -247,3 +247,32 @@ def top_pairs_per_outcome(z: torch.Tensor, weight: torch.Tensor, k: int, table: 
         scores[bad], rows[bad], cols[bad], status[bad] = s_b, r_b, c_b, st_b
         rounds += 1
     return scores, rows, cols, status, rounds
+
+
+def bind_host_thread_to_gpu(device_index: int):
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index` (intersected with the cores
+    the process is allowed to use), so that pinned host buffers allocated afterwards are placed on the GPU's NUMA node
+    and the D2H stream of the rank tensor does not cross the inter-socket link.  One process per GPU, call it before
+    allocating pinned memory.  Returns (previous cpu set, new cpu set) or None when NVML / affinity information is
+    unavailable or the intersection is empty (nothing is changed then)."""
+    import os
+    if not hasattr(os, "sched_getaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (max(ncpu, 1024) + 63) // 64)
+    except Exception:
+        return None
+    local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+    before = set(os.sched_getaffinity(0))
+    target = before & local
+    if not target or target == before:
+        return None
+    try:
+        os.sched_setaffinity(0, target)
+    except OSError:
+        return None
+    return before, target
