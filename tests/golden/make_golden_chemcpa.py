@@ -46,6 +46,8 @@ for case in synth.CHEMCPA_CASES:
                                          return_latent_basal=True, return_latent_treated=True)
     out[f"{case['name']}.basal"] = basal.numpy()
     out[f"{case['name']}.treated"] = treated.numpy()
+    out[f"{case['name']}.keys"] = np.asarray([k for k in model.state_dict().keys()
+                                              if not k.startswith(("decoder.", "adversary_"))])
     out[f"{case['name']}.checksum"] = np.asarray(synth.params_checksum([sd[k] for k in sd] + [table]))
     print(case["name"], basal.shape, float(np.abs(treated.numpy()).max()))
 np.savez_compressed(os.path.join(HERE, "golden_chemcpa.npz"), **out)

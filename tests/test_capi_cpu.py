@@ -64,3 +64,22 @@ def test_python_ops_refuse_cpu_tensors():
     W = torch.zeros(1, 128, 128)
     with pytest.raises(RuntimeError, match="CUDA"):
         mb.pair_score(z, z, W)
+
+
+def test_chemcpa_dropin_has_the_reference_state_dict_keys():
+    """madrigal_b200.chemcpa.TxAdaptingComPert registers exactly the reference module's parameters / buffers for the
+    parts on the path (keys recorded from the reference by tests/golden/make_golden_chemcpa.py; its decoder.* and
+    adversary_* entries have no counterpart).  Module construction only: no GPU call."""
+    import numpy as np
+    import torch
+    import synth
+    from madrigal_b200 import chemcpa
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_chemcpa.npz"))
+    for case in synth.CHEMCPA_CASES:
+        _, table, _ = synth.chemcpa_case(case)
+        emb = torch.nn.Embedding.from_pretrained(torch.from_numpy(table), freeze=True)
+        mod = chemcpa.TxAdaptingComPert(num_genes=case["num_genes"], num_drugs=case["num_drugs"],
+                                        covariate_names_unique={"cell_iname": [f"C{i}" for i in range(case["n_cell"])]},
+                                        doser_type=case["doser_type"], hparams=dict(case["hparams"]),
+                                        drug_embeddings=emb, use_drugs=case["use_drugs"], disable_adv=True)
+        assert list(mod.state_dict().keys()) == [str(k) for k in g[f"{case['name']}.keys"]], case["name"]
