@@ -303,7 +303,7 @@ template <typename TIn>
 int launch_attention_t(const FusionPlan& pl, const TIn* qkv, long long ld, const uint8_t* key_mask,
                        const uint8_t* src_mask, long long Bc, cudaStream_t stream) {
   const char* mma_knob = getenv("MDG_ATTENTION_MMA");
-  const bool mma_all = std::is_same<TIn, __nv_bfloat16>::value && mma_knob != nullptr && mma_knob[0] == 'a' && pl.hd == 64 && !pl.split;
+  const bool mma_all = std::is_same<TIn, __nv_bfloat16>::value && mma_knob != nullptr && mma_knob[0] == 'a' && (pl.hd == 64 || pl.hd == 128 || pl.hd == 256) && !pl.split;
   if (pl.T <= 8 && pl.hd <= 64 && !mma_all) {  // few tokens: head dimension on lanes, registers only
     const long long items = Bc * pl.H;
     long long blocks = (items + 7) / 8;
@@ -327,15 +327,28 @@ int launch_attention_t(const FusionPlan& pl, const TIn* qkv, long long ld, const
     const char* knob = getenv("MDG_ATTENTION_MMA");  // "0": FMA kernels; "all": also for T <= 8
     const bool off = knob != nullptr && knob[0] == '0';
     const bool all = knob != nullptr && knob[0] == 'a';
-    if (pl.hd == 64 && pl.T <= 32 && !pl.split && !off && (pl.T > 8 || all) && ld % 8 == 0) {
+    if ((pl.hd == 64 || pl.hd == 128 || pl.hd == 256) && pl.T <= 32 && !pl.split && !off && (pl.T > 8 || all) && ld % 8 == 0) {
       const int warps = 4;
-      const size_t smem = static_cast<size_t>(warps) * 3 * 4096;
+      const size_t smem = static_cast<size_t>(warps) * 3 * 32 * pl.hd * 2;  // q, k, v tiles of 32 rows per warp
+      static bool attr_mma[64] = {false};
+      int dev = 0;
+      MDG_CUDA(cudaGetDevice(&dev));
+      if (dev >= 0 && dev < 64 && !attr_mma[dev]) {
+        MDG_CUDA(cudaFuncSetAttribute(mdg::attention_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        MDG_CUDA(cudaFuncSetAttribute(mdg::attention_mma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
+        attr_mma[dev] = true;
+      }
       const long long items = Bc * pl.H;
       long long blocks = (items + warps - 1) / warps;
       const long long cap = static_cast<long long>(num_sms()) * 16;
       if (blocks > cap) blocks = cap;
-      mdg::attention_mma_kernel<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(
-          qkv, ld, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl));
+      const unsigned nb = static_cast<unsigned>(blocks);
+      if (pl.hd == 64)
+        mdg::attention_mma_kernel<64><<<nb, warps * 32, smem, stream>>>(qkv, ld, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl));
+      else if (pl.hd == 128)
+        mdg::attention_mma_kernel<128><<<nb, warps * 32, smem, stream>>>(qkv, ld, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl));
+      else
+        mdg::attention_mma_kernel<256><<<nb, warps * 32, smem, stream>>>(qkv, ld, key_mask, src_mask, Bc, pl.T, pl.H, pl.ob, kpad_of(pl.Dl));
       MDG_CUDA(cudaGetLastError());
       ++g_last_launches;
       return MDG_OK;

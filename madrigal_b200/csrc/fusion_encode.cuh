@@ -249,24 +249,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Tensor-core variant for bf16 q|k|v rows, head_dim 64, T <= 32 (the production shapes: T = 21 / 23, 8 heads of 64).
-// One (drug, head) per warp, FlashAttention-style on warp-level MMAs: the item's q, k, v rows (T x 128 bytes each) are
-// copied with 16-byte coalesced loads into XOR-swizzled shared memory, S = Q.K^T is 2 x 4 x 4 m16n8k16 MMAs with the
-// fragments from ldmatrix, the softmax runs on the accumulator fragments (a row lives in 4 lanes: two shuffles per
-// reduction), P is re-used in place as the A operand of O = P.V (V fragments from ldmatrix.trans), and O goes back
-// through shared memory so that global stores are 16-byte coalesced rows.  Against attention_rows_kernel (fp32 FMAs,
-// ~180 instructions per query) this is ~60 MMAs + ~150 other instructions per item: the kernel becomes a stream over
-// the q|k|v rows.  P is rounded to bf16 for the second product (bf16 mode only; the fp32-parity mode keeps the FMA
-// kernels).  Rows >= T of the staged tiles stay zero; their scores are masked (-inf) and their outputs never stored.
+// Tensor-core variant for bf16 q|k|v rows, head_dim 64 / 128 / 256, T <= 32 (the shipped production shapes: T = 23 with
+// 8 heads of 64, T = 21 with 2 heads of 256).  One (drug, head) per warp, FlashAttention-style on warp-level MMAs: the
+// item's q, k, v rows (T x 2 HD bytes each) are copied with 16-byte cp.async into XOR-swizzled shared memory,
+// S = Q.K^T is m16n8k16 MMAs on ldmatrix fragments, the softmax runs on the accumulator fragments (a row lives in 4
+// lanes: two shuffles per reduction), P is re-used in place as the A operand of O = P.V (V fragments from
+// ldmatrix.trans, 64 head dimensions at a time), and O goes back through the Q tile so that global stores are 16-byte
+// coalesced rows.  Against the FMA kernels (~180 instructions per query at HD = 64, far more at 256) the kernel becomes
+// a stream over the q|k|v rows.  P is rounded to bf16 for the second product (bf16 mode only; the fp32-parity mode
+// keeps the FMA kernels).  Rows >= T of the staged tiles stay zero; their scores are masked (-inf) and their outputs
+// never stored.
+template <int HD>
 __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld,
                                                             const uint8_t* __restrict__ key_mask,
                                                             const uint8_t* __restrict__ src_mask, long long B, int T,
                                                             int H, __nv_bfloat16* __restrict__ out, int k_pad) {
-  constexpr int HD = 64;
+  constexpr int PITCH = HD * 2;            // bytes per staged row
+  constexpr int PIECES = HD / 8;           // 16-byte pieces per row
+  constexpr uint32_t TILE = 32u * PITCH;   // one 32-row tile
   extern __shared__ __align__(128) uint8_t att_mma_smem[];
   const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t sQ = smem_u32(att_mma_smem) + static_cast<uint32_t>(wid) * 3u * 4096u, sK = sQ + 4096u, sV = sK + 4096u;
-  for (int i = lane; i < 3 * 256; i += 32) st_shared_v4(sQ + i * 16, 0u, 0u, 0u, 0u);
+  const uint32_t sQ = smem_u32(att_mma_smem) + static_cast<uint32_t>(wid) * 3u * TILE, sK = sQ + TILE, sV = sK + TILE;
+  for (uint32_t i = lane; i < 3u * TILE / 16u; i += 32) st_shared_v4(sQ + i * 16, 0u, 0u, 0u, 0u);
   const int Dl = H * HD;
   const float qscale = 1.0f / sqrtf(static_cast<float>(HD));
   const int g = lane >> 2, t = lane & 3;
@@ -283,36 +287,25 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
           for (int j = 0; j < T; ++j) blocked[mt][hh] |= (src_mask[row * T + j] != 0 ? 1u : 0u) << j;
       }
   const uint32_t beyond = T >= 32 ? 0u : ~((1u << T) - 1u);  // keys >= T
-  const int lr = lane >> 3, lp = lane & 7;                     // staging copy: row within a group of 4, 16-byte piece
+  auto swz = [](int row, int piece) { return static_cast<uint32_t>(row * PITCH + ((piece ^ (row & 7)) << 4)); };
   const long long total = B * H;
   for (long long item = static_cast<long long>(blockIdx.x) * warps + wid; item < total;
        item += static_cast<long long>(gridDim.x) * warps) {
     const long long b = item / H;
     const int h = static_cast<int>(item - b * H);
-    const __nv_bfloat16* base = qkv + (b * T) * ld + h * HD + lp * 8;
+    const __nv_bfloat16* base = qkv + (b * T) * ld + h * HD;
     __syncwarp();  // the previous item's output rows have left the Q tile
-    uint4 rq[8], rk[8], rv[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = lr + 4 * it;
-      if (r < T) {
-        const __nv_bfloat16* row = base + static_cast<long long>(r) * ld;
-        rq[it] = __ldg(reinterpret_cast<const uint4*>(row));
-        rk[it] = __ldg(reinterpret_cast<const uint4*>(row + Dl));
-        rv[it] = __ldg(reinterpret_cast<const uint4*>(row + 2 * Dl));
-      }
+    for (int e = lane; e < T * PIECES; e += 32) {
+      const int r = e / PIECES, pc = e - r * PIECES;
+      const __nv_bfloat16* src = base + static_cast<long long>(r) * ld + pc * 8;
+      const uint32_t off = swz(r, pc);
+      cp_async_16(sQ + off, src);
+      cp_async_16(sK + off, src + Dl);
+      cp_async_16(sV + off, src + 2 * Dl);
     }
+    cp_async_commit();
     const uint32_t km = __ballot_sync(0xffffffffu, lane < T && key_mask[b * T + lane] != 0) | beyond;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = lr + 4 * it;
-      if (r < T) {
-        const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(lp ^ (r & 7)) << 4);
-        st_shared_v4(sQ + off, rq[it].x, rq[it].y, rq[it].z, rq[it].w);
-        st_shared_v4(sK + off, rk[it].x, rk[it].y, rk[it].z, rk[it].w);
-        st_shared_v4(sV + off, rv[it].x, rv[it].y, rv[it].z, rv[it].w);
-      }
-    }
+    cp_async_wait_all();
     __syncwarp();
     // ---- S = Q.K^T
     float S[2][4][4];
@@ -322,21 +315,21 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) S[mt][nt][e] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll 4
+    for (int ks = 0; ks < HD / 16; ++ks) {
       uint32_t a[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
         if (mt < n_mt) {
           const int row = 16 * mt + (lane & 7) + 8 * ((lane >> 3) & 1), piece = 2 * ks + (lane >> 4);
-          ldmatrix_x4(sQ + row * 128 + ((piece ^ (row & 7)) << 4), a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
+          ldmatrix_x4(sQ + swz(row, piece), a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
         }
 #pragma unroll
       for (int np = 0; np < 2; ++np)  // pairs of key tiles: one ldmatrix.x4 = (nt, nt+1) x (pieces 2ks, 2ks+1)
         if (2 * np < n_nt) {
           const int row = 16 * np + (lane & 7) + 8 * (lane >> 4), piece = 2 * ks + ((lane >> 3) & 1);
           uint32_t b0, b1, b2, b3;
-          ldmatrix_x4(sK + row * 128 + ((piece ^ (row & 7)) << 4), b0, b1, b2, b3);
+          ldmatrix_x4(sK + swz(row, piece), b0, b1, b2, b3);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
             if (mt < n_mt) {
@@ -380,53 +373,51 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) P[mt][nt][hh] = pack_bf16x2_rn(S[mt][nt][2 * hh], S[mt][nt][2 * hh + 1]);
       }
-    // ---- O = P.V
-    float O[2][8][4];
+    __syncwarp();  // every lane has read its Q fragments: the Q tile becomes the output staging tile
+    // ---- O = P.V, 64 head dimensions at a time; normalised rows are staged in the Q tile
+    for (int dc = 0; dc < HD / 64; ++dc) {
+      float O[2][8][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int dn = 0; dn < 8; ++dn)
+        for (int dn = 0; dn < 8; ++dn)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) O[mt][dn][e] = 0.f;
+          for (int e = 0; e < 4; ++e) O[mt][dn][e] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk)
-      if (kk < n_kk) {
+      for (int kk = 0; kk < 2; ++kk)
+        if (kk < n_kk) {
 #pragma unroll
-        for (int dp = 0; dp < 4; ++dp) {  // pairs of 8-dimension tiles
-          const int row = 16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), piece = 2 * dp + (lane >> 4);
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4_trans(sV + row * 128 + ((piece ^ (row & 7)) << 4), b0, b1, b2, b3);
+          for (int dp = 0; dp < 4; ++dp) {  // pairs of 8-dimension tiles
+            const int row = 16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1), piece = 8 * dc + 2 * dp + (lane >> 4);
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4_trans(sV + swz(row, piece), b0, b1, b2, b3);
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-            if (mt < n_mt) {
-              mma_bf16_16816(O[mt][2 * dp], P[mt][2 * kk][0], P[mt][2 * kk][1], P[mt][2 * kk + 1][0], P[mt][2 * kk + 1][1], b0, b1);
-              mma_bf16_16816(O[mt][2 * dp + 1], P[mt][2 * kk][0], P[mt][2 * kk][1], P[mt][2 * kk + 1][0], P[mt][2 * kk + 1][1], b2, b3);
-            }
+            for (int mt = 0; mt < 2; ++mt)
+              if (mt < n_mt) {
+                mma_bf16_16816(O[mt][2 * dp], P[mt][2 * kk][0], P[mt][2 * kk][1], P[mt][2 * kk + 1][0], P[mt][2 * kk + 1][1], b0, b1);
+                mma_bf16_16816(O[mt][2 * dp + 1], P[mt][2 * kk][0], P[mt][2 * kk][1], P[mt][2 * kk + 1][0], P[mt][2 * kk + 1][1], b2, b3);
+              }
+          }
         }
-      }
-    // ---- normalise, stage in the Q tile, store rows coalesced
-    __syncwarp();  // every lane has read its Q fragments
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-      if (mt < n_mt)
+      for (int mt = 0; mt < 2; ++mt)
+        if (mt < n_mt)
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int row = 16 * mt + g + 8 * hh;
+          for (int hh = 0; hh < 2; ++hh) {
+            const int row = 16 * mt + g + 8 * hh;
 #pragma unroll
-          for (int dn = 0; dn < 8; ++dn)
-            st_shared_u32(sQ + row * 128 + ((dn ^ (row & 7)) << 4) + t * 4,
-                          pack_bf16x2_rn(O[mt][dn][2 * hh] * inv[mt][hh], O[mt][dn][2 * hh + 1] * inv[mt][hh]));
-        }
+            for (int dn = 0; dn < 8; ++dn)
+              st_shared_u32(sQ + swz(row, 8 * dc + dn) + t * 4,
+                            pack_bf16x2_rn(O[mt][dn][2 * hh] * inv[mt][hh], O[mt][dn][2 * hh + 1] * inv[mt][hh]));
+          }
+    }
     __syncwarp();
-    __nv_bfloat16* obase = out + (b * T) * static_cast<long long>(k_pad) + h * HD + lp * 8;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = lr + 4 * it;
-      if (r < T) {
-        uint4 v4;
-        ld_shared_v4(sQ + r * 128 + ((lp ^ (r & 7)) << 4), v4.x, v4.y, v4.z, v4.w);
-        *reinterpret_cast<uint4*>(obase + static_cast<long long>(r) * k_pad) = v4;
-      }
+    __nv_bfloat16* obase = out + (b * T) * static_cast<long long>(k_pad) + h * HD;
+    for (int e = lane; e < T * PIECES; e += 32) {
+      const int r = e / PIECES, pc = e - r * PIECES;
+      uint4 v4;
+      ld_shared_v4(sQ + swz(r, pc), v4.x, v4.y, v4.z, v4.w);
+      *reinterpret_cast<uint4*>(obase + static_cast<long long>(r) * k_pad + pc * 8) = v4;
     }
   }
 }

@@ -174,6 +174,13 @@ __device__ __forceinline__ void stmatrix_x4_trans(uint32_t row_addr, uint32_t r0
   asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(row_addr), "r"(r0),
                "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
+// 16-byte asynchronous global -> shared copies (LDGSTS: no staging registers), grouped and awaited per thread
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ldmatrix: four 8x8 b16 matrices from shared memory into the mma fragment layout (addresses as for stmatrix).
 __device__ __forceinline__ void ldmatrix_x4(uint32_t row_addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"

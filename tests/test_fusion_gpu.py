@@ -359,3 +359,51 @@ def test_chemcpa_mlp_rejects_training_mode_and_cpu(mb, cuda_device):
         m.eval()(torch.zeros(2, 16))  # CPU tensor: no fallback
     assert list(mb.chemcpa.MLP([4, 5, 6], append_layer_width=3, append_layer_position="first").state_dict())[:2] == \
         ["network.append_linear.weight", "network.append_linear.bias"]
+
+
+@pytest.mark.parametrize("agg,T,nb,B,dims", [
+    ("x-attn", 23, 4, 70, (128, 8, 64, 256)),    # production DrugBank shape: 8 heads of 64
+    ("x-attn", 21, 2, 50, (128, 2, 256, 512)),   # production TWOSIDES shape: 2 heads of 256
+    ("mean", 9, 0, 33, (64, 3, 128, 128)),       # head_dim 128, one query tile of 16 rows, two key tiles
+    ("cls", 16, 0, 40, (64, 2, 64, 96)),         # T = 16 exactly (no second query tile)
+    ("max", 32, 0, 21, (96, 1, 128, 64)),        # T = 32: every key tile full
+])
+def test_tensor_core_attention_vs_fma_attention(mb, cuda_device, agg, T, nb, B, dims):
+    """bf16 mode, 8 < T <= 32, head_dim 64/128/256: attention_mma_kernel (warp-level MMAs) vs the FMA attention kernels
+    (MDG_ATTENTION_MMA=0) and the fp64 oracle; missing-modality masks, src_mask and bottleneck tokens included."""
+    E, H, hd, F = dims
+    case = dict(embed_dim=E, num_layers=2, num_heads=H, head_dim=hd, ffn_dim=F, actn="gelu", norm_first=True,
+                agg=agg, nb=nb, seed=51 + T)
+    mod, sd = make_module(mb, case, cuda_device, precision="bf16")
+    tokens, mask = synth.fusion_inputs(B, T, E, case["seed"], always_visible=(0,) + tuple(range(3, 3 + nb)))
+    src = None
+    if nb > 0:
+        src = np.zeros((T, T), bool)
+        src[:3, T - 16:] = True
+        src[T - 16:, :3] = True
+    pool = None
+    if agg == "x-attn":
+        pool = np.zeros(T, bool)
+        if nb > 0:
+            pool[:3] = True
+            pool[-16:] = True
+        mod.x_attn_key_padding_mask = torch.from_numpy(pool)[None, :]
+    ref = oracle.fusion_forward(sd, case, tokens, mask, src, pool, dtype=np.float64)
+    args = (gpu(tokens, cuda_device), gpu(mask, cuda_device), None if src is None else gpu(src, cuda_device))
+    os.environ["MDG_FUSION_GENERIC"] = "1"   # latent <= 256 shapes would otherwise take the fused encoder kernel
+    try:
+        with torch.no_grad():
+            z = mod(*args).cpu().numpy()
+            os.environ["MDG_ATTENTION_MMA"] = "0"
+            try:
+                zf = mod(*args).cpu().numpy()
+            finally:
+                del os.environ["MDG_ATTENTION_MMA"]
+    finally:
+        del os.environ["MDG_FUSION_GENERIC"]
+    rms = np.sqrt(np.mean(ref ** 2))
+    bound = 3e-2 * max(rms, np.abs(ref).max() * 0.1)
+    assert np.isfinite(z).all() and np.isfinite(zf).all()
+    assert np.abs(z - ref).max() <= bound, "tensor-core attention vs fp64 oracle"
+    assert np.abs(zf - ref).max() <= bound, "FMA attention vs fp64 oracle"
+    assert np.abs(z - zf).max() <= bound and not np.array_equal(z, zf), "the two attention kernels both ran"
