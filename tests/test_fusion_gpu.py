@@ -407,3 +407,40 @@ def test_tensor_core_attention_vs_fma_attention(mb, cuda_device, agg, T, nb, B, 
     assert np.abs(z - ref).max() <= bound, "tensor-core attention vs fp64 oracle"
     assert np.abs(zf - ref).max() <= bound, "FMA attention vs fp64 oracle"
     assert np.abs(z - zf).max() <= bound and not np.array_equal(z, zf), "the two attention kernels both ran"
+
+
+@pytest.mark.parametrize("agg,nb,T", [("x-attn", 4, 23), ("mean", 0, 4)])
+def test_torch_op_fusion_encode_matches_module(mb, cuda_device, agg, nb, T):
+    """torch.ops.madrigal_b200.fusion_encode (functional form: state_dict tensors in, z out) == TransformerFusion.forward;
+    the parameter tensors are adopted without a copy; CPU tensors have no kernel."""
+    E, H, hd, F = 64, 4, 16, 96
+    case = dict(embed_dim=E, num_layers=2, num_heads=H, head_dim=hd, ffn_dim=F, actn="gelu", norm_first=True,
+                agg=agg, nb=nb, seed=91)
+    for precision in ("fp32", "bf16"):
+        mod, _ = make_module(mb, case, cuda_device, precision=precision)
+        tokens, mask = synth.fusion_inputs(37, T, E, 91, always_visible=(0,) + tuple(range(3, 3 + nb)))
+        src = None
+        if nb > 0:
+            src = np.zeros((T, T), bool)
+            src[:3, T - 16:] = True
+            src[T - 16:, :3] = True
+            src = gpu(src, cuda_device)
+        params = list(mod.state_dict().values())
+        cfg = [E, nb, 2, H, hd, F, 1]
+        with torch.no_grad():
+            want = mod(gpu(tokens, cuda_device), gpu(mask, cuda_device), src)
+        got = torch.ops.madrigal_b200.fusion_encode(gpu(tokens, cuda_device), gpu(mask, cuda_device), src, None, params,
+                                                    cfg, "gelu", agg, precision)
+        assert torch.equal(got, want)
+        if agg == "x-attn":  # explicit pooling key mask (the 4-token configurations of BASELINE use this)
+            pool = torch.zeros(T, dtype=torch.bool, device=cuda_device)
+            pool[1] = True
+            mod.x_attn_key_padding_mask = pool.cpu()[None, :]
+            with torch.no_grad():
+                want2 = mod(gpu(tokens, cuda_device), gpu(mask, cuda_device), src)
+            got2 = torch.ops.madrigal_b200.fusion_encode(gpu(tokens, cuda_device), gpu(mask, cuda_device), src, pool,
+                                                         params, cfg, "gelu", agg, precision)
+            assert torch.equal(got2, want2) and not torch.equal(got2, got)
+    with pytest.raises(NotImplementedError):
+        torch.ops.madrigal_b200.fusion_encode(torch.zeros(2, T, E), torch.zeros(2, T, dtype=torch.bool), None, None,
+                                              [p.cpu() for p in params], cfg, "gelu", agg, "fp32")
