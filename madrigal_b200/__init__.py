@@ -7,10 +7,10 @@ from .decoder import (BilinearDDIScorer, RankTable, Symmetric, ensemble_reduce, 
                       pair_score_gather, pair_topk)
 from .fusion import (FusionEncoder, MLPAdaptor, MLPEncoder, PositionEncodingLearnable, PositionEncodingSinusoidal,  # noqa: F401
                      TransformerFusion, masked_pool)
-from .model import NovelDDIMultilabel, PrecomputedEmbeddingEncoder  # noqa: F401
+from .model import NovelDDIEncoder, NovelDDIMultilabel, PrecomputedEmbeddingEncoder  # noqa: F401
 from . import chemcpa  # noqa: F401  (tx modality encoder: chemcpa.TxAdaptingComPert, chemcpa.MLP)
 from . import ops  # noqa: F401  (registers torch.ops.madrigal_b200.*)
 
 __all__ = ["BilinearDDIScorer", "RankTable", "Symmetric", "pair_score", "pair_topk", "pair_score_gather", "ensemble_reduce", "TransformerFusion", "MLPAdaptor", "MLPEncoder",
            "FusionEncoder", "PositionEncodingSinusoidal", "PositionEncodingLearnable", "masked_pool",
-           "NovelDDIMultilabel", "PrecomputedEmbeddingEncoder", "chemcpa"]
+           "NovelDDIEncoder", "NovelDDIMultilabel", "PrecomputedEmbeddingEncoder", "chemcpa"]

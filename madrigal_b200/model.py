@@ -64,3 +64,102 @@ class PrecomputedEmbeddingEncoder(nn.Module):
 
     def forward(self, batch_drugs, batch_masks, batch_mols, batch_kg, batch_cv, batch_tx_dict, **kwargs):
         return self.fusion_encoder(batch_tx_dict['all_embeds'], batch_masks)
+
+
+class NovelDDIEncoder(nn.Module):
+    """The reference encoder's call signature (`NovelDDIEncoder.encode`, models.py:717-900) around `FusionEncoder`.
+
+    The modality encoders are passed in as modules and called exactly as the reference calls them (models.py:720-769):
+    the structure / knowledge-graph encoders are the reference's own GNNs (out of scope here), `cv_encoder` and
+    `tx_encoder_dict` may be `madrigal_b200.MLPEncoder`s and `tx_encoder` a `madrigal_b200.chemcpa.TxAdaptingComPert`.
+    Everything from `all_embeds` on (:772-896: stacking, bottleneck tokens, masks, positional encoding, fusion
+    transformer, unimodal bypass) is `fusion_encoder`.  Attribute names follow the reference so that its checkpoints'
+    encoder entries line up (`str_encoder.*`, `kg_encoder.*`, `cv_encoder.*`, `tx_encoder.*`; the fusion section's
+    parameters live under `fusion_encoder.*`).
+    """
+
+    def __init__(self, fusion_encoder, str_encoder, kg_encoder, cv_encoder, tx_encoder=None, tx_encoder_dict=None,
+                 tabular_mod_encoders=None, kg_encoder_name: str = 'hgt', use_tx_basal: bool = False,
+                 tx_cell_line_onehot_encoder=None):
+        super().__init__()
+        from .constants import CELL_LINES, NON_TX_MODALITIES
+        if (tx_encoder is None) == (tx_encoder_dict is None):
+            raise ValueError("give exactly one of tx_encoder (chemCPA) and tx_encoder_dict (one encoder per cell line)")
+        self.fusion_encoder = fusion_encoder
+        self.embed_dim = fusion_encoder.embed_dim
+        self.str_encoder, self.kg_encoder, self.cv_encoder = str_encoder, kg_encoder, cv_encoder
+        self.kg_encoder_name = kg_encoder_name
+        self.tx_encoder = tx_encoder
+        self.tx_encoder_dict = tx_encoder_dict if tx_encoder_dict is None or isinstance(tx_encoder_dict, nn.Module) \
+            else _as_module_dict(tx_encoder_dict)
+        mods = tabular_mod_encoders or {}
+        self.tabular_mod_encoders = mods if isinstance(mods, nn.Module) else _as_module_dict(mods)
+        self.use_tx_basal = use_tx_basal
+        self.tx_cell_line_onehot_encoder = tx_cell_line_onehot_encoder
+        self._cell_lines, self._extra_mods = list(CELL_LINES), list(NON_TX_MODALITIES[3:])
+
+    def encode(self, batch_drugs, batch_masks, batch_mols, batch_kg, batch_cv, batch_tx_dict, raw_encoder_output=False,
+               **kwargs):
+        # structure (models.py:720-721)
+        str_out = self.str_encoder(batch_mols, batch_mols.node_feature.float())["graph_feature"]
+        # knowledge graph (:724-736)
+        kg_data, kg_map = batch_kg['data'], batch_kg['drug_index_map']
+        if 'han' in self.kg_encoder_name or 'hgt' in self.kg_encoder_name:
+            kg_valid = self.kg_encoder(kg_data.x_dict, kg_data.edge_index_dict)['drug']
+        elif 'rgcn' in self.kg_encoder_name:
+            kg_valid = self.kg_encoder(kg_data.node_embeddings, kg_data.edge_index, kg_data.node_type,
+                                       kg_data.edge_type)[:(kg_data.node_type == 0).sum().item()]
+        else:
+            raise NotImplementedError(self.kg_encoder_name)
+        # drugs outside the KG get a filler row: the reference draws randn (:733), the slot is masked either way
+        n_rows = max(int(batch_drugs.max().item()) + 1, int(kg_map.max().item()) + 1)
+        kg_out = torch.zeros((n_rows, self.embed_dim), dtype=kg_valid.dtype, device=kg_valid.device)
+        kg_out[kg_map.to(kg_valid.device)] = kg_valid
+        kg_out = kg_out[batch_drugs.to(kg_valid.device)]
+        cv_out = self.cv_encoder(batch_cv)  # :741
+        other = []
+        if len(self.tabular_mod_encoders) > 0:  # :746-750
+            for mod in self._extra_mods:
+                if kwargs.get(mod, None) is None:
+                    raise AssertionError(f"Missing {mod} in the input batch")
+                other.append(self.tabular_mod_encoders[mod](kwargs[mod]))
+        if self.tx_encoder_dict is not None:  # :753-754
+            tx_out = [self.tx_encoder_dict[c](batch_tx_dict[c]['sigs']) for c in self._cell_lines]
+        else:  # chemCPA over all cell lines at once (:756-769)
+            import numpy as np
+            sigs = torch.cat([batch_tx_dict[c]['sigs'] for c in self._cell_lines], dim=0)
+            drugs = torch.cat([batch_tx_dict[c]['drugs'] for c in self._cell_lines], dim=0)
+            dosages = torch.cat([batch_tx_dict[c]['dosages'] for c in self._cell_lines], dim=0)
+            cells = np.concatenate([batch_tx_dict[c]['cell_lines'] for c in self._cell_lines], axis=0)
+            onehot = torch.from_numpy(self.tx_cell_line_onehot_encoder.transform(cells.reshape(-1, 1))).long().to(sigs.device)
+            lat = self.tx_encoder.predict(genes=sigs, drugs_idx=drugs, dosages=dosages, covariates=[onehot],
+                                          return_latent_basal=self.use_tx_basal,
+                                          return_latent_treated=(not self.use_tx_basal))[2]
+            tx_out = list(torch.split(lat, lat.shape[0] // len(self._cell_lines), dim=0))
+        all_embeds = torch.stack([str_out, kg_out, cv_out] + other + tx_out, dim=1).float().contiguous()  # :772-775
+        if raw_encoder_output:  # :889-893
+            uni = all_embeds[~batch_masks.to(torch.bool), :]
+            if self.fusion_encoder.normalize:
+                uni = torch.nn.functional.normalize(uni, p=2, dim=-1)
+            return self.fusion_encoder.uni_projector(uni.contiguous())
+        return self.fusion_encoder(all_embeds, batch_masks)
+
+    def forward(self, batch_drugs, batch_masks, batch_mols, batch_kg, batch_cv, batch_tx_dict, raw_encoder_output=False,
+                **kwargs):
+        return self.encode(batch_drugs, batch_masks, batch_mols, batch_kg, batch_cv, batch_tx_dict, raw_encoder_output,
+                           **kwargs)
+
+
+class _Callable(nn.Module):
+    """Wraps a plain callable so that it can sit in an nn.ModuleDict next to real modules."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def forward(self, *a, **k):
+        return self.fn(*a, **k)
+
+
+def _as_module_dict(d):
+    return nn.ModuleDict({k: (v if isinstance(v, nn.Module) else _Callable(v)) for k, v in d.items()})

@@ -150,9 +150,8 @@ def test_mlp_adaptor_vs_reference_golden(mb, cuda_device, case):
     assert_close(y, g[f"{case['name']}.y"], 1e-3, case["name"])
 
 
-@pytest.mark.parametrize("case", META["encode"], ids=lambda c: c["name"])
-def test_fusion_encoder_vs_reference_encode_golden(mb, cuda_device, case):
-    """FusionEncoder (assembly kernel + encoder + unimodal bypass) vs the reference's own NovelDDIEncoder.encode."""
+def _encode_case(mb, case, cuda_device):
+    """FusionEncoder + inputs of one golden `encode` case (tests/golden/make_golden.py: encode_goldens)."""
     g = np.load(os.path.join(HERE, "golden", "golden_encode.npz"))
     name, E, seed, B = case["name"], case["E"], case["seed"], case["B"]
     rng = np.random.default_rng(seed)
@@ -189,9 +188,46 @@ def test_fusion_encoder_vs_reference_encode_golden(mb, cuda_device, case):
             for o, x in zip(lin, [x for x in enc.uni_fuser.fc if isinstance(x, (torch.nn.Linear, torch.nn.LayerNorm))]):
                 x.weight.copy_(torch.from_numpy(o["w"]))
                 x.bias.copy_(torch.from_numpy(o["b"]))
-        enc = enc.to(cuda_device).eval()
+    return enc.to(cuda_device).eval(), embeds, masks, g[f"{name}.z"]
+
+
+@pytest.mark.parametrize("case", META["encode"], ids=lambda c: c["name"])
+def test_fusion_encoder_vs_reference_encode_golden(mb, cuda_device, case):
+    """FusionEncoder (assembly kernel + encoder + unimodal bypass) vs the reference's own NovelDDIEncoder.encode."""
+    enc, embeds, masks, want = _encode_case(mb, case, cuda_device)
+    with torch.no_grad():
         z = enc(gpu(embeds, cuda_device), gpu(masks, cuda_device)).cpu().numpy()
-    assert_close(z, g[f"{name}.z"], 1e-3, name)
+    assert_close(z, want, 1e-3, case["name"])
+
+
+@pytest.mark.parametrize("case", META["encode"], ids=lambda c: c["name"])
+def test_novel_ddi_encoder_dropin_vs_reference_encode_golden(mb, cuda_device, case):
+    """madrigal_b200.NovelDDIEncoder.encode — the reference's call signature, driven exactly as the golden generator
+    drove the reference's own encode (stub modality encoders returning the seeded embeddings, KG rows in a permuted
+    node order behind `drug_index_map`) — against the reference's output."""
+    fe, embeds, masks, want = _encode_case(mb, case, cuda_device)
+    B = embeds.shape[0]
+    e = gpu(embeds, cuda_device)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+
+    class Mols:
+        node_feature = torch.zeros(1)
+
+    class KG:
+        x_dict = None
+        edge_index_dict = None
+
+    enc = mb.NovelDDIEncoder(fe, str_encoder=lambda mols, feats: {"graph_feature": e[:, 0]},
+                             kg_encoder=lambda x, ei: {"drug": e[:, 1][perm]}, cv_encoder=lambda cv: e[:, 2],
+                             tx_encoder_dict={cl: (lambda sigs: sigs) for cl in synth.CELL_LINES}, kg_encoder_name="hgt")
+    tx = {cl: {"sigs": e[:, 3 + i]} for i, cl in enumerate(synth.CELL_LINES)}
+    kg = {"data": KG(), "drug_index_map": perm}
+    with torch.no_grad():
+        z = enc.encode(torch.arange(B, device=cuda_device), gpu(masks, cuda_device), Mols(), kg, None, tx)
+        raw = enc(torch.arange(B, device=cuda_device), gpu(masks, cuda_device), Mols(), kg, None, tx,
+                  raw_encoder_output=True)
+    assert_close(z.cpu().numpy(), want, 1e-3, case["name"])
+    assert raw.shape == (int((~masks).sum()), embeds.shape[2]) and torch.isfinite(raw).all()
 
 
 def test_model_wrapper_end_to_end(mb, cuda_device):

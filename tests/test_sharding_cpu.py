@@ -51,3 +51,69 @@ def test_two_rank_sharded_scoring_matches_single_rank(tmp_path):
     full = oracle.bilinear_scores(z, z, W)
     got = np.concatenate([np.load(tmp_path / f"part{r}.npy") for r in range(world)], axis=0)
     assert np.array_equal(got, full)  # sharding does not change any arithmetic
+
+
+def test_novel_ddi_encoder_dropin_plumbing_cpu():
+    """Host logic of madrigal_b200.NovelDDIEncoder.encode (models.py:717-775, 889-893) with stub modality encoders and
+    a stub fusion section: token order [str, kg, cv, tx...], KG rows behind a permuted drug_index_map, per-cell-line
+    encoders vs the chemCPA call (one predict over all cell lines, split back), raw_encoder_output."""
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    import madrigal_b200 as mb
+    from madrigal_b200.constants import CELL_LINES
+
+    class FakeFusion(nn.Module):
+        embed_dim, normalize = 8, True
+
+        def __init__(self):
+            super().__init__()
+            self.uni_projector = nn.Identity()
+
+        def forward(self, e, m):
+            return (e * (~m)[:, :, None]).sum(1)
+
+    B, E = 5, 8
+    rng = np.random.default_rng(0)
+    embeds = torch.from_numpy(rng.standard_normal((B, 19, E)).astype(np.float32))
+    masks = torch.from_numpy(rng.random((B, 19)) < 0.5)
+    masks[:, 0] = False
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+
+    class Mols:
+        node_feature = torch.zeros(1)
+
+    class KG:
+        x_dict = None
+        edge_index_dict = None
+
+    common = dict(str_encoder=lambda m, f: {"graph_feature": embeds[:, 0]},
+                  kg_encoder=lambda x, e: {"drug": embeds[:, 1][perm]}, cv_encoder=lambda cv: embeds[:, 2])
+    kg = {"data": KG(), "drug_index_map": perm}
+    enc = mb.NovelDDIEncoder(FakeFusion(), tx_encoder_dict={c: (lambda s: s) for c in CELL_LINES}, **common)
+    tx = {c: {"sigs": embeds[:, 3 + i]} for i, c in enumerate(CELL_LINES)}
+    z = enc(torch.arange(B), masks, Mols(), kg, None, tx)
+    assert torch.allclose(z, FakeFusion()(embeds, masks))
+    raw = enc.encode(torch.arange(B), masks, Mols(), kg, None, tx, raw_encoder_output=True)
+    assert raw.shape == (int((~masks).sum()), E)
+
+    class StubTx(nn.Module):
+        def predict(self, genes, drugs_idx, dosages, covariates, return_latent_basal, return_latent_treated):
+            assert covariates[0].shape == (genes.shape[0], len(CELL_LINES))
+            assert (return_latent_basal, return_latent_treated) == (False, True)
+            return None, None, genes + covariates[0].argmax(1)[:, None].float()
+
+    class OneHot:
+        def transform(self, a):
+            return np.eye(len(CELL_LINES))[[CELL_LINES.index(x) for x in a[:, 0]]]
+
+    tx2 = {c: {"sigs": embeds[:, 3 + i], "drugs": torch.arange(B), "dosages": torch.ones(B),
+               "cell_lines": np.array([c] * B)} for i, c in enumerate(CELL_LINES)}
+    enc2 = mb.NovelDDIEncoder(FakeFusion(), tx_encoder=StubTx(), tx_cell_line_onehot_encoder=OneHot(), **common)
+    want = embeds.clone()
+    for i in range(len(CELL_LINES)):
+        want[:, 3 + i] += i
+    assert torch.allclose(enc2(torch.arange(B), masks, Mols(), kg, None, tx2), FakeFusion()(want, masks))
+    import pytest
+    with pytest.raises(ValueError):
+        mb.NovelDDIEncoder(FakeFusion(), **common)
