@@ -117,3 +117,16 @@ def test_novel_ddi_encoder_dropin_plumbing_cpu():
     import pytest
     with pytest.raises(ValueError):
         mb.NovelDDIEncoder(FakeFusion(), **common)
+
+
+def test_bind_host_thread_to_gpu_is_a_noop_without_nvml_affinity():
+    """scoring.bind_host_thread_to_gpu: on a host without NVML / NUMA affinity information nothing changes."""
+    import os
+    from madrigal_b200 import scoring
+    before = set(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None
+    res = scoring.bind_host_thread_to_gpu(0)
+    if res is None and before is not None:
+        assert set(os.sched_getaffinity(0)) == before
+    elif res is not None:  # a host with affinity information: the new set is a subset of the old one; restore
+        assert res[1] <= res[0]
+        os.sched_setaffinity(0, res[0])
