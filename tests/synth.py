@@ -168,3 +168,23 @@ def chemcpa_case(case):
                   dosages=(rng.random(B) * 3.0).astype(F32),
                   cov_idx=rng.integers(0, case["n_cell"], B).astype(np.int64))
     return sd, table, inputs
+
+
+# ------------------------------------------------------------------------- MLPEncoder (cv / tx 'mlp' encoders, f-4)
+MLPENCODER_CASES = [
+    dict(name="cv_default_no_norm", in_dim=96, hidden=[64, 48], out_dim=32, p=0.1, norm=None, actn="relu", order="nd", B=9, seed=11),
+    dict(name="tx_ln_gelu", in_dim=978, hidden=[128, 64, 64], out_dim=128, p=0.0, norm="ln", actn="gelu", order="nd", B=7, seed=12),
+    dict(name="ln_dropout_first", in_dim=40, hidden=[32, 24], out_dim=16, p=0.2, norm="ln", actn="relu", order="dn", B=5, seed=13),
+]
+
+
+def mlp_encoder_ops(case):
+    """Op list (see oracle.mlp_adaptor) of MLPEncoder(in_dim, hidden, out_dim, p, norm, actn, order) in eval mode:
+    Linear, act, [norm?, Linear, act]*, Linear (models.py:133-143, 146-176); Dropout is the identity."""
+    ops = mlp_adaptor_params(case["in_dim"], case["hidden"], case["out_dim"], case["seed"])
+    for o in ops:
+        if o["op"] == "act":
+            o["actn"] = case["actn"]
+    if case["norm"] is None:
+        ops = [o for o in ops if o["op"] != "ln"]
+    return ops

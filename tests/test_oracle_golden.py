@@ -245,3 +245,19 @@ def test_chemcpa_tx_latents_match_reference(case):
                                                drugs_idx=inp["drugs_idx"], dosages=inp["dosages"])
     np.testing.assert_allclose(basal, g[f"{case['name']}.basal"], rtol=2e-5, atol=2e-5)
     np.testing.assert_allclose(treated, g[f"{case['name']}.treated"], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", synth.MLPENCODER_CASES, ids=lambda c: c["name"])
+def test_mlp_encoder_matches_reference(case):
+    """oracle.mlp_adaptor on MLPEncoder's op list vs the reference `MLPEncoder` (models.py:121-180; goldens from
+    tests/golden/make_golden_mlpencoder.py), and the drop-in's `fc.*` keys vs the reference module's."""
+    g = np.load(os.path.join(G, "golden_mlpencoder.npz"))
+    ops = synth.mlp_encoder_ops(case)
+    params = [o for o in ops if o["op"] in ("linear", "ln")]
+    chk = synth.params_checksum([o["w"] for o in params] + [o["b"] for o in params])
+    assert abs(chk - float(g[f"{case['name']}.checksum"])) < 1e-6
+    x = np.random.default_rng(case["seed"]).standard_normal((case["B"], case["in_dim"])).astype(np.float32)
+    np.testing.assert_allclose(oracle.mlp_adaptor(ops, x), g[f"{case['name']}.y"], rtol=2e-5, atol=2e-5)
+    import madrigal_b200 as mb
+    mod = mb.MLPEncoder(case["in_dim"], case["hidden"], case["out_dim"], case["p"], case["norm"], case["actn"], case["order"])
+    assert list(mod.state_dict().keys()) == [str(k) for k in g[f"{case['name']}.keys"]]
