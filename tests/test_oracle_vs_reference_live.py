@@ -76,3 +76,46 @@ def test_random_decoder_and_normaliser_match_reference(ref, seed):
     for l in range(L):
         run_slice((l, l + 1))  # normalize_scores.py:78-85 maps run_slice over single-outcome slices
     assert np.array_equal(oracle.normalize_scores(raw), want_norm)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_chemcpa_configs_match_reference(seed):
+    """oracle.chemcpa_tx_latents vs the reference TxAdaptingComPert.predict (chemcpa/chemCPA/model.py, loaded by file
+    path) on random widths / depths / doser types."""
+    import importlib.util
+    import os
+    from oracle.ref_import import REFERENCE_ROOT
+    spec = importlib.util.spec_from_file_location(
+        "ref_chemcpa_model_live", os.path.join(REFERENCE_ROOT, "madrigal", "chemcpa", "chemCPA", "model.py"))
+    ref_model = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_model)
+    torch.set_grad_enabled(False)
+    rng = np.random.default_rng(9200 + seed)
+    doser = [None, "sigm", "logsigm", "amortized"][seed % 4]
+    case = dict(name=f"live{seed}", num_genes=int(rng.integers(10, 80)), num_drugs=int(rng.integers(3, 9)),
+                n_cell=int(rng.integers(2, 7)), use_drugs=bool(seed != 0), doser_type=doser if doser else "logsigm",
+                hparams=dict(dim=int(rng.choice([8, 16, 24])), autoencoder_width=int(rng.choice([16, 32])),
+                             autoencoder_depth=int(rng.integers(0, 4)), dosers_width=8, dosers_depth=int(rng.integers(1, 3)),
+                             embedding_encoder_width=12, embedding_encoder_depth=int(rng.integers(0, 3))),
+                emb_dim=int(rng.choice([6, 10])), B=int(rng.integers(2, 12)), seed=9200 + seed)
+    sd, table, inp = synth.chemcpa_case(case)
+    train_hp = dict(autoencoder_lr=1e-3, autoencoder_wd=0.0, adversary_lr=1e-3, adversary_wd=0.0, dosers_lr=1e-3,
+                    dosers_wd=0.0, step_size_lr=45, adversary_width=8, adversary_depth=1)
+    emb = torch.nn.Embedding.from_pretrained(torch.from_numpy(table), freeze=True)
+    model = ref_model.TxAdaptingComPert(num_genes=case["num_genes"], num_drugs=case["num_drugs"],
+                                        covariate_names_unique={"cell_iname": [f"C{i}" for i in range(case["n_cell"])]},
+                                        doser_type=case["doser_type"], hparams=dict(case["hparams"], **train_hp),
+                                        drug_embeddings=emb, append_layer_width=None, use_drugs=case["use_drugs"],
+                                        disable_adv=True)
+    res = model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
+    assert not res.unexpected_keys
+    model.eval()
+    onehot = torch.nn.functional.one_hot(torch.from_numpy(inp["cov_idx"]), case["n_cell"]).long()
+    _, _, basal, treated = model.predict(genes=torch.from_numpy(inp["genes"]), drugs_idx=torch.from_numpy(inp["drugs_idx"]),
+                                         dosages=torch.from_numpy(inp["dosages"]), covariates=[onehot],
+                                         return_latent_basal=True, return_latent_treated=True)
+    b, t = oracle.chemcpa_tx_latents(sd, inp["genes"], [inp["cov_idx"]], use_drugs=case["use_drugs"],
+                                     doser_type=case["doser_type"], drug_table=table, drugs_idx=inp["drugs_idx"],
+                                     dosages=inp["dosages"])
+    np.testing.assert_allclose(b, basal.numpy(), rtol=3e-5, atol=3e-5)
+    np.testing.assert_allclose(t, treated.numpy(), rtol=3e-5, atol=3e-5)
