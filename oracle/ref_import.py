@@ -41,7 +41,12 @@ def _stub_module(name, **attrs):
     mod = types.ModuleType(name)
     mod.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)
     mod.__path__ = []  # behave like a package so `import a.b` works
-    mod.__getattr__ = lambda attr: _Anything  # any other symbol
+    def _any(attr):  # any other symbol; dunder lookups (inspect's __file__ probes ...) must fail normally
+        if attr.startswith("__") and attr.endswith("__"):
+            raise AttributeError(attr)
+        return _Anything
+
+    mod.__getattr__ = _any
     for k, v in attrs.items():
         setattr(mod, k, v)
     sys.modules[name] = mod
