@@ -83,3 +83,23 @@ def test_chemcpa_dropin_has_the_reference_state_dict_keys():
                                         doser_type=case["doser_type"], hparams=dict(case["hparams"]),
                                         drug_embeddings=emb, use_drugs=case["use_drugs"], disable_adv=True)
         assert list(mod.state_dict().keys()) == [str(k) for k in g[f"{case['name']}.keys"]], case["name"]
+
+
+def test_more_entry_points_validate_arguments_first(handle):
+    """Every entry point added after the first ABI draft rejects NULL / out-of-range arguments with a message before it
+    touches the device (so these calls are safe on a machine without a GPU)."""
+    buf = ctypes.create_string_buffer(256)
+    p = ctypes.addressof(buf)
+    assert handle.mdg_tx_latent_combine(None, None, None, None, None, None, 0, None, None, 4, 8, None, None) == 1
+    assert b"NULL" in handle.mdg_last_error()
+    assert handle.mdg_tx_latent_combine(p, None, None, None, None, None, 7, None, None, 4, 8, p, None) != 0
+    assert b"doser" in handle.mdg_last_error()
+    assert handle.mdg_tx_latent_combine(p, p, p, None, None, None, 2, None, None, 4, 8, p, None) == 1   # logsigm needs idx/beta/bias
+    assert handle.mdg_tx_latent_combine(p, None, None, None, None, None, 0, p, None, 4, 8, p, None) == 1  # table without index
+    assert handle.mdg_tx_latent_combine(p, None, None, None, None, None, 0, None, None, 0, 8, p, None) == 0  # empty batch: no-op
+    assert handle.mdg_masked_pool(None, None, 4, 4, 8, 0, None, None) == 1
+    assert handle.mdg_masked_pool(p, p, 4, 4, 8, 5, p, None) == 1 and b"bad arguments" in handle.mdg_last_error()
+    assert handle.mdg_exact_rank(None, 1, 8, None, None, 0, None) == 1
+    assert handle.mdg_exact_rank(p, 1, 100000, p, p, 256, None) == 2 and b"32 bits" in handle.mdg_last_error()
+    assert handle.mdg_exact_rank_workspace_bytes(100000) == 0 and handle.mdg_exact_rank_workspace_bytes(4096) > 0
+    assert handle.mdg_exact_rank(p, 0, 8, p, None, 0, None) == 0   # no outcomes: no-op
