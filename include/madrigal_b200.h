@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 2
+#define MDG_ABI_VERSION 3
 
 typedef enum MdgStatus {
   MDG_OK = 0,
@@ -142,6 +142,28 @@ size_t mdg_pair_score_workspace_bytes(int64_t Nr, int64_t Nc, int64_t D, int64_t
 int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
                    int64_t L, int precision, int out_mode, int pairs, int normalize_rows,
                    const MdgRankTable* table, void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Prepared decoder: the outcome weights converted ONCE to the GEMM-operand form (bf16, K-major, [hi | lo] in the
+ * fp32-parity mode) — W is constant between checkpoints loads, the reference re-reads it through the Symmetric
+ * parametrisation on every decoder call (models.py:537-547, 922).  `prepared`: caller-owned device buffer of
+ * mdg_pair_prepared_bytes(D, L, precision) bytes, 256-byte aligned, for ALL L outcomes of the decoder.
+ * mdg_pair_score_prepared is mdg_pair_score for outcomes [first_outcome, first_outcome + L) of that buffer (the
+ * reference's `label_range`, predict.py:420-429) without the per-call weight conversion.
+ */
+size_t mdg_pair_prepared_bytes(int64_t D, int64_t L, int precision);
+int mdg_pair_prepare(const float* W, int64_t D, int64_t L, int precision, void* prepared, size_t prepared_bytes,
+                     void* stream);
+int mdg_pair_score_prepared(const float* z_rows, const float* z_cols, const void* prepared, int64_t first_outcome,
+                            int64_t Nr, int64_t Nc, int64_t D, int64_t L, int precision, int out_mode, int pairs,
+                            int normalize_rows, const MdgRankTable* table, void* out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* F.normalize(x, p=2, dim=-1) with eps 1e-12 on rows of x [rows, dim] fp32 -> out (may alias x).  The reference applies
+ * it to single tokens on its unimodal-bypass, raw-encoder-output and 'mean'/'add' fusion paths (models.py:849-850,
+ * 861-862, 870-878, 890-891); the transformer path's token normalisation is fused into mdg_assemble_tokens and the
+ * decoder's into mdg_pair_score (normalize_rows). */
+int mdg_l2_normalize_rows(const float* x, int64_t rows, int32_t dim, float* out, void* stream);
 
 /*
  * Per-outcome top-k pairs without materialising any dense output (BASELINE config 4: "per-outcome top-1000").

@@ -8,6 +8,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 from .build import LIB_PATH
 
+EXPECTED_ABI = 3  # MDG_ABI_VERSION of include/madrigal_b200.h these ctypes structs/signatures were written for
 MDG_MAX_LAYERS = 8
 MDG_MAX_TOKENS = 32
 MDG_MAX_MLP_LINEAR = 8
@@ -67,6 +68,12 @@ SIGNATURES = {
     "mdg_pair_score_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "mdg_pair_score": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                c_int, POINTER(MdgRankTable), c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mdg_pair_prepared_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "mdg_pair_prepare": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "mdg_pair_score_prepared": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
+                                        c_int, c_int, c_int, POINTER(MdgRankTable), c_void_p, c_void_p, c_size_t,
+                                        c_void_p]),
+    "mdg_l2_normalize_rows": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "mdg_pair_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int32]),
     "mdg_pair_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                               c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
@@ -110,6 +117,16 @@ def lib():
                 f"{LIB_PATH} not found: build it with `python -m madrigal_b200.build` (nvcc, sm_100a). "
                 "madrigal_b200 has no CPU or PyTorch fallback.")
         handle = ctypes.CDLL(LIB_PATH)
+        handle.mdg_abi_version.restype = c_int
+        abi = handle.mdg_abi_version()
+        if abi != EXPECTED_ABI:  # structs are passed by pointer: a stale .so would corrupt memory silently
+            raise RuntimeError(f"{LIB_PATH} has ABI version {abi}, this binding expects {EXPECTED_ABI}: rebuild it "
+                               f"with `python -m madrigal_b200.build --force`")
+        from .build import library_is_current
+        if not library_is_current():
+            import warnings
+            warnings.warn(f"{LIB_PATH} was built from different sources than the ones in this tree "
+                          f"(`python -m madrigal_b200.build` rebuilds it)", RuntimeWarning)
         for name, (restype, argtypes) in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the symbol is missing
             fn.restype = restype

@@ -4,10 +4,12 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/madrigal_b200.h"
 #include "exact_rank.cuh"
@@ -52,13 +54,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(p);
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
   return fn;
 }
 
@@ -82,16 +85,46 @@ int make_map_3d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const vo
   return MDG_OK;
 }
 
+constexpr int kMaxDevices = 64;
+
+// Per-device lazily initialised state is guarded by one std::once_flag per device: the library may be entered by one
+// host thread per GPU at the same time (include/madrigal_b200.h, threading contract).
 int num_sms() {
-  static int n[64] = {0};
+  static int n[kMaxDevices];
+  static std::once_flag once[kMaxDevices];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-  if (n[dev] == 0) {
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  std::call_once(once[dev], [dev] {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
     n[dev] = v;
-  }
+  });
   return n[dev];
+}
+
+// Programmatic dependent launch on/off (MDG_NO_PDL=1 restores plain stream-ordered launches: A/B knob).
+bool use_pdl() {
+  static const bool on = getenv("MDG_NO_PDL") == nullptr;
+  return on;
+}
+
+// Launch `kernel` on `stream`, optionally with the programmatic-stream-serialization attribute (the kernel MUST call
+// mdg::pdl_wait() before its first global-memory access).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                      Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && use_pdl()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 struct PairWorkspace {
@@ -134,16 +167,18 @@ template <int EPI, int NE>
 int launch_pair_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                          const CUtensorMap& tmOut2, const mdg::PairScoreParams& p, int grid, cudaStream_t stream) {
   using SM = mdg::PairSmem<NE>;
-  static bool attr_set[64] = {false};
+  static std::once_flag attr_once[kMaxDevices];
+  static cudaError_t attr_err[kMaxDevices];
   int dev = 0;
   MDG_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    MDG_CUDA(cudaFuncSetAttribute(mdg::pair_score_kernel<EPI, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  SM::kBytes));
-    attr_set[dev] = true;
-  }
-  mdg::pair_score_kernel<EPI, NE><<<grid, SM::kThreads, SM::kBytes, stream>>>(tmA, tmB, tmOut, tmOut2, p);
-  MDG_CUDA(cudaGetLastError());
+  if (dev < 0 || dev >= kMaxDevices) return fail(MDG_ERR_UNSUPPORTED, "device index %d out of range", dev);
+  std::call_once(attr_once[dev], [dev] {
+    attr_err[dev] = cudaFuncSetAttribute(mdg::pair_score_kernel<EPI, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SM::kBytes);
+  });
+  MDG_CUDA(attr_err[dev]);
+  MDG_CUDA(launch_ex(mdg::pair_score_kernel<EPI, NE>, dim3(grid), dim3(SM::kThreads), SM::kBytes, stream, true, tmA, tmB,
+                     tmOut, tmOut2, p));
   return MDG_OK;
 }
 
@@ -302,11 +337,13 @@ struct GatherArgs {
   int sigmoid;
 };
 
+// `prepared_wt` != NULL: the decoder weights already in GEMM-operand form (mdg_pair_prepare), W is not read.
 static int pair_score_impl(const float* z_rows, const float* z_cols, const float* W, int64_t Nr, int64_t Nc, int64_t D,
                            int64_t L, int precision, int out_mode, int pairs, int normalize_rows,
                            const MdgRankTable* table, void* out, void* workspace, size_t workspace_bytes,
-                           cudaStream_t stream, const TopkArgs* topk, const GatherArgs* gather = nullptr) {
-  if (!z_rows || !z_cols || !W || (!out && out_mode != kOutTopk))
+                           cudaStream_t stream, const TopkArgs* topk, const GatherArgs* gather = nullptr,
+                           const __nv_bfloat16* prepared_wt = nullptr) {
+  if (!z_rows || !z_cols || (!W && !prepared_wt) || (!out && out_mode != kOutTopk))
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: NULL pointer");
   if (Nr < 0 || Nc < 0 || L < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: negative size");
   if (D != 64 && D != 128 && D != 192 && D != 256)
@@ -346,22 +383,35 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
   const int kb = static_cast<int>(D / 64);
   const int64_t ka = ws.ka;
 
-  // ---- operand preparation: fp32 -> bf16 (hi | lo), W transposed to K-major
+  // ---- operand preparation: fp32 -> bf16 (hi | lo), W transposed to K-major (skipped for a prepared decoder).
+  //      One catalogue scored against itself (z_rows == z_cols) is converted once.  The LAST conversion kernel also
+  //      zeroes the dynamic scheduler's task counter, so that convert_z -> GEMM 1 -> GEMM 2 is an unbroken PDL chain.
+  static const bool static_sched = getenv("MDG_STATIC_SCHED") != nullptr;  // tuning/debug knob
+  const bool dyn_sched = !static_sched && out_mode != kOutGather;
+  const bool same_z = z_rows == z_cols && Nr == Nc;
+  if (same_z) ws.zc = ws.zr;
   {
+    if (!prepared_wt) {
+      dim3 g(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>(L));
+      mdg::convert_w_kernel<<<g, 256, 0, stream>>>(W, static_cast<int>(D), split, ws.wt);
+      MDG_CUDA(cudaGetLastError());
+      ++g_last_launches;
+    }
     const int wpb = 8;
-    mdg::convert_z_kernel<<<static_cast<unsigned>((ws.nr_pad + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-        z_rows, static_cast<int>(Nr), static_cast<int>(ws.nr_pad), static_cast<int>(D), split, normalize_rows, ws.zr);
-    MDG_CUDA(cudaGetLastError());
-    ++g_last_launches;
-    mdg::convert_z_kernel<<<static_cast<unsigned>((ws.nc_pad + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-        z_cols, static_cast<int>(Nc), static_cast<int>(ws.nc_pad), static_cast<int>(D), split, normalize_rows, ws.zc);
-    MDG_CUDA(cudaGetLastError());
-    ++g_last_launches;
-    dim3 g(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>(L));
-    mdg::convert_w_kernel<<<g, 256, 0, stream>>>(W, static_cast<int>(D), split, ws.wt);
-    MDG_CUDA(cudaGetLastError());
+    if (!same_z) {
+      mdg::convert_z_kernel<<<static_cast<unsigned>((ws.nc_pad + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+          z_cols, static_cast<int>(Nc), static_cast<int>(ws.nc_pad), static_cast<int>(D), split, normalize_rows, ws.zc,
+          nullptr);
+      MDG_CUDA(cudaGetLastError());
+      ++g_last_launches;
+    }
+    MDG_CUDA(launch_ex(mdg::convert_z_kernel, dim3(static_cast<unsigned>((ws.nr_pad + wpb - 1) / wpb)), dim3(wpb * 32), 0,
+                       stream, /*pdl=*/true, z_rows, static_cast<int>(Nr),
+                       static_cast<int>(ws.nr_pad), static_cast<int>(D), split, normalize_rows, ws.zr,
+                       dyn_sched ? ws.sched : static_cast<unsigned int*>(nullptr)));
     ++g_last_launches;
   }
+  const __nv_bfloat16* wt = prepared_wt ? prepared_wt : ws.wt;
 
   CUtensorMap tmA, tmB, tmOut;
   // ---- GEMM 1:  Y[l] = z_rows . W[l]      A = zr [1, nr_pad, ka], B = wt [L, D, ka], out = y [L, nr_pad, ka]
@@ -369,7 +419,7 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     rc = make_map_3d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.zr, ka, ws.nr_pad, 1, ka, ws.nr_pad * ka, 64, 128,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.wt, ka, D, L, ka, D * ka, 64, 128,
+    rc = make_map_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, ka, D, L, ka, D * ka, 64, 128,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_map_3d(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.y, ka, ws.nr_pad, L, ka, ws.nr_pad * ka, 32, 32,
@@ -426,11 +476,7 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     p.out = out;
     p.out_ld = Nc;
     p.out_batch_stride = Nr * Nc;
-    static const bool static_sched = getenv("MDG_STATIC_SCHED") != nullptr;  // tuning/debug knob
-    if (!static_sched) {
-      MDG_CUDA(cudaMemsetAsync(ws.sched, 0, 256, stream));
-      p.sched_counter = ws.sched;
-    }
+    if (dyn_sched) p.sched_counter = ws.sched;  // zeroed by convert_z_kernel above
     int elem = 4;
     CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     int epi = mdg::EPI_F32;
@@ -492,6 +538,65 @@ int mdg_pair_score(const float* z_rows, const float* z_cols, const float* W, int
   if (out_mode == kOutTopk) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: out_mode=%d", out_mode);
   return pair_score_impl(z_rows, z_cols, W, Nr, Nc, D, L, precision, out_mode, pairs, normalize_rows, table, out,
                          workspace, workspace_bytes, static_cast<cudaStream_t>(stream_v), nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------ prepared decoder
+static size_t prepared_wt_bytes(int64_t D, int64_t L, int precision) {
+  const int64_t ka = (precision == MDG_PREC_FP32) ? 2 * D : D;
+  return static_cast<size_t>((L * D * ka * 2 + 1023) / 1024 * 1024);
+}
+
+size_t mdg_pair_prepared_bytes(int64_t D, int64_t L, int precision) {
+  if (D <= 0 || L < 0 || (precision != MDG_PREC_BF16 && precision != MDG_PREC_FP32)) return 0;
+  return prepared_wt_bytes(D, L > 0 ? L : 1, precision);
+}
+
+int mdg_pair_prepare(const float* W, int64_t D, int64_t L, int precision, void* prepared, size_t prepared_bytes,
+                     void* stream_v) {
+  if (!W || !prepared) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_prepare: NULL pointer");
+  if (D != 64 && D != 128 && D != 192 && D != 256)
+    return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_prepare: D=%lld (supported: 64, 128, 192, 256)", (long long)D);
+  if (precision != MDG_PREC_BF16 && precision != MDG_PREC_FP32)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_prepare: precision=%d", precision);
+  if (L < 0 || L > (1 << 24)) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_prepare: L=%lld", (long long)L);
+  if (L == 0) return MDG_OK;
+  if (reinterpret_cast<uintptr_t>(prepared) % 256 != 0 || prepared_bytes < prepared_wt_bytes(D, L, precision))
+    return fail(MDG_ERR_WORKSPACE, "mdg_pair_prepare: buffer (%zu B) too small or misaligned, need %zu", prepared_bytes,
+                prepared_wt_bytes(D, L, precision));
+  dim3 g(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>(L));
+  mdg::convert_w_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      W, static_cast<int>(D), precision == MDG_PREC_FP32, static_cast<__nv_bfloat16*>(prepared));
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
+}
+
+int mdg_pair_score_prepared(const float* z_rows, const float* z_cols, const void* prepared, int64_t first_outcome,
+                            int64_t Nr, int64_t Nc, int64_t D, int64_t L, int precision, int out_mode, int pairs,
+                            int normalize_rows, const MdgRankTable* table, void* out, void* workspace,
+                            size_t workspace_bytes, void* stream_v) {
+  g_last_launches = 0;
+  if (out_mode == kOutTopk || out_mode == kOutGather)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score_prepared: out_mode=%d", out_mode);
+  if (!prepared || first_outcome < 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score_prepared: bad prepared handle");
+  if (D <= 0 || (precision != MDG_PREC_BF16 && precision != MDG_PREC_FP32))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score_prepared: D=%lld precision=%d", (long long)D, precision);
+  const int64_t ka = (precision == MDG_PREC_FP32) ? 2 * D : D;
+  const __nv_bfloat16* wt = static_cast<const __nv_bfloat16*>(prepared) + first_outcome * D * ka;
+  return pair_score_impl(z_rows, z_cols, nullptr, Nr, Nc, D, L, precision, out_mode, pairs, normalize_rows, table, out,
+                         workspace, workspace_bytes, static_cast<cudaStream_t>(stream_v), nullptr, nullptr, wt);
+}
+
+// ------------------------------------------------------------------------------------------------ row normalisation
+int mdg_l2_normalize_rows(const float* x, int64_t rows, int32_t dim, float* out, void* stream_v) {
+  if (!x || !out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_l2_normalize_rows: NULL pointer");
+  if (rows < 0 || dim <= 0) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_l2_normalize_rows: rows=%lld dim=%d", (long long)rows, dim);
+  if (rows == 0) return MDG_OK;
+  const long long blocks = (rows + 7) / 8;  // one warp per row
+  if (blocks > 0x7fffffffLL) return fail(MDG_ERR_UNSUPPORTED, "mdg_l2_normalize_rows: too many rows");
+  mdg::l2_normalize_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      x, rows, dim, out);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ triple gather

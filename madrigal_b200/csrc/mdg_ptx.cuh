@@ -243,6 +243,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running: pdl_wait() blocks until the predecessor has COMPLETED and its writes are visible (a no-op
+// for a normally launched kernel); pdl_launch_dependents() allows the successor's CTAs to be scheduled as SM
+// resources free up, so that its prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps our tail.
+// Every kernel of a chain waits before touching global memory, so completion is transitive along the chain.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

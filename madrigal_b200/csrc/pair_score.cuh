@@ -278,6 +278,9 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + SM::kBar + 96);
+  // PDL: everything above overlapped the predecessor's tail; from here on its output (operands, task counter) is read
+  pdl_wait();
+  pdl_launch_dependents();
 
   // Task order: outcome-major.  Static mode deals tasks round-robin; dynamic mode (sched_counter != NULL) hands them
   // out in the same order through an atomic counter (needed when tasks are uneven, e.g. lower-triangle mode).
@@ -1014,8 +1017,14 @@ __global__ void __launch_bounds__(256) ensemble_reduce_kernel(EnsemblePtrs in, i
 // ------------------------------------------------------------------------------------------------ operand prep
 // z [N, D] fp32 -> bf16 [Npad, Ka]  with Ka = D (hi only) or 2D ([hi | lo]); rows >= N are zero.
 // Optional row L2 normalisation (F.normalize: x / max(||x||_2, 1e-12), models.py:947-949).  One warp per row.
+// Also zeroes the dynamic tile scheduler's task counter for the N^2 GEMM two launches later (`sched_zero`, may be
+// NULL), which keeps a memset node out of the PDL chain convert_z -> GEMM 1 -> GEMM 2.
 __global__ void __launch_bounds__(256) convert_z_kernel(const float* __restrict__ z, int N, int Npad, int D,
-                                                        int split, int normalize, __nv_bfloat16* __restrict__ out) {
+                                                        int split, int normalize, __nv_bfloat16* __restrict__ out,
+                                                        unsigned int* __restrict__ sched_zero) {
+  pdl_wait();  // z is the predecessor's output; the counter may still be in use by the previous step's GEMM
+  pdl_launch_dependents();
+  if (sched_zero != nullptr && blockIdx.x == 0 && threadIdx.x < 8) sched_zero[threadIdx.x] = 0u;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= Npad) return;
@@ -1046,6 +1055,22 @@ __global__ void __launch_bounds__(256) convert_z_kernel(const float* __restrict_
       if (split) o[D + d] = __float2bfloat16_rn(vals[i] - __bfloat162float(hi));
     }
   }
+}
+
+// F.normalize(x, p=2, dim=-1): x / max(||x||_2, 1e-12) per row (reference: models.py:849-850, 861-862, 890-891 — the
+// token normalisation of the unimodal bypass / raw-encoder-output / 'mean'-'add' fusion paths).  One warp per row.
+__global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __restrict__ x, long long rows, int dim,
+                                                                float* __restrict__ out) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * dim;
+  float ss = 0.f;
+  for (int d = lane; d < dim; d += 32) ss = fmaf(xr[d], xr[d], ss);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  for (int d = lane; d < dim; d += 32) out[row * dim + d] = xr[d] / denom;
 }
 
 // W [L, D, D] fp32 (W[l][a][b]) -> Wt bf16 [L, D, Ka] with Wt[l][b][a] (+ lo half at K offset D): the B operand of

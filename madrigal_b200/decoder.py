@@ -22,15 +22,31 @@ _workspaces = {}
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Grow-only per-device scratch buffer (operand copies in bf16 + the intermediate z.W_l)."""
-    key = (device.type, device.index)
+    """Grow-only scratch buffer (operand copies in bf16, the intermediate z.W_l, the tile scheduler's counter), one per
+    (device, CUDA stream): calls enqueued on different streams of a device never share operands or task counters, and
+    a buffer is only ever used on the stream it was allocated on, so the caching allocator's stream-ordered reuse of
+    a replaced (smaller) block is safe."""
+    stream = torch.cuda.current_stream(device)
+    key = (device.type, device.index, stream.cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = None
         _workspaces.pop(key, None)
-        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+def l2_normalize_rows(x: torch.Tensor) -> torch.Tensor:
+    """F.normalize(x, p=2, dim=-1) (eps 1e-12) on the last dimension through mdg_l2_normalize_rows."""
+    x2 = _require_cuda_f32(x, "x")
+    out = torch.empty_like(x2)
+    rows = x2.numel() // max(x2.shape[-1], 1)
+    with torch.cuda.device(x2.device):
+        _lib.check(_lib.lib().mdg_l2_normalize_rows(x2.data_ptr(), rows, x2.shape[-1], out.data_ptr(),
+                                                    _stream_ptr(x2.device)), "mdg_l2_normalize_rows")
+    return out
 
 
 def _stream_ptr(device) -> int:
@@ -98,7 +114,46 @@ class RankTable:
         return out
 
 
-def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight: torch.Tensor, *, precision: str = "fp32",
+class PreparedDecoder:
+    """The decoder weights [L, D, D] converted ONCE to the tensor-core operand form (mdg_pair_prepare).  The reference
+    re-reads `decoder.weight` through the Symmetric parametrisation on every call (models.py:537-547, 922); a scoring
+    driver that loops outcome chunks or steps over fixed weights passes `weight=PreparedDecoder(W, precision)` (or
+    `BilinearDDIScorer.prepared()`) and skips the per-call conversion.  `pd[l0:l1]` selects a `label_range`."""
+
+    def __init__(self, weight: torch.Tensor, precision: str = "bf16", _view=None):
+        if _view is not None:
+            self.buf, self.precision, self.D, self.L_total, self.l0, self.l1 = _view
+            return
+        W = _require_cuda_f32(weight, "weight")
+        if W.dim() != 3 or W.shape[1] != W.shape[2]:
+            raise ValueError("weight must be [L, D, D]")
+        self.precision, self.D, self.L_total = precision, W.shape[1], W.shape[0]
+        self.l0, self.l1 = 0, W.shape[0]
+        prec = _PRECISION[precision]
+        fn = _lib.lib()
+        nbytes = fn.mdg_pair_prepared_bytes(self.D, self.L_total, prec)
+        self.buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=W.device)
+        with torch.cuda.device(W.device):
+            _lib.check(fn.mdg_pair_prepare(W.data_ptr(), self.D, self.L_total, prec, self.buf.data_ptr(),
+                                           self.buf.numel(), _stream_ptr(W.device)), "mdg_pair_prepare")
+
+    @property
+    def shape(self):
+        return (self.l1 - self.l0, self.D, self.D)
+
+    @property
+    def device(self):
+        return self.buf.device
+
+    def __getitem__(self, idx):
+        if not isinstance(idx, slice) or idx.step not in (None, 1):
+            raise TypeError("PreparedDecoder supports contiguous outcome slices only")
+        a, b, _ = idx.indices(self.l1 - self.l0)
+        return PreparedDecoder(None, _view=(self.buf, self.precision, self.D, self.L_total, self.l0 + a,
+                                            self.l0 + max(a, b)))
+
+
+def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight, *, precision: str = "fp32",
                out: str = "logit", table: Optional[RankTable] = None, table_offset: int = 0,
                normalize: bool = False, out_tensor: Optional[torch.Tensor] = None,
                symmetric: bool = False) -> torch.Tensor:
@@ -107,20 +162,32 @@ def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight: torch.Tensor,
     out='logit' | 'sigmoid' -> float32 [L, Nr, Nc];  out='rank' -> uint16 quantile ranks against `table`
     (rows table_offset .. table_offset+L of the table).  symmetric=True (out='rank', z_rows is z_cols): compute only
     row > col and write each rank at [i,j] and [j,i] with a zero diagonal — the reference normaliser's layout
-    (normalize_scores.py:67-70) at half the MMAs and look-ups.
+    (normalize_scores.py:67-70) at half the MMAs and look-ups.  `weight`: fp32 [L, D, D] or a `PreparedDecoder`
+    (then `precision` is the prepared one).
     """
     zr = _require_cuda_f32(z_rows, "z_rows")
     zc = zr if z_cols is z_rows else _require_cuda_f32(z_cols, "z_cols")
-    W = _require_cuda_f32(weight, "weight")
+    prepared = weight if isinstance(weight, PreparedDecoder) else None
+    if prepared is not None:
+        precision = prepared.precision
+        if prepared.device != zr.device:
+            raise RuntimeError("madrigal_b200: prepared decoder and embeddings are on different devices")
+        W = None
+        wshape = prepared.shape
+    else:
+        W = _require_cuda_f32(weight, "weight")
+        if W.dim() != 3:
+            raise ValueError("expected z_rows [Nr,D], z_cols [Nc,D], weight [L,D,D]")
+        wshape = tuple(W.shape)
     if symmetric and (out != "rank" or zc.data_ptr() != zr.data_ptr() or zc.shape != zr.shape):
         raise ValueError("symmetric=True needs out='rank' and z_cols is z_rows")
-    if zr.dim() != 2 or zc.dim() != 2 or W.dim() != 3:
+    if zr.dim() != 2 or zc.dim() != 2:
         raise ValueError("expected z_rows [Nr,D], z_cols [Nc,D], weight [L,D,D]")
     Nr, D = zr.shape
     Nc = zc.shape[0]
-    L = W.shape[0]
-    if zc.shape[1] != D or W.shape[1] != D or W.shape[2] != D:
-        raise ValueError(f"shape mismatch: z_rows {tuple(zr.shape)}, z_cols {tuple(zc.shape)}, weight {tuple(W.shape)}")
+    L = wshape[0]
+    if zc.shape[1] != D or wshape[1] != D or wshape[2] != D:
+        raise ValueError(f"shape mismatch: z_rows {tuple(zr.shape)}, z_cols {tuple(zc.shape)}, weight {wshape}")
     mode, dtype = _OUT[out]
     prec = _PRECISION[precision]
     if out_tensor is None:
@@ -136,12 +203,18 @@ def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight: torch.Tensor,
     fn = _lib.lib()
     nbytes = fn.mdg_pair_score_workspace_bytes(Nr, Nc, D, L, prec)
     ws = _workspace(zr.device, nbytes)
+    pairs = _lib.MDG_PAIRS_SYMMETRIC if symmetric else _lib.MDG_PAIRS_FULL
+    tbl_ref = ctypes.byref(tbl) if tbl is not None else None
     with torch.cuda.device(zr.device):
-        _lib.check(fn.mdg_pair_score(zr.data_ptr(), zc.data_ptr(), W.data_ptr(), Nr, Nc, D, L, prec, mode,
-                                     _lib.MDG_PAIRS_SYMMETRIC if symmetric else _lib.MDG_PAIRS_FULL,
-                                     int(bool(normalize)),
-                                     ctypes.byref(tbl) if tbl is not None else None, out_tensor.data_ptr(),
-                                     ws.data_ptr(), ws.numel(), _stream_ptr(zr.device)), "mdg_pair_score")
+        if prepared is not None:
+            _lib.check(fn.mdg_pair_score_prepared(zr.data_ptr(), zc.data_ptr(), prepared.buf.data_ptr(), prepared.l0,
+                                                  Nr, Nc, D, L, prec, mode, pairs, int(bool(normalize)), tbl_ref,
+                                                  out_tensor.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  _stream_ptr(zr.device)), "mdg_pair_score_prepared")
+        else:
+            _lib.check(fn.mdg_pair_score(zr.data_ptr(), zc.data_ptr(), W.data_ptr(), Nr, Nc, D, L, prec, mode, pairs,
+                                         int(bool(normalize)), tbl_ref, out_tensor.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), _stream_ptr(zr.device)), "mdg_pair_score")
     return out_tensor
 
 
@@ -228,6 +301,17 @@ class BilinearDDIScorer(nn.Bilinear):
 
     def bilinear(self, input1: torch.Tensor, input2: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
         return pair_score(input1, input2, weight, precision=self.precision, out="logit")
+
+    def prepared(self) -> PreparedDecoder:
+        """The (parametrised) weight in operand form, cached until the underlying parameter changes."""
+        raw = self.parametrizations.weight.original if hasattr(self, "parametrizations") else self.weight
+        key = (self.precision, raw.data_ptr(), raw._version, str(raw.device))
+        cache = getattr(self, "_mdg_prepared", None)
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                cache = (key, PreparedDecoder(self.weight.detach(), self.precision))
+            self._mdg_prepared = cache
+        return cache[1]
 
     def forward(self, input1: torch.Tensor, input2: torch.Tensor, label_range: Optional[Tuple[int, int]] = None):
         weight = self.weight  # through the parametrisation, if one is registered

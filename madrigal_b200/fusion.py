@@ -13,8 +13,8 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import MdgFusionCfg, MdgFusionWeights, MdgMlp
-from .constants import CELL_LINES, NUM_MODALITIES, NUM_NON_TX_MODALITIES
-from .decoder import _PRECISION, _require_cuda_f32, _stream_ptr, _workspace
+from .constants import CELL_LINES, resolve_non_tx
+from .decoder import _PRECISION, _require_cuda_f32, _stream_ptr, _workspace, l2_normalize_rows
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -38,8 +38,9 @@ class TransformerFusion(nn.Module):
     def __init__(self, embed_dim, num_tx_bottlenecks, transformer_num_layers, transformer_att_heads,
                  transformer_head_dim, transformer_ffn_dim, transformer_dropout=0.1, transformer_actn='relu',
                  transformer_norm_first=False, transformer_batch_first=True, transformer_agg='mean',
-                 precision: str = "fp32"):
+                 precision: str = "fp32", non_tx_modalities=None):
         super().__init__()
+        n_non_tx = len(resolve_non_tx(non_tx_modalities))  # reference: module-level NUM_NON_TX_MODALITIES (utils.py:36)
         if transformer_actn not in _lib.MDG_ACTN:
             raise NotImplementedError(f"transformer_actn={transformer_actn!r} (supported: relu, gelu)")
         if transformer_agg not in _lib.MDG_AGG:
@@ -70,9 +71,9 @@ class TransformerFusion(nn.Module):
                                                           dropout=transformer_dropout, batch_first=False)
             self.x_attn_query = nn.Parameter(torch.randn(1, self.latent_dim))
             # constant pooling key mask (models.py:382-385): with bottlenecks only they are visible
-            m = torch.zeros(1, NUM_MODALITIES + num_tx_bottlenecks, dtype=torch.bool)
+            m = torch.zeros(1, n_non_tx + len(CELL_LINES) + num_tx_bottlenecks, dtype=torch.bool)
             if num_tx_bottlenecks > 0:
-                m[:, :NUM_NON_TX_MODALITIES] = True
+                m[:, :n_non_tx] = True
                 m[:, -len(CELL_LINES):] = True
             self.x_attn_key_padding_mask = m
 
@@ -230,9 +231,10 @@ class PositionEncodingSinusoidal(nn.Module):
     """Buffer `pe` built exactly as models.py:551-579 (zero-padded beyond max_len when bottlenecks are used)."""
 
     def __init__(self, d_model: int, dropout: float = 0.1, max_len: int = 19, num_tx_bottlenecks: int = 0,
-                 transformer_agg: str = 'cls'):
+                 transformer_agg: str = 'cls', non_tx_modalities=None):
         super().__init__()
         import math
+        NUM_MODALITIES = len(resolve_non_tx(non_tx_modalities)) + len(CELL_LINES)
         position = torch.arange(max_len).unsqueeze(1)
         div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
         pe = torch.zeros(1, max_len, d_model)
@@ -282,14 +284,19 @@ class FusionEncoder(nn.Module):
     `load_state_dict(reference_encoder_state_dict, strict=False)` picks them up; the modality encoders (GNNs, chemCPA)
     are out of scope and stay the reference's.
 
-    forward(all_embeds [B, 19, E] in the order [str, kg, cv, tx_a375 ... tx_yapc] (models.py:772, utils.py:28),
-            batch_masks [B, 19] bool True = modality missing) -> z [B, E]
+    forward(all_embeds [B, 19, E] in the order [str, kg, cv, (extra tabular modalities), tx_a375 ... tx_yapc]
+            (models.py:772, utils.py:28), batch_masks [B, 19] bool True = modality missing) -> z [B, E]
+    `non_tx_modalities`: the reference's NON_TX_MODALITIES knob (utils.py:30-37) as a constructor argument — None
+    (environment / default 3), a count, or the list of names; 19 becomes len(non_tx) + 16.
     """
 
     def __init__(self, feat_dim, num_tx_bottlenecks, pos_emb_dropout, transformer_fusion_hparams, proj_hparams,
                  fusion='transformer_uni_proj', normalize=False, pos_emb_type='learnable', adapt_before_fusion=False,
-                 precision: str = "fp32", **kwargs):
+                 precision: str = "fp32", non_tx_modalities=None, **kwargs):
         super().__init__()
+        self.non_tx_modalities = resolve_non_tx(non_tx_modalities)
+        NUM_NON_TX_MODALITIES = len(self.non_tx_modalities)
+        NUM_MODALITIES = NUM_NON_TX_MODALITIES + len(CELL_LINES)
         self.embed_dim, self.fusion, self.normalize = feat_dim, fusion, normalize
         self.adapt_before_fusion = adapt_before_fusion
         self.num_tx_bottlenecks = num_tx_bottlenecks
@@ -306,11 +313,11 @@ class FusionEncoder(nn.Module):
                                                          self.transformer_agg)
         elif pos_emb_type == 'sinusoidal':
             self.pos_encoder = PositionEncodingSinusoidal(feat_dim, pos_emb_dropout, max_len, num_tx_bottlenecks,
-                                                          self.transformer_agg)
+                                                          self.transformer_agg, self.non_tx_modalities)
         else:
             raise NotImplementedError(pos_emb_type)
         self.transformer = TransformerFusion(feat_dim, num_tx_bottlenecks, precision=precision,
-                                             **transformer_fusion_hparams)
+                                             non_tx_modalities=self.non_tx_modalities, **transformer_fusion_hparams)
         if self.transformer_agg == 'cls':
             self.cls = nn.Parameter(torch.randn(1, feat_dim))
         mk = lambda: MLPAdaptor(feat_dim, proj_hparams['proj_hidden_dims'], feat_dim, proj_hparams['proj_dropout'],
@@ -324,8 +331,8 @@ class FusionEncoder(nn.Module):
         nb = self.num_tx_bottlenecks
         if nb == 0:
             return None
-        n_tx, n_non = len(CELL_LINES), NUM_NON_TX_MODALITIES
-        T = NUM_MODALITIES + nb
+        n_tx, n_non = len(CELL_LINES), len(self.non_tx_modalities)
+        T = n_non + n_tx + nb
         sm = torch.zeros((T, T), dtype=torch.bool)
         sm[:n_non, T - n_tx:] = True  # non-TX queries never see TX keys ...
         sm[T - n_tx:, :n_non] = True  # ... and vice versa; bottleneck tokens see everything (models.py:813-816)
@@ -349,7 +356,7 @@ class FusionEncoder(nn.Module):
         smask = torch.empty((B, T), dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().mdg_assemble_tokens(
-                x.data_ptr(), km.data_ptr(), B, M, E, NUM_NON_TX_MODALITIES, nb,
+                x.data_ptr(), km.data_ptr(), B, M, E, len(self.non_tx_modalities), nb,
                 _ptr(self.tx_bottleneck_tokens) if nb > 0 else None, _ptr(self.cls) if has_cls else None,
                 pe2.data_ptr(), min(pe2.shape[0], T), int(bool(self.normalize)), seq.data_ptr(), smask.data_ptr(),
                 _stream_ptr(x.device)), "mdg_assemble_tokens")
@@ -361,7 +368,7 @@ class FusionEncoder(nn.Module):
         if self.adapt_before_fusion:
             embeds = self.uni_projector(embeds)  # models.py:776-777
         if self.fusion in ('mean', 'add'):  # models.py:870-878
-            x = torch.nn.functional.normalize(embeds, p=2, dim=-1) if self.normalize else embeds
+            x = l2_normalize_rows(embeds) if self.normalize else embeds
             return masked_pool(x, masks, self.fusion)
         if self.fusion not in ('transformer', 'transformer_uni_proj'):
             raise NotImplementedError(self.fusion)
@@ -381,6 +388,6 @@ class FusionEncoder(nn.Module):
             uni_mod = (~masks[uni_rows]).to(torch.uint8).argmax(dim=1)
             uni = embeds[uni_rows, uni_mod].contiguous()
             if self.normalize:
-                uni = torch.nn.functional.normalize(uni, p=2, dim=-1)
+                uni = l2_normalize_rows(uni)
             z[uni_rows] = self.uni_fuser(uni)
         return z

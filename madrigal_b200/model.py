@@ -4,7 +4,7 @@ from typing import Optional, Tuple
 import torch
 import torch.nn as nn
 
-from .decoder import BilinearDDIScorer, Symmetric, pair_score, pair_score_gather
+from .decoder import BilinearDDIScorer, Symmetric, l2_normalize_rows, pair_score, pair_score_gather
 
 
 class NovelDDIMultilabel(nn.Module):
@@ -26,12 +26,29 @@ class NovelDDIMultilabel(nn.Module):
         self.decoder = BilinearDDIScorer(feat_dim, feat_dim, prediction_dim, precision=precision)
         nn.utils.parametrize.register_parametrization(self.decoder, 'weight', Symmetric())
 
+    def _tabular_mods(self, batch_head, batch_tail):
+        """Extra tabular modalities forwarded to the encoder as keyword arguments when the token layout has more than
+        str / kg / cv (models.py:936-943).  The count comes from the encoder's own layout when it exposes one
+        (`non_tx_modalities`), else from the module default (environment variable, as in the reference)."""
+        from .constants import NUM_NON_TX_MODALITIES
+        enc = self.encoder
+        mods = getattr(getattr(enc, 'fusion_encoder', enc), 'non_tx_modalities', None)
+        n_non_tx = len(mods) if mods is not None else NUM_NON_TX_MODALITIES
+        head, tail = {}, {}
+        if n_non_tx > 3:
+            for mod in batch_head.keys():
+                if mod not in ('drugs', 'strs', 'masks', 'cv', 'tx'):
+                    head[mod] = batch_head[mod]
+                    tail[mod] = batch_tail[mod]
+        return head, tail
+
     def forward(self, batch_head, batch_tail, batch_head_mod_masks, batch_tail_mod_masks, batch_kg,
                 label_range: Optional[Tuple[int, int]] = None, single_drug=False):
+        head_extra, tail_extra = self._tabular_mods(batch_head, batch_tail)
         z_head = self.encoder(batch_head['drugs'], batch_head_mod_masks, batch_head['strs'], batch_kg,
-                              batch_head['cv'], batch_head['tx'])
+                              batch_head['cv'], batch_head['tx'], **head_extra)
         z_tail = self.encoder(batch_tail['drugs'], batch_tail_mod_masks, batch_tail['strs'], batch_kg,
-                              batch_tail['cv'], batch_tail['tx'])
+                              batch_tail['cv'], batch_tail['tx'], **tail_extra)
         weight = self.decoder.weight
         if label_range is not None:
             assert len(label_range) == 2
@@ -45,10 +62,11 @@ class NovelDDIMultilabel(nn.Module):
                         head_idx, tail_idx, sigmoid: bool = True):
         """`sigmoid(model(...))[ddi_labels, head_idx, tail_idx]` (train_ddi_batch.py:285-286, evaluate.py:191-195)
         without the dense [L, Nh, Nt] tensor the reference materialises first."""
+        head_extra, tail_extra = self._tabular_mods(batch_head, batch_tail)
         z_head = self.encoder(batch_head['drugs'], batch_head_mod_masks, batch_head['strs'], batch_kg,
-                              batch_head['cv'], batch_head['tx'])
+                              batch_head['cv'], batch_head['tx'], **head_extra)
         z_tail = self.encoder(batch_tail['drugs'], batch_tail_mod_masks, batch_tail['strs'], batch_kg,
-                              batch_tail['cv'], batch_tail['tx'])
+                              batch_tail['cv'], batch_tail['tx'], **tail_extra)
         return pair_score_gather(z_head, z_tail, self.decoder.weight, ddi_labels, head_idx, tail_idx,
                                  precision=self.decoder.precision, out="sigmoid" if sigmoid else "logit",
                                  normalize=bool(self.normalize))
@@ -82,7 +100,7 @@ class NovelDDIEncoder(nn.Module):
                  tabular_mod_encoders=None, kg_encoder_name: str = 'hgt', use_tx_basal: bool = False,
                  tx_cell_line_onehot_encoder=None):
         super().__init__()
-        from .constants import CELL_LINES, NON_TX_MODALITIES
+        from .constants import CELL_LINES
         if (tx_encoder is None) == (tx_encoder_dict is None):
             raise ValueError("give exactly one of tx_encoder (chemCPA) and tx_encoder_dict (one encoder per cell line)")
         self.fusion_encoder = fusion_encoder
@@ -96,7 +114,13 @@ class NovelDDIEncoder(nn.Module):
         self.tabular_mod_encoders = mods if isinstance(mods, nn.Module) else _as_module_dict(mods)
         self.use_tx_basal = use_tx_basal
         self.tx_cell_line_onehot_encoder = tx_cell_line_onehot_encoder
-        self._cell_lines, self._extra_mods = list(CELL_LINES), list(NON_TX_MODALITIES[3:])
+        self._cell_lines = list(CELL_LINES)
+        from .constants import resolve_non_tx
+        mods = resolve_non_tx(getattr(fusion_encoder, 'non_tx_modalities', None))
+        self._extra_mods = list(mods[3:])  # reference: NON_TX_MODALITIES[3:] (models.py:747)
+        if len(self.tabular_mod_encoders) > 0 and sorted(self.tabular_mod_encoders.keys()) != sorted(self._extra_mods):
+            raise ValueError(f"tabular_mod_encoders {sorted(self.tabular_mod_encoders.keys())} do not match the fusion "
+                             f"encoder's extra non-TX modalities {self._extra_mods}")
 
     def encode(self, batch_drugs, batch_masks, batch_mols, batch_kg, batch_cv, batch_tx_dict, raw_encoder_output=False,
                **kwargs):
@@ -116,6 +140,9 @@ class NovelDDIEncoder(nn.Module):
         kg_out = torch.zeros((n_rows, self.embed_dim), dtype=kg_valid.dtype, device=kg_valid.device)
         kg_out[kg_map.to(kg_valid.device)] = kg_valid
         kg_out = kg_out[batch_drugs.to(kg_valid.device)]
+        # every drug whose KG view is marked present must be in the KG (models.py:738)
+        bm = batch_masks.to(torch.bool)
+        assert torch.isin(batch_drugs[~bm[:, 1]].to(kg_map.device), kg_map).all()
         cv_out = self.cv_encoder(batch_cv)  # :741
         other = []
         if len(self.tabular_mod_encoders) > 0:  # :746-750
@@ -140,7 +167,7 @@ class NovelDDIEncoder(nn.Module):
         if raw_encoder_output:  # :889-893
             uni = all_embeds[~batch_masks.to(torch.bool), :]
             if self.fusion_encoder.normalize:
-                uni = torch.nn.functional.normalize(uni, p=2, dim=-1)
+                uni = l2_normalize_rows(uni.contiguous())
             return self.fusion_encoder.uni_projector(uni.contiguous())
         return self.fusion_encoder(all_embeds, batch_masks)
 

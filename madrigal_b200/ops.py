@@ -1,7 +1,8 @@
 """torch.ops.madrigal_b200.* — the hot-path entry points as PyTorch custom ops (torch.library), so that code written
 against `torch.ops` (and torch.compile / export graphs built around the reference model) can call them.  Each op is a
 thin shim over the C ABI (ctypes, include/madrigal_b200.h); only a CUDA implementation is registered — calling an op
-with CPU tensors raises, there is no fallback.
+with CPU tensors raises, there is no fallback.  Shape-only "fake" implementations are registered as well, so that
+tracing (torch.export / torch.compile's front end, meta tensors) sees the output shapes without running anything.
 
   torch.ops.madrigal_b200.pair_score(z_rows, z_cols, weight, precision, out_mode, normalize) -> Tensor [L, Nr, Nc] f32
   torch.ops.madrigal_b200.pair_score_gather(z_rows, z_cols, weight, labels, heads, tails, precision, sigmoid, normalize)
@@ -66,7 +67,7 @@ def _fusion_encode(tokens, key_mask, src_mask, pool_key_mask, params, cfg, actn,
         if agg == "x-attn":  # the constant pooling mask was created on the meta device: rebuild it for real
             m = torch.zeros(mod.x_attn_key_padding_mask.shape, dtype=torch.bool)
             if int(cfg[1]) > 0:
-                from .fusion import CELL_LINES, NUM_NON_TX_MODALITIES
+                from .constants import CELL_LINES, NUM_NON_TX_MODALITIES
                 m[:, :NUM_NON_TX_MODALITIES] = True
                 m[:, -len(CELL_LINES):] = True
             mod.x_attn_key_padding_mask = m
@@ -83,3 +84,24 @@ _LIB.impl("pair_score", _pair_score, "CUDA")
 _LIB.impl("pair_score_gather", _pair_score_gather, "CUDA")
 _LIB.impl("exact_normalized_ranks", _exact_normalized_ranks, "CUDA")
 _LIB.impl("fusion_encode", _fusion_encode, "CUDA")
+
+
+# ---- shape-only implementations for tracing (no arithmetic, no device work)
+@torch.library.register_fake("madrigal_b200::pair_score")
+def _pair_score_fake(z_rows, z_cols, weight, precision, out_mode, normalize):
+    return z_rows.new_empty((weight.shape[0], z_rows.shape[0], z_cols.shape[0]), dtype=torch.float32)
+
+
+@torch.library.register_fake("madrigal_b200::pair_score_gather")
+def _pair_score_gather_fake(z_rows, z_cols, weight, labels, heads, tails, precision, sigmoid, normalize):
+    return z_rows.new_empty((labels.numel(),), dtype=torch.float32)
+
+
+@torch.library.register_fake("madrigal_b200::exact_normalized_ranks")
+def _exact_normalized_ranks_fake(scores):
+    return torch.empty_like(scores, dtype=torch.float32)
+
+
+@torch.library.register_fake("madrigal_b200::fusion_encode")
+def _fusion_encode_fake(tokens, key_mask, src_mask, pool_key_mask, params, cfg, actn, agg, precision):
+    return tokens.new_empty((tokens.shape[0], tokens.shape[2]), dtype=torch.float32)

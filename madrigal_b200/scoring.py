@@ -28,17 +28,24 @@ def row_shard(N: int, rank: int, world_size: int) -> Tuple[int, int]:
     return outcome_shard(N, rank, world_size)
 
 
-def all_gather_embeddings(z_shard: torch.Tensor, N: int, group=None) -> torch.Tensor:
+def all_gather_embeddings(z_shard: torch.Tensor, N: int, group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The path's ONLY collective: replicate the fused-embedding table [N, D] from per-rank row shards.
 
-    Shards are the `row_shard` partition (sizes differ by at most one row), padded to equal length for
-    `all_gather_into_tensor` (NCCL over NVLink on GPUs; gloo in the CPU tests).
+    Shards are the `row_shard` partition.  When N divides evenly the shards land straight in the final [N, D] buffer
+    (`out`, reusable across steps) with one `all_gather_into_tensor` — no padding, no concatenation; otherwise sizes
+    differ by one row and the shards are padded to equal length first (NCCL over NVLink on GPUs; gloo in the CPU tests).
     """
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    per = -(-N // world)
     D = z_shard.shape[1]
+    if N % world == 0:
+        if z_shard.shape[0] != N // world:
+            raise ValueError("z_shard is not this rank's row_shard of N")
+        if out is None:
+            out = torch.empty((N, D), dtype=z_shard.dtype, device=z_shard.device)
+        dist.all_gather_into_tensor(out, z_shard.contiguous(), group=group)
+        return out
+    per = -(-N // world)
     padded = torch.zeros((per, D), dtype=z_shard.dtype, device=z_shard.device)
     padded[: z_shard.shape[0]] = z_shard
     gathered = torch.empty((world * per, D), dtype=z_shard.dtype, device=z_shard.device)
@@ -47,7 +54,6 @@ def all_gather_embeddings(z_shard: torch.Tensor, N: int, group=None) -> torch.Te
     for r in range(world):
         s, e = row_shard(N, r, world)
         parts.append(gathered[r * per: r * per + (e - s)])
-    del rank
     return torch.cat(parts, dim=0)
 
 
@@ -102,6 +108,11 @@ def score_all_pairs_to_host(z: torch.Tensor, weight: torch.Tensor, out_host: tor
             ev.record(copy)
             done_copy[b] = ev
     compute.wait_stream(copy)
+    # The reference writes each chunk into its memmap synchronously (predict.py:428-429): when this function returns the
+    # host buffer must hold every chunk, so wait for the last device-to-host copies here, not in the caller.
+    for ev in done_copy:
+        if ev is not None:
+            ev.synchronize()
     return out_host
 
 

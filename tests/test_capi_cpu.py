@@ -32,7 +32,7 @@ def test_header_symbols_all_exported(handle):
 
 
 def test_abi_version_and_error_string(handle):
-    assert handle.mdg_abi_version() == 2
+    assert handle.mdg_abi_version() == _lib.EXPECTED_ABI == 3
     assert isinstance(handle.mdg_last_error(), bytes)
 
 
@@ -103,3 +103,46 @@ def test_more_entry_points_validate_arguments_first(handle):
     assert handle.mdg_exact_rank(p, 1, 100000, p, p, 256, None) == 2 and b"32 bits" in handle.mdg_last_error()
     assert handle.mdg_exact_rank_workspace_bytes(100000) == 0 and handle.mdg_exact_rank_workspace_bytes(4096) > 0
     assert handle.mdg_exact_rank(p, 0, 8, p, None, 0, None) == 0   # no outcomes: no-op
+    # prepared decoder / row normalisation (ABI 3)
+    assert handle.mdg_pair_prepared_bytes(256, 86, 0) == 86 * 256 * 256 * 2
+    assert handle.mdg_pair_prepared_bytes(256, 86, 1) == 2 * 86 * 256 * 256 * 2
+    assert handle.mdg_pair_prepare(None, 256, 86, 0, None, 0, None) == 1 and b"NULL" in handle.mdg_last_error()
+    assert handle.mdg_pair_prepare(p, 100, 1, 0, p, 256, None) == 2 and b"D=100" in handle.mdg_last_error()
+    assert handle.mdg_pair_prepare(p, 128, 1, 0, p, 256, None) == 3   # buffer too small
+    assert handle.mdg_pair_score_prepared(p, p, None, 0, 4, 4, 128, 1, 0, 0, 0, 0, None, p, None, 0, None) == 1
+    assert handle.mdg_pair_score_prepared(p, p, p, -1, 4, 4, 128, 1, 0, 0, 0, 0, None, p, None, 0, None) == 1
+    assert handle.mdg_l2_normalize_rows(None, 4, 8, None, None) == 1
+    assert handle.mdg_l2_normalize_rows(p, 4, 0, p, None) == 1
+    assert handle.mdg_l2_normalize_rows(p, 0, 8, p, None) == 0     # no rows: no-op
+
+
+def test_stale_library_abi_is_rejected(monkeypatch):
+    """_lib.lib() refuses a library whose mdg_abi_version() differs from the binding's (structs go by pointer)."""
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "EXPECTED_ABI", 999)
+    with pytest.raises(RuntimeError, match="ABI version"):
+        _lib.lib()
+    monkeypatch.setattr(_lib, "EXPECTED_ABI", 3)
+    monkeypatch.setattr(_lib, "_LIB", None)
+    assert _lib.lib() is not None
+
+
+def test_non_tx_modalities_is_a_constructor_argument():
+    """The reference reads NON_TX_MODALITIES from the environment at import (utils.py:30-37); here it is also a
+    constructor argument: token count, pooling key mask, positional-encoding length and src_mask follow it."""
+    import madrigal_b200 as mb
+    hp = dict(transformer_num_layers=1, transformer_att_heads=2, transformer_head_dim=32, transformer_ffn_dim=64,
+              transformer_dropout=0.0, transformer_actn='gelu', transformer_norm_first=True,
+              transformer_batch_first=False, transformer_agg='x-attn')
+    proj = dict(proj_hidden_dims=[32], proj_dropout=0.0, proj_norm='ln', proj_actn='relu', proj_order='nd')
+    for mods, n in ((None, 3), (4, 4), (["str", "kg", "cv", "bs"], 4)):
+        enc = mb.FusionEncoder(64, 2, 0.0, hp, proj, fusion='transformer', pos_emb_type='sinusoidal',
+                               non_tx_modalities=mods)
+        T = n + 16 + 2
+        assert enc.transformer.x_attn_key_padding_mask.shape == (1, T)
+        assert enc.transformer.x_attn_key_padding_mask[0].tolist() == [True] * n + [False] * 2 + [True] * 16
+        assert enc.pos_encoder.pe.shape == (1, T, 64) and enc.pos_emb_max_len == n
+        sm = enc._src_mask("cpu")
+        assert sm.shape == (T, T) and bool(sm[0, T - 1]) and bool(sm[T - 1, 0]) and not bool(sm[n, 0])
+    with pytest.raises(ValueError):
+        mb.FusionEncoder(64, 0, 0.0, hp, proj, non_tx_modalities=["kg", "str", "cv"])
