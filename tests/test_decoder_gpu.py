@@ -467,3 +467,77 @@ def test_scores_to_npy_file_like_the_reference_driver(mb, cuda_device, tmp_path)
     got2 = scoring.score_all_pairs_to_npy(zt, Wt, path2, out="sigmoid", outcome_inds=sel, precision="fp32", chunk=2)
     ref2 = oracle.sigmoid(oracle.bilinear_scores(z, z, W, dtype=np.float64)[sel])
     assert got2.shape == (3, N, N) and np.abs(np.asarray(got2) - ref2).max() <= 1e-4
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_prepared_decoder_is_bit_identical_and_sliceable(mb, cuda_device, prec):
+    """mdg_pair_prepare + mdg_pair_score_prepared (weights converted once, `label_range` as a slice of the handle) give
+    the same bits as the per-call conversion, for logits, sigmoid and ranks; BilinearDDIScorer.prepared() caches."""
+    N, D, L = 300, 128, 7
+    z, W = synth.decoder_inputs(N, D, L, seed=77)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    pd = mb.PreparedDecoder(Wt, prec)
+    assert pd.shape == (L, D, D)
+    for out in ("logit", "sigmoid"):
+        a = mb.pair_score(zt, zt, Wt, precision=prec, out=out)
+        b = mb.pair_score(zt, zt, pd, out=out)
+        assert torch.equal(a, b), out
+        c = mb.pair_score(zt, zt, pd[2:5], out=out)
+        assert torch.equal(a[2:5], c), out + " slice"
+    from madrigal_b200 import normalize
+    table = normalize.build_rank_table(zt, Wt, 1024, precision=prec)
+    for sym in (False, True):
+        a = mb.pair_score(zt, zt, Wt, precision=prec, out="rank", table=table, symmetric=sym)
+        b = mb.pair_score(zt, zt, pd, out="rank", table=table, symmetric=sym)
+        c = mb.pair_score(zt, zt, pd[3:], out="rank", table=table, table_offset=3, symmetric=sym)
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+        assert torch.equal(a[3:].view(torch.int16), c.view(torch.int16))
+    # distinct row / column catalogues still convert both operands
+    z2, _ = synth.decoder_inputs(77, D, 1, seed=78)
+    z2t = gpu(z2, cuda_device)
+    assert torch.equal(mb.pair_score(zt, z2t, Wt, precision=prec), mb.pair_score(zt, z2t, pd))
+    dec = mb.BilinearDDIScorer(D, D, L, precision=prec).to(cuda_device)
+    with torch.no_grad():
+        dec.weight.copy_(Wt)
+    p1 = dec.prepared()
+    assert dec.prepared() is p1
+    with torch.no_grad():
+        dec.weight.mul_(2.0)
+    assert dec.prepared() is not p1
+    assert torch.equal(mb.pair_score(zt, zt, dec.prepared()), dec(zt, zt))
+
+
+def test_l2_normalize_rows_kernel(mb, cuda_device):
+    """mdg_l2_normalize_rows == F.normalize(x, p=2, dim=-1) (eps 1e-12), incl. an all-zero row and a 3-D input."""
+    from madrigal_b200.decoder import l2_normalize_rows
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((37, 5, 96)).astype(np.float32)
+    x[3, 2] = 0.0
+    got = l2_normalize_rows(gpu(x, cuda_device)).cpu().numpy()
+    ref = x / np.maximum(np.sqrt((x.astype(np.float64) ** 2).sum(-1, keepdims=True)), 1e-12)
+    assert got.shape == x.shape and np.abs(got - ref).max() <= 2e-7
+    assert np.all(got[3, 2] == 0.0)
+
+
+def test_concurrent_streams_use_separate_workspaces(mb, cuda_device):
+    """Two decoder calls enqueued on different CUDA streams must not share operand scratch or the tile scheduler's
+    counter (the workspace cache is keyed by (device, stream))."""
+    N, D, L = 512, 128, 6
+    z1, W1 = synth.decoder_inputs(N, D, L, seed=1)
+    z2, W2 = synth.decoder_inputs(N, D, L, seed=2)
+    a = [gpu(v, cuda_device) for v in (z1, W1)]
+    b = [gpu(v, cuda_device) for v in (z2, W2)]
+    ref_a = mb.pair_score(a[0], a[0], a[1], precision="bf16")
+    ref_b = mb.pair_score(b[0], b[0], b[1], precision="bf16")
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            oa = mb.pair_score(a[0], a[0], a[1], precision="bf16")
+        with torch.cuda.stream(s2):
+            ob = mb.pair_score(b[0], b[0], b[1], precision="bf16")
+        outs.append((oa, ob))
+    torch.cuda.synchronize()
+    for oa, ob in outs:
+        assert torch.equal(oa, ref_a) and torch.equal(ob, ref_b)
