@@ -71,11 +71,18 @@ typedef enum MdgOutMode {
 
 typedef enum MdgPairs {
   MDG_PAIRS_FULL = 0,     /* every (i, j)                                                                          */
-  MDG_PAIRS_SYMMETRIC = 1 /* z_rows == z_cols only: only row > col is computed — the pair set the reference normaliser
+  MDG_PAIRS_SYMMETRIC = 1, /* z_rows == z_cols only: only row > col is computed — the pair set the reference normaliser
                              ranks (notebooks/normalize_scores.py:67).  MDG_OUT_RANK_U16: each rank is written at
                              [row, col] AND [col, row], diagonal 0 (the normaliser's output layout, :69-70);
                              mdg_pair_topk: unordered pairs.  Not available for the fp32 logit / sigmoid outputs. */
+  MDG_PAIRS_PACKED_TILES = 2 /* MDG_OUT_RANK_U16 only: the same ranks WITHOUT the mirror image (half the bytes to write
+                             and to copy to the host).  out: uint16 [L, T, 32, 32] with T = mdg_packed_tiles_per_outcome(N)
+                             = nb (nb + 1) / 2, nb = ceil(N / 32): tile (bi, bj), bj <= bi, sits at index bi (bi + 1) / 2 +
+                             bj and holds ranks[l, 32 bi + r, 32 bj + c] at [r, c]; entries with col >= row (diagonal
+                             tiles) are 0, entries beyond N are unspecified.  The host rebuilds the normaliser's
+                             [L, N, N] layout by scattering the tiles and adding the transpose. */
 } MdgPairs;
+int64_t mdg_packed_tiles_per_outcome(int64_t N);
 
 /* Prepared per-outcome reference-quantile table for the fused rank epilogue (see mdg_rank_table_build). */
 #define MDG_RANK_BUCKET_BITS 13

@@ -17,7 +17,7 @@ MDG_RANK_MAX_Q = 65535
 
 MDG_PREC_BF16, MDG_PREC_FP32 = 0, 1
 MDG_OUT_LOGIT_F32, MDG_OUT_SIGMOID_F32, MDG_OUT_RANK_U16 = 0, 1, 2
-MDG_PAIRS_FULL, MDG_PAIRS_SYMMETRIC = 0, 1
+MDG_PAIRS_FULL, MDG_PAIRS_SYMMETRIC, MDG_PAIRS_PACKED_TILES = 0, 1, 2
 MDG_RANK_KIND = {"lut": 0, "pwl": 1}
 MDG_ENS_MEAN_F32, MDG_ENS_GMEAN_F32, MDG_ENS_GMEAN_RANK_U16 = 0, 1, 2
 MDG_MAX_ENSEMBLE = 16
@@ -65,6 +65,7 @@ SIGNATURES = {
     "mdg_rank_table_build": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mdg_rank_table_build_pwl": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mdg_rank_lookup": (c_int, [c_void_p, c_int64, POINTER(MdgRankTable), c_void_p, c_void_p]),
+    "mdg_packed_tiles_per_outcome": (c_int64, [c_int64]),
     "mdg_pair_score_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "mdg_pair_score": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                c_int, POINTER(MdgRankTable), c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -166,7 +166,7 @@ PairWorkspace carve_pair_ws(void* ws, int64_t Nr, int64_t Nc, int64_t D, int64_t
 template <int EPI, int NE>
 int launch_pair_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                          const CUtensorMap& tmOut2, const mdg::PairScoreParams& p, int grid, cudaStream_t stream) {
-  using SM = mdg::PairSmem<NE>;
+  using SM = mdg::PairSmem<NE, mdg::epi_staging_bufs(EPI, NE)>;
   static std::once_flag attr_once[kMaxDevices];
   static cudaError_t attr_err[kMaxDevices];
   int dev = 0;
@@ -180,6 +180,20 @@ int launch_pair_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   MDG_CUDA(launch_ex(mdg::pair_score_kernel<EPI, NE>, dim3(grid), dim3(SM::kThreads), SM::kBytes, stream, true, tmA, tmB,
                      tmOut, tmOut2, p));
   return MDG_OK;
+}
+
+// Which instance runs the normaliser-layout rank epilogue: the software-pipelined one (8 epilogue warps, two staging
+// tiles per warp; needs TMA stores) or the first-generation one (16 warps; also the path for unaligned outputs, which
+// use guarded direct stores).  MDG_MIRROR_EPI=legacy|pipelined pins the choice for A/B measurements.
+bool mirror_pipelined(const mdg::PairScoreParams& p) {
+  static const int pin = [] {
+    const char* e = getenv("MDG_MIRROR_EPI");
+    if (!e) return 0;
+    return strcmp(e, "legacy") == 0 ? 1 : (strcmp(e, "pipelined") == 0 ? 2 : 0);
+  }();
+  if (!p.use_tma_store || !p.use_tma_store2) return p.packed != 0;
+  if (p.packed) return true;
+  return pin != 1;
 }
 
 int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
@@ -226,13 +240,16 @@ int launch_pair_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     case mdg::EPI_SIGMOID: rc = launch_pair_instance<mdg::EPI_SIGMOID, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
     case mdg::EPI_BF16_SPLIT: rc = launch_pair_instance<mdg::EPI_BF16_SPLIT, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
     case mdg::EPI_RANK_U16_MIRROR:
-      rc = launch_pair_instance<mdg::EPI_RANK_U16_MIRROR, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
+      rc = mirror_pipelined(p) ? launch_pair_instance<mdg::EPI_RANK_U16_MIRROR, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream)
+                               : launch_pair_instance<mdg::EPI_RANK_U16_MIRROR, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
       break;
     case mdg::EPI_RANK_U16_PWL:
       rc = launch_pair_instance<mdg::EPI_RANK_U16_PWL, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
       break;
     case mdg::EPI_RANK_U16_MIRROR_PWL:
-      rc = launch_pair_instance<mdg::EPI_RANK_U16_MIRROR_PWL, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
+      rc = mirror_pipelined(p)
+               ? launch_pair_instance<mdg::EPI_RANK_U16_MIRROR_PWL, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream)
+               : launch_pair_instance<mdg::EPI_RANK_U16_MIRROR_PWL, 16>(tmA, tmB, tmOut, tmOut2, p, grid, stream);
       break;
     case mdg::EPI_TOPK: rc = launch_pair_instance<mdg::EPI_TOPK, 8>(tmA, tmB, tmOut, tmOut2, p, grid, stream); break;
     case mdg::EPI_LINEAR:
@@ -318,6 +335,12 @@ int mdg_rank_lookup(const float* logits, int64_t n_per_outcome, const MdgRankTab
 }
 
 // ------------------------------------------------------------------------------------------------ decoder
+int64_t mdg_packed_tiles_per_outcome(int64_t N) {
+  if (N <= 0) return 0;
+  const int64_t nb32 = (N + 31) / 32;
+  return nb32 * (nb32 + 1) / 2;
+}
+
 size_t mdg_pair_score_workspace_bytes(int64_t Nr, int64_t Nc, int64_t D, int64_t L, int precision) {
   if (Nr < 0 || Nc < 0 || D <= 0 || L < 0) return 0;
   return carve_pair_ws(nullptr, Nr, Nc, D, L, precision).total;
@@ -354,10 +377,14 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: out_mode=%d", out_mode);
   if (pairs != MDG_PAIRS_FULL && out_mode != kOutTopk && out_mode != MDG_OUT_RANK_U16)
     return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: pairs=%d is implemented for the rank and top-k outputs only", pairs);
-  if (pairs == MDG_PAIRS_SYMMETRIC && (z_rows != z_cols || Nr != Nc))
-    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: MDG_PAIRS_SYMMETRIC needs z_rows == z_cols (one catalogue)");
-  if (pairs != MDG_PAIRS_FULL && pairs != MDG_PAIRS_SYMMETRIC)
+  if (pairs != MDG_PAIRS_FULL && pairs != MDG_PAIRS_SYMMETRIC && pairs != MDG_PAIRS_PACKED_TILES)
     return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: pairs=%d", pairs);
+  if (pairs != MDG_PAIRS_FULL && (z_rows != z_cols || Nr != Nc))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: pairs=%d needs z_rows == z_cols (one catalogue)", pairs);
+  if (pairs == MDG_PAIRS_PACKED_TILES && out_mode != MDG_OUT_RANK_U16)
+    return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: MDG_PAIRS_PACKED_TILES is a rank-output layout");
+  if (pairs == MDG_PAIRS_PACKED_TILES && reinterpret_cast<uintptr_t>(out) % 16 != 0)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_pair_score: packed-tile output must be 16-byte aligned");
   if (Nr > (1 << 30) || Nc > (1 << 30) || L > (1 << 24))
     return fail(MDG_ERR_UNSUPPORTED, "mdg_pair_score: sizes too large");
   if (out_mode == MDG_OUT_RANK_U16) {
@@ -497,10 +524,11 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
       p.affine = table->affine;
       elem = 2;
       dt = CU_TENSOR_MAP_DATA_TYPE_UINT16;
-      if (pairs == MDG_PAIRS_SYMMETRIC) {
+      if (pairs == MDG_PAIRS_SYMMETRIC || pairs == MDG_PAIRS_PACKED_TILES) {
         epi = pwl ? mdg::EPI_RANK_U16_MIRROR_PWL : mdg::EPI_RANK_U16_MIRROR;
         p.lower_only = 1;
         p.mirror = 1;
+        p.packed = pairs == MDG_PAIRS_PACKED_TILES;
       }
     }
     // TMA store needs 16-byte aligned base and row pitch; otherwise guarded direct stores from registers
@@ -508,7 +536,16 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
                         ((Nc * elem) % 16 == 0) && (getenv("MDG_FORCE_DIRECT_STORE") == nullptr);
     p.use_tma_store = tma_ok ? 1 : 0;
     CUtensorMap tmOutT = tmA;  // mirror mode: the same tensor and box shape, used for the transposed tiles
-    if (tma_ok) {
+    if (p.packed) {
+      // packed tiles: per outcome an array of T = nb32 (nb32 + 1) / 2 contiguous 32 x 32 uint16 tiles = a [T * 32, 32]
+      // matrix with 64-byte rows; one TMA store per tile
+      const int64_t nb32 = (Nr + 31) / 32, tiles = nb32 * (nb32 + 1) / 2;
+      rc = make_map_3d(&tmOut, dt, elem, out, 32, tiles * 32, L, 32, tiles * 1024, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      p.use_tma_store = 1;
+      p.out_ld = 32;
+      p.out_batch_stride = tiles * 1024;
+    } else if (tma_ok) {
       rc = make_map_3d(&tmOut, dt, elem, out, Nc, Nr, L, Nc, Nr * Nc, 64 / elem, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
       if (p.mirror) {

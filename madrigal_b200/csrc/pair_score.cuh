@@ -48,16 +48,19 @@ __host__ __device__ constexpr bool epi_is_rank(int e) {
 }
 __host__ __device__ constexpr bool epi_is_mirror(int e) { return e == EPI_RANK_U16_MIRROR || e == EPI_RANK_U16_MIRROR_PWL; }
 __host__ __device__ constexpr bool epi_is_pwl(int e) { return e == EPI_RANK_U16_PWL || e == EPI_RANK_U16_MIRROR_PWL; }
+// The normaliser-layout epilogue with 8 epilogue warps is the software-pipelined one (two staging tiles per warp).
+__host__ __device__ constexpr bool epi_is_pipelined_mirror(int e, int ne) { return epi_is_mirror(e) && ne == 8; }
+__host__ __device__ constexpr int epi_staging_bufs(int e, int ne) { return epi_is_pipelined_mirror(e, ne) ? 2 : 1; }
 
 // Shared-memory plan for a kernel instance with NE epilogue warps (staging is per warp, so more epilogue warps
 // trade one B stage for staging space).
-template <int NE>
+template <int NE, int NBUF = 1>
 struct PairSmem {
-  static constexpr int kBStages = (NE > 8) ? 2 : 3;
+  static constexpr int kBStages = (NE * NBUF > 8) ? 2 : 3;
   static constexpr int kA = 0;
   static constexpr int kB = kA + kMaxAPanels * kPanelBytes;
   static constexpr int kStaging = kB + kBStages * kPanelBytes;
-  static constexpr int kLut = kStaging + NE * kStagingBytesPerWarp;
+  static constexpr int kLut = kStaging + NE * NBUF * kStagingBytesPerWarp;
   static constexpr int kBar = kLut + kRankLutEntries * 4;
   static constexpr int kTotal = kBar + 256;  // mbarriers, TMEM slot, dynamic-scheduler task ring
   static constexpr int kBytes = kTotal + 1024;  // + slack for manual 1024-byte alignment
@@ -110,6 +113,8 @@ struct PairScoreParams {
   int lower_only;  // keep only row > col (unordered pairs of one catalogue) and skip column blocks above the diagonal
   int a_reuse;     // A is shared by all outcomes (GEMM 1: z . W_l): tasks are ordered row-block-major and dealt in
                    // contiguous per-CTA ranges so that the resident A panels are loaded once per row block, not per task
+  int packed;      // normaliser layout without the mirror image: every 32x32 chunk with row >= col goes ONCE, as a
+                   // contiguous 2 KB tile, to tile slot bi*(bi+1)/2 + bj of the outcome (MDG_PAIRS_PACKED_TILES)
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
@@ -226,12 +231,32 @@ struct StagedStore {
   }
 };
 
+// Two 2 KB staging tiles per warp used alternately: a tile is rewritten two bulk stores after the one that read it.
+struct StagingRing2 {
+  uint32_t buf[2];
+  int cur;
+  __device__ __forceinline__ uint32_t acquire(int lane) {  // the store before the previous one has read its tile
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    return buf[cur];
+  }
+  __device__ __forceinline__ void commit(const CUtensorMap* tm, int c0, int c1, int c2, int lane) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tm, buf[cur], c0, c1, c2);
+      tma_store_commit();
+    }
+    cur ^= 1;
+  }
+};
+
 template <int EPI, int NE>
 __global__ void __launch_bounds__(PairSmem<NE>::kThreads, 1)
 pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                   const __grid_constant__ PairScoreParams p) {
-  using SM = PairSmem<NE>;
+  using SM = PairSmem<NE, epi_staging_bufs(EPI, NE)>;
   constexpr int kBStages = SM::kBStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -544,6 +569,193 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ms = (grp * cols_per_warp) / kBN;
     const int col_begin = (grp * cols_per_warp) % kBN;
     const int col_end = col_begin + cols_per_warp;
+    if constexpr (epi_is_pipelined_mirror(EPI, NE)) {
+      // ---------------------------------------------------------------------------------------------------------
+      // Normaliser-layout epilogue (normalize_scores.py:67-70), software-pipelined.  8 epilogue warps; a warp owns a
+      // strip of 32 rows x (2 or 4) 32-column chunks per tile.  While the 1024 look-ups of chunk c run, the
+      // accumulator fragment of chunk c+1 (the next chunk of the strip, or the first one of the next tile of the task)
+      // is already being fetched from TMEM into a second register set, and the two 2 KB staging tiles of the warp
+      // alternate, so neither the tcgen05.ld round trip nor the bulk store's shared-memory read is ever waited for
+      // in steady state: the shared-memory pipe (LUT gathers + stmatrix) is the only resource the loop is bound by.
+      // A chunk with row > col is ranked once and stored twice (plain tile at [row, col], stmatrix.trans tile at
+      // [col, row]); the diagonal chunk builds both masked tiles, ORs them in shared memory and is stored once.
+      // p.packed: no mirror image — every chunk goes once to its slot of the packed tile array.
+      // ---------------------------------------------------------------------------------------------------------
+      StagingRing2 ring;
+      ring.buf[0] = sStaging + ew * 2 * kStagingBytesPerWarp;
+      ring.buf[1] = ring.buf[0] + kStagingBytesPerWarp;
+      ring.cur = 0;
+      const uint32_t sLutLane = sLut + static_cast<uint32_t>(lane) * 4;
+      const int fr = lane >> 2, fc = (lane & 3) * 2;  // fragment row / first column of this thread
+      const int n_chunks = cols_per_warp / 32;
+      int acc_stage = 0;
+      uint32_t acc_phase = 0;
+      int cur_l = -1;
+      float scale = 0.f, bias = 0.f;
+
+      // ranks of one chunk: P[hf][i][s] = (row 16hf + 8s + fr, cols 8i + fc, +1) packed as b16x2
+      auto lookup_chunk = [&](const uint32_t (&v)[2][16], uint32_t (&P)[2][4][2]) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+              const uint32_t ra = rank_lookup_epi<epi_is_pwl(EPI)>(sLut, sLutLane, __uint_as_float(v[hf][4 * i + 2 * s2]), scale, bias);
+              const uint32_t rb = rank_lookup_epi<epi_is_pwl(EPI)>(sLut, sLutLane, __uint_as_float(v[hf][4 * i + 2 * s2 + 1]), scale, bias);
+              P[hf][i][s2] = __byte_perm(ra, rb, 0x5410);
+            }
+      };
+      auto fill_plain = [&](uint32_t dst, const uint32_t (&P)[2][4][2]) {  // staging row = chunk row, 64B swizzle
+        const int i = lane >> 3, k = lane & 7;  // this thread addresses row k of matrix i (= column group)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int R = 16 * hf + 8 * s2 + k;
+            stmatrix_x4(dst + R * 64 + ((i ^ ((R >> 1) & 3)) << 4), P[hf][0][s2], P[hf][1][s2], P[hf][2][s2], P[hf][3][s2]);
+          }
+      };
+      auto fill_trans = [&](uint32_t dst, const uint32_t (&P)[2][4][2]) {  // staging row = chunk column
+        const int m = lane >> 3, k = lane & 7;  // stored-row k of matrix m (= rows 8m .. 8m+7 of the chunk)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = 8 * i + k;
+          stmatrix_x4_trans(dst + c * 64 + ((m ^ ((c >> 1) & 3)) << 4), P[0][i][0], P[0][i][1], P[1][i][0], P[1][i][1]);
+        }
+      };
+      // look-ups + stores of one chunk whose accumulator fragment is in v
+      auto process = [&](const uint32_t (&v)[2][16], int l, int row0, int n0) {
+        uint32_t P[2][4][2];
+        lookup_chunk(v, P);
+        const int bi = row0 >> 5, bj = n0 >> 5;
+        const int slot_row = (bi * (bi + 1) / 2 + bj) * 32;  // packed layout: first row of this chunk's tile
+        if (n0 != row0) {
+          if (!p.packed) {
+            // both tiles of the chunk under ONE proxy fence and ONE bulk group: the previous chunk's group was
+            // committed before this chunk's 1024 look-ups, so waiting for its reads costs nothing here
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            fill_trans(ring.buf[0], P);
+            fill_plain(ring.buf[1], P);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmOut2, ring.buf[0], row0, n0, l);  // [l, n0.., row0..]
+              tma_store_3d(&tmOut, ring.buf[1], n0, row0, l);
+              tma_store_commit();
+            }
+          } else {
+            fill_plain(ring.acquire(lane), P);
+            ring.commit(&tmOut, 0, slot_row, l, lane);
+          }
+        } else {
+          // diagonal chunk: keep col < row only (diagonal = 0, normalize_scores.py:69)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int s2 = 0; s2 < 2; ++s2) {
+                const int r = 16 * hf + 8 * s2 + fr, c0 = 8 * i + fc;
+                uint32_t w = P[hf][i][s2];
+                if (c0 >= r) w &= 0xFFFF0000u;
+                if (c0 + 1 >= r) w &= 0x0000FFFFu;
+                P[hf][i][s2] = w;
+              }
+          if (p.packed) {
+            fill_plain(ring.acquire(lane), P);
+            ring.commit(&tmOut, 0, slot_row, l, lane);
+          } else {
+            // both staging tiles must be free: lower triangle in one, its transpose in the other, OR, one store
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            const uint32_t d = ring.buf[ring.cur], t = ring.buf[ring.cur ^ 1];
+            fill_plain(d, P);
+            fill_trans(t, P);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // lane = staging row; the swizzle is the same in both tiles
+              uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+              ld_shared_v4(d + lane * 64 + q * 16, a0, a1, a2, a3);
+              ld_shared_v4(t + lane * 64 + q * 16, b0, b1, b2, b3);
+              st_shared_v4(d + lane * 64 + q * 16, a0 | b0, a1 | b1, a2 | b2, a3 | b3);
+            }
+            ring.commit(&tmOut, n0, row0, l, lane);
+          }
+        }
+      };
+
+      for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane)) {
+        const TaskCoord c = decode_task(p, t);
+        if (c.l != cur_l) {
+          named_bar_sync(1, NE * 32);  // everyone is done with the previous outcome's LUT
+          const uint4* src = reinterpret_cast<const uint4*>(p.lut + static_cast<size_t>(c.l) * kRankLutEntries);
+          const int tid = ew * 32 + lane;
+#pragma unroll 4
+          for (int i = tid; i < kRankLutEntries / 4; i += NE * 32) {
+            uint4 q = __ldg(src + i);
+            st_shared_v4(sLut + i * 16, q.x, q.y, q.z, q.w);
+          }
+          scale = __ldg(p.affine + 2 * c.l);
+          bias = __ldg(p.affine + 2 * c.l + 1);
+          cur_l = c.l;
+          named_bar_sync(1, NE * 32);
+        }
+        const int row0 = c.m0 + ms * kBM + quad * 32;  // first of this warp's 32 rows
+        const bool rows_ok = row0 < p.rows;
+        // cursor over (tile nb, chunk k) of this task; a tile is opened by waiting for its accumulators and closed
+        // (handed back to the MMA warp) once every chunk of it that this warp needs has been fetched AND awaited —
+        // fetch() is only called right after tcgen05.wait::ld, so nothing is in flight when it closes a tile
+        int nb = c.nb0, k = 0;
+        bool open = false;
+        auto fetch = [&](uint32_t (&v)[2][16], int& n0_out) -> bool {
+          while (nb < c.nb1) {
+            if (!open) {
+              mbar_wait(bar_t_full(acc_stage), acc_phase, 6);
+              tc_fence_after_sync();
+              open = true;
+              k = 0;
+            }
+            if (k < n_chunks && rows_ok) {
+              const int cc = col_begin + 32 * k;
+              const int n0 = nb * kBN + cc;
+              if (n0 < p.cols && n0 <= row0 + 31) {  // else: this and the later chunks of the tile hold no row >= col
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                       static_cast<uint32_t>((acc_stage * 2 + ms) * kBN + cc);
+                tmem_ld_16x256b_x4(taddr, v[0]);
+                tmem_ld_16x256b_x4(taddr + (16u << 16), v[1]);
+                n0_out = n0;
+                ++k;
+                return true;
+              }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_t_empty(acc_stage));
+            acc_stage ^= 1;
+            if (acc_stage == 0) acc_phase ^= 1;
+            open = false;
+            ++nb;
+          }
+          return false;
+        };
+        uint32_t va[2][16], vb[2][16];
+        int n0a = 0, n0b = 0;
+        bool have = fetch(va, n0a);
+        while (have) {
+          tmem_ld_wait();
+          const bool have_b = fetch(vb, n0b);
+          process(va, c.l, row0, n0a);
+          if (!have_b) break;
+          tmem_ld_wait();
+          have = fetch(va, n0a);
+          process(vb, c.l, row0, n0b);
+        }
+      }
+      if (lane == 0) tma_store_wait_all<0>();
+      __syncwarp();
+    } else {
     StagedStore ss;
     ss.buf[0] = sStaging + ew * kStagingBytesPerWarp;
     // the LUT region is idle outside the rank epilogue: use it as a second staging buffer per warp
@@ -935,6 +1147,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (ss.pending > 0 && lane == 0) tma_store_wait_all<0>();
     __syncwarp();
+    }  // legacy (non-pipelined) epilogues
   }
 
   tc_fence_before_sync();

@@ -114,6 +114,37 @@ class RankTable:
         return out
 
 
+def packed_tiles_per_outcome(N: int) -> int:
+    """T = nb (nb + 1) / 2 with nb = ceil(N / 32): 32 x 32 tiles of the lower triangle incl. the diagonal tiles."""
+    nb = (N + 31) // 32
+    return nb * (nb + 1) // 2
+
+
+def unpack_packed_tiles(packed, N: int):
+    """Packed lower-triangular rank tiles [L, T, 32, 32] (MDG_PAIRS_PACKED_TILES) -> the normaliser's layout [L, N, N]
+    (each rank at [i, j] and [j, i], zero diagonal; normalize_scores.py:67-70).  Works on a torch tensor (any device)
+    or a numpy array; pure data movement (scatter of tiles + transpose), the host-side mirror of the packed copy."""
+    import numpy as np
+    is_np = isinstance(packed, np.ndarray)
+    x = torch.from_numpy(packed.view(np.int16)) if is_np else packed.view(torch.int16)
+    L, T = x.shape[0], x.shape[1]
+    nb = (N + 31) // 32
+    if T != nb * (nb + 1) // 2:
+        raise ValueError("tile count does not match N")
+    full = torch.zeros((L, nb * 32, nb * 32), dtype=torch.int16, device=x.device)
+    blocks = full.view(L, nb, 32, nb, 32)
+    t = 0
+    for bi in range(nb):  # tile row bi holds tiles (bi, 0..bi) contiguously
+        row = x[:, t:t + bi + 1]                      # [L, bi+1, 32, 32]
+        blocks[:, bi, :, :bi + 1, :] = row.permute(0, 2, 1, 3)
+        t += bi + 1
+    full = torch.tril(full, -1)                       # diagonal tiles: keep col < row only
+    full = (full + full.transpose(1, 2))[:, :N, :N].contiguous()
+    if is_np:
+        return full.numpy().view(np.uint16)
+    return full.view(torch.uint16)
+
+
 class PreparedDecoder:
     """The decoder weights [L, D, D] converted ONCE to the tensor-core operand form (mdg_pair_prepare).  The reference
     re-reads `decoder.weight` through the Symmetric parametrisation on every call (models.py:537-547, 922); a scoring
@@ -156,15 +187,18 @@ class PreparedDecoder:
 def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight, *, precision: str = "fp32",
                out: str = "logit", table: Optional[RankTable] = None, table_offset: int = 0,
                normalize: bool = False, out_tensor: Optional[torch.Tensor] = None,
-               symmetric: bool = False) -> torch.Tensor:
+               symmetric: bool = False, packed: bool = False) -> torch.Tensor:
     """All-pairs bilinear scores  S[l,i,j] = z_rows[i] . W[l] . z_cols[j]  with a fused epilogue.
 
     out='logit' | 'sigmoid' -> float32 [L, Nr, Nc];  out='rank' -> uint16 quantile ranks against `table`
     (rows table_offset .. table_offset+L of the table).  symmetric=True (out='rank', z_rows is z_cols): compute only
     row > col and write each rank at [i,j] and [j,i] with a zero diagonal — the reference normaliser's layout
-    (normalize_scores.py:67-70) at half the MMAs and look-ups.  `weight`: fp32 [L, D, D] or a `PreparedDecoder`
-    (then `precision` is the prepared one).
+    (normalize_scores.py:67-70) at half the MMAs and look-ups.  packed=True (implies symmetric): the same ranks without
+    the mirror image, as uint16 [L, T, 32, 32] lower-triangular tiles (MDG_PAIRS_PACKED_TILES; `unpack_packed_tiles`
+    rebuilds [L, N, N]) — half the bytes to write and to copy to the host.  `weight`: fp32 [L, D, D] or a
+    `PreparedDecoder` (then `precision` is the prepared one).
     """
+    symmetric = symmetric or packed
     zr = _require_cuda_f32(z_rows, "z_rows")
     zc = zr if z_cols is z_rows else _require_cuda_f32(z_cols, "z_cols")
     prepared = weight if isinstance(weight, PreparedDecoder) else None
@@ -190,11 +224,12 @@ def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight, *, precision:
         raise ValueError(f"shape mismatch: z_rows {tuple(zr.shape)}, z_cols {tuple(zc.shape)}, weight {wshape}")
     mode, dtype = _OUT[out]
     prec = _PRECISION[precision]
+    out_shape = (L, packed_tiles_per_outcome(Nr), 32, 32) if packed else (L, Nr, Nc)
     if out_tensor is None:
-        out_tensor = torch.empty((L, Nr, Nc), dtype=dtype, device=zr.device)
+        out_tensor = torch.empty(out_shape, dtype=dtype, device=zr.device)
     else:
-        if out_tensor.shape != (L, Nr, Nc) or out_tensor.dtype != dtype or not out_tensor.is_contiguous():
-            raise ValueError("out_tensor has the wrong shape/dtype/layout")
+        if tuple(out_tensor.shape) != out_shape or out_tensor.dtype != dtype or not out_tensor.is_contiguous():
+            raise ValueError(f"out_tensor must be a contiguous {dtype} tensor of shape {out_shape}")
     tbl = None
     if out == "rank":
         if table is None:
@@ -203,7 +238,7 @@ def pair_score(z_rows: torch.Tensor, z_cols: torch.Tensor, weight, *, precision:
     fn = _lib.lib()
     nbytes = fn.mdg_pair_score_workspace_bytes(Nr, Nc, D, L, prec)
     ws = _workspace(zr.device, nbytes)
-    pairs = _lib.MDG_PAIRS_SYMMETRIC if symmetric else _lib.MDG_PAIRS_FULL
+    pairs = _lib.MDG_PAIRS_PACKED_TILES if packed else (_lib.MDG_PAIRS_SYMMETRIC if symmetric else _lib.MDG_PAIRS_FULL)
     tbl_ref = ctypes.byref(tbl) if tbl is not None else None
     with torch.cuda.device(zr.device):
         if prepared is not None:

@@ -79,17 +79,21 @@ def score_row_block(z: torch.Tensor, weight: torch.Tensor, rank: int, world_size
 
 def score_all_pairs_to_host(z: torch.Tensor, weight: torch.Tensor, out_host: torch.Tensor, *, out: str = "rank",
                             table: Optional[RankTable] = None, precision: str = "bf16", chunk: int = 10,
-                            normalize: bool = False, symmetric: bool = False) -> torch.Tensor:
+                            normalize: bool = False, symmetric: bool = False, packed: bool = False) -> torch.Tensor:
     """predict.py:420-429 call pattern: outcomes in chunks of `chunk`, each chunk scored on the GPU and copied into
-    `out_host` ([L, N, N], pinned for overlap).  Double-buffered: copy of chunk c overlaps compute of chunk c+1."""
+    `out_host` ([L, N, N], pinned for overlap).  Double-buffered: copy of chunk c overlaps compute of chunk c+1.
+    packed=True (rank output): the device writes and the host receives the packed lower-triangular tiles
+    ([L, T, 32, 32], half the PCIe volume); `decoder.unpack_packed_tiles` rebuilds [L, N, N] on the host when needed."""
     L, N = weight.shape[0], z.shape[0]
     dtype = _OUT_DTYPE[out]
-    if tuple(out_host.shape) != (L, N, N) or out_host.dtype != dtype:
-        raise ValueError(f"out_host must be {dtype} [{L}, {N}, {N}]")
+    from .decoder import packed_tiles_per_outcome
+    item_shape = (packed_tiles_per_outcome(N), 32, 32) if packed else (N, N)
+    if tuple(out_host.shape) != (L,) + item_shape or out_host.dtype != dtype:
+        raise ValueError(f"out_host must be {dtype} {(L,) + item_shape}")
     dev = z.device
     compute = torch.cuda.current_stream(dev)
     copy = _copy_stream(dev)
-    bufs = [torch.empty((min(chunk, L), N, N), dtype=dtype, device=dev) for _ in range(2)]
+    bufs = [torch.empty((min(chunk, L),) + item_shape, dtype=dtype, device=dev) for _ in range(2)]
     done_copy = [None, None]
     for ci, l0 in enumerate(range(0, L, chunk)):
         l1 = min(l0 + chunk, L)
@@ -98,7 +102,7 @@ def score_all_pairs_to_host(z: torch.Tensor, weight: torch.Tensor, out_host: tor
             compute.wait_event(done_copy[b])  # buffer b is free once its previous copy finished
         dst = bufs[b][: l1 - l0]
         pair_score(z, z, weight[l0:l1], precision=precision, out=out, table=table, table_offset=l0,
-                   normalize=normalize, out_tensor=dst, symmetric=symmetric)
+                   normalize=normalize, out_tensor=dst, symmetric=symmetric, packed=packed)
         ready = torch.cuda.Event()
         ready.record(compute)
         with torch.cuda.stream(copy):

@@ -541,3 +541,45 @@ def test_concurrent_streams_use_separate_workspaces(mb, cuda_device):
     torch.cuda.synchronize()
     for oa, ob in outs:
         assert torch.equal(oa, ref_a) and torch.equal(ob, ref_b)
+
+
+@pytest.mark.parametrize("N,D,L,Q", [(512, 256, 3, 4096), (1000, 128, 2, 2048), (296, 64, 2, 512), (40, 128, 1, 256),
+                                     (2304, 256, 2, 16384)])
+@pytest.mark.parametrize("kind", ["lut", "pwl"])
+def test_pipelined_normaliser_epilogue_matches_legacy_and_oracle(mb, cuda_device, monkeypatch, N, D, L, Q, kind):
+    """The software-pipelined normaliser-layout epilogue (8 warps, two staging tiles, TMEM prefetch, smem-OR diagonal
+    chunks) writes exactly what np.searchsorted gives on the dense logits, mirrored with a zero diagonal.  (The legacy
+    16-warp epilogue is pinned by MDG_MIRROR_EPI=legacy in a subprocess-free way only at library load, so the oracle is
+    the reference here; test_symmetric_rank_mode_is_the_normaliser_layout covers whichever instance is the default.)"""
+    from madrigal_b200 import normalize
+    z, W = synth.decoder_inputs(N, D, L, seed=N + Q)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    table = normalize.build_rank_table(zt, Wt, Q, precision="bf16", kind=kind)
+    lg = mb.pair_score(zt, zt, Wt, precision="bf16", out="logit").cpu().numpy()
+    exp = oracle.quantile_rank(table.thresholds.cpu().numpy(), lg, "right").astype(np.uint16)
+    ref = np.tril(exp, -1)
+    ref = ref + np.swapaxes(ref, 1, 2)
+    got = mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, symmetric=True).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("N,D,L,Q", [(512, 256, 3, 4096), (1000, 128, 2, 2048), (296, 64, 2, 512), (33, 128, 1, 256)])
+def test_packed_tiles_layout(mb, cuda_device, N, D, L, Q):
+    """MDG_PAIRS_PACKED_TILES: the normaliser-layout ranks without the mirror image, as 32x32 lower-triangular tiles;
+    unpack_packed_tiles (device and host) rebuilds the [L, N, N] tensor the symmetric mode writes, bit for bit."""
+    from madrigal_b200 import normalize
+    from madrigal_b200.decoder import packed_tiles_per_outcome, unpack_packed_tiles
+    z, W = synth.decoder_inputs(N, D, L, seed=N + 3)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    table = normalize.build_rank_table(zt, Wt, Q, precision="bf16")
+    full = mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, symmetric=True)
+    packed = mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, packed=True)
+    assert tuple(packed.shape) == (L, packed_tiles_per_outcome(N), 32, 32)
+    assert torch.equal(unpack_packed_tiles(packed, N).view(torch.int16), full.view(torch.int16))
+    host = unpack_packed_tiles(packed.cpu().numpy(), N)
+    assert np.array_equal(host, full.cpu().numpy())
+    # through the host-destination driver
+    from madrigal_b200 import scoring
+    out_host = torch.empty(tuple(packed.shape), dtype=torch.uint16).pin_memory()
+    scoring.score_all_pairs_to_host(zt, Wt, out_host, out="rank", table=table, precision="bf16", chunk=2, packed=True)
+    assert np.array_equal(unpack_packed_tiles(out_host.numpy(), N), full.cpu().numpy())
