@@ -49,6 +49,8 @@ FUSION_CASES = [
          norm_first=True, agg="x-attn", nb=4, n_tx=16, B=3),  # configs/ddi_finetune/DrugBank/*elated_sweep_163.yaml
     dict(name="production_twosides_hd256", embed_dim=128, num_layers=2, num_heads=2, head_dim=256, ffn_dim=512,
          actn="gelu", norm_first=True, agg="x-attn", nb=2, n_tx=16, B=2),  # TWOSIDES/good_sweep_105.yaml
+    dict(name="production_twosides_hd256x8", embed_dim=128, num_layers=2, num_heads=8, head_dim=256, ffn_dim=1024,
+         actn="gelu", norm_first=True, agg="x-attn", nb=2, n_tx=16, B=3),  # TWOSIDES/hardy_sweep_321.yaml:17,31-34: latent 2048
 ]
 
 
@@ -193,12 +195,18 @@ def encode_goldens():
         dict(name="enc_cls_nb0_sin", agg="cls", nb=0, pos="sinusoidal", fusion="transformer_uni_proj", normalize=False,
              B=7),
         dict(name="enc_mean_fusion", agg="x-attn", nb=0, pos="sinusoidal", fusion="mean", normalize=True, B=5),
+        # the shipped TWOSIDES hardy_sweep_321 configuration at full size (sweep_config_hardy_sweep_321.yaml:17, 21,
+        # 31-34): feature_dim 128, 8 heads x 256 = latent 2048, FFN 1024, 2 bottlenecks, sinusoidal positions,
+        # fusion 'transformer_uni_proj' (unimodal drugs bypass the transformer through uni_fuser)
+        dict(name="enc_twosides_hd256x8_uniproj", agg="x-attn", nb=2, pos="sinusoidal", fusion="transformer_uni_proj",
+             normalize=False, B=6, E=128, tf=dict(num_heads=8, head_dim=256, ffn_dim=1024)),
     ]
-    E = 32
-    hp = dict(transformer_num_layers=2, transformer_att_heads=4, transformer_head_dim=8, transformer_ffn_dim=64,
-              transformer_dropout=0.1, transformer_actn="gelu", transformer_norm_first=True,
-              transformer_batch_first=False)
     for idx, c in enumerate(cases):
+        E = c.get("E", 32)
+        tf = c.get("tf", dict(num_heads=4, head_dim=8, ffn_dim=64))
+        hp = dict(transformer_num_layers=2, transformer_att_heads=tf["num_heads"], transformer_head_dim=tf["head_dim"],
+                  transformer_ffn_dim=tf["ffn_dim"], transformer_dropout=0.1, transformer_actn="gelu",
+                  transformer_norm_first=True, transformer_batch_first=False)
         seed = 500 + idx
         rng = np.random.default_rng(seed)
         B = c["B"]
@@ -222,7 +230,8 @@ def encode_goldens():
         enc.tx_encoder_dict = {cl: (lambda sigs: sigs) for cl in synth.CELL_LINES}
         enc.num_tx_bottlenecks, enc.transformer_agg = c["nb"], c["agg"]
         max_len = (19 if c["nb"] == 0 else 3) + (1 if c["agg"] == "cls" else 0)  # models.py:668-676
-        cfg = dict(embed_dim=E, num_layers=2, num_heads=4, head_dim=8, ffn_dim=64, agg=c["agg"])
+        cfg = dict(embed_dim=E, num_layers=2, num_heads=tf["num_heads"], head_dim=tf["head_dim"], ffn_dim=tf["ffn_dim"],
+                   agg=c["agg"])
         sd = synth.fusion_state_dict(cfg, seed)
         extra = {}
         if c["nb"] > 0:
@@ -260,7 +269,7 @@ def encode_goldens():
         out[f"{c['name']}.z"] = z.astype(np.float32)
         for k, v in extra.items():
             out[f"{c['name']}.{k}"] = v
-        meta.append(dict(c, seed=seed, E=E, max_len=max_len,
+        meta.append(dict(c, seed=seed, E=E, tf=tf, max_len=max_len,
                          checksum=synth.params_checksum([sd[k] for k in sorted(sd)] + [embeds])))
     return out, meta
 

@@ -150,7 +150,7 @@ def test_mlp_adaptor_vs_reference_golden(mb, cuda_device, case):
     assert_close(y, g[f"{case['name']}.y"], 1e-3, case["name"])
 
 
-def _encode_case(mb, case, cuda_device):
+def _encode_case(mb, case, cuda_device, precision="fp32"):
     """FusionEncoder + inputs of one golden `encode` case (tests/golden/make_golden.py: encode_goldens)."""
     g = np.load(os.path.join(HERE, "golden", "golden_encode.npz"))
     name, E, seed, B = case["name"], case["E"], case["seed"], case["B"]
@@ -163,13 +163,15 @@ def _encode_case(mb, case, cuda_device):
         masks[1, 0] = False
         masks[4, :] = True
         masks[4, 2] = False
-    hp = dict(transformer_num_layers=2, transformer_att_heads=4, transformer_head_dim=8, transformer_ffn_dim=64,
-              transformer_dropout=0.1, transformer_actn="gelu", transformer_norm_first=True,
-              transformer_batch_first=False, transformer_agg=case["agg"])
+    tf = case.get("tf", dict(num_heads=4, head_dim=8, ffn_dim=64))
+    hp = dict(transformer_num_layers=2, transformer_att_heads=tf["num_heads"], transformer_head_dim=tf["head_dim"],
+              transformer_ffn_dim=tf["ffn_dim"], transformer_dropout=0.1, transformer_actn="gelu",
+              transformer_norm_first=True, transformer_batch_first=False, transformer_agg=case["agg"])
     proj = dict(proj_hidden_dims=[48, 40], proj_dropout=0.2, proj_norm="ln", proj_actn="relu", proj_order="nd")
     enc = mb.FusionEncoder(E, case["nb"], 0.1, hp, proj, fusion=case["fusion"], normalize=case["normalize"],
-                           pos_emb_type="learnable" if case["pos"] == "learnable" else "sinusoidal")
-    cfg = dict(embed_dim=E, num_layers=2, num_heads=4, head_dim=8, ffn_dim=64, agg=case["agg"])
+                           pos_emb_type="learnable" if case["pos"] == "learnable" else "sinusoidal", precision=precision)
+    cfg = dict(embed_dim=E, num_layers=2, num_heads=tf["num_heads"], head_dim=tf["head_dim"], ffn_dim=tf["ffn_dim"],
+               agg=case["agg"])
     sd = synth.fusion_state_dict(cfg, seed)
     if not np.isclose(synth.params_checksum([sd[k] for k in sorted(sd)] + [embeds]), case["checksum"], rtol=1e-9):
         pytest.skip("numpy Generator stream drift")
@@ -480,3 +482,102 @@ def test_torch_op_fusion_encode_matches_module(mb, cuda_device, agg, nb, T):
     with pytest.raises(NotImplementedError):
         torch.ops.madrigal_b200.fusion_encode(torch.zeros(2, T, E), torch.zeros(2, T, dtype=torch.bool), None, None,
                                               [p.cpu() for p in params], cfg, "gelu", agg, "fp32")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Shipped production shapes in bf16 mode, incl. latent 2048 (8 heads x 256, TWOSIDES hardy_sweep_321.yaml:31-34): the
+# generic path's streamed-A GEMMs (K = 2048 does not fit the resident operand buffer) and its workspace plan
+# ---------------------------------------------------------------------------------------------------------------
+PRODUCTION = [c for c in META["fusion"] if c["name"].startswith("production_")]
+
+
+@pytest.mark.parametrize("case", PRODUCTION, ids=lambda c: c["name"])
+def test_production_shapes_bf16_vs_reference_golden(mb, cuda_device, case):
+    """bf16-operand / fp32-accumulate encoder on the reference's shipped shapes against the reference's own fp32
+    output: |dz| <= 1e-2 * max|z_ref| element-wise (north-star bf16 bar, taken against the scale of the tensor because
+    z has entries near zero), and <= 3e-3 * max|z_ref| on average."""
+    g = np.load(os.path.join(HERE, "golden", "golden_fusion.npz"))
+    mod, sd = make_module(mb, case, cuda_device, precision="bf16")
+    tokens, mask = synth.fusion_inputs(case["B"], case["T"], case["embed_dim"], case["seed"],
+                                       always_visible=tuple(case["always_visible"]))
+    if not np.isclose(synth.params_checksum([sd[k] for k in sorted(sd)] + [tokens]), case["checksum"], rtol=1e-9):
+        pytest.skip("numpy Generator stream drift")
+    name = case["name"]
+    src = gpu(g[f"{name}.src_mask"], cuda_device)
+    mod.x_attn_key_padding_mask = torch.from_numpy(g[f"{name}.pool_mask"])[None, :]
+    with torch.no_grad():
+        z = mod(gpu(tokens, cuda_device), gpu(mask, cuda_device), src).cpu().numpy()
+    ref = g[f"{name}.z"].astype(np.float64)
+    err = np.abs(z - ref)
+    assert np.isfinite(z).all()
+    assert err.max() <= 1e-2 * np.abs(ref).max(), f"{name}: {err.max():.3e} vs max|ref| {np.abs(ref).max():.3e}"
+    assert err.mean() <= 3e-3 * np.abs(ref).max(), name
+
+
+def test_latent_2048_uniproj_encode_bf16_vs_reference_golden(mb, cuda_device):
+    """The whole fusion section of the shipped TWOSIDES hardy_sweep_321 configuration (latent 2048, FFN 1024, 2
+    bottlenecks, sinusoidal positions, fusion='transformer_uni_proj') in bf16 mode against the reference's own
+    NovelDDIEncoder.encode (fp32 mode is covered by test_fusion_encoder_vs_reference_encode_golden)."""
+    case = [c for c in META["encode"] if c["name"] == "enc_twosides_hd256x8_uniproj"][0]
+    enc, embeds, masks, want = _encode_case(mb, case, cuda_device, precision="bf16")
+    with torch.no_grad():
+        z = enc(gpu(embeds, cuda_device), gpu(masks, cuda_device)).cpu().numpy()
+    err = np.abs(z - want.astype(np.float64))
+    assert np.isfinite(z).all() and err.max() <= 1e-2 * np.abs(want).max(), err.max()
+
+
+@pytest.mark.parametrize("path", ["fused", "generic"])
+def test_bf16_logit_level_chain_T23_xattn(mb, cuda_device, path):
+    """North-star bf16 bar at the LOGIT level through the production token layout: 23 tokens (3 non-TX + 4 bottleneck
+    + 16 TX, src_mask, x-attn pooling over the bottlenecks) -> encoder (fused one-launch kernel / generic multi-kernel
+    path) -> bilinear decoder, all bf16-operand / fp32-accumulate, against the fp64 oracle chain:
+    max |logit - ref| <= 1e-2 * max|ref|."""
+    E, H, hd, F, T, nb, B, L = 128, 8, 32, 512, 23, 4, 512, 6
+    case = dict(embed_dim=E, num_layers=2, num_heads=H, head_dim=hd, ffn_dim=F, actn="gelu", norm_first=True,
+                agg="x-attn", nb=nb, seed=77)
+    mod, sd = make_module(mb, case, cuda_device, precision="bf16")
+    tokens, mask = synth.fusion_inputs(B, T, E, case["seed"], always_visible=(0,) + tuple(range(3, 3 + nb)))
+    src = np.zeros((T, T), bool)
+    src[:3, T - 16:] = True
+    src[T - 16:, :3] = True
+    pool = np.zeros(T, bool)
+    pool[:3] = True
+    pool[-16:] = True
+    mod.x_attn_key_padding_mask = torch.from_numpy(pool)[None, :]
+    _, W = synth.decoder_inputs(1, E, L, seed=78)
+    z_ref = oracle.fusion_forward(sd, case, tokens, mask, src, pool, dtype=np.float64)
+    lg_ref = oracle.bilinear_scores(z_ref, z_ref, W, dtype=np.float64)
+    if path == "generic":
+        os.environ["MDG_FUSION_GENERIC"] = "1"
+    try:
+        with torch.no_grad():
+            z = mod(gpu(tokens, cuda_device), gpu(mask, cuda_device), gpu(src, cuda_device))
+            assert (mod.last_launch_count == 1) == (path == "fused")
+            lg = mb.pair_score(z, z, gpu(W, cuda_device), precision="bf16", out="logit").cpu().numpy()
+    finally:
+        os.environ.pop("MDG_FUSION_GENERIC", None)
+    err = np.abs(lg - lg_ref)
+    assert np.isfinite(lg).all()
+    assert err.max() <= 1e-2 * np.abs(lg_ref).max(), f"{path}: {err.max():.3e} vs {np.abs(lg_ref).max():.3e}"
+    assert err.mean() <= 2e-3 * np.abs(lg_ref).max(), path
+
+
+def test_normalize_paths_use_the_row_normalise_kernel(mb, cuda_device):
+    """fusion='mean' with normalize=True and the unimodal bypass with normalize=True go through mdg_l2_normalize_rows
+    (no eager PyTorch arithmetic): compare with the oracle restatement (models.py:849-850, 861-862, 870-873)."""
+    E, B = 64, 37
+    rng = np.random.default_rng(9)
+    embeds = rng.standard_normal((B, 19, E)).astype(np.float32)
+    masks = rng.random((B, 19)) < 0.5
+    masks[:, 0] = False
+    hp = dict(transformer_num_layers=1, transformer_att_heads=2, transformer_head_dim=32, transformer_ffn_dim=64,
+              transformer_dropout=0.0, transformer_actn="gelu", transformer_norm_first=True,
+              transformer_batch_first=False, transformer_agg="x-attn")
+    proj = dict(proj_hidden_dims=[32], proj_dropout=0.0, proj_norm="ln", proj_actn="relu", proj_order="nd")
+    enc = mb.FusionEncoder(E, 0, 0.0, hp, proj, fusion="mean", normalize=True, pos_emb_type="sinusoidal").to(cuda_device)
+    with torch.no_grad():
+        z = enc(gpu(embeds, cuda_device), gpu(masks, cuda_device)).cpu().numpy()
+    x = embeds / np.maximum(np.sqrt((embeds.astype(np.float64) ** 2).sum(-1, keepdims=True)), 1e-12)
+    keep = ~masks
+    ref = (x * keep[:, :, None]).sum(1) / keep.sum(1, keepdims=True)
+    assert np.abs(z - ref).max() <= 1e-5

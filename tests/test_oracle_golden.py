@@ -175,8 +175,9 @@ def test_encode_assembly_matches_reference(case):
         masks[1, 0] = False
         masks[4, :] = True
         masks[4, 2] = False
-    cfg = dict(embed_dim=E, num_layers=2, num_heads=4, head_dim=8, ffn_dim=64, agg=case["agg"], actn="gelu",
-               norm_first=True)
+    tf = case.get("tf", dict(num_heads=4, head_dim=8, ffn_dim=64))
+    cfg = dict(embed_dim=E, num_layers=2, num_heads=tf["num_heads"], head_dim=tf["head_dim"], ffn_dim=tf["ffn_dim"],
+               agg=case["agg"], actn="gelu", norm_first=True)
     sd = synth.fusion_state_dict(cfg, seed)
     _check_stream(case, [sd[k] for k in sorted(sd)] + [embeds])
     get = lambda k: g[f"{name}.{k}"] if f"{name}.{k}" in g.files else None
