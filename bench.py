@@ -311,7 +311,7 @@ class Job:
         self.quantiles = normalize.build_reference_quantiles(self.z_full, self.W, Q_TABLE, panel=PANEL, precision="bf16")
         self.table = mb.RankTable(self.quantiles)
         self.out = torch.empty((l1 - l0, n, n), dtype=torch.uint16, device=dev) if alloc_out else None
-        self.z_buf = torch.empty((n, HIDDEN), dtype=torch.float32, device=dev)
+        self.gatherer = ctx["gatherer"](n) if world > 1 else None
         self.launches = 0
         torch.cuda.synchronize()
 
@@ -320,7 +320,7 @@ class Job:
         z = self.ctx["encoder"](self.tok_shard, self.mask_shard)        # fusion encoder on this rank's drugs
         self.launches = self.ctx["encoder"].last_launch_count
         if self.world > 1:
-            z = scoring.all_gather_embeddings(z, self.n, out=self.z_buf)  # the path's only collective
+            z = self.gatherer.gather(z)                                  # the path's only exchange step
             self.launches += 1
         return z
 
@@ -415,7 +415,14 @@ def run_gpu_arm(args):
         t, m = host_inputs[n]
         return torch.from_numpy(t).to(dev), torch.from_numpy(m).to(dev)
 
-    ctx = {"dev": dev, "encoder": encoder, "inputs": inputs}
+    gatherers = {}
+
+    def gatherer(n):   # one peer-mapped table pair per catalogue size (shared by the jobs of this process)
+        if n not in gatherers:
+            gatherers[n] = scoring.PeerAllGather(n, HIDDEN, dev)
+        return gatherers[n]
+
+    ctx = {"dev": dev, "encoder": encoder, "inputs": inputs, "gatherer": gatherer}
 
     def barrier():
         if world > 1:
@@ -521,14 +528,13 @@ def run_gpu_arm(args):
     mask_host = torch.from_numpy(mask_np[r0:r1]).pin_memory()
     W_host = job.W[:Le].cpu().pin_memory()
     out_host = torch.empty((Le, N, N), dtype=torch.uint16).pin_memory()
-    z_buf2 = torch.empty((N, HIDDEN), dtype=torch.float32, device=dev)
 
     @torch.no_grad()
     def e2e_step():
         zd = encoder(tok_host.to(dev, non_blocking=True), mask_host.to(dev, non_blocking=True))
         Wd = W_host.to(dev, non_blocking=True)
         if world > 1:
-            zd = scoring.all_gather_embeddings(zd, N, out=z_buf2)
+            zd = gatherer(N).gather(zd)
         scoring.score_all_pairs_to_host(zd, Wd, out_host, out="rank", table=job.table, precision="bf16", chunk=10,
                                         symmetric=True)
 
@@ -657,6 +663,10 @@ def run_gpu_arm(args):
             line["config3_20k_x_953"] = big
         if enc_block is not None:
             line["encoder"] = enc_block
+        if world > 1:
+            g0 = gatherer(N)
+            line["exchange"] = {"mode": g0.mode, "note": "peer = mdg_peer_allgather (NVLink push kernel + epoch flags, one "
+                                "launch); collective = NCCL all_gather_into_tensor", "fallback_reason": g0.reason}
         if numa is not None:
             line["host_affinity"] = {"cores_before": len(numa[0]), "cores_gpu_local": len(numa[1])}
         if world == 1 and not args.no_cpu_baseline:

@@ -166,6 +166,24 @@ int mdg_pair_score_prepared(const float* z_rows, const float* z_cols, const void
                             int normalize_rows, const MdgRankTable* table, void* out, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/*
+ * The path's only exchange step (the reference is single-GPU): replicate the fused-embedding table
+ * z [N, D] on every GPU of one node.  Each rank pushes its row shard into EVERY rank's copy of the table through
+ * NVLink peer-mapped pointers and the ranks exchange one epoch flag; when the kernel retires on a rank, that rank's
+ * table holds all rows.  No library collective, no staging buffers, nothing on the host.
+ *   shard             [shard_rows, D] fp32, this rank's rows (16-byte aligned); lands at rows [row_offset, +shard_rows)
+ *   peer_tables_host  HOST array of `world` device pointers: rank r's table [N, D] as mapped into this process
+ *                     (e.g. torch symmetric memory / cudaIpc mappings); entry `rank` is the local table
+ *   peer_flags_host   HOST array of `world` device pointers to >= 16 zero-initialised uint32 per rank, same mapping
+ *   epoch             strictly increasing over successive calls, identical on all ranks (all ranks call in lockstep);
+ *                     a table must not be rewritten while a peer may still read it: alternate two tables (the Python
+ *                     wrapper does) or separate the calls by another synchronisation.
+ * A peer that never arrives trips a ~15 s in-kernel timeout (the launch fails) instead of hanging the device.
+ */
+int mdg_peer_allgather(const float* shard, int64_t shard_rows, int64_t row_offset, int32_t D,
+                       void* const* peer_tables_host, void* const* peer_flags_host, int32_t world, int32_t rank,
+                       uint32_t epoch, void* stream);
+
 /* F.normalize(x, p=2, dim=-1) with eps 1e-12 on rows of x [rows, dim] fp32 -> out (may alias x).  The reference applies
  * it to single tokens on its unimodal-bypass, raw-encoder-output and 'mean'/'add' fusion paths (models.py:849-850,
  * 861-862, 870-878, 890-891); the transformer path's token normalisation is fused into mdg_assemble_tokens and the

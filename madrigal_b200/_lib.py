@@ -74,6 +74,8 @@ SIGNATURES = {
     "mdg_pair_score_prepared": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
                                         c_int, c_int, c_int, POINTER(MdgRankTable), c_void_p, c_void_p, c_size_t,
                                         c_void_p]),
+    "mdg_peer_allgather": (c_int, [c_void_p, c_int64, c_int64, c_int32, POINTER(c_void_p), POINTER(c_void_p), c_int32,
+                                   c_int32, c_uint32, c_void_p]),
     "mdg_l2_normalize_rows": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "mdg_pair_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int32]),
     "mdg_pair_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int,

@@ -623,6 +623,36 @@ int mdg_pair_score_prepared(const float* z_rows, const float* z_cols, const void
                          workspace, workspace_bytes, static_cast<cudaStream_t>(stream_v), nullptr, nullptr, wt);
 }
 
+// ------------------------------------------------------------------------------------------------ peer all-gather
+int mdg_peer_allgather(const float* shard, int64_t shard_rows, int64_t row_offset, int32_t D,
+                       void* const* peer_tables_host, void* const* peer_flags_host, int32_t world, int32_t rank,
+                       uint32_t epoch, void* stream_v) {
+  if (!peer_tables_host || !peer_flags_host) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_peer_allgather: NULL pointer table");
+  if (world < 1 || world > mdg::kMaxPeers || rank < 0 || rank >= world)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_peer_allgather: world=%d rank=%d (1..%d ranks)", world, rank, mdg::kMaxPeers);
+  if (shard_rows < 0 || row_offset < 0 || D <= 0 || (D % 4) != 0)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_peer_allgather: rows=%lld offset=%lld D=%d (D must be a multiple of 4)",
+                (long long)shard_rows, (long long)row_offset, D);
+  if (shard_rows > 0 && (!shard || reinterpret_cast<uintptr_t>(shard) % 16 != 0))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_peer_allgather: shard must be a 16-byte aligned device pointer");
+  mdg::PeerTable pt;
+  memset(&pt, 0, sizeof(pt));
+  for (int r = 0; r < world; ++r) {
+    if (!peer_tables_host[r] || !peer_flags_host[r] || reinterpret_cast<uintptr_t>(peer_tables_host[r]) % 16 != 0)
+      return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_peer_allgather: table/flag pointer of rank %d is NULL or misaligned", r);
+    pt.buf[r] = static_cast<float*>(peer_tables_host[r]);
+    pt.flags[r] = static_cast<unsigned int*>(peer_flags_host[r]);
+  }
+  const long long n16 = shard_rows * (D / 4), off16 = row_offset * (D / 4);
+  long long blocks = (n16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 64) blocks = 64;
+  MDG_CUDA(launch_ex(mdg::peer_allgather_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream_v), /*pdl=*/true, reinterpret_cast<const float4*>(shard), n16, off16,
+                     pt, static_cast<int>(world), static_cast<int>(rank), static_cast<unsigned int>(epoch)));
+  return MDG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ row normalisation
 int mdg_l2_normalize_rows(const float* x, int64_t rows, int32_t dim, float* out, void* stream_v) {
   if (!x || !out) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_l2_normalize_rows: NULL pointer");

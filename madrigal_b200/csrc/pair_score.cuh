@@ -1270,6 +1270,59 @@ __global__ void __launch_bounds__(256) convert_z_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ peer all-gather
+// The path's only exchange step: every GPU replicates the fused-embedding table z [N, D].  Instead
+// of a library collective, each rank PUSHES its row shard into every rank's copy of the table through NVLink
+// peer-mapped pointers (16-byte stores, all G destinations from one load), then the last CTA to finish signals an
+// epoch flag on every peer (st.release.sys) and waits for the peers' flags (ld.acquire.sys): when the kernel retires,
+// the local table holds every rank's rows.  One launch, no intermediate buffers, no host synchronisation.
+constexpr int kMaxPeers = 8;
+struct PeerTable {
+  float* buf[kMaxPeers];           // rank r's table [N, D] as mapped into THIS process
+  unsigned int* flags[kMaxPeers];  // rank r's flag words: [0, 8) one slot per sender, [8] local CTA counter
+};
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256) peer_allgather_kernel(const float4* __restrict__ shard, long long n16,
+                                                             long long dst_off16, PeerTable pt, int world, int rank,
+                                                             unsigned int epoch) {
+  pdl_wait();  // the shard is the predecessor's (the encoder's) output
+  pdl_launch_dependents();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = shard[i];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q)
+      if (q < world) reinterpret_cast<float4*>(pt.buf[q])[dst_off16 + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int s_last;
+  unsigned int* mine = pt.flags[rank];
+  if (threadIdx.x == 0) s_last = (atomicAdd(mine + 8, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) mine[8] = 0u;  // for the next launch (stream-ordered after this one)
+  __threadfence_system();
+  if (threadIdx.x < world) {
+    st_release_sys(pt.flags[threadIdx.x] + rank, epoch);  // "rank's rows of epoch `epoch` have landed on you"
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_acquire_sys(mine + threadIdx.x) - epoch) < 0) {
+      if (clock64() - t0 > (1ll << 35)) {  // ~15 s: a peer never arrived; fail the launch instead of hanging the GPU
+        g_hang_code = 0x90000000u | threadIdx.x;
+        __threadfence_system();
+        asm volatile("trap;");
+      }
+    }
+  }
+}
+
 // F.normalize(x, p=2, dim=-1): x / max(||x||_2, 1e-12) per row (reference: models.py:849-850, 861-862, 890-891 — the
 // token normalisation of the unimodal bypass / raw-encoder-output / 'mean'-'add' fusion paths).  One warp per row.
 __global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __restrict__ x, long long rows, int dim,

@@ -57,6 +57,68 @@ def all_gather_embeddings(z_shard: torch.Tensor, N: int, group=None, out: Option
     return torch.cat(parts, dim=0)
 
 
+class PeerAllGather:
+    """Replicates the fused-embedding table with the library's own NVLink push kernel (mdg_peer_allgather) instead of
+    a collective library call: each rank stores its row shard straight into every rank's copy of the table through
+    peer-mapped pointers and the ranks exchange one epoch flag, all in ONE kernel launch on the caller's stream.
+
+    torch's symmetric-memory allocator is used for the plumbing only (allocate + exchange peer mappings of one buffer
+    holding two alternating tables and the flag words).  Where peer mappings are unavailable (CPU / gloo tests, no P2P
+    between the devices) `mode` is 'collective' and `gather` falls back to `all_gather_embeddings` (NCCL / gloo).
+    """
+
+    def __init__(self, N: int, D: int, device: torch.device, group=None):
+        import ctypes
+        import torch.distributed as dist
+        self.N, self.D, self.group = N, D, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.r0, self.r1 = row_shard(N, self.rank, self.world)
+        self.epoch = 0
+        self.mode, self.reason = "collective", ""
+        self._fallback = None
+        if device.type != "cuda" or self.world > 8 or D % 4 != 0:
+            self.reason = "needs CUDA devices, <= 8 ranks and D % 4 == 0"
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            table = N * D                                    # floats per table
+            total = 2 * table + 64                           # two alternating tables + 64 flag words
+            self._buf = symm_mem.empty(total, dtype=torch.float32, device=device)
+            self._buf.zero_()
+            pg = group if group is not None else dist.group.WORLD
+            self._hdl = symm_mem.rendezvous(self._buf, pg)
+            ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            if len(ptrs) != self.world or ptrs[self.rank] != self._buf.data_ptr():
+                raise RuntimeError("unexpected peer pointer table")
+            self._tables = [(ctypes.c_void_p * self.world)(*[p + 4 * k * table for p in ptrs]) for k in (0, 1)]
+            self._flags = (ctypes.c_void_p * self.world)(*[p + 4 * 2 * table for p in ptrs])
+            self._local = [self._buf[k * table:(k + 1) * table].view(N, D) for k in (0, 1)]
+            self._hdl.barrier()                               # every rank's flags are zero before anyone signals
+            self.mode = "peer"
+        except Exception as e:  # no symmetric memory / no P2P: use the collective
+            self.reason = f"{type(e).__name__}: {e}"
+
+    def gather(self, z_shard: torch.Tensor) -> torch.Tensor:
+        """[rows of this rank, D] -> the full table [N, D] (valid until the call after next)."""
+        if self.mode != "peer":
+            if self._fallback is None and self.N % self.world == 0:
+                self._fallback = torch.empty((self.N, self.D), dtype=z_shard.dtype, device=z_shard.device)
+            return all_gather_embeddings(z_shard, self.N, self.group, out=self._fallback)
+        from . import _lib
+        from .decoder import _require_cuda_f32, _stream_ptr
+        z = _require_cuda_f32(z_shard, "z_shard")
+        if tuple(z.shape) != (self.r1 - self.r0, self.D):
+            raise ValueError("z_shard is not this rank's row_shard of the table")
+        self.epoch += 1
+        k = self.epoch & 1
+        with torch.cuda.device(z.device):
+            _lib.check(_lib.lib().mdg_peer_allgather(z.data_ptr(), z.shape[0], self.r0, self.D, self._tables[k],
+                                                     self._flags, self.world, self.rank, self.epoch,
+                                                     _stream_ptr(z.device)), "mdg_peer_allgather")
+        return self._local[k]
+
+
 def score_all_pairs(z: torch.Tensor, weight: torch.Tensor, *, out: str = "rank", table: Optional[RankTable] = None,
                     precision: str = "bf16", label_range: Optional[Tuple[int, int]] = None,
                     normalize: bool = False, out_tensor: Optional[torch.Tensor] = None,

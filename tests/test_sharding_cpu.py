@@ -34,6 +34,15 @@ def _worker(rank, world, port, N, D, L, tmp):
     r0, r1 = scoring.row_shard(N, rank, world)
     z = scoring.all_gather_embeddings(torch.from_numpy(z_full[r0:r1].copy()), N)
     assert torch.equal(z, torch.from_numpy(z_full))
+    # the exchange-step object the scoring drivers use: on CPU tensors it reports the collective fallback and gives the
+    # same table (its peer-push mode needs CUDA peer mappings and is covered on the GPUs); equal shards reuse `out`
+    g = scoring.PeerAllGather(N, D, torch.device("cpu"))
+    assert g.mode == "collective" and (g.r0, g.r1) == (r0, r1)
+    assert torch.equal(g.gather(torch.from_numpy(z_full[r0:r1].copy())), torch.from_numpy(z_full))
+    if N % world == 0:
+        buf = torch.empty((N, D))
+        z2 = scoring.all_gather_embeddings(torch.from_numpy(z_full[r0:r1].copy()), N, out=buf)
+        assert z2.data_ptr() == buf.data_ptr() and torch.equal(z2, torch.from_numpy(z_full))
     l0, l1 = scoring.outcome_shard(L, rank, world)
     part = oracle.bilinear_scores(z.numpy(), z.numpy(), W, (l0, l1))
     np.save(os.path.join(tmp, f"part{rank}.npy"), part)
@@ -51,6 +60,12 @@ def test_two_rank_sharded_scoring_matches_single_rank(tmp_path):
     full = oracle.bilinear_scores(z, z, W)
     got = np.concatenate([np.load(tmp_path / f"part{r}.npy") for r in range(world)], axis=0)
     assert np.array_equal(got, full)  # sharding does not change any arithmetic
+
+
+def test_two_rank_equal_shards_gather_in_place(tmp_path):
+    N, D, L, world = 40, 16, 4, 2   # N divisible by the world size: all_gather_into_tensor straight into the table
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, N, D, L, str(tmp_path)), nprocs=world, join=True)
 
 
 def test_novel_ddi_encoder_dropin_plumbing_cpu():
