@@ -34,7 +34,7 @@ def _sources():
 def source_hash() -> str:
     h = hashlib.sha256()
     for f in _sources():
-        h.update(f.encode())
+        h.update(os.path.relpath(f, REPO_ROOT).encode())  # relative: the tree is copied to another root on the GPU box
         h.update(open(f, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()

@@ -51,6 +51,15 @@ __host__ __device__ constexpr bool epi_is_pwl(int e) { return e == EPI_RANK_U16_
 // The normaliser-layout epilogue with 8 epilogue warps is the software-pipelined one (two staging tiles per warp).
 __host__ __device__ constexpr bool epi_is_pipelined_mirror(int e, int ne) { return epi_is_mirror(e) && ne == 8; }
 __host__ __device__ constexpr int epi_staging_bufs(int e, int ne) { return epi_is_pipelined_mirror(e, ne) ? 2 : 1; }
+// Accumulator chunks (32 columns each) fetched per tcgen05.wait::ld by the row-per-lane epilogues.  Measured (round
+// 2, B200): fetching the warp's whole strip at once (4 chunks, stage released before the stores) does NOT pay outside
+// the top-k epilogue — fp32 logits 1.24 vs 1.18 ms (the per-chunk loop overlaps the next TMEM load with the previous
+// store), GEMM 1 unchanged, EPI_LINEAR with 2 chunks spills and slows the production encoder by 4 % — so it is 1.
+__host__ __device__ constexpr int epi_burst(int e, int ne) {
+  (void)e;
+  (void)ne;
+  return 1;
+}
 
 // Shared-memory plan for a kernel instance with NE epilogue warps (staging is per warp, so more epilogue warps
 // trade one B stage for staging space).
@@ -961,16 +970,45 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (acc_stage == 0) acc_phase ^= 1;
           continue;
         }
+        bool released = false;
         if (row0 < p.rows) {
-          for (int cc = col_begin; cc < col_end; cc += 32) {
+          // A tcgen05.ld issued while MMAs are queued only completes once the queue drains (~1.2k cycles), so the
+          // epilogues with registers to spare fetch kBurst chunks of the warp's strip per tcgen05.wait::ld instead of
+          // paying one round trip per chunk, and hand the accumulator stage back to the MMA warp as soon as the last
+          // burst has landed — before the stores.
+          constexpr int kBurst = epi_burst(EPI, NE);
+          for (int cc0 = col_begin; cc0 < col_end; cc0 += 32 * kBurst) {
+            uint32_t vv[kBurst][32];
+            if constexpr (kBurst > 1) {
+#pragma unroll
+              for (int q = 0; q < kBurst; ++q) {
+                const int ccq = cc0 + 32 * q, n0q = nb * kBN + ccq;
+                if (ccq < col_end && n0q < p.cols && !(p.lower_only && n0q > row0 + 31))
+                  tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                    static_cast<uint32_t>((acc_stage * 2 + ms) * kBN + ccq), vv[q]);
+              }
+              tmem_ld_wait();
+              if (cc0 + 32 * kBurst >= col_end) {  // every chunk of the tile this warp needs is in registers
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_t_empty(acc_stage));
+                released = true;
+              }
+            }
+#pragma unroll
+          for (int q = 0; q < kBurst; ++q) {
+            const int cc = cc0 + 32 * q;
+            if (cc >= col_end) break;
             const int n0 = nb * kBN + cc;
             if (n0 >= p.cols) break;
             if (p.lower_only && n0 > row0 + 31) break;  // every (row, col) of this chunk has col > row
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                   static_cast<uint32_t>((acc_stage * 2 + ms) * kBN + cc);
-            tmem_ld_32x32(taddr, v);
-            if constexpr (EPI != EPI_LINEAR) tmem_ld_wait();  // LINEAR overlaps its global loads with the TMEM load
+            uint32_t (&v)[32] = vv[q];
+            if constexpr (kBurst == 1) {
+              const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                     static_cast<uint32_t>((acc_stage * 2 + ms) * kBN + cc);
+              tmem_ld_32x32(taddr, v);
+              if constexpr (EPI != EPI_LINEAR) tmem_ld_wait();  // LINEAR overlaps its global loads with the TMEM load
+            }
 
             if constexpr (epi_is_rank(EPI)) {  // full layout (the normaliser layout has its own branch above)
               uint32_t pk[16];
@@ -1137,10 +1175,13 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
+          }
         }
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_t_empty(acc_stage));
+        if (!released) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_t_empty(acc_stage));
+        }
         acc_stage ^= 1;
         if (acc_stage == 0) acc_phase ^= 1;
       }

@@ -26,6 +26,6 @@ for _ in range(20): fn()
 torch.cuda.synchronize()
 buf = (ctypes.c_float * 256)(); n = _lib.lib().mdg_profile_read(buf, 256)
 ms = np.array(buf[:n])
-chk = int(out.view(torch.int16).to(torch.int64).sum().item())
+chk = sum(int(out[l].view(torch.int16).sum(dtype=torch.int64).item()) for l in range(L))
 print(f"epi={os.environ.get('MDG_MIRROR_EPI', 'default')} packed={packed} kind={kind} sym={sym} N={N} D={D} L={L}: kernel {ms.mean():.4f} ms (min {ms.min():.4f}) -> "
       f"{out.numel()*2.0/ms.mean()/1e6:.0f} GB/s out ({L*N*N/ms.mean()/1e9:.3f} T triples/s), checksum {chk}")
