@@ -367,8 +367,9 @@ class Job:
         lg = mb.pair_score(self.z_full[rows].contiguous(), self.z_full, self.W[j:j + 1], precision="bf16",
                            out="logit").cpu().numpy()                       # [1, R, n]
         exp = oracle.quantile_rank(thr, lg, "right")[0].astype(np.uint16)
-        got = self.out[j][rows].cpu().numpy()
-        got_t = self.out[j][:, rows].cpu().numpy().T
+        o16 = self.out[j].view(torch.int16)     # torch has no CUDA index kernel for uint16: same bits as int16
+        got = o16[rows].cpu().numpy().view(np.uint16)
+        got_t = o16[:, rows].cpu().numpy().view(np.uint16).T
         ok = True
         for k, r in enumerate(sample_rows):
             ok &= bool(np.array_equal(exp[k, :r], got[k, :r])) and int(got[k, r]) == 0   # row > col part + diagonal
@@ -557,7 +558,32 @@ def run_gpu_arm(args):
     e2e_matches = all_true(bool(torch.equal(out_host[:1].view(torch.int16), job.out[:1].cpu().view(torch.int16))))
     h2d = tok_host.numel() * 4 + mask_host.numel() + W_host.numel() * 4
     d2h = out_host.numel() * 2
-    del out_host, W_host
+    del out_host
+
+    # ---- the same call with the reduced-volume output layout (MDG_PAIRS_PACKED_TILES: no mirror image, half the D2H)
+    from madrigal_b200.decoder import packed_tiles_per_outcome, unpack_packed_tiles
+    packed_host = torch.empty((Le, packed_tiles_per_outcome(N), 32, 32), dtype=torch.uint16).pin_memory()
+
+    @torch.no_grad()
+    def e2e_packed_step():
+        zd = encoder(tok_host.to(dev, non_blocking=True), mask_host.to(dev, non_blocking=True))
+        Wd = W_host.to(dev, non_blocking=True)
+        if world > 1:
+            zd = gatherer(N).gather(zd)
+        scoring.score_all_pairs_to_host(zd, Wd, packed_host, out="rank", table=job.table, precision="bf16", chunk=10,
+                                        packed=True)
+
+    e2e_packed_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_packed_step()
+    barrier()
+    e2e_packed_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    packed_matches = all_true(bool(torch.equal(
+        unpack_packed_tiles(packed_host[:1].to(dev), N).view(torch.int16), job.out[:1].view(torch.int16))))
+    d2h_packed = packed_host.numel() * 2
+    del packed_host, W_host
 
     # ================================================================== strong-scaling anchor + checksum (N > 1)
     single = None
@@ -588,10 +614,14 @@ def run_gpu_arm(args):
 
     # ================================================================== configs[3] leg (needs >= 6 GPUs of 180 GB)
     big = None
-    if world >= 6 and args.workload == "auto":
+    dry = os.environ.get("MDG_BENCH_CONFIG3_DRYRUN")   # "drugs,outcomes": exercise the leg at a reduced size (test knob)
+    if (world >= 6 and args.workload == "auto") or dry:
         job.out = None
         del job
         torch.cuda.empty_cache()
+        if dry:
+            WORKLOADS["configs3"] = dict(name="DRY RUN of the configs[3] leg", drugs=int(dry.split(",")[0]),
+                                         outcomes=int(dry.split(",")[1]))
         big = run_config3_leg(ctx, world, rank, barrier, max_over_ranks, all_true, timed)
 
     # ================================================================== encoder stress (configs[4]) on one GPU
@@ -657,6 +687,13 @@ def run_gpu_arm(args):
                     "sample": (f"{int(le_t.item())} of {L_total} outcomes (pinned host output bounded to 10 GiB per rank)"
                                if int(le_t.item()) != L_total else "all outcomes"),
                     "aggregate_d2h_gbs": 2.0 * e2e_triples / (e2e_ms * 1e-3) / 1e9},
+            "e2e_packed_tiles": {"value": e2e_triples / (e2e_packed_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_packed_ms,
+                                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_packed,
+                                 "unpacked_equals_device_output": packed_matches,
+                                 "note": "same public call with packed=True: every unordered pair's rank reaches the host once, "
+                                         "as 32x32 lower-triangular tiles (half the PCIe volume); `value` counts the same ordered "
+                                         "triples; rebuilding the mirrored [L,N,N] array on the host "
+                                         "(decoder.unpack_packed_tiles) is NOT in this time — `e2e` above is the drop-in layout"},
             "gpu_launches": launches_per_step * steps,
         }
         if single is not None:
@@ -704,7 +741,8 @@ def run_config3_leg(ctx, world, rank, barrier, max_over_ranks, all_true, timed):
     sym_ok = all_true(sym_ok)
     s0, _ = job.checksum()
     ck = torch.tensor([s0], dtype=torch.int64, device=ctx["dev"])
-    dist.all_reduce(ck)
+    if world > 1:
+        dist.all_reduce(ck)
     job.out = None
     torch.cuda.empty_cache()
 

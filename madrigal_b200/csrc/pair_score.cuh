@@ -299,6 +299,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(sBar + 128 + 8 * i, 1);
       mbar_init(sBar + 160 + 8 * i, 1 + NE);
     }
+    mbar_init(sBar + 224, 1);  // rank-table bulk load (pipelined normaliser-layout epilogue)
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -601,6 +602,8 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t acc_phase = 0;
       int cur_l = -1;
       float scale = 0.f, bias = 0.f;
+      const uint32_t bar_lut = sBar + 224;
+      uint32_t lut_phase = 0;
 
       // ranks of one chunk: P[hf][i][s] = (row 16hf + 8s + fr, cols 8i + fc, +1) packed as b16x2
       auto lookup_chunk = [&](const uint32_t (&v)[2][16], uint32_t (&P)[2][4][2]) {
@@ -698,18 +701,17 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane)) {
         const TaskCoord c = decode_task(p, t);
         if (c.l != cur_l) {
-          named_bar_sync(1, NE * 32);  // everyone is done with the previous outcome's LUT
-          const uint4* src = reinterpret_cast<const uint4*>(p.lut + static_cast<size_t>(c.l) * kRankLutEntries);
-          const int tid = ew * 32 + lane;
-#pragma unroll 4
-          for (int i = tid; i < kRankLutEntries / 4; i += NE * 32) {
-            uint4 q = __ldg(src + i);
-            st_shared_v4(sLut + i * 16, q.x, q.y, q.z, q.w);
+          // new outcome: one bulk copy (TMA, 32 KB) of its table once every warp is done with the old one
+          named_bar_sync(1, NE * 32);
+          if (ew == 0 && elect_one()) {
+            mbar_arrive_expect_tx(bar_lut, kRankLutEntries * 4);
+            bulk_load_1d(sLut, p.lut + static_cast<size_t>(c.l) * kRankLutEntries, kRankLutEntries * 4, bar_lut);
           }
           scale = __ldg(p.affine + 2 * c.l);
           bias = __ldg(p.affine + 2 * c.l + 1);
           cur_l = c.l;
-          named_bar_sync(1, NE * 32);
+          mbar_wait(bar_lut, lut_phase, 9);
+          lut_phase ^= 1;
         }
         const int row0 = c.m0 + ms * kBM + quad * 32;  // first of this warp's 32 rows
         const bool rows_ok = row0 < p.rows;

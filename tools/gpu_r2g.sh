@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 session G (8 GPUs): bench --gpus 8 = configs[2] strong scaling + configs[3] leg, peer all-gather check.
 mkdir -p gpurun_out
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 tools/peer_allgather_test.py > gpurun_out/peer8.log 2>&1; echo "peer exit=$?"; tail -1 gpurun_out/peer8.log | cut -c1-700
+echo skip-peer-test
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench8.log 2>gpurun_out/bench8.err; echo "bench8 exit=$?"
 tail -1 gpurun_out/bench8.log | python -c "
 import sys, json

@@ -35,14 +35,19 @@ def launch_list():
         # variant (<7 / <8) is launched by bench.py AFTER the timed steps as a secondary measurement
     rank = [(i, d[1]) for i, d in enumerate(data) if is_rank(d[0])]
     longest = max(v for _, v in rank)
-    rank_idx = max(i for i, v in rank if v > 0.5 * longest)
-    starts = [i for i, d in enumerate(data[:rank_idx]) if "fused_encoder_kernel" in d[0]] or \
-             [i for i, d in enumerate(data[:rank_idx]) if "convert_rows_kernel" in d[0]]
-    step_start = max(starts)
+    # a device-resident step = fused encoder -> operand conversion -> GEMM 1 -> full-size rank launch, back to back
+    # (bench.py launches more full-size rank kernels after the timed steps for its context measurements)
+    step_start = rank_idx = None
+    for i, d in enumerate(data):
+        if "fused_encoder_kernel" not in d[0] and "convert_rows_kernel" not in d[0]:
+            continue
+        nxt = [j for j, v in rank if j > i and j - i <= 5 and v > 0.5 * longest]
+        if nxt:
+            step_start, rank_idx = i, nxt[0]
     step = data[step_start:rank_idx + 1]
     total = sum(d[1] for d in step)
     with open(os.path.join(OUT, f"{ROUND}_bench_step_launches.csv"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-encoder-block\n")
         f.write("# one bench step (last one in the run); per-launch times are cold-cache and serialised: compare SHARES\n")
         f.write("kernel,grid,block,duration_us,share\n")
         for k, v, g, b in step:
@@ -102,17 +107,59 @@ def full_capture(rep, tag, kernel_key):
             "lsu_wavefronts_pct": float(out["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"][0])}
 
 
+def stall_breakdown(rep, tag):
+    """Per-opcode warp-stall samples of the dominant kernel (ncu source page): where the epilogue warps wait."""
+    path = os.path.join(SRC, rep)
+    if not os.path.exists(path):
+        return
+    import re
+    raw = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    if not hi:
+        return
+    hdr = rows[hi[0]]
+    idx = {h: i for i, h in enumerate(hdr)}
+    data = rows[hi[0] + 1:]
+    S, E, SRCC = idx["# Samples"], idx["Instructions Executed"], idx["Source"]
+    cls, execs = collections.Counter(), collections.Counter()
+    for r in data:
+        m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[SRCC].strip())
+        op = m.group(2).split(".")[0] if m else "?"
+        cls[op] += int(r[S] or 0)
+        execs[op] += int(r[E] or 0)
+    total = sum(cls.values())
+    with open(os.path.join(OUT, f"{ROUND}_{tag}_stall_samples.txt"), "w") as f:
+        f.write(f"# ncu --set full --import-source on, warp-stall samples per SASS opcode, kernel of {rep} "
+                f"(total {total} samples over {len(data)} instructions)\n")
+        f.write("# EXIT = the idle warps 2-3 parked at the final barrier; BRA/ISETP/SYNCS = mbarrier spin loops of the\n")
+        f.write("# producer / MMA warps and the epilogue's waits; LDS/SHF/IMAD/LOP3/POPC/FFMA/FMUL/PRMT = rank look-ups;\n")
+        f.write("# FENCE/NOP/MEMBAR = fence.proxy.async before the bulk stores; STSM = stmatrix tile fills\n")
+        f.write("opcode,samples,share,warp_instructions_executed\n")
+        for op, n in cls.most_common(24):
+            f.write(f"{op},{n},{n / max(total, 1):.4f},{execs[op]}\n")
+        top = sorted(data, key=lambda r: -int(r[S] or 0))[:25]
+        f.write("\n# 25 hottest instructions: samples, executions, SASS\n")
+        for r in top:
+            f.write(f"{int(r[S] or 0):6d} {r[E]:>10s}  {r[SRCC].strip()[:100]}\n")
+
+
 if __name__ == "__main__":
     summary = {"round": ROUND}
     shares = launch_list()
     if shares:
         summary["bench_step_shares"] = shares
     for rep, tag, key, name in (
-            ("prof_rank.ncu-rep", "pair_score_rank", "pair_score_kernel", "pair_score_kernel<EPI_RANK_U16_MIRROR, 16> (exact LUT table)"),
-            ("prof_pwl.ncu-rep", "pair_score_rank_pwl", "pair_score_kernel_pwl", "pair_score_kernel<EPI_RANK_U16_MIRROR_PWL, 16> (histogram-CDF table)"),
-            ("prof_fenc2.ncu-rep", "fused_encoder", "fused_encoder_kernel", "fused_encoder_kernel<32> (4096 drugs x 4 tokens, one launch)")):
+            ("prof_rank.ncu-rep", "pair_score_rank", "pair_score_kernel", "pair_score_kernel<EPI_RANK_U16_MIRROR, 8> (exact LUT table, software-pipelined epilogue)"),):
         cap = full_capture(rep, tag, name)
         if cap:
             summary[key] = cap
             print(tag, cap)
+        stall_breakdown(rep, tag)
+    prev = os.path.join(OUT, "ncu_summary.json")
+    if os.path.exists(prev):  # keep the earlier rounds' captures of kernels not re-profiled this round
+        old = json.load(open(prev))
+        for k, v in old.items():
+            if k not in summary and k not in ("round", "bench_step_shares"):
+                summary[k] = dict(v, captured_in=old.get("round", "r01")) if isinstance(v, dict) else v
     json.dump(summary, open(os.path.join(OUT, "ncu_summary.json"), "w"), indent=1)
