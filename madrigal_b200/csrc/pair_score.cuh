@@ -56,9 +56,7 @@ __host__ __device__ constexpr int epi_staging_bufs(int e, int ne) { return epi_i
 // the top-k epilogue — fp32 logits 1.24 vs 1.18 ms (the per-chunk loop overlaps the next TMEM load with the previous
 // store), GEMM 1 unchanged, EPI_LINEAR with 2 chunks spills and slows the production encoder by 4 % — so it is 1.
 __host__ __device__ constexpr int epi_burst(int e, int ne) {
-  (void)e;
-  (void)ne;
-  return 1;
+  return (e == EPI_BF16_SPLIT && ne == 8) ? 4 : 1;
 }
 
 // Shared-memory plan for a kernel instance with NE epilogue warps (staging is per warp, so more epilogue warps
@@ -388,7 +386,8 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     {
       int stage = 0;
       uint32_t b_phase = 0;
-      int it = 0;  // executed tasks (parity of the A barriers)
+      int it = 0;  // executed tasks
+      int na = 0;  // tasks so far that (re)loaded the A panels: phase counter of the two A barriers
       int last_m0 = -1;
       if (p.stream_a) {
         const int ksteps = (p.nterm == 1) ? kb : 3 * kb;
@@ -416,25 +415,29 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else
       for (int t = tasks.next_producer(p.sched_counter); t >= 0; t = tasks.next_producer(p.sched_counter), ++it) {
         const TaskCoord c = decode_task(p, t);
-        mbar_wait(bar_a_empty, (it & 1) ^ 1, 1);
-        const bool a_resident = p.a_reuse && !p.a_batched && it > 0 && c.m0 == last_m0;  // same panels as the last task
+        // GEMM 1 (a_reuse): consecutive tasks of a CTA share the row block, so its z panels stay in shared memory and
+        // neither warp touches the A barriers — the B ring keeps streaming across the task boundary instead of
+        // draining at every task (one tile per task there: the drain was 2/3 of GEMM 1's time)
+        const bool a_resident = p.a_reuse && !p.a_batched && it > 0 && c.m0 == last_m0;
         last_m0 = c.m0;
-        if (a_resident) {
-          if (elect_one()) mbar_arrive(bar_a_full);
-        } else if (elect_one()) {
-          mbar_arrive_expect_tx(bar_a_full, n_apanels * kPanelBytes);
-          for (int pn = 0; pn < n_apanels; ++pn) {
-            int row, kc;
-            if (p.nterm == 1) {
-              int ms = pn / kb;
-              row = c.m0 + ms * kBM;
-              kc = (pn - ms * kb) * kBK;
-            } else {
-              row = c.m0;
-              kc = pn * kBK;
+        if (!a_resident) {
+          mbar_wait(bar_a_empty, (na & 1) ^ 1, 1);  // every MMA that read the previous panels has completed
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_a_full, n_apanels * kPanelBytes);
+            for (int pn = 0; pn < n_apanels; ++pn) {
+              int row, kc;
+              if (p.nterm == 1) {
+                int ms = pn / kb;
+                row = c.m0 + ms * kBM;
+                kc = (pn - ms * kb) * kBK;
+              } else {
+                row = c.m0;
+                kc = pn * kBK;
+              }
+              tma_load_3d(sA + pn * kPanelBytes, &tmA, bar_a_full, kc, row, p.a_batched ? c.l : 0);
             }
-            tma_load_3d(sA + pn * kPanelBytes, &tmA, bar_a_full, kc, row, p.a_batched ? c.l : 0);
           }
+          ++na;
         }
         __syncwarp();
         for (int nb = c.nb0; nb < c.nb1; ++nb) {
@@ -471,6 +474,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int acc_stage = 0;
       uint32_t acc_phase = 0;
       int it = 0;
+      int na = 0, last_m0 = -1;  // A-barrier phase counter / row block of the previous task (as in the producer)
       if (p.stream_a) {
         const int ksteps = (p.nterm == 1) ? kb : 3 * kb;
         for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane)) {
@@ -506,7 +510,16 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else
       for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane), ++it) {
         const TaskCoord c = decode_task(p, t);
-        mbar_wait(bar_a_full, it & 1, 3);
+        const bool a_resident = p.a_reuse && !p.a_batched && it > 0 && c.m0 == last_m0;  // as in the producer
+        last_m0 = c.m0;
+        if (!a_resident) {
+          if (it > 0) {  // hand the old panels back: tracks every MMA issued so far
+            if (elect_one()) umma_commit(bar_a_empty);
+            __syncwarp();
+          }
+          mbar_wait(bar_a_full, na & 1, 3);
+          ++na;
+        }
         for (int nb = c.nb0; nb < c.nb1; ++nb) {
           mbar_wait(bar_t_empty(acc_stage), acc_phase ^ 1, 4);
           tc_fence_after_sync();
@@ -565,8 +578,6 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           acc_stage ^= 1;
           if (acc_stage == 0) acc_phase ^= 1;
         }
-        if (elect_one()) umma_commit(bar_a_empty);  // every MMA of this task has read the resident A panels
-        __syncwarp();
       }
     }
   } else if (warp >= kFirstEpiWarp) {
