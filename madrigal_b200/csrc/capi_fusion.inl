@@ -76,6 +76,9 @@ int run_linear(const __nv_bfloat16* A, long long rows, const __nv_bfloat16* W, i
     if (rc) return rc;
     p.use_tma_store2 = 1;
   }
+  // in-place residual stream (h += linear(...)): fetch the residual tile by TMA through the output's tensor map
+  static const bool no_res_tma = getenv("MDG_LINEAR_RES_DIRECT") != nullptr;  // A/B knob: per-lane residual row loads
+  p.res_tma = (!no_res_tma && p.use_tma_store && residual != nullptr && residual == out_f32 && res_ld == out_ld) ? 1 : 0;
   return launch_pair_kernel(tmA, tmB, tmO1, p, mdg::EPI_LINEAR, stream, &tmO2);
 }
 

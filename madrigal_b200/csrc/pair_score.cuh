@@ -69,7 +69,7 @@ struct PairSmem {
   static constexpr int kStaging = kB + kBStages * kPanelBytes;
   static constexpr int kLut = kStaging + NE * NBUF * kStagingBytesPerWarp;
   static constexpr int kBar = kLut + kRankLutEntries * 4;
-  static constexpr int kTotal = kBar + 256;  // mbarriers, TMEM slot, dynamic-scheduler task ring
+  static constexpr int kTotal = kBar + 512;  // mbarriers, TMEM slot, dynamic-scheduler task ring, per-warp residual barriers
   static constexpr int kBytes = kTotal + 1024;  // + slack for manual 1024-byte alignment
   static constexpr int kThreads = (kFirstEpiWarp + NE) * 32;
   static_assert(kBytes <= 232448, "exceeds 227 KB of shared memory per CTA");
@@ -110,6 +110,8 @@ struct PairScoreParams {
   long long bf16_ld;
   int bf16_lo_off;
   int act;  // 0 none, 1 relu, 2 exact-erf gelu
+  int res_tma;  // the residual IS the fp32 output tensor (in-place residual stream) and it is TMA-addressable: the
+                // residual tile is fetched with a TMA load through tmOut into the staging tile the result is stored from
   // ---- EPI_TOPK: append every score >= topk_thresh[l] to the outcome's candidate list (no dense output at all)
   const float* topk_thresh;       // [L]
   unsigned int* topk_count;       // [L] atomic counters (may exceed topk_cap: overflow is detected by the caller)
@@ -298,6 +300,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(sBar + 160 + 8 * i, 1 + NE);
     }
     mbar_init(sBar + 224, 1);  // rank-table bulk load (pipelined normaliser-layout epilogue)
+    for (int i = 0; i < 2 * NE; ++i) mbar_init(sBar + 256 + 8 * i, 1);  // EPI_LINEAR: residual tile loads, two per warp
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -786,6 +789,8 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ss.swz = static_cast<uint32_t>((lane >> 1) & 3);  // 64-byte swizzle: chunk ^= (row >> 1) & 3
     ss.cur = 0;
     ss.pending = 0;
+    const uint32_t res_bar = sBar + 256 + 16 * ew;  // EPI_LINEAR: this warp's two residual-tile barriers
+    uint32_t res_phase = 0;                         // bit hf = phase of barrier hf
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     int cur_l = -1;
@@ -1065,7 +1070,26 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               // residual, likewise issued before the accumulator is needed
               float rs[32];
               const bool row_ok = my_row < p.rows;
-              if (p.residual != nullptr && row_ok) {
+              const bool res_tma = p.res_tma != 0;
+              if (res_tma) {
+                // in-place residual stream: the two 16-column halves of this chunk's residual tile are TMA-loaded into
+                // the warp's two staging tiles (the tiles the result is stored from, same tensor map and coordinates)
+                // while the accumulator is still on its way — instead of 8 per-lane 16-byte row loads that touch 32
+                // different lines each (the LSU-bound pattern of the round-1 epilogue)
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+                ss.pending = 0;
+                if (lane == 0) {
+#pragma unroll
+                  for (int hf = 0; hf < 2; ++hf) {
+                    if (n0 + hf * 16 >= p.cols) break;
+                    mbar_arrive_expect_tx(res_bar + 8 * hf, kStagingBytesPerWarp);
+                    tma_load_3d(ss.buf[hf], &tmOut, res_bar + 8 * hf, n0 + hf * 16, row0, 0);
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) rs[j] = 0.f;
+              } else if (p.residual != nullptr && row_ok) {
                 const float* r = p.residual + static_cast<long long>(my_row) * p.res_ld + n0;
                 if (full && (p.res_ld & 3) == 0) {
 #pragma unroll
@@ -1097,7 +1121,34 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
 #pragma unroll
               for (int j = 0; j < 32; ++j) y[j] += rs[j];
-              if (p.out_f32 != nullptr) {
+              if (res_tma) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  if (n0 + hf * 16 >= p.cols) break;
+                  mbar_wait(res_bar + 8 * hf, (res_phase >> hf) & 1u, 10);
+                  res_phase ^= 1u << hf;
+                  const uint32_t base = ss.buf[hf] + ss.row_off;  // this lane's row of the residual tile (64B swizzle)
+#pragma unroll
+                  for (int ch = 0; ch < 4; ++ch) {
+                    const uint32_t addr = base + ((static_cast<uint32_t>(ch) ^ ss.swz) << 4);
+                    uint32_t r0, r1, r2, r3;
+                    ld_shared_v4(addr, r0, r1, r2, r3);
+                    y[hf * 16 + 4 * ch] += __uint_as_float(r0);
+                    y[hf * 16 + 4 * ch + 1] += __uint_as_float(r1);
+                    y[hf * 16 + 4 * ch + 2] += __uint_as_float(r2);
+                    y[hf * 16 + 4 * ch + 3] += __uint_as_float(r3);
+                    st_shared_v4(addr, __float_as_uint(y[hf * 16 + 4 * ch]), __float_as_uint(y[hf * 16 + 4 * ch + 1]),
+                                 __float_as_uint(y[hf * 16 + 4 * ch + 2]), __float_as_uint(y[hf * 16 + 4 * ch + 3]));
+                  }
+                  fence_proxy_async_smem();
+                  __syncwarp();
+                  if (lane == 0) {
+                    tma_store_3d(&tmOut, ss.buf[hf], n0 + hf * 16, row0, 0);
+                    tma_store_commit();
+                  }
+                  ++ss.pending;
+                }
+              } else if (p.out_f32 != nullptr) {
                 if (p.use_tma_store) {
 #pragma unroll
                   for (int hf = 0; hf < 2; ++hf) {  // two 16-column (64-byte) fills
