@@ -167,14 +167,16 @@ class TransformerFusion(nn.Module):
 
 class MLPAdaptor(nn.Module):
     """Drop-in for the reference `MLPAdaptor` (models.py:459-518): same ctor and `fc.*` state_dict keys.
-    Eval-mode arithmetic only (Dropout = identity); norm 'ln' or None; activation relu or gelu."""
+    Eval-mode arithmetic only (Dropout = identity); norm 'ln', 'bn' or None; activation relu or gelu.  norm='bn'
+    (nn.BatchNorm1d, models.py:154,492) is an inference-only path: in eval mode it is a per-feature affine map of the
+    running statistics, folded once into the Linear that follows it (W' = W diag(s), b' = b + W t) on the device."""
 
     def __init__(self, in_dim: int, hidden_dims: list, output_dim: int, p: float, norm: str, actn: str,
                  order: str = 'nd', precision: str = "fp32"):
         super().__init__()
         if actn not in _lib.MDG_ACTN:
             raise NotImplementedError(actn)
-        if norm not in ('ln', None, 'None'):
+        if norm not in ('ln', 'bn', None, 'None'):
             raise NotImplementedError(norm)
         if order not in ('nd', 'dn'):
             raise NotImplementedError(order)
@@ -183,7 +185,7 @@ class MLPAdaptor(nn.Module):
         layers = [nn.Linear(in_dim, hidden_dims[0]), act()]
         for i in range(len(hidden_dims) - 1):
             block = []
-            nrm = nn.LayerNorm(hidden_dims[i]) if norm == 'ln' else None
+            nrm = nn.LayerNorm(hidden_dims[i]) if norm == 'ln' else (nn.BatchNorm1d(hidden_dims[i]) if norm == 'bn' else None)
             drop = nn.Dropout(p) if p != 0 else None
             for m in ((nrm, drop) if order == 'nd' else (drop, nrm)):
                 if m is not None:
@@ -191,8 +193,36 @@ class MLPAdaptor(nn.Module):
             layers += block + [nn.Linear(hidden_dims[i], hidden_dims[i + 1]), act()]
         layers.append(nn.Linear(hidden_dims[-1], output_dim))
         self.fc = nn.Sequential(*layers)  # container only
+        self._bn_folded = None
+
+    def _fold_batchnorm(self):
+        """{index of the Linear: (W', b')} with the preceding eval-mode BatchNorm1d folded in; cached until a parameter
+        or running statistic changes.  Weight preprocessing (like mdg_fusion_prepare's LayerNorm fold), not path
+        arithmetic: the activations only ever see mdg_mlp_forward."""
+        mods = list(self.fc)
+        tensors = [t for m in mods for t in list(m.parameters(recurse=False)) + list(m.buffers(recurse=False))]
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._bn_folded is not None and self._bn_folded[0] == key:
+            return self._bn_folded[1]
+        out, pending = {}, None
+        with torch.no_grad():
+            for i, m in enumerate(mods):
+                if isinstance(m, nn.BatchNorm1d):
+                    s = m.weight / torch.sqrt(m.running_var + m.eps)
+                    pending = (s, m.bias - m.running_mean * s)
+                elif isinstance(m, nn.Linear) and pending is not None:
+                    s, t = pending
+                    out[i] = ((m.weight * s[None, :]).contiguous(), (m.bias + m.weight @ t).contiguous())
+                    pending = None
+        self._bn_folded = (key, out)
+        return out
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        has_bn = any(isinstance(m, nn.BatchNorm1d) for m in self.fc)
+        if has_bn and self.training:
+            raise RuntimeError("madrigal_b200.MLPAdaptor(norm='bn') is an inference path (BatchNorm1d uses its running "
+                               "statistics): call .eval() first")
+        folded = self._fold_batchnorm() if has_bn else {}
         x2 = _require_cuda_f32(x, "x")
         lead = x2.shape[:-1]
         x2 = x2.reshape(-1, x2.shape[-1]).contiguous()
@@ -206,13 +236,14 @@ class MLPAdaptor(nn.Module):
         m.actn = _lib.MDG_ACTN[self.actn]
         pending_ln = None
         i = 0
-        for layer in self.fc:
+        for pos, layer in enumerate(self.fc):
             if isinstance(layer, nn.LayerNorm):
                 pending_ln = layer
             elif isinstance(layer, nn.Linear):
                 m.dims[i] = layer.in_features
                 m.dims[i + 1] = layer.out_features
-                m.weight[i], m.bias[i] = layer.weight.data_ptr(), layer.bias.data_ptr()
+                wt, bs = folded.get(pos, (layer.weight, layer.bias))
+                m.weight[i], m.bias[i] = wt.data_ptr(), bs.data_ptr()
                 if pending_ln is not None:
                     m.ln_weight[i], m.ln_bias[i] = pending_ln.weight.data_ptr(), pending_ln.bias.data_ptr()
                     pending_ln = None

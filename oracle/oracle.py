@@ -275,7 +275,9 @@ def sinusoidal_pe(d_model: int, max_len: int, seq_len: int) -> np.ndarray:
 def mlp_adaptor(layers: Sequence[dict], x: np.ndarray, dtype=F32) -> np.ndarray:
     """MLPAdaptor.forward (eval), models.py:459-518, as a list of ops in nn.Sequential order.
 
-    Each entry: {'op': 'linear', 'w', 'b'} | {'op': 'ln', 'w', 'b'} | {'op': 'act', 'actn'}.
+    Each entry: {'op': 'linear', 'w', 'b'} | {'op': 'ln', 'w', 'b'} | {'op': 'bn', 'w', 'b', 'mean', 'var'} (eval-mode
+    nn.BatchNorm1d, norm='bn' at models.py:154,492: (h - running_mean) / sqrt(running_var + 1e-5) * w + b) |
+    {'op': 'act', 'actn'}.
     """
     h = x.astype(dtype)
     for L in layers:
@@ -283,6 +285,9 @@ def mlp_adaptor(layers: Sequence[dict], x: np.ndarray, dtype=F32) -> np.ndarray:
             h = _linear(h, L["w"].astype(dtype), L["b"].astype(dtype))
         elif L["op"] == "ln":
             h = _layer_norm(h, L["w"].astype(dtype), L["b"].astype(dtype))
+        elif L["op"] == "bn":
+            h = ((h - L["mean"].astype(dtype)) / np.sqrt(L["var"].astype(dtype) + dtype(1e-5)) * L["w"].astype(dtype)
+                 + L["b"].astype(dtype)).astype(dtype)
         elif L["op"] == "act":
             h = _activation(h, L["actn"])
         else:

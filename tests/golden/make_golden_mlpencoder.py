@@ -26,13 +26,16 @@ out = {}
 for case in synth.MLPENCODER_CASES:
     ops = synth.mlp_encoder_ops(case)
     mod = m.MLPEncoder(case["in_dim"], case["hidden"], case["out_dim"], case["p"], case["norm"], case["actn"], case["order"])
-    layers = [x for x in mod.fc if isinstance(x, (nn.Linear, nn.LayerNorm))]
-    params = [o for o in ops if o["op"] in ("linear", "ln")]
+    layers = [x for x in mod.fc if isinstance(x, (nn.Linear, nn.LayerNorm, nn.BatchNorm1d))]
+    params = [o for o in ops if o["op"] in ("linear", "ln", "bn")]
     assert len(layers) == len(params), (len(layers), len(params))
     for x, o in zip(layers, params):
         assert tuple(x.weight.shape) == o["w"].shape
         x.weight.data = torch.from_numpy(o["w"])
         x.bias.data = torch.from_numpy(o["b"])
+        if o["op"] == "bn":
+            x.running_mean.data = torch.from_numpy(o["mean"])
+            x.running_var.data = torch.from_numpy(o["var"])
     mod.eval()
     x = np.random.default_rng(case["seed"]).standard_normal((case["B"], case["in_dim"])).astype(np.float32)
     y = mod(torch.from_numpy(x)).numpy()

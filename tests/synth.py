@@ -175,6 +175,7 @@ MLPENCODER_CASES = [
     dict(name="cv_default_no_norm", in_dim=96, hidden=[64, 48], out_dim=32, p=0.1, norm=None, actn="relu", order="nd", B=9, seed=11),
     dict(name="tx_ln_gelu", in_dim=978, hidden=[128, 64, 64], out_dim=128, p=0.0, norm="ln", actn="gelu", order="nd", B=7, seed=12),
     dict(name="ln_dropout_first", in_dim=40, hidden=[32, 24], out_dim=16, p=0.2, norm="ln", actn="relu", order="dn", B=5, seed=13),
+    dict(name="bn_eval_running_stats", in_dim=56, hidden=[48, 40, 24], out_dim=32, p=0.1, norm="bn", actn="gelu", order="nd", B=6, seed=14),
 ]
 
 
@@ -187,4 +188,11 @@ def mlp_encoder_ops(case):
             o["actn"] = case["actn"]
     if case["norm"] is None:
         ops = [o for o in ops if o["op"] != "ln"]
+    if case["norm"] == "bn":  # eval-mode BatchNorm1d in the norm slots: same affine parameters + running statistics
+        rng = np.random.default_rng(case["seed"] + 3000)
+        for o in ops:
+            if o["op"] == "ln":
+                o["op"] = "bn"
+                o["mean"] = (0.3 * rng.standard_normal(o["w"].shape[0])).astype(F32)
+                o["var"] = (0.5 + rng.random(o["w"].shape[0])).astype(F32)
     return ops

@@ -581,3 +581,34 @@ def test_normalize_paths_use_the_row_normalise_kernel(mb, cuda_device):
     keep = ~masks
     ref = (x * keep[:, :, None]).sum(1) / keep.sum(1, keepdims=True)
     assert np.abs(z - ref).max() <= 1e-5
+
+
+@pytest.mark.parametrize("case", synth.MLPENCODER_CASES, ids=lambda c: c["name"])
+def test_mlp_encoder_vs_reference_golden(mb, cuda_device, case):
+    """madrigal_b200.MLPEncoder against the reference `MLPEncoder` outputs (golden_mlpencoder.npz), norm None / 'ln' /
+    'bn' (eval-mode BatchNorm1d folded into the following Linear), both dropout orders; fp32-parity mode, 1e-3."""
+    g = np.load(os.path.join(HERE, "golden", "golden_mlpencoder.npz"))
+    ops = synth.mlp_encoder_ops(case)
+    params = [o for o in ops if o["op"] in ("linear", "ln", "bn")]
+    mod = mb.MLPEncoder(case["in_dim"], case["hidden"], case["out_dim"], case["p"], case["norm"], case["actn"], case["order"])
+    layers = [x for x in mod.fc if isinstance(x, (torch.nn.Linear, torch.nn.LayerNorm, torch.nn.BatchNorm1d))]
+    assert len(layers) == len(params)
+    with torch.no_grad():
+        for x, o in zip(layers, params):
+            x.weight.copy_(torch.from_numpy(o["w"]))
+            x.bias.copy_(torch.from_numpy(o["b"]))
+            if o["op"] == "bn":
+                x.running_mean.copy_(torch.from_numpy(o["mean"]))
+                x.running_var.copy_(torch.from_numpy(o["var"]))
+    mod = mod.to(cuda_device)
+    xin = np.random.default_rng(case["seed"]).standard_normal((case["B"], case["in_dim"])).astype(np.float32)
+    if case["norm"] == "bn":
+        with pytest.raises(RuntimeError, match="inference"):
+            mod.train()(gpu(xin, cuda_device))
+    y = mod.eval()(gpu(xin, cuda_device)).detach().cpu().numpy()
+    assert_close(y, g[f"{case['name']}.y"], 1e-3, case["name"])
+    if case["norm"] == "bn":  # the fold is refreshed when a running statistic changes
+        with torch.no_grad():
+            [m for m in mod.fc if isinstance(m, torch.nn.BatchNorm1d)][0].running_mean.add_(0.5)
+        y2 = mod(gpu(xin, cuda_device)).detach().cpu().numpy()
+        assert np.abs(y2 - y).max() > 1e-4

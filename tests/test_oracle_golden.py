@@ -254,7 +254,7 @@ def test_mlp_encoder_matches_reference(case):
     tests/golden/make_golden_mlpencoder.py), and the drop-in's `fc.*` keys vs the reference module's."""
     g = np.load(os.path.join(G, "golden_mlpencoder.npz"))
     ops = synth.mlp_encoder_ops(case)
-    params = [o for o in ops if o["op"] in ("linear", "ln")]
+    params = [o for o in ops if o["op"] in ("linear", "ln", "bn")]
     chk = synth.params_checksum([o["w"] for o in params] + [o["b"] for o in params])
     assert abs(chk - float(g[f"{case['name']}.checksum"])) < 1e-6
     x = np.random.default_rng(case["seed"]).standard_normal((case["B"], case["in_dim"])).astype(np.float32)
