@@ -217,17 +217,20 @@ bool fused_encoder_aligned(const MdgFusionWeights* w, const MdgFusionCfg* cfg, c
 
 template <int HD>
 int launch_fused_instance(const CUtensorMap* tm, const mdg::FusedEncParams& p, int grid, cudaStream_t stream) {
-  static bool attr_set[64] = {false};
+  static std::once_flag attr_once[kMaxDevices];
+  static cudaError_t attr_err[kMaxDevices];
   int dev = 0;
   MDG_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    MDG_CUDA(cudaFuncSetAttribute(mdg::fused_encoder_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  mdg::kFeSmemBytes));
-    attr_set[dev] = true;
-  }
-  mdg::fused_encoder_kernel<HD><<<grid, mdg::kFeThreads, mdg::kFeSmemBytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
-                                                                                     tm[5], tm[6], tm[7], p);
-  MDG_CUDA(cudaGetLastError());
+  if (dev < 0 || dev >= kMaxDevices) return fail(MDG_ERR_UNSUPPORTED, "device index %d out of range", dev);
+  std::call_once(attr_once[dev], [dev] {
+    attr_err[dev] = cudaFuncSetAttribute(mdg::fused_encoder_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         mdg::kFeSmemBytes);
+  });
+  MDG_CUDA(attr_err[dev]);
+  // programmatic dependent launch: barrier init, TMEM allocation and descriptor prefetch overlap the previous
+  // kernel's tail; the kernel waits (griddepcontrol.wait) before it reads the tokens
+  MDG_CUDA(launch_ex(mdg::fused_encoder_kernel<HD>, dim3(grid), dim3(mdg::kFeThreads), mdg::kFeSmemBytes, stream, true,
+                     tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], p));
   ++g_last_launches;
   return MDG_OK;
 }

@@ -199,6 +199,11 @@ fused_encoder_kernel(const __grid_constant__ CUtensorMap tm_e2l, const __grid_co
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kFeSmemBar + 64);
+  // PDL launch: the prologue above overlapped the previous kernel's tail; the tokens may be that kernel's output, so
+  // everything else waits for it.  (Waiting only before the first z store instead was measured: -2 us per bench
+  // step, not worth an aliasing rule on the inputs.)
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int Dl = p.Dl, kp_d = p.kp_d, kp_e = p.kp_e;
   constexpr int hd = HD;

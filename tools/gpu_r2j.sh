@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 python -c "from madrigal_b200 import build; import sys; sys.exit(0 if build.library_is_current() else 1)" || { echo "STALE LIBRARY: rebuild before gpurun"; exit 1; }
 python -m pytest tests -x -q -m gpu > gpurun_out/pytest.log 2>&1; echo "pytest exit=$?"; tail -2 gpurun_out/pytest.log
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench.log 2>gpurun_out/bench.err; echo "bench exit=$?"
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-encoder-block > gpurun_out/bench.log 2>gpurun_out/bench.err; echo "bench exit=$?"
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/bench.log").read().strip().splitlines()[-1])
