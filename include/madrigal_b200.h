@@ -237,6 +237,23 @@ typedef enum MdgEnsembleMode { MDG_ENS_MEAN_F32 = 0, MDG_ENS_GMEAN_F32 = 1, MDG_
 int mdg_ensemble_reduce(const void* const* members_host, int32_t K, int64_t n, int mode, float rank_scale, float* out,
                         void* stream);
 
+/*
+ * Ensemble of FUSED quantile ranks (reference: scipy gmean of the checkpoints' normalised ranks followed by the same
+ * rank normalisation, notebooks/generate_embeddings.ipynb:434, 634-649) in the quantile-table formulation, uint16 in,
+ * uint16 out:
+ *     g[l, i]   = sum_k ilog_table[ members[k][l, i] ]                     (the gmean's log-sum, fixed point)
+ *     ranks_out = np.searchsorted(ens_table->thresholds[l], float32(g), side='right'), 0 where every member rank is 0
+ *                 (the diagonal of the normaliser layout)
+ *  or logsum_out = float32(g)  — builder mode: feed a reference panel's g to mdg_lower_triangle_quantiles and
+ *                 mdg_rank_table_build to obtain `ens_table` (exact-LUT kind).
+ * members_host: HOST array of K device pointers to uint16 [L, n_per_outcome] (16-byte aligned; n % 8 == 0 unless L == 1);
+ * ilog_table: device uint16 [Q + 1], e.g. round(1024 * (log2(max(r, 0.5)) + 1)) — it DEFINES the fixed-point log, so a
+ * host restatement with the same table is bit-exact.  Exactly one of ranks_out / logsum_out is non-NULL.
+ */
+int mdg_ensemble_rank_u16(const void* const* members_host, int32_t K, int64_t L, int64_t n_per_outcome,
+                          const uint16_t* ilog_table, int32_t Q, const MdgRankTable* ens_table, uint16_t* ranks_out,
+                          float* logsum_out, void* stream);
+
 /* Number of kernel launches the last successful mdg_pair_score call on this thread enqueued (for bench accounting). */
 int mdg_last_launch_count(void);
 

@@ -85,6 +85,8 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t,
                                       c_void_p]),
     "mdg_ensemble_reduce": (c_int, [POINTER(c_void_p), c_int32, c_int64, c_int, c_float, c_void_p, c_void_p]),
+    "mdg_ensemble_rank_u16": (c_int, [POINTER(c_void_p), c_int32, c_int64, c_int64, c_void_p, c_int32,
+                                      POINTER(MdgRankTable), c_void_p, c_void_p, c_void_p]),
     "mdg_last_launch_count": (c_int, []),
     "mdg_profile_enable": (c_int, [c_int]),
     "mdg_profile_read": (c_int, [POINTER(c_float), c_int]),

@@ -709,6 +709,58 @@ int mdg_ensemble_reduce(const void* const* members_host, int32_t K, int64_t n, i
   return MDG_OK;
 }
 
+int mdg_ensemble_rank_u16(const void* const* members_host, int32_t K, int64_t L, int64_t n_per_outcome,
+                          const uint16_t* ilog_table, int32_t Q, const MdgRankTable* ens_table, uint16_t* ranks_out,
+                          float* logsum_out, void* stream_v) {
+  if (!members_host || !ilog_table) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_ensemble_rank_u16: NULL pointer");
+  if ((ranks_out == nullptr) == (logsum_out == nullptr))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_ensemble_rank_u16: give exactly one of ranks_out and logsum_out");
+  if (K < 1 || K > MDG_MAX_ENSEMBLE) return fail(MDG_ERR_UNSUPPORTED, "mdg_ensemble_rank_u16: K=%d (1..%d)", K, MDG_MAX_ENSEMBLE);
+  if (L < 0 || n_per_outcome < 0 || L > 65535) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_ensemble_rank_u16: bad sizes");
+  if (Q < 1 || Q > MDG_RANK_MAX_Q) return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_ensemble_rank_u16: Q=%d", Q);
+  if (ranks_out) {
+    if (!ens_table || !ens_table->lut || !ens_table->affine)
+      return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_ensemble_rank_u16: rank output needs the ensemble rank table");
+    if (ens_table->kind != MDG_RANK_LUT) return fail(MDG_ERR_UNSUPPORTED, "mdg_ensemble_rank_u16: exact-LUT tables only");
+    if (ens_table->L < L) return fail(MDG_ERR_INVALID_ARGUMENT, "ensemble table has %d outcomes, need %lld", ens_table->L, (long long)L);
+  }
+  if ((n_per_outcome % 8) != 0 && L > 1)
+    return fail(MDG_ERR_UNSUPPORTED, "mdg_ensemble_rank_u16: n_per_outcome must be a multiple of 8 when L > 1 (16-byte accesses)");
+  if (L == 0 || n_per_outcome == 0) return MDG_OK;
+  mdg::EnsemblePtrs ptrs;
+  for (int k = 0; k < 16; ++k) ptrs.p[k] = k < K ? members_host[k] : nullptr;
+  for (int k = 0; k < K; ++k)
+    if (!ptrs.p[k] || reinterpret_cast<uintptr_t>(ptrs.p[k]) % 16 != 0)
+      return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_ensemble_rank_u16: member %d is NULL or not 16-byte aligned", k);
+  const size_t smem = ((static_cast<size_t>(Q) + 1) * 2 + 15) / 16 * 16 + (ranks_out ? MDG_RANK_LUT_ENTRIES * 4 : 0);
+  static std::once_flag once[kMaxDevices][2];
+  static cudaError_t err[kMaxDevices][2];
+  int dev = 0;
+  MDG_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail(MDG_ERR_UNSUPPORTED, "device index %d out of range", dev);
+  const int which = ranks_out ? 1 : 0;
+  std::call_once(once[dev][which], [dev, which] {
+    err[dev][which] = which ? cudaFuncSetAttribute(mdg::ensemble_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                            : cudaFuncSetAttribute(mdg::ensemble_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  MDG_CUDA(err[dev][which]);
+  if (smem > 200 * 1024) return fail(MDG_ERR_UNSUPPORTED, "mdg_ensemble_rank_u16: Q too large for shared memory");
+  long long bx = (n_per_outcome / 8 + 255) / 256;
+  const long long cap = (static_cast<long long>(num_sms()) * 4 + L - 1) / L;  // ~4 blocks per SM in total
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(L));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (ranks_out)
+    mdg::ensemble_rank_kernel<true><<<grid, 256, smem, stream>>>(ptrs, K, n_per_outcome, ilog_table, Q, ens_table->lut,
+                                                                 ens_table->affine, ranks_out, nullptr);
+  else
+    mdg::ensemble_rank_kernel<false><<<grid, 256, smem, stream>>>(ptrs, K, n_per_outcome, ilog_table, Q, nullptr, nullptr,
+                                                                  nullptr, logsum_out);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ top-k output
 struct TopkWs {
   unsigned int* counts;

@@ -1332,6 +1332,79 @@ __global__ void __launch_bounds__(256) ensemble_reduce_kernel(EnsemblePtrs in, i
   }
 }
 
+// Ensemble of FUSED quantile ranks (reference: geometric mean of the checkpoints' normalised ranks, then the same rank
+// normalisation again — generate_embeddings.ipynb cells 18 + 20) without ever leaving uint16:
+//   g[i]   = sum_k ilog[ r_k[i] ]              ilog = caller-supplied fixed-point log2 table [Q + 1] (the gmean's log-sum)
+//   out[i] = #{ t in ens thresholds[l] : t <= float(g[i]) }   through the ensemble table's LUT (rank_lookup_raw), or
+//   outf[i] = float(g[i])                      (builder mode: feeds mdg_lower_triangle_quantiles -> the ensemble table)
+// An element whose member ranks are all 0 (the diagonal of the normaliser layout) stays 0.  One block column per
+// outcome slice; the ilog table and the outcome's LUT sit in shared memory; 8 elements per thread and 16-byte accesses.
+template <bool TO_RANK>
+__global__ void __launch_bounds__(256) ensemble_rank_kernel(EnsemblePtrs in, int K, long long n,
+                                                            const uint16_t* __restrict__ ilog, int Q,
+                                                            const uint32_t* __restrict__ lut_all,
+                                                            const float* __restrict__ affine,
+                                                            uint16_t* __restrict__ out, float* __restrict__ outf) {
+  extern __shared__ __align__(16) uint8_t ens_smem[];
+  uint16_t* s_ilog = reinterpret_cast<uint16_t*>(ens_smem);                                   // [Q + 1] (padded to 16 B)
+  uint32_t* s_lut = reinterpret_cast<uint32_t*>(ens_smem + ((static_cast<size_t>(Q) + 1) * 2 + 15) / 16 * 16);
+  const int l = blockIdx.y;
+  for (int i = threadIdx.x; i <= Q; i += blockDim.x) s_ilog[i] = ilog[i];
+  float scale = 0.f, bias = 0.f;
+  if (TO_RANK) {
+    const uint32_t* lut = lut_all + static_cast<size_t>(l) * kRankLutEntries;
+    for (int i = threadIdx.x; i < kRankLutEntries; i += blockDim.x) s_lut[i] = lut[i];
+    scale = affine[2 * l];
+    bias = affine[2 * l + 1];
+  }
+  __syncthreads();
+  const long long base = static_cast<long long>(l) * n;
+  const long long n8 = n / 8;
+  for (long long i8 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i8 < n8;
+       i8 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint32_t g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t any[4] = {0, 0, 0, 0};
+    for (int k = 0; k < K; ++k) {
+      const uint4 v = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(in.p[k]) + base + i8 * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        any[j] |= w[j];
+        g[2 * j] += s_ilog[min(w[j] & 0xFFFFu, static_cast<uint32_t>(Q))];
+        g[2 * j + 1] += s_ilog[min(w[j] >> 16, static_cast<uint32_t>(Q))];
+      }
+    }
+    if (TO_RANK) {
+      uint32_t r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t lo = rank_lookup_raw(s_lut, static_cast<float>(g[2 * j]), scale, bias) & 0xFFFFu;
+        uint32_t hi = rank_lookup_raw(s_lut, static_cast<float>(g[2 * j + 1]), scale, bias) & 0xFFFFu;
+        if ((any[j] & 0xFFFFu) == 0) lo = 0;
+        if ((any[j] >> 16) == 0) hi = 0;
+        r[j] = lo | (hi << 16);
+      }
+      *reinterpret_cast<uint4*>(out + base + i8 * 8) = make_uint4(r[0], r[1], r[2], r[3]);
+    } else {
+      float4* o = reinterpret_cast<float4*>(outf + base + i8 * 8);
+      o[0] = make_float4(static_cast<float>(g[0]), static_cast<float>(g[1]), static_cast<float>(g[2]), static_cast<float>(g[3]));
+      o[1] = make_float4(static_cast<float>(g[4]), static_cast<float>(g[5]), static_cast<float>(g[6]), static_cast<float>(g[7]));
+    }
+  }
+  // tail (n % 8 elements), one thread each
+  for (long long i = n8 * 8 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint32_t g = 0, any = 0;
+    for (int k = 0; k < K; ++k) {
+      const uint32_t r = static_cast<const uint16_t*>(in.p[k])[base + i];
+      any |= r;
+      g += s_ilog[min(r, static_cast<uint32_t>(Q))];
+    }
+    if (TO_RANK) out[base + i] = any ? static_cast<uint16_t>(rank_lookup_raw(s_lut, static_cast<float>(g), scale, bias) & 0xFFFFu) : 0;
+    else outf[base + i] = static_cast<float>(g);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ operand prep
 // z [N, D] fp32 -> bf16 [Npad, Ka]  with Ka = D (hi only) or 2D ([hi | lo]); rows >= N are zero.
 // Optional row L2 normalisation (F.normalize: x / max(||x||_2, 1e-12), models.py:947-949).  One warp per row.

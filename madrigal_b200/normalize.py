@@ -98,3 +98,90 @@ def ensemble_normalized_ranks(members, Q: Optional[int] = None) -> torch.Tensor:
     """The reference's final ensemble tensor (ipynb cells 18 + 20): gmean of the checkpoints' normalised ranks,
     re-normalised with the same in-sample rank (`run_slice` again)."""
     return exact_normalized_ranks(gmean_normalized_ranks(members, Q))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Ensemble in the quantile-table formulation (reference: generate_embeddings.ipynb:434, 634-649 — scipy gmean of the
+# checkpoints' normalised ranks, then run_slice again).  Members are FUSED uint16 ranks; the geometric mean's log-sum is
+# taken in fixed point through a table (which DEFINES the logarithm, so the CPU oracle reproduces every bit) and the
+# re-normalisation is a second quantile lookup against an ensemble table built from a reference panel.
+# ------------------------------------------------------------------------------------------------------------------
+ILOG_SCALE = 2048
+
+
+def ilog_table(Q: int, scale: int = ILOG_SCALE):
+    """uint16 [Q + 1]: round(scale * (log2(max(r, 1/2)) + 1)) — rank 0 (below every threshold) counts as half a rank."""
+    import numpy as np
+    r = np.arange(Q + 1, dtype=np.float64)
+    t = np.round(scale * (np.log2(np.maximum(r, 0.5)) + 1.0))
+    if t.max() > 65535:
+        raise ValueError("ilog table does not fit uint16: lower `scale`")
+    return t.astype(np.uint16)
+
+
+class EnsembleRankTable:
+    """ilog table of the member ranks + the rank table the log-sum is looked up in (`mdg_ensemble_rank_u16`)."""
+
+    def __init__(self, member_Q: int, quantiles: torch.Tensor, scale: int = ILOG_SCALE):
+        self.member_Q, self.scale = member_Q, scale
+        self.ilog_host = ilog_table(member_Q, scale)
+        self.ilog = torch.from_numpy(self.ilog_host.view("int16")).to(quantiles.device)
+        self.table = RankTable(quantiles)  # exact LUT over float32(g)
+        self.Q = self.table.Q
+
+
+def _member_ptrs(members):
+    import ctypes
+    members = list(members)
+    first = members[0]
+    if not 1 <= len(members) <= _lib.MDG_MAX_ENSEMBLE:
+        raise ValueError(f"need 1..{_lib.MDG_MAX_ENSEMBLE} members")
+    ms = []
+    for m in members:
+        if not m.is_cuda or m.dtype != torch.uint16 or m.shape != first.shape or m.device != first.device:
+            raise RuntimeError("madrigal_b200: ensemble members must be same-shape uint16 CUDA tensors on one device")
+        ms.append(m.contiguous())
+    return ms, (ctypes.c_void_p * len(ms))(*[m.data_ptr() for m in ms])
+
+
+def ensemble_logsum(members, member_Q: int, scale: int = ILOG_SCALE) -> torch.Tensor:
+    """float32(sum_k ilog[r_k]) of K uint16 rank tensors [L, ...] (builder mode of mdg_ensemble_rank_u16)."""
+    ms, ptrs = _member_ptrs(members)
+    first = ms[0]
+    L = first.shape[0]
+    n = first[0].numel() if L > 0 else 0
+    ilog = torch.from_numpy(ilog_table(member_Q, scale).view("int16")).to(first.device)
+    out = torch.empty(first.shape, dtype=torch.float32, device=first.device)
+    with torch.cuda.device(first.device):
+        _lib.check(_lib.lib().mdg_ensemble_rank_u16(ptrs, len(ms), L, n, ilog.data_ptr(), member_Q, None, None,
+                                                    out.data_ptr(), _stream_ptr(first.device)), "mdg_ensemble_rank_u16")
+    return out
+
+
+def build_ensemble_rank_table(panel_members, member_Q: int, Q: int = 16384, scale: int = ILOG_SCALE) -> EnsembleRankTable:
+    """Ensemble table from the members' fused ranks over a reference panel: K uint16 [L, n, n] tensors in the
+    normaliser layout -> Q order statistics of the strict-lower-triangle log-sums per outcome."""
+    g = ensemble_logsum(panel_members, member_Q, scale)
+    n = g.shape[1]
+    Q = min(Q, n * (n - 1) // 2)
+    return EnsembleRankTable(member_Q, lower_triangle_quantiles(g, Q), scale)
+
+
+def ensemble_fused_ranks(members, table: EnsembleRankTable, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint16 ensemble ranks of K fused-rank tensors [L, ...]: searchsorted(table thresholds, float32(log-sum), 'right'),
+    0 where every member is 0 (the diagonal).  `table.table.thresholds` is what the CPU oracle is run against."""
+    import ctypes
+    ms, ptrs = _member_ptrs(members)
+    first = ms[0]
+    L = first.shape[0]
+    if L > table.table.L:
+        raise ValueError("more outcomes than the ensemble table holds")
+    n = first[0].numel() if L > 0 else 0
+    if out is None:
+        out = torch.empty(first.shape, dtype=torch.uint16, device=first.device)
+    st = table.table.struct(0, L)
+    with torch.cuda.device(first.device):
+        _lib.check(_lib.lib().mdg_ensemble_rank_u16(ptrs, len(ms), L, n, table.ilog.data_ptr(), table.member_Q,
+                                                    ctypes.byref(st), out.data_ptr(), None, _stream_ptr(first.device)),
+                   "mdg_ensemble_rank_u16")
+    return out

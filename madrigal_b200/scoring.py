@@ -279,6 +279,51 @@ def ensemble_normalized_ranks_chunks(z_list, weight_list, *, precision: str = "f
         yield l0, l1, exact_normalized_ranks(g)
 
 
+def ensemble_fused_ranks_chunks(z_list, weight_list, member_tables, ens_table, *, precision: str = "bf16",
+                                chunk: int = 16, normalize: bool = False, packed: bool = False):
+    """The ensemble normalisation in the quantile formulation, streamed by outcome chunk: per checkpoint k the fused
+    uint16 ranks against its own table (one kernel, logits never materialised), then `mdg_ensemble_rank_u16` (fixed-point
+    log-sum + ensemble-table lookup).  Yields (l0, l1, ranks uint16 [l1-l0, N, N] in the normaliser layout); the yielded
+    tensor is reused by the next iteration.  `weight_list` entries may be PreparedDecoder handles.  Build `ens_table`
+    with `normalize.build_ensemble_rank_table` from the members' ranks over a reference panel.
+    packed=True: members and result stay in the packed lower-triangular tile layout ([.., T, 32, 32], no mirror image):
+    half the look-ups' traffic in every kernel; `decoder.unpack_packed_tiles` gives the mirrored array."""
+    from .decoder import packed_tiles_per_outcome
+    from .normalize import ensemble_fused_ranks
+    L = weight_list[0].shape[0]
+    N = z_list[0].shape[0]
+    K = len(z_list)
+    dev = z_list[0].device
+    item = (packed_tiles_per_outcome(N), 32, 32) if packed else (N, N)
+    bufs = [torch.empty((min(chunk, L),) + item, dtype=torch.uint16, device=dev) for _ in range(K)]
+    out = torch.empty((min(chunk, L),) + item, dtype=torch.uint16, device=dev)
+    for l0 in range(0, L, chunk):
+        l1 = min(l0 + chunk, L)
+        members = []
+        for k, (z, W, tbl) in enumerate(zip(z_list, weight_list, member_tables)):
+            members.append(pair_score(z, z, W[l0:l1], precision=precision, out="rank", table=tbl, table_offset=l0,
+                                      normalize=normalize, out_tensor=bufs[k][: l1 - l0], symmetric=True, packed=packed))
+        sub = _EnsembleView(ens_table, l0, l1)
+        yield l0, l1, ensemble_fused_ranks(members, sub, out=out[: l1 - l0])
+
+
+class _EnsembleView:
+    """Outcome slice [l0, l1) of an EnsembleRankTable (same ilog table, offset rank table)."""
+
+    def __init__(self, ens, l0, l1):
+        self.ilog, self.member_Q = ens.ilog, ens.member_Q
+        self.table = _TableView(ens.table, l0, l1)
+
+
+class _TableView:
+    def __init__(self, table, l0, l1):
+        self._t, self._l0, self.L = table, l0, l1 - l0
+
+    def struct(self, a=0, b=None):
+        b = self.L if b is None else b
+        return self._t.struct(self._l0 + a, self._l0 + b)
+
+
 def top_pairs_per_outcome(z: torch.Tensor, weight: torch.Tensor, k: int, table: RankTable, *, precision: str = "bf16",
                           cap: int = 65536, max_rounds: int = 20, normalize: bool = False):
     """Per-outcome top-k unordered pairs of one catalogue (BASELINE "top-1000 per outcome") with the candidate

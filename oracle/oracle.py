@@ -152,6 +152,26 @@ def ensemble_normalized_ranks(members: Sequence[np.ndarray], kind: Optional[str]
     return normalize_scores(gmean_normalized_ranks(members), kind=kind)
 
 
+def ilog_table(Q: int, scale: int = 2048) -> np.ndarray:
+    """Fixed-point log2 table of the quantile-formulation ensemble: round(scale * (log2(max(r, 1/2)) + 1)), r = 0..Q."""
+    r = np.arange(Q + 1, dtype=np.float64)
+    return np.round(scale * (np.log2(np.maximum(r, 0.5)) + 1.0)).astype(np.uint16)
+
+
+def ensemble_quantile_ranks(members: Sequence[np.ndarray], ilog: np.ndarray, thresholds: np.ndarray) -> np.ndarray:
+    """Ensemble of fused uint16 ranks in the quantile formulation (generate_embeddings.ipynb:434, 634-649 restated on
+    quantile ranks): g = sum_k ilog[r_k] (the gmean's log-sum in fixed point), rank = searchsorted(thresholds[l],
+    float32(g), 'right'), 0 where every member rank is 0 (the diagonal).  members: K uint16 [L, ...]."""
+    g = np.zeros(members[0].shape, dtype=np.int64)
+    anyr = np.zeros(members[0].shape, dtype=bool)
+    for m in members:
+        g += ilog[np.minimum(m.astype(np.int64), len(ilog) - 1)].astype(np.int64)
+        anyr |= m != 0
+    out = quantile_rank(thresholds.astype(F32), g.astype(F32), "right")
+    out[~anyr] = 0
+    return out
+
+
 def gather_triples(scores: np.ndarray, labels: np.ndarray, heads: np.ndarray, tails: np.ndarray) -> np.ndarray:
     """`pred[ddi_labels, head_idx, tail_idx]` (train_ddi_batch.py:286, evaluate.py:195) on a dense [L, Nh, Nt] array."""
     return scores[labels, heads, tails]
