@@ -1,10 +1,10 @@
-"""SASS mnemonic counts per kernel of libmadrigal_b200.so -> profiles/r01_sass_evidence.csv (runs without a GPU)."""
+"""SASS mnemonic counts per kernel of libmadrigal_b200.so -> profiles/r02_sass_evidence.csv (runs without a GPU)."""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "madrigal_b200", "lib", "libmadrigal_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
 names = subprocess.run(["c++filt"], input="\n".join(re.findall(r"Function : (\S+)", sass)), capture_output=True, text=True).stdout.split("\n")
-cols = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "STSM", "LDSM", "LDGSTS", "HMMA"]
+cols = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "STSM", "LDSM", "LDGSTS", "HMMA", "ACQBULK"]
 counts, cur, i = collections.OrderedDict(), None, 0
 for line in sass.split("\n"):
     m = re.search(r"Function : (\S+)", line)
@@ -31,5 +31,5 @@ for k, c in counts.items():
         continue
     short = re.sub(r"\(.*", "", k.replace("void ", ""))
     out.append('"%s",' % short + ",".join(str(c[x]) for x in cols))
-open(os.path.join(ROOT, "profiles", "r01_sass_evidence.csv"), "w").write("\n".join(out) + "\n")
+open(os.path.join(ROOT, "profiles", "r02_sass_evidence.csv"), "w").write("\n".join(out) + "\n")
 print("\n".join(out[:40]))
