@@ -418,6 +418,10 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else
       for (int t = tasks.next_producer(p.sched_counter); t >= 0; t = tasks.next_producer(p.sched_counter), ++it) {
         const TaskCoord c = decode_task(p, t);
+        if (c.nb0 >= c.nb1) {  // a column chunk entirely above the diagonal (normaliser layout): nothing to load
+          --it;
+          continue;
+        }
         // GEMM 1 (a_reuse): consecutive tasks of a CTA share the row block, so its z panels stay in shared memory and
         // neither warp touches the A barriers — the B ring keeps streaming across the task boundary instead of
         // draining at every task (one tile per task there: the drain was 2/3 of GEMM 1's time)
@@ -513,6 +517,10 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else
       for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane), ++it) {
         const TaskCoord c = decode_task(p, t);
+        if (c.nb0 >= c.nb1) {  // empty task: skipped by the producer as well
+          --it;
+          continue;
+        }
         const bool a_resident = p.a_reuse && !p.a_batched && it > 0 && c.m0 == last_m0;  // as in the producer
         last_m0 = c.m0;
         if (!a_resident) {
@@ -714,6 +722,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane)) {
         const TaskCoord c = decode_task(p, t);
+        if (c.nb0 >= c.nb1) continue;  // empty task (column chunk above the diagonal)
         if (c.l != cur_l) {
           // new outcome: one bulk copy (TMA, 32 KB) of its table once every warp is done with the old one
           named_bar_sync(1, NE * 32);
@@ -798,6 +807,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     for (int t = tasks.next_consumer(lane); t >= 0; t = tasks.next_consumer(lane)) {
       const TaskCoord c = decode_task(p, t);
+      if (c.nb0 >= c.nb1) continue;  // empty task (column chunk above the diagonal)
       if (epi_is_rank(EPI) && c.l != cur_l) {
         named_bar_sync(1, NE * 32);  // everyone is done with the previous outcome's LUT
         const uint4* src = reinterpret_cast<const uint4*>(p.lut + static_cast<size_t>(c.l) * kRankLutEntries);
