@@ -195,7 +195,7 @@ def _cpu_sample_text(n_out, wl, cores, kind, dt):
 def cpu_baseline(wl_key):
     wl = WORKLOADS[wl_key]
     cores = _cpu_cores()
-    n_out = max(1, min(2 * cores, wl["outcomes"]))  # two outcomes per worker: ~10-15 s wall
+    n_out = max(1, min(4 * cores, wl["outcomes"]))  # four outcomes per worker: ~12 s wall on the 16-core box
     dt, kind = cpu_reference_pass(wl["drugs"], n_out, cores)
     v = n_out * wl["drugs"] * wl["drugs"] / dt
     return {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "value_per_core": v / cores,
@@ -585,6 +585,27 @@ def run_gpu_arm(args):
     d2h_packed = packed_host.numel() * 2
     del packed_host, W_host
 
+    # ================================================================== configs[2] on this one GPU (N = 1 line): the anchor
+    # the strong-scaled N > 1 lines are compared with (same code path as their `single_gpu_same_workload` leg)
+    c2_single = None
+    if world == 1 and wl_key == "configs1" and not args.no_encoder_block:
+        del job.out
+        job.out = None
+        torch.cuda.empty_cache()
+        wl2 = WORKLOADS["configs2"]
+        job2 = Job(ctx, "configs2", 0, wl2["outcomes"], 1, 0)
+        ms2, kern2 = timed(job2.step, 5, 2, profile=True)
+        ok2 = job2.parity_one_outcome(wl2["outcomes"] - 1)
+        c0, c1 = job2.checksum()
+        tr2 = wl2["outcomes"] * wl2["drugs"] * wl2["drugs"]
+        c2_single = {"workload": f"{wl2['name']}: {wl2['drugs']} drugs x {wl2['outcomes']} outcomes on this ONE GPU "
+                                 f"(what `bench.py --gpus N` strong-scales for N > 1), 5 steps after 2 warm-ups",
+                     "ms_per_step": ms2, "value": tr2 / (ms2 * 1e-3), "unit": UNIT, "kernel_ms": kern2,
+                     "kernel_frac_of_hbm": (2.0 * tr2 / (kern2 * 1e-3) / 1e9 / load_peaks()["hbm_gbs"]) if kern2 else None,
+                     "parity_last_outcome_vs_oracle": ok2, "checksum": [c0, c1]}
+        del job2
+        torch.cuda.empty_cache()
+
     # ================================================================== strong-scaling anchor + checksum (N > 1)
     single = None
     if world > 1 and wl_key == "configs2":
@@ -700,6 +721,8 @@ def run_gpu_arm(args):
             line["single_gpu_same_workload"] = single
             line["parity"]["checksum_equals_single_gpu"] = single["checksum_equals_sharded_run"]
             line["strong_scaling_efficiency_vs_single_gpu_same_box"] = value / (world * single["value"])
+        if c2_single is not None:
+            line["config2_4096_x_963_single_gpu"] = c2_single
         if big is not None:
             line["config3_20k_x_953"] = big
         if enc_block is not None:
