@@ -449,11 +449,17 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
     rc = make_map_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, ka, D, L, ka, D * ka, 64, 128,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map_3d(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.y, ka, ws.nr_pad, L, ka, ws.nr_pad * ka, 32, 32,
-                     CU_TENSOR_MAP_SWIZZLE_64B);
+    static const bool narrow_store = getenv("MDG_GEMM1_NARROW_STORE") != nullptr;  // A/B knob: 32-column (64-byte-row) tiles
+    if (narrow_store)
+      rc = make_map_3d(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.y, ka, ws.nr_pad, L, ka, ws.nr_pad * ka, 32, 32,
+                       CU_TENSOR_MAP_SWIZZLE_64B);
+    else
+      rc = make_map_3d(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws.y, ka, ws.nr_pad, L, ka, ws.nr_pad * ka, 64, 32,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     mdg::PairScoreParams p;
     memset(&p, 0, sizeof(p));
+    p.wide_store = narrow_store ? 0 : 1;
     p.L = static_cast<int>(L);
     p.rows = static_cast<int>(ws.nr_pad);
     p.cols = static_cast<int>(D);

@@ -110,6 +110,7 @@ struct PairScoreParams {
   long long bf16_ld;
   int bf16_lo_off;
   int act;  // 0 none, 1 relu, 2 exact-erf gelu
+  int wide_store;  // EPI_BF16_SPLIT: tmOut has 64-column boxes (128-byte rows, 128B swizzle): one 4 KB store per two chunks
   int res_tma;  // the residual IS the fp32 output tensor (in-place residual stream) and it is TMA-addressable: the
                 // residual tile is fetched with a TMA load through tmOut into the staging tile the result is stored from
   // ---- EPI_TOPK: append every score >= topk_thresh[l] to the outcome's candidate list (no dense output at all)
@@ -1021,6 +1022,50 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_t_empty(acc_stage));
                 released = true;
+              }
+            }
+            if constexpr (EPI == EPI_BF16_SPLIT && kBurst == 4) {
+              if (p.wide_store) {
+                // GEMM 1's output path was 40 % of its time (one fill + proxy fence + 2 KB store + commit per 32-column
+                // chunk, serialised per warp): with the whole strip in registers two chunks form one 128-byte-row tile
+                // (32 rows x 64 bf16, 128B swizzle) in the warp's 4 KB slice of the (idle) table region
+                const uint32_t wbuf = sLut + static_cast<uint32_t>(ew) * 4096u;
+                for (int part = 0; part < (p.write_lo ? 2 : 1); ++part) {
+#pragma unroll
+                  for (int pr = 0; pr < 2; ++pr) {
+                    const int cc = cc0 + 64 * pr, n0 = nb * kBN + cc;
+                    if (cc >= col_end || n0 >= p.cols) break;
+                    if (lane == 0) tma_store_wait_read<0>();  // the previous tile has left the buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                      const uint32_t (&vh)[32] = vv[2 * pr + h];
+                      uint32_t pk[16];
+#pragma unroll
+                      for (int j = 0; j < 16; ++j) {
+                        float a = __uint_as_float(vh[2 * j]), b = __uint_as_float(vh[2 * j + 1]);
+                        if (part == 1) {
+                          a -= __bfloat162float(__float2bfloat16_rn(a));
+                          b -= __bfloat162float(__float2bfloat16_rn(b));
+                        }
+                        pk[j] = pack_bf16x2(a, b);
+                      }
+#pragma unroll
+                      for (int c4 = 0; c4 < 4; ++c4)
+                        st_shared_v4(wbuf + static_cast<uint32_t>(lane) * 128u +
+                                         ((static_cast<uint32_t>(4 * h + c4) ^ static_cast<uint32_t>(lane & 7)) << 4),
+                                     pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                      tma_store_3d(&tmOut, wbuf, n0 + part * p.lo_col_offset, row0, c.l);
+                      tma_store_commit();
+                    }
+                    ss.pending = 1;  // the kernel's final wait covers these groups
+                  }
+                }
+                continue;
               }
             }
 #pragma unroll
