@@ -583,3 +583,39 @@ def test_packed_tiles_layout(mb, cuda_device, N, D, L, Q):
     out_host = torch.empty(tuple(packed.shape), dtype=torch.uint16).pin_memory()
     scoring.score_all_pairs_to_host(zt, Wt, out_host, out="rank", table=table, precision="bf16", chunk=2, packed=True)
     assert np.array_equal(unpack_packed_tiles(out_host.numpy(), N), full.cpu().numpy())
+
+
+@pytest.mark.parametrize("N,D,L", [(1000, 128, 2), (296, 64, 3), (33, 128, 1), (520, 256, 2)])
+def test_outputs_are_written_inside_their_buffers_only(mb, cuda_device, N, D, L):
+    """compute-sanitizer is not available on this pool, so out-of-bounds writes are hunted with guard bands: every output
+    tensor is a slice of a larger sentinel-filled allocation (ragged N: TMA clipping, diagonal chunks, packed tiles, the
+    mirrored stores of the normaliser layout, GEMM 1's wide tiles through the logit path) and the bands must survive."""
+    from madrigal_b200 import normalize
+    from madrigal_b200.decoder import packed_tiles_per_outcome
+    z, W = synth.decoder_inputs(N, D, L, seed=N)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    table = normalize.build_rank_table(zt, Wt, 512, precision="bf16")
+    GUARD = 4096  # elements on either side (16-byte aligned for every dtype used)
+
+    def guarded(shape, dtype, sentinel):
+        n = int(np.prod(shape))
+        flat = torch.full((n + 2 * GUARD,), sentinel, dtype=torch.int16 if dtype == torch.uint16 else dtype, device=cuda_device)
+        view = flat[GUARD:GUARD + n].view(dtype).view(shape) if dtype == torch.uint16 else flat[GUARD:GUARD + n].view(shape)
+        return flat, view
+
+    def bands_intact(flat, sentinel):
+        return bool((flat[:GUARD] == sentinel).all()) and bool((flat[-GUARD:] == sentinel).all())
+
+    for sym, packed in ((False, False), (True, False), (True, True)):
+        shape = (L, packed_tiles_per_outcome(N), 32, 32) if packed else (L, N, N)
+        flat, out = guarded(shape, torch.uint16, -12345)
+        mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, out_tensor=out, symmetric=sym, packed=packed)
+        torch.cuda.synchronize()
+        assert bands_intact(flat, -12345), (sym, packed)
+        if not packed:  # and every element inside was written (ranks are <= Q = 512, never the sentinel's bit pattern)
+            assert bool((out.view(torch.int16) != -12345).all()), (sym, packed)
+    for prec in ("bf16", "fp32"):
+        flat, out = guarded((L, N, N), torch.float32, -7.5e30)
+        mb.pair_score(zt, zt, Wt, precision=prec, out="logit", out_tensor=out)
+        torch.cuda.synchronize()
+        assert bands_intact(flat, -7.5e30) and bool((out != -7.5e30).all()), prec

@@ -239,3 +239,28 @@ def test_quantile_formulation_ensemble_is_bit_exact_and_tracks_the_reference(nor
     outs = np.concatenate([r.cpu().numpy().copy() for _, _, r in
                            scoring.ensemble_fused_ranks_chunks(zs, Ws, tables, ens, precision="bf16", chunk=2)])
     assert np.array_equal(outs, got)
+
+
+def test_ensemble_kernel_writes_inside_its_output_only(norm, cuda_device):
+    """Guard bands around mdg_ensemble_rank_u16's output (n not a multiple of 8 for L = 1: the scalar tail path)."""
+    import madrigal_b200 as mb
+    import synth
+    N, D, K, Q = 123, 64, 3, 256
+    members, tables = [], []
+    for k in range(K):
+        z, W = synth.decoder_inputs(N, D, 1, seed=70 + k)
+        zt, Wt = torch.from_numpy(z).to(cuda_device), torch.from_numpy(W).to(cuda_device)
+        tbl = norm.build_rank_table(zt, Wt, Q, precision="bf16")
+        members.append(mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=tbl, symmetric=True))
+    ens = norm.build_ensemble_rank_table(members, Q, Q=Q)
+    n = N * N
+    assert n % 8 != 0
+    GUARD = 1024
+    flat = torch.full((n + 2 * GUARD,), -12345, dtype=torch.int16, device=cuda_device)
+    out = flat[GUARD:GUARD + n].view(torch.uint16).view(1, N, N)
+    got = norm.ensemble_fused_ranks(members, ens, out=out)
+    torch.cuda.synchronize()
+    assert bool((flat[:GUARD] == -12345).all()) and bool((flat[-GUARD:] == -12345).all())
+    exp = oracle.ensemble_quantile_ranks([m.cpu().numpy() for m in members], oracle.ilog_table(Q),
+                                         ens.table.thresholds.cpu().numpy())
+    assert np.array_equal(got.cpu().numpy(), exp)
