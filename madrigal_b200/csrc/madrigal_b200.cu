@@ -406,7 +406,11 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
 
   const int split = precision == MDG_PREC_FP32;
   const int nterm = split ? 3 : 1;
-  const int msub = split ? 1 : 2;
+  static const int msub_pin = [] {
+    const char* e = getenv("MDG_MSUB");  // tuning knob: 1 = 128-row tasks (half the resident A operand)
+    return (e && atoi(e) == 1) ? 1 : 0;
+  }();
+  const int msub = (split || msub_pin == 1) ? 1 : 2;
   const int kb = static_cast<int>(D / 64);
   const int64_t ka = ws.ka;
 
