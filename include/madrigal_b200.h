@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 3
+#define MDG_ABI_VERSION 4
 
 typedef enum MdgStatus {
   MDG_OK = 0,
@@ -421,6 +421,18 @@ int mdg_mlp_forward(const MdgMlp* mlp, const float* x, float* y, int64_t B, int 
 int mdg_tx_latent_combine(const float* basal, const float* drug_latent, const float* dosage, const int64_t* drug_idx,
                           const float* doser_beta, const float* doser_bias, int32_t doser, const float* cov_table,
                           const int64_t* cov_idx, int64_t B, int32_t dim, float* out, void* stream);
+
+/* Per-drug 'mlp' dosers (reference: TxAdaptingComPert, chemCPA/model.py:405-416 construction, :609-621 use):
+ *   scale_out[b] = sigmoid(MLP_i(dosage[b])),  i = drug_idx[b],
+ *   MLP_i = Linear(1, width) -> ReLU -> [Linear(width, width) -> ReLU] x (depth - 1) -> Linear(width, 1)
+ * (chemCPA `MLP([1] + [width] * depth + [1], batch_norm=False)`, one per drug).  Parameters stacked over drugs:
+ *   w_in, b_in [num_drugs, width]; w_hid [num_drugs, depth - 1, width, width] (out, in), b_hid [num_drugs, depth - 1,
+ *   width] (both NULL when depth == 1); w_out [num_drugs, width]; b_out [num_drugs].
+ * The result is the precomputed dose scale mdg_tx_latent_combine takes with doser = 3.  width <= 256.  A drug index
+ * outside [0, num_drugs) gives NaN for that sample (the reference raises IndexError).  fp32 device pointers. */
+int mdg_doser_mlp(const float* dosage, const int64_t* drug_idx, int64_t B, int32_t num_drugs, int32_t width,
+                  int32_t depth, const float* w_in, const float* b_in, const float* w_hid, const float* b_hid,
+                  const float* w_out, const float* b_out, float* scale_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 from .build import LIB_PATH
 
-EXPECTED_ABI = 3  # MDG_ABI_VERSION of include/madrigal_b200.h these ctypes structs/signatures were written for
+EXPECTED_ABI = 4  # MDG_ABI_VERSION of include/madrigal_b200.h these ctypes structs/signatures were written for
 MDG_MAX_LAYERS = 8
 MDG_MAX_TOKENS = 32
 MDG_MAX_MLP_LINEAR = 8
@@ -108,6 +108,8 @@ SIGNATURES = {
     "mdg_mlp_forward": (c_int, [POINTER(MdgMlp), c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "mdg_tx_latent_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
                                       c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "mdg_doser_mlp": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _LIB = None

@@ -28,7 +28,7 @@ from ._lib import MdgMlp
 from .decoder import _require_cuda_f32, _stream_ptr, _workspace
 from .fusion import _PRECISION
 
-_DOSER = {None: 0, "sigm": 1, "logsigm": 2, "amortized": 3}
+_DOSER = {None: 0, "sigm": 1, "logsigm": 2, "amortized": 3, "mlp": 3}  # 3 = the scale is computed before the combine
 
 
 class MLP(nn.Module):
@@ -168,13 +168,19 @@ class TxAdaptingComPert(nn.Module):
             self.num_genes = append_layer_width
         if use_drugs:
             if doser_type not in _DOSER:
-                raise NotImplementedError(f"doser_type={doser_type!r} (per-drug 'mlp' dosers are not supported)")
+                raise NotImplementedError(f"doser_type={doser_type!r}")
             self.drug_embeddings = drug_embeddings if drug_embeddings is not None else nn.Embedding(num_drugs, hp["dim"])
             self.drug_embedding_encoder = MLP(
                 [self.drug_embeddings.embedding_dim]
                 + [hp.get("embedding_encoder_width", 512)] * hp.get("embedding_encoder_depth", 0) + [hp["dim"]],
                 last_layer_act="linear", precision=precision)
-            if doser_type == "amortized":
+            if doser_type == "mlp":  # one small MLP per drug on the scalar dosage (model.py:405-416)
+                if hp["dosers_depth"] < 1:
+                    raise NotImplementedError("'mlp' dosers need dosers_depth >= 1")
+                self.dosers = nn.ModuleList([MLP([1] + [hp["dosers_width"]] * hp["dosers_depth"] + [1], batch_norm=False)
+                                             for _ in range(num_drugs)])
+                self._doser_stack, self._doser_key = None, None
+            elif doser_type == "amortized":
                 self.dosers = MLP([self.drug_embeddings.embedding_dim + 1]
                                   + [hp["dosers_width"]] * hp["dosers_depth"] + [1], precision=precision)
             else:
@@ -183,6 +189,37 @@ class TxAdaptingComPert(nn.Module):
         else:
             self.drug_embeddings = self.drug_embedding_encoder = self.dosers = None
         self.covariates_embeddings = nn.ModuleList([nn.Embedding(n, hp["dim"]) for n in self.num_covariates])
+
+    def _mlp_doser_scale(self, dosage, idx):
+        """sigmoid(dosers[idx[b]](dosage[b])) for the per-drug 'mlp' dosers (model.py:609-621) through mdg_doser_mlp; the
+        drugs' parameters are stacked once ([num_drugs, ...]) and re-stacked when any of them changes."""
+        lin = [[m for m in d.network if isinstance(m, nn.Linear)] for d in self.dosers]
+        tensors = [t for ls in lin for m in ls for t in (m.weight, m.bias)]
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._doser_stack is None or key != self._doser_key:
+            f = lambda t: t.detach().float()
+            w = lin[0][0].out_features
+            st = dict(
+                w_in=torch.stack([f(ls[0].weight).reshape(w) for ls in lin]).contiguous(),
+                b_in=torch.stack([f(ls[0].bias) for ls in lin]).contiguous(),
+                w_out=torch.stack([f(ls[-1].weight).reshape(w) for ls in lin]).contiguous(),
+                b_out=torch.stack([f(ls[-1].bias).reshape(()) for ls in lin]).contiguous(),
+                w_hid=None, b_hid=None, width=w, depth=len(lin[0]) - 1)
+            if st["depth"] > 1:
+                st["w_hid"] = torch.stack([torch.stack([f(m.weight) for m in ls[1:-1]]) for ls in lin]).contiguous()
+                st["b_hid"] = torch.stack([torch.stack([f(m.bias) for m in ls[1:-1]]) for ls in lin]).contiguous()
+            self._doser_stack, self._doser_key = st, key
+        st = self._doser_stack
+        if st["w_in"].device != dosage.device:
+            raise ValueError("module parameters and input are on different devices")
+        scale = torch.empty_like(dosage)
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        with torch.cuda.device(dosage.device):
+            _lib.check(_lib.lib().mdg_doser_mlp(
+                dosage.data_ptr(), idx.data_ptr(), dosage.shape[0], len(self.dosers), st["width"], st["depth"],
+                ptr(st["w_in"]), ptr(st["b_in"]), ptr(st["w_hid"]), ptr(st["b_hid"]), ptr(st["w_out"]), ptr(st["b_out"]),
+                scale.data_ptr(), _stream_ptr(dosage.device)), "mdg_doser_mlp")
+        return scale
 
     def _combine(self, basal, drug_latent, dosage, drugs_idx, cov_table, cov_idx, doser):
         B, dim = basal.shape
@@ -225,7 +262,9 @@ class TxAdaptingComPert(nn.Module):
             assert idx.shape == dosage.shape and idx.shape[0] == genes.shape[0]
             emb = self.drug_embeddings.weight.detach().float()[idx]  # gather (plumbing), model.py:601
             doser = _DOSER[self.doser_type]
-            if doser == 3:  # amortized: MLP over [embedding | dosage] (model.py:622-627)
+            if self.doser_type == "mlp":
+                dosage = self._mlp_doser_scale(dosage, idx)
+            elif doser == 3:  # amortized: MLP over [embedding | dosage] (model.py:622-627)
                 dosage = self.dosers(torch.cat([emb, dosage[:, None]], dim=1)).reshape(-1).contiguous()
             drug_latent = self.drug_embedding_encoder(emb.contiguous())
         latent = latent_basal

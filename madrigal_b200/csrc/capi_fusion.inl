@@ -734,6 +734,22 @@ int mdg_tx_latent_combine(const float* basal, const float* drug_latent, const fl
   return MDG_OK;
 }
 
+int mdg_doser_mlp(const float* dosage, const int64_t* drug_idx, int64_t B, int32_t num_drugs, int32_t width,
+                  int32_t depth, const float* w_in, const float* b_in, const float* w_hid, const float* b_hid,
+                  const float* w_out, const float* b_out, float* scale_out, void* stream_v) {
+  if (B < 0 || num_drugs <= 0 || width <= 0 || depth < 1)
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_doser_mlp: bad sizes");
+  if (width > mdg::kDoserMaxWidth) return fail(MDG_ERR_UNSUPPORTED, "mdg_doser_mlp: width %d > %d", width, mdg::kDoserMaxWidth);
+  if (B == 0) return MDG_OK;
+  if (!dosage || !drug_idx || !w_in || !b_in || !w_out || !b_out || !scale_out || (depth > 1 && (!w_hid || !b_hid)))
+    return fail(MDG_ERR_INVALID_ARGUMENT, "mdg_doser_mlp: NULL pointer");
+  mdg::doser_mlp_kernel<<<static_cast<unsigned>((B + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      dosage, reinterpret_cast<const long long*>(drug_idx), B, num_drugs, width, depth, w_in, b_in, w_hid, b_hid, w_out,
+      b_out, scale_out);
+  MDG_CUDA(cudaGetLastError());
+  return MDG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ token assembly
 int mdg_assemble_tokens(const float* embeds, const uint8_t* masks, int64_t B, int32_t M, int32_t E, int32_t n_non_tx,
                         int32_t num_bottlenecks, const float* bottleneck_tokens, const float* cls_token,

@@ -621,6 +621,56 @@ __global__ void __launch_bounds__(256) tx_latent_combine_kernel(
   out[idx] = v;
 }
 
+// Per-drug 'mlp' dosers (reference: TxAdaptingComPert.__init__ / compute_drug_embeddings_, chemCPA/model.py:405-416,
+// 609-621): scale[b] = sigmoid(MLP_i(dosage[b])), i = drug_idx[b], MLP_i = Linear(1, w) -> ReLU ->
+// [Linear(w, w) -> ReLU] x (depth - 1) -> Linear(w, 1) with its own parameters per drug (batch_norm=False).
+// One warp per sample: the hidden vector lives in the warp's shared-memory row, lane j owns units j, j + 32, ...
+// Stacked parameters: w_in / b_in [nd, w], w_hid [nd, depth - 1, w(out), w(in)], b_hid [nd, depth - 1, w],
+// w_out [nd, w], b_out [nd].  A drug index outside [0, nd) yields NaN (the reference raises IndexError).
+constexpr int kDoserMaxWidth = 256;
+__global__ void __launch_bounds__(128) doser_mlp_kernel(const float* __restrict__ dosage,
+                                                        const long long* __restrict__ drug_idx, long long B, int nd,
+                                                        int w, int depth, const float* __restrict__ w_in,
+                                                        const float* __restrict__ b_in,
+                                                        const float* __restrict__ w_hid,
+                                                        const float* __restrict__ b_hid,
+                                                        const float* __restrict__ w_out,
+                                                        const float* __restrict__ b_out, float* __restrict__ scale) {
+  __shared__ float hbuf[4][2][kDoserMaxWidth];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = static_cast<long long>(blockIdx.x) * 4 + wid;
+  if (b >= B) return;
+  const long long i = drug_idx[b];
+  if (i < 0 || i >= nd) {
+    if (lane == 0) scale[b] = CUDART_NAN_F;
+    return;
+  }
+  const float x = dosage[b];
+  float* h = hbuf[wid][0];
+  float* h2 = hbuf[wid][1];
+  for (int j = lane; j < w; j += 32) h[j] = fmaxf(fmaf(w_in[i * w + j], x, b_in[i * w + j]), 0.f);
+  __syncwarp();
+  for (int l = 0; l < depth - 1; ++l) {
+    const float* W = w_hid + (static_cast<size_t>(i) * (depth - 1) + l) * w * w;
+    const float* bb = b_hid + (static_cast<size_t>(i) * (depth - 1) + l) * w;
+    for (int j = lane; j < w; j += 32) {
+      const float* row = W + static_cast<size_t>(j) * w;
+      float acc = 0.f;
+      for (int k = 0; k < w; ++k) acc = fmaf(row[k], h[k], acc);
+      h2[j] = fmaxf(acc + bb[j], 0.f);
+    }
+    __syncwarp();
+    float* t = h;
+    h = h2;
+    h2 = t;
+  }
+  float acc = 0.f;
+  for (int j = lane; j < w; j += 32) acc = fmaf(w_out[i * w + j], h[j], acc);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) scale[b] = tx_sigmoid(acc + b_out[i]);
+}
+
 // Token assembly (reference: NovelDDIEncoder.encode, models.py:772-852): builds the position-encoded fusion sequence
 // and its key mask from the stacked modality embeddings.
 //   embeds [B, M, E] (order [non-TX..., TX...], models.py:772), masks [B, M] (non-zero = missing)

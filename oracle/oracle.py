@@ -350,7 +350,7 @@ def chemcpa_tx_latents(sd: dict, genes: np.ndarray, cov_idx: Sequence[np.ndarray
                        drugs_idx: Optional[np.ndarray] = None, dosages: Optional[np.ndarray] = None, dtype=F32):
     """`TxAdaptingComPert.predict` restricted to its latents (model.py:678-697) -> (latent_basal, latent_treated).
     Dose scale per compute_drug_embeddings_ (:601-653) with the dosers of :259-271 ('sigm'/'logsigm'), :622-627
-    ('amortized') or the dosage itself (nonlin None)."""
+    ('amortized'), :609-621 (per-drug 'mlp') or the dosage itself (nonlin None)."""
     sig = lambda v: 1.0 / (1.0 + np.exp(-v))
     basal = chemcpa_mlp(sd, "encoder.", genes, dtype)
     treated = basal
@@ -364,6 +364,9 @@ def chemcpa_tx_latents(sd: dict, genes: np.ndarray, cov_idx: Sequence[np.ndarray
             scale = sig(xx * beta + bias) - sig(bias)
         elif doser_type == "amortized":
             scale = chemcpa_mlp(sd, "dosers.", np.concatenate([emb, d[:, None]], axis=1), dtype).reshape(-1)
+        elif doser_type == "mlp":  # :609-621 — the drug's own MLP on the scalar dosage, then a sigmoid
+            scale = np.asarray([sig(chemcpa_mlp(sd, f"dosers.{int(i)}.", np.asarray([[x]], dtype), dtype)[0, 0])
+                                for i, x in zip(drugs_idx, d)], dtype)
         elif doser_type is None:
             scale = d
         else:

@@ -124,6 +124,9 @@ CHEMCPA_CASES = [
     dict(name="drugs_sigm_depth0", num_genes=50, num_drugs=5, n_cell=3, use_drugs=True, doser_type="sigm",
          hparams=dict(dim=16, autoencoder_width=48, autoencoder_depth=0, dosers_width=16, dosers_depth=2,
                       embedding_encoder_width=40, embedding_encoder_depth=0), emb_dim=12, B=8, seed=6),
+    dict(name="drugs_mlp_dosers", num_genes=72, num_drugs=7, n_cell=4, use_drugs=True, doser_type="mlp",
+         hparams=dict(dim=24, autoencoder_width=40, autoencoder_depth=1, dosers_width=24, dosers_depth=3,
+                      embedding_encoder_width=16, embedding_encoder_depth=0), emb_dim=10, B=21, seed=8),
 ]
 
 
@@ -158,6 +161,10 @@ def chemcpa_case(case):
         sd.update(_chemcpa_mlp_state(rng, "drug_embedding_encoder.", [case["emb_dim"]] + [hp["embedding_encoder_width"]] * hp["embedding_encoder_depth"] + [hp["dim"]]))
         if case["doser_type"] == "amortized":
             sd.update(_chemcpa_mlp_state(rng, "dosers.", [case["emb_dim"] + 1] + [hp["dosers_width"]] * hp["dosers_depth"] + [1]))
+        elif case["doser_type"] == "mlp":  # one MLP([1] + [w] * depth + [1], batch_norm=False) per drug (model.py:405-416)
+            for d in range(case["num_drugs"]):
+                sd.update(_chemcpa_mlp_state(rng, f"dosers.{d}.", [1] + [hp["dosers_width"]] * hp["dosers_depth"] + [1],
+                                             batch_norm=False))
         else:
             sd["dosers.beta"] = (1.0 + 0.3 * rng.standard_normal((1, case["num_drugs"]))).astype(F32)
             sd["dosers.bias"] = (0.3 * rng.standard_normal((1, case["num_drugs"]))).astype(F32)

@@ -32,7 +32,7 @@ def test_header_symbols_all_exported(handle):
 
 
 def test_abi_version_and_error_string(handle):
-    assert handle.mdg_abi_version() == _lib.EXPECTED_ABI == 3
+    assert handle.mdg_abi_version() == _lib.EXPECTED_ABI == 4
     assert isinstance(handle.mdg_last_error(), bytes)
 
 
@@ -114,6 +114,11 @@ def test_more_entry_points_validate_arguments_first(handle):
     assert handle.mdg_l2_normalize_rows(None, 4, 8, None, None) == 1
     assert handle.mdg_l2_normalize_rows(p, 4, 0, p, None) == 1
     assert handle.mdg_l2_normalize_rows(p, 0, 8, p, None) == 0     # no rows: no-op
+    # per-drug 'mlp' dosers (ABI 4)
+    assert handle.mdg_doser_mlp(p, p, 4, 0, 8, 2, p, p, p, p, p, p, p, None) == 1 and b"bad sizes" in handle.mdg_last_error()
+    assert handle.mdg_doser_mlp(p, p, 4, 3, 512, 2, p, p, p, p, p, p, p, None) == 2 and b"width" in handle.mdg_last_error()
+    assert handle.mdg_doser_mlp(p, p, 4, 3, 8, 2, p, p, None, None, p, p, p, None) == 1   # depth 2 needs the hidden layer
+    assert handle.mdg_doser_mlp(None, None, 0, 3, 8, 1, None, None, None, None, None, None, None, None) == 0  # empty batch
 
 
 def test_stale_library_abi_is_rejected(monkeypatch):
@@ -122,7 +127,7 @@ def test_stale_library_abi_is_rejected(monkeypatch):
     monkeypatch.setattr(_lib, "EXPECTED_ABI", 999)
     with pytest.raises(RuntimeError, match="ABI version"):
         _lib.lib()
-    monkeypatch.setattr(_lib, "EXPECTED_ABI", 3)
+    monkeypatch.setattr(_lib, "EXPECTED_ABI", 4)
     monkeypatch.setattr(_lib, "_LIB", None)
     assert _lib.lib() is not None
 

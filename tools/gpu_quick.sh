@@ -1,8 +1,6 @@
 #!/bin/bash
+# Quick GPU check after a small change: stale-library guard, the GPU suite, smoke.
 mkdir -p gpurun_out
-python -m pytest tests -x -q -m gpu > gpurun_out/pytest.log 2>&1; echo "pytest exit=$?"; tail -2 gpurun_out/pytest.log
-python tools/time_topk.py 2>&1 | tail -4
-python tools/time_pair_score.py 2>&1 | tail -6
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1
-python -c "import json;d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1]);print('bench', d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['clocks'], d['gpu_launches'])"
-python tools/time_encoder.py 2>&1 | tail -8
+python -c "from madrigal_b200 import build; import sys; sys.exit(0 if build.library_is_current() else 1)" || { echo "STALE LIBRARY"; exit 1; }
+python -m pytest tests -x -q -m gpu "$@" > gpurun_out/pytest.log 2>&1; echo "pytest exit=$?"; tail -15 gpurun_out/pytest.log
+python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit=$?"; tail -1 gpurun_out/smoke.log
