@@ -8,6 +8,9 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 from .build import LIB_PATH
 
+# A/B measurements of compile-time variants: MDG_LIB_PATH points at another build of the SAME sources/ABI.
+LIB_PATH = os.environ.get("MDG_LIB_PATH", LIB_PATH)
+
 EXPECTED_ABI = 4  # MDG_ABI_VERSION of include/madrigal_b200.h these ctypes structs/signatures were written for
 MDG_MAX_LAYERS = 8
 MDG_MAX_TOKENS = 32

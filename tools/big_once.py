@@ -5,7 +5,7 @@ import madrigal_b200 as mb
 from madrigal_b200 import normalize
 from synth import decoder_inputs
 dev = torch.device("cuda:0")
-N, D, L = 16384, 256, 8
+N, D, L = int(os.environ.get("BIG_N", "16384")), 256, int(os.environ.get("BIG_L", "8"))
 z, W = decoder_inputs(N, D, L, 0)
 zt, Wt = torch.from_numpy(z).to(dev), torch.from_numpy(W).to(dev)
 table = normalize.build_rank_table(zt, Wt, 16384, kind=os.environ.get("KIND", "lut"), panel=2048, precision="bf16")
