@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDG_ABI_VERSION 4
+#define MDG_ABI_VERSION 5
 
 typedef enum MdgStatus {
   MDG_OK = 0,
@@ -83,6 +83,12 @@ typedef enum MdgPairs {
                              [L, N, N] layout by scattering the tiles and adding the transpose. */
 } MdgPairs;
 int64_t mdg_packed_tiles_per_outcome(int64_t N);
+/* Host half of a packed device-to-host transfer: scatters MDG_PAIRS_PACKED_TILES tiles that have been copied to host
+   memory ([L, T, 32, 32] uint16) into the normaliser's layout out_host [L, N, N] — every rank at [i, j] and [j, i], zero
+   diagonal (the mirror step of notebooks/normalize_scores.py:67-70, applied to ranks the GPU has already computed).
+   Pure data movement on `threads` host threads (<= 0: all hardware threads); HOST pointers, no CUDA call, blocks until
+   done.  scoring.score_all_pairs_to_host uses it so that only half of the rank tensor crosses PCIe. */
+int mdg_host_mirror_tiles(const uint16_t* tiles_host, int64_t L, int64_t N, uint16_t* out_host, int32_t threads);
 
 /* Prepared per-outcome reference-quantile table for the fused rank epilogue (see mdg_rank_table_build). */
 #define MDG_RANK_BUCKET_BITS 13

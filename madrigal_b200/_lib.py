@@ -11,7 +11,7 @@ from .build import LIB_PATH
 # A/B measurements of compile-time variants: MDG_LIB_PATH points at another build of the SAME sources/ABI.
 LIB_PATH = os.environ.get("MDG_LIB_PATH", LIB_PATH)
 
-EXPECTED_ABI = 4  # MDG_ABI_VERSION of include/madrigal_b200.h these ctypes structs/signatures were written for
+EXPECTED_ABI = 5  # MDG_ABI_VERSION of include/madrigal_b200.h these ctypes structs/signatures were written for
 MDG_MAX_LAYERS = 8
 MDG_MAX_TOKENS = 32
 MDG_MAX_MLP_LINEAR = 8
@@ -69,6 +69,7 @@ SIGNATURES = {
     "mdg_rank_table_build_pwl": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mdg_rank_lookup": (c_int, [c_void_p, c_int64, POINTER(MdgRankTable), c_void_p, c_void_p]),
     "mdg_packed_tiles_per_outcome": (c_int64, [c_int64]),
+    "mdg_host_mirror_tiles": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32]),
     "mdg_pair_score_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "mdg_pair_score": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                c_int, POINTER(MdgRankTable), c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -1,6 +1,7 @@
 // C-ABI entry points of libmadrigal_b200.so (see include/madrigal_b200.h for the contract and the reference
 // symbols each entry point replaces).  Host-side glue only: argument checking, workspace carving, TMA descriptor
-// encoding and kernel launches on the caller's stream.  No allocation, no synchronisation, no CPU compute path.
+// encoding and kernel launches on the caller's stream.  No allocation, no synchronisation, no CPU compute path (the one
+// host-side routine, mdg_host_mirror_tiles in host_mirror.inl, moves ranks the GPU computed; it computes nothing).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -539,6 +540,15 @@ static int pair_score_impl(const float* z_rows, const float* z_cols, const float
         p.lower_only = 1;
         p.mirror = 1;
         p.packed = pairs == MDG_PAIRS_PACKED_TILES;
+        // measurement knob (results invalid): 1 = skip the table look-ups, 2 = skip the staging fills and stores
+        static const int dbg_epi = [] { const char* e = getenv("MDG_DEBUG_EPI"); return e ? atoi(e) : 0; }();
+        p.debug_epi = dbg_epi;
+        // long rows: evict-first hint on the rank stores (pair_score.cuh); MDG_STORE_HINT=normal|evict_first pins it
+        static const int hint_pin = [] {
+          const char* e = getenv("MDG_STORE_HINT");
+          return !e ? 0 : (strcmp(e, "evict_first") == 0 ? 2 : (strcmp(e, "normal") == 0 ? 1 : 0));
+        }();
+        p.store_evict_first = hint_pin ? (hint_pin == 2) : (Nc >= 8192);
       }
     }
     // TMA store needs 16-byte aligned base and row pitch; otherwise guarded direct stores from registers
@@ -877,6 +887,7 @@ int mdg_profile_read(float* ms_out_host, int max_records) {
 }
 
 #include "capi_fusion_fwd.inl"
+#include "host_mirror.inl"
 }  // extern "C"
 
 #include "capi_fusion.inl"

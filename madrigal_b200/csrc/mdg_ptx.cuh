@@ -113,6 +113,17 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem
                : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy encodings as used by the public CUTLASS TMA::CacheHintSm90)
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2,
+                                                  uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+               : "memory");
+}
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the smem source of all but the newest N committed store groups has been read
 template <int N>

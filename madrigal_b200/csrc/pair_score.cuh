@@ -123,6 +123,8 @@ struct PairScoreParams {
   int lower_only;  // keep only row > col (unordered pairs of one catalogue) and skip column blocks above the diagonal
   int a_reuse;     // A is shared by all outcomes (GEMM 1: z . W_l): tasks are ordered row-block-major and dealt in
                    // contiguous per-CTA ranges so that the resident A panels are loaded once per row block, not per task
+  int debug_epi;   // measurement knob of the pipelined normaliser-layout epilogue: 1 = no look-ups, 2 = no stores (invalid output)
+  int store_evict_first;  // pipelined normaliser-layout epilogue: L2 evict-first hint on the rank stores (long rows)
   int packed;      // normaliser layout without the mirror image: every 32x32 chunk with row >= col goes ONCE, as a
                    // contiguous 2 KB tile, to tile slot bi*(bi+1)/2 + bj of the outcome (MDG_PAIRS_PACKED_TILES)
 };
@@ -627,6 +629,11 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float scale = 0.f, bias = 0.f;
       const uint32_t bar_lut = sBar + 224;
       uint32_t lut_phase = 0;
+      // L2 eviction priority of the rank stores.  With long rows (N >= 8192: 32 box rows of a tile are >= 0.5 MB apart)
+      // lines that sit in L2 until capacity evicts them go out to DRAM in an order that scatters over pages; marking
+      // them evict-first drains them while their neighbours are still arriving (measured, 12 GB of output: N = 20,000
+      // 3.09 -> 2.91 ms, N = 16,384 2.91 -> 2.83 ms; N <= 6,144 unchanged, hence the threshold on the host side)
+      const uint64_t store_policy = p.store_evict_first ? kL2EvictFirst : kL2EvictNormal;
 
       // ranks of one chunk: P[hf][i][s] = (row 16hf + 8s + fr, cols 8i + fc, +1) packed as b16x2
       auto lookup_chunk = [&](const uint32_t (&v)[2][16], uint32_t (&P)[2][4][2]) {
@@ -662,7 +669,25 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // look-ups + stores of one chunk whose accumulator fragment is in v
       auto process = [&](const uint32_t (&v)[2][16], int l, int row0, int n0) {
         uint32_t P[2][4][2];
-        lookup_chunk(v, P);
+        if (p.debug_epi & 1) {  // measurement only: the store path without the look-ups
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int s2 = 0; s2 < 2; ++s2) P[hf][i][s2] = __byte_perm(v[hf][4 * i + 2 * s2], v[hf][4 * i + 2 * s2 + 1], 0x7632);
+        } else {
+          lookup_chunk(v, P);
+        }
+        if (p.debug_epi & 2) {  // measurement only: the look-ups without the store path
+          uint32_t acc = 0;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc ^= P[hf][i][0] ^ P[hf][i][1];
+          if (acc == 0x12345678u && lane == 33) st_shared_u32(ring.buf[0], acc);  // keeps the look-ups alive
+          return;
+        }
         const int bi = row0 >> 5, bj = n0 >> 5;
         const int slot_row = (bi * (bi + 1) / 2 + bj) * 32;  // packed layout: first row of this chunk's tile
         if (n0 != row0) {
@@ -676,8 +701,8 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(&tmOut2, ring.buf[0], row0, n0, l);  // [l, n0.., row0..]
-              tma_store_3d(&tmOut, ring.buf[1], n0, row0, l);
+              tma_store_3d_hint(&tmOut2, ring.buf[0], row0, n0, l, store_policy);  // [l, n0.., row0..]
+              tma_store_3d_hint(&tmOut, ring.buf[1], n0, row0, l, store_policy);
               tma_store_commit();
             }
           } else {

@@ -145,6 +145,28 @@ def unpack_packed_tiles(packed, N: int):
     return full.view(torch.uint16)
 
 
+def mirror_packed_tiles_host(packed: torch.Tensor, N: int, out: Optional[torch.Tensor] = None,
+                             threads: int = 0) -> torch.Tensor:
+    """Host half of a packed device-to-host transfer (mdg_host_mirror_tiles): packed rank tiles that already sit in
+    HOST memory ([L, T, 32, 32] uint16) -> the normaliser's layout [L, N, N] (rank at [i, j] and [j, i], zero diagonal;
+    normalize_scores.py:67-70) on `threads` host threads (0: all).  Pure data movement — the ranks were computed on the
+    GPU; this only spares PCIe the mirror image.  Same result as `unpack_packed_tiles`, which is the slow pure-torch
+    statement of the layout."""
+    if packed.is_cuda or packed.dtype != torch.uint16 or packed.dim() != 4 or tuple(packed.shape[2:]) != (32, 32):
+        raise ValueError("packed must be a host uint16 tensor [L, T, 32, 32]")
+    L, T = packed.shape[0], packed.shape[1]
+    if T != packed_tiles_per_outcome(N):
+        raise ValueError("tile count does not match N")
+    packed = packed.contiguous()
+    if out is None:
+        out = torch.empty((L, N, N), dtype=torch.uint16)
+    if out.is_cuda or out.dtype != torch.uint16 or tuple(out.shape) != (L, N, N) or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous host uint16 tensor {(L, N, N)}")
+    _lib.check(_lib.lib().mdg_host_mirror_tiles(packed.data_ptr(), L, N, out.data_ptr(), int(threads)),
+               "mdg_host_mirror_tiles")
+    return out
+
+
 class PreparedDecoder:
     """The decoder weights [L, D, D] converted ONCE to the tensor-core operand form (mdg_pair_prepare).  The reference
     re-reads `decoder.weight` through the Symmetric parametrisation on every call (models.py:537-547, 922); a scoring

@@ -141,11 +141,21 @@ def score_row_block(z: torch.Tensor, weight: torch.Tensor, rank: int, world_size
 
 def score_all_pairs_to_host(z: torch.Tensor, weight: torch.Tensor, out_host: torch.Tensor, *, out: str = "rank",
                             table: Optional[RankTable] = None, precision: str = "bf16", chunk: int = 10,
-                            normalize: bool = False, symmetric: bool = False, packed: bool = False) -> torch.Tensor:
+                            normalize: bool = False, symmetric: bool = False, packed: bool = False,
+                            host_mirror: bool = False, mirror_threads: int = 0) -> torch.Tensor:
     """predict.py:420-429 call pattern: outcomes in chunks of `chunk`, each chunk scored on the GPU and copied into
     `out_host` ([L, N, N], pinned for overlap).  Double-buffered: copy of chunk c overlaps compute of chunk c+1.
     packed=True (rank output): the device writes and the host receives the packed lower-triangular tiles
-    ([L, T, 32, 32], half the PCIe volume); `decoder.unpack_packed_tiles` rebuilds [L, N, N] on the host when needed."""
+    ([L, T, 32, 32], half the PCIe volume); `decoder.unpack_packed_tiles` rebuilds [L, N, N] on the host when needed.
+    host_mirror=True (symmetric rank output): `out_host` is still the drop-in [L, N, N] array, but only the packed tiles
+    cross PCIe (into a cached pinned staging buffer) and `mdg_host_mirror_tiles` writes the mirror image on
+    `mirror_threads` host threads while the next chunk is computed and copied — worth it where the host's memory
+    system is faster than its PCIe link."""
+    if host_mirror:
+        if out != "rank" or not symmetric or packed:
+            raise ValueError("host_mirror=True needs out='rank', symmetric=True, packed=False")
+        return _score_all_pairs_to_host_mirrored(z, weight, out_host, table=table, precision=precision, chunk=chunk,
+                                                 normalize=normalize, threads=mirror_threads)
     L, N = weight.shape[0], z.shape[0]
     dtype = _OUT_DTYPE[out]
     from .decoder import packed_tiles_per_outcome
@@ -179,6 +189,63 @@ def score_all_pairs_to_host(z: torch.Tensor, weight: torch.Tensor, out_host: tor
     for ev in done_copy:
         if ev is not None:
             ev.synchronize()
+    return out_host
+
+
+_pinned_staging = {}
+
+
+def _pinned(shape, dtype, slot: int) -> torch.Tensor:
+    """Cached pinned staging buffers (page-locking hundreds of MB costs tens of ms: never inside a scoring call twice)."""
+    key = (tuple(shape), dtype, slot)
+    if key not in _pinned_staging:
+        _pinned_staging[key] = torch.empty(shape, dtype=dtype).pin_memory()
+    return _pinned_staging[key]
+
+
+def _score_all_pairs_to_host_mirrored(z, weight, out_host, *, table, precision, chunk, normalize, threads):
+    """score_all_pairs_to_host(host_mirror=True): kernel c+1 and the packed copy of chunk c+1 run on the GPU while the
+    host threads mirror chunk c into `out_host`."""
+    from .decoder import mirror_packed_tiles_host, packed_tiles_per_outcome
+    L, N = weight.shape[0], z.shape[0]
+    if tuple(out_host.shape) != (L, N, N) or out_host.dtype != torch.uint16 or out_host.is_cuda \
+            or not out_host.is_contiguous():
+        raise ValueError(f"out_host must be a contiguous host uint16 tensor {(L, N, N)}")
+    dev = z.device
+    T = packed_tiles_per_outcome(N)
+    n = min(chunk, L) if L > 0 else 1
+    compute = torch.cuda.current_stream(dev)
+    copy = _copy_stream(dev)
+    dbufs = [torch.empty((n, T, 32, 32), dtype=torch.uint16, device=dev) for _ in range(2)]
+    hbufs = [_pinned((n, T, 32, 32), torch.uint16, b) for b in range(2)]
+    pending = [None, None]  # (copy-done event, l0, l1) per buffer pair
+
+    def drain(b):
+        if pending[b] is not None:
+            ev, a0, a1 = pending[b]
+            ev.synchronize()
+            mirror_packed_tiles_host(hbufs[b][: a1 - a0], N, out=out_host[a0:a1], threads=threads)
+            pending[b] = None
+
+    for ci, l0 in enumerate(range(0, L, chunk)):
+        l1 = min(l0 + chunk, L)
+        b = ci & 1
+        drain(b)  # chunk ci - 2 is on the host and mirrored: both buffers of pair b are free (host-synchronous)
+        dst = dbufs[b][: l1 - l0]
+        pair_score(z, z, weight[l0:l1], precision=precision, out="rank", table=table, table_offset=l0,
+                   normalize=normalize, out_tensor=dst, symmetric=True, packed=True)
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        with torch.cuda.stream(copy):
+            copy.wait_event(ready)
+            hbufs[b][: l1 - l0].copy_(dst, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        pending[b] = (ev, l0, l1)
+    nch = (L + chunk - 1) // chunk
+    drain(nch & 1)        # the older of the two chunks still in flight first
+    drain((nch & 1) ^ 1)
+    compute.wait_stream(copy)
     return out_host
 
 

@@ -32,7 +32,7 @@ def test_header_symbols_all_exported(handle):
 
 
 def test_abi_version_and_error_string(handle):
-    assert handle.mdg_abi_version() == _lib.EXPECTED_ABI == 4
+    assert handle.mdg_abi_version() == _lib.EXPECTED_ABI == 5
     assert isinstance(handle.mdg_last_error(), bytes)
 
 
@@ -119,6 +119,10 @@ def test_more_entry_points_validate_arguments_first(handle):
     assert handle.mdg_doser_mlp(p, p, 4, 3, 512, 2, p, p, p, p, p, p, p, None) == 2 and b"width" in handle.mdg_last_error()
     assert handle.mdg_doser_mlp(p, p, 4, 3, 8, 2, p, p, None, None, p, p, p, None) == 1   # depth 2 needs the hidden layer
     assert handle.mdg_doser_mlp(None, None, 0, 3, 8, 1, None, None, None, None, None, None, None, None) == 0  # empty batch
+    # host half of the packed transfer (ABI 5)
+    assert handle.mdg_host_mirror_tiles(None, 1, 32, None, 1) == 1 and b"NULL" in handle.mdg_last_error()
+    assert handle.mdg_host_mirror_tiles(p, -1, 32, p, 1) == 1
+    assert handle.mdg_host_mirror_tiles(p, 0, 32, p, 1) == 0      # no outcomes: no-op
 
 
 def test_stale_library_abi_is_rejected(monkeypatch):
@@ -127,7 +131,7 @@ def test_stale_library_abi_is_rejected(monkeypatch):
     monkeypatch.setattr(_lib, "EXPECTED_ABI", 999)
     with pytest.raises(RuntimeError, match="ABI version"):
         _lib.lib()
-    monkeypatch.setattr(_lib, "EXPECTED_ABI", 4)
+    monkeypatch.setattr(_lib, "EXPECTED_ABI", 5)
     monkeypatch.setattr(_lib, "_LIB", None)
     assert _lib.lib() is not None
 
@@ -151,3 +155,39 @@ def test_non_tx_modalities_is_a_constructor_argument():
         assert sm.shape == (T, T) and bool(sm[0, T - 1]) and bool(sm[T - 1, 0]) and not bool(sm[n, 0])
     with pytest.raises(ValueError):
         mb.FusionEncoder(64, 0, 0.0, hp, proj, non_tx_modalities=["kg", "str", "cv"])
+
+
+@pytest.mark.parametrize("N", [1, 31, 32, 33, 64, 100, 257, 1000])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_host_mirror_of_packed_tiles_equals_the_layout_definition(N, threads):
+    """mdg_host_mirror_tiles (the host half of score_all_pairs_to_host(host_mirror=True): packed lower-triangular rank
+    tiles -> the normaliser's [L, N, N] layout, normalize_scores.py:67-70) against `unpack_packed_tiles`, the plain
+    statement of MDG_PAIRS_PACKED_TILES: ragged N, garbage beyond N inside the edge tiles, zero diagonal, both the
+    streaming-store path (N % 32 == 0) and the plain one, guard bands around the output."""
+    import numpy as np
+    import torch
+    from madrigal_b200 import decoder
+    L = 3
+    nb = (N + 31) // 32
+    T = nb * (nb + 1) // 2
+    rng = np.random.default_rng(N)
+    full = rng.integers(1, 65535, size=(L, nb * 32, nb * 32), dtype=np.uint16)   # incl. garbage in rows/cols >= N
+    packed = np.zeros((L, T, 32, 32), dtype=np.uint16)
+    t = 0
+    for bi in range(nb):
+        for bj in range(bi + 1):
+            tile = full[:, 32 * bi:32 * bi + 32, 32 * bj:32 * bj + 32].copy()
+            packed[:, t] = np.tril(tile, -1) if bi == bj else tile
+            t += 1
+    want = decoder.unpack_packed_tiles(packed, N)
+    assert np.array_equal(want, np.swapaxes(want, 1, 2)) and not want[:, np.arange(N), np.arange(N)].any()
+    guard = 512
+    flat = torch.full((L * N * N + 2 * guard,), 0x5A5A, dtype=torch.int16)
+    out = flat[guard:guard + L * N * N].view(torch.uint16).view(L, N, N)
+    got = decoder.mirror_packed_tiles_host(torch.from_numpy(packed.view(np.int16)).view(torch.uint16), N, out=out,
+                                           threads=threads)
+    assert got.data_ptr() == out.data_ptr()
+    assert np.array_equal(got.view(torch.int16).numpy().view(np.uint16), want)
+    assert bool((flat[:guard] == 0x5A5A).all()) and bool((flat[guard + L * N * N:] == 0x5A5A).all())
+    with pytest.raises(ValueError):
+        decoder.mirror_packed_tiles_host(torch.zeros((L, T + 1, 32, 32), dtype=torch.int16).view(torch.uint16), N)

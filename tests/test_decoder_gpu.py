@@ -583,6 +583,15 @@ def test_packed_tiles_layout(mb, cuda_device, N, D, L, Q):
     out_host = torch.empty(tuple(packed.shape), dtype=torch.uint16).pin_memory()
     scoring.score_all_pairs_to_host(zt, Wt, out_host, out="rank", table=table, precision="bf16", chunk=2, packed=True)
     assert np.array_equal(unpack_packed_tiles(out_host.numpy(), N), full.cpu().numpy())
+    # the drop-in [L, N, N] host array with only the packed tiles crossing PCIe (host threads write the mirror image)
+    for pinned in (True, False):
+        mirrored = torch.full((L, N, N), 0x7777, dtype=torch.int16).view(torch.uint16)
+        mirrored = mirrored.pin_memory() if pinned else mirrored
+        scoring.score_all_pairs_to_host(zt, Wt, mirrored, out="rank", table=table, precision="bf16", chunk=2,
+                                        symmetric=True, host_mirror=True, mirror_threads=3)
+        assert np.array_equal(mirrored.view(torch.int16).numpy().view(np.uint16), full.cpu().numpy())
+    with pytest.raises(ValueError):
+        scoring.score_all_pairs_to_host(zt, Wt, mirrored, out="rank", table=table, symmetric=False, host_mirror=True)
 
 
 @pytest.mark.parametrize("N,D,L", [(1000, 128, 2), (296, 64, 3), (33, 128, 1), (520, 256, 2)])
