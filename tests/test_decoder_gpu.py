@@ -563,6 +563,24 @@ def test_pipelined_normaliser_epilogue_matches_legacy_and_oracle(mb, cuda_device
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("N", [8192, 8200])
+def test_long_row_catalogue_takes_the_evict_first_store_path(mb, cuda_device, N):
+    """N >= 8192: the normaliser-layout rank stores carry the L2 evict-first hint.  Same contract: every
+    rank equals searchsorted over the dense logits (checked on the device), mirrored, zero diagonal; also a ragged row
+    length (N % 32 != 0: clipped boxes)."""
+    from madrigal_b200 import normalize
+    D, L, Q = 64, 1, 2048
+    z, W = synth.decoder_inputs(N, D, L, seed=N)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    table = normalize.build_rank_table(zt, Wt, Q, precision="bf16", panel=1024)
+    lg = mb.pair_score(zt, zt, Wt, precision="bf16", out="logit")
+    exp = torch.searchsorted(table.thresholds[0].contiguous(), lg[0].contiguous(), right=True).to(torch.int32)
+    exp = torch.tril(exp, -1)
+    exp = exp + exp.T
+    got = mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, symmetric=True)[0].to(torch.int32)
+    assert torch.equal(got, exp)
+
+
 @pytest.mark.parametrize("N,D,L,Q", [(512, 256, 3, 4096), (1000, 128, 2, 2048), (296, 64, 2, 512), (33, 128, 1, 256)])
 def test_packed_tiles_layout(mb, cuda_device, N, D, L, Q):
     """MDG_PAIRS_PACKED_TILES: the normaliser-layout ranks without the mirror image, as 32x32 lower-triangular tiles;
