@@ -248,14 +248,14 @@ struct StagingRing2 {
   uint32_t buf[2];
   int cur;
   __device__ __forceinline__ uint32_t acquire(int lane) {  // the store before the previous one has read its tile
-    if (lane == 0) tma_store_wait_read<1>();
+    if (elect_one()) tma_store_wait_read<1>();
     __syncwarp();
     return buf[cur];
   }
   __device__ __forceinline__ void commit(const CUtensorMap* tm, int c0, int c1, int c2, int lane) {
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
+    if (elect_one()) {
       tma_store_3d(tm, buf[cur], c0, c1, c2);
       tma_store_commit();
     }
@@ -694,13 +694,13 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (!p.packed) {
             // both tiles of the chunk under ONE proxy fence and ONE bulk group: the previous chunk's group was
             // committed before this chunk's 1024 look-ups, so waiting for its reads costs nothing here
-            if (lane == 0) tma_store_wait_read<0>();
+            if (elect_one()) tma_store_wait_read<0>();
             __syncwarp();
             fill_trans(ring.buf[0], P);
             fill_plain(ring.buf[1], P);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
               tma_store_3d_hint(&tmOut2, ring.buf[0], row0, n0, l, store_policy);  // [l, n0.., row0..]
               tma_store_3d_hint(&tmOut, ring.buf[1], n0, row0, l, store_policy);
               tma_store_commit();
@@ -728,7 +728,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ring.commit(&tmOut, 0, slot_row, l, lane);
           } else {
             // both staging tiles must be free: lower triangle in one, its transpose in the other, OR, one store
-            if (lane == 0) tma_store_wait_read<0>();
+            if (elect_one()) tma_store_wait_read<0>();
             __syncwarp();
             const uint32_t d = ring.buf[ring.cur], t = ring.buf[ring.cur ^ 1];
             fill_plain(d, P);
@@ -792,7 +792,7 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_t_empty(acc_stage));
+            if (elect_one()) mbar_arrive(bar_t_empty(acc_stage));
             acc_stage ^= 1;
             if (acc_stage == 0) acc_phase ^= 1;
             open = false;

@@ -563,6 +563,28 @@ def test_pipelined_normaliser_epilogue_matches_legacy_and_oracle(mb, cuda_device
     assert np.array_equal(got, ref)
 
 
+def test_config3_catalogue_size_one_outcome(mb, cuda_device):
+    """BASELINE configs[3]'s catalogue size on one GPU: 20,000 drugs (row pitch 40,000 B: not a multiple of 128, 79 row
+    blocks with a 32-row remainder, 157 column blocks), ONE outcome.  Every one of the 4e8 uint16 ranks equals
+    searchsorted over the dense logits (compared on the device), mirrored, zero diagonal; packed tiles agree."""
+    from madrigal_b200 import normalize
+    from madrigal_b200.decoder import unpack_packed_tiles
+    N, D, Q = 20000, 256, 16384
+    z, W = synth.decoder_inputs(N, D, 1, seed=3)
+    zt, Wt = gpu(z, cuda_device), gpu(W, cuda_device)
+    table = normalize.build_rank_table(zt, Wt, Q, precision="bf16", panel=2048)
+    lg = mb.pair_score(zt, zt, Wt, precision="bf16", out="logit")
+    exp = torch.searchsorted(table.thresholds[0].contiguous(), lg[0].contiguous(), right=True).to(torch.int16)
+    del lg
+    exp = torch.tril(exp, -1)
+    exp = exp + exp.T
+    got = mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, symmetric=True)
+    assert torch.equal(got[0].view(torch.int16), exp)
+    packed = mb.pair_score(zt, zt, Wt, precision="bf16", out="rank", table=table, packed=True)
+    del exp
+    assert torch.equal(unpack_packed_tiles(packed, N).view(torch.int16), got.view(torch.int16))
+
+
 @pytest.mark.parametrize("N", [8192, 8200])
 def test_long_row_catalogue_takes_the_evict_first_store_path(mb, cuda_device, N):
     """N >= 8192: the normaliser-layout rank stores carry the L2 evict-first hint.  Same contract: every
