@@ -28,6 +28,20 @@ def row_shard(N: int, rank: int, world_size: int) -> Tuple[int, int]:
     return outcome_shard(N, rank, world_size)
 
 
+def encoder_is_replicated(n_drugs: int, tokens_per_drug: int, world_size: int, device=None) -> bool:
+    """Multi-GPU plan of the encoder stage.  The fused encoder works on 128-token-row tiles, one per SM:
+    a catalogue that fits ONE wave (tiles <= SMs) takes one tile latency whether a rank encodes all of it or only its row
+    shard, so every rank encodes the whole catalogue and the exchange of z disappears from the step; larger catalogues
+    are row-sharded and replicated by the one exchange (`PeerAllGather` / `all_gather_embeddings`)."""
+    if world_size <= 1:
+        return True
+    sms = 148
+    if device is not None and torch.device(device).type == "cuda":
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+    drugs_per_tile = max(1, 128 // max(1, tokens_per_drug))
+    return (n_drugs + drugs_per_tile - 1) // drugs_per_tile <= sms
+
+
 def all_gather_embeddings(z_shard: torch.Tensor, N: int, group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The path's ONLY collective: replicate the fused-embedding table [N, D] from per-rank row shards.
 

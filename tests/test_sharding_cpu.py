@@ -145,3 +145,15 @@ def test_bind_host_thread_to_gpu_is_a_noop_without_nvml_affinity():
     elif res is not None:  # a host with affinity information: the new set is a subset of the old one; restore
         assert res[1] <= res[0]
         os.sched_setaffinity(0, res[0])
+
+
+def test_encoder_plan_replicates_single_wave_catalogues():
+    """scoring.encoder_is_replicated: one wave of 128-row encoder tiles (<= 148 SMs) -> every rank encodes the whole
+    catalogue and the step has no exchange; more tiles -> row shards + the one all-gather of z."""
+    from madrigal_b200 import scoring
+    assert scoring.encoder_is_replicated(4096, 4, 8)          # BASELINE configs[2]: 128 tiles
+    assert scoring.encoder_is_replicated(4736, 4, 2)          # exactly 148 tiles
+    assert not scoring.encoder_is_replicated(4737, 4, 2)
+    assert not scoring.encoder_is_replicated(20000, 4, 8)     # configs[3]: 625 tiles, sharded
+    assert not scoring.encoder_is_replicated(4096, 23, 4)     # production T = 23: 5 drugs per tile
+    assert scoring.encoder_is_replicated(10 ** 6, 4, 1)       # one rank: nothing to exchange
