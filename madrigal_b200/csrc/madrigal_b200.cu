@@ -167,7 +167,7 @@ PairWorkspace carve_pair_ws(void* ws, int64_t Nr, int64_t Nc, int64_t D, int64_t
 template <int EPI, int NE>
 int launch_pair_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                          const CUtensorMap& tmOut2, const mdg::PairScoreParams& p, int grid, cudaStream_t stream) {
-  using SM = mdg::PairSmem<NE, mdg::epi_staging_bufs(EPI, NE)>;
+  using SM = mdg::PairSmem<NE, mdg::epi_staging_bufs(EPI, NE), mdg::epi_needs_aux32(EPI)>;
   static std::once_flag attr_once[kMaxDevices];
   static cudaError_t attr_err[kMaxDevices];
   int dev = 0;

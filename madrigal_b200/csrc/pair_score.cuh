@@ -51,6 +51,8 @@ __host__ __device__ constexpr bool epi_is_pwl(int e) { return e == EPI_RANK_U16_
 // The normaliser-layout epilogue with 8 epilogue warps is the software-pipelined one (two staging tiles per warp).
 __host__ __device__ constexpr bool epi_is_pipelined_mirror(int e, int ne) { return epi_is_mirror(e) && ne == 8; }
 __host__ __device__ constexpr int epi_staging_bufs(int e, int ne) { return epi_is_pipelined_mirror(e, ne) ? 2 : 1; }
+// does the instance use the 32 KB auxiliary shared-memory region (see PairSmem)?
+__host__ __device__ constexpr bool epi_needs_aux32(int e) { return epi_is_rank(e) || e == EPI_BF16_SPLIT; }
 // Accumulator chunks (32 columns each) fetched per tcgen05.wait::ld by the row-per-lane epilogues.  Measured (round
 // 2, B200): fetching the warp's whole strip at once (4 chunks, stage released before the stores) does NOT pay outside
 // the top-k epilogue — fp32 logits 1.24 vs 1.18 ms (the per-chunk loop overlaps the next TMEM load with the previous
@@ -61,15 +63,19 @@ __host__ __device__ constexpr int epi_burst(int e, int ne) {
 
 // Shared-memory plan for a kernel instance with NE epilogue warps (staging is per warp, so more epilogue warps
 // trade one B stage for staging space).
-template <int NE, int NBUF = 1>
+// kAux32: the instance needs the 32 KB auxiliary region behind the staging tiles (rank table; GEMM 1's wide 4 KB tiles).
+// The other epilogues only keep a second 2 KB staging tile per warp there, which leaves room for a FOURTH B stage with 8
+// epilogue warps: the B ring is what bounds the tensor-bound instances (a stage comes back ~1,000 cycles after it was
+// freed; 3 stages of 256 MMA cycles each keep the tensor pipe 61 % busy, 4 stages 81 %).
+template <int NE, int NBUF = 1, bool kAux32 = true>
 struct PairSmem {
-  static constexpr int kBStages = (NE * NBUF > 8) ? 2 : 3;
+  static constexpr int kBStages = (NE * NBUF > 8) ? 2 : ((kAux32 || NE > 8) ? 3 : 4);
   static constexpr int kA = 0;
   static constexpr int kB = kA + kMaxAPanels * kPanelBytes;
   static constexpr int kStaging = kB + kBStages * kPanelBytes;
   static constexpr int kLut = kStaging + NE * NBUF * kStagingBytesPerWarp;
-  static constexpr int kBar = kLut + kRankLutEntries * 4;
-  static constexpr int kTotal = kBar + 512;  // mbarriers, TMEM slot, dynamic-scheduler task ring, per-warp residual barriers
+  static constexpr int kBar = kLut + (kAux32 ? kRankLutEntries * 4 : NE * kStagingBytesPerWarp);
+  static constexpr int kTotal = kBar + 640;  // mbarriers, TMEM slot, dynamic-scheduler task ring, per-warp residual barriers, B ring
   static constexpr int kBytes = kTotal + 1024;  // + slack for manual 1024-byte alignment
   static constexpr int kThreads = (kFirstEpiWarp + NE) * 32;
   static_assert(kBytes <= 232448, "exceeds 227 KB of shared memory per CTA");
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(PairSmem<NE>::kThreads, 1)
 pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                   const __grid_constant__ PairScoreParams p) {
-  using SM = PairSmem<NE, epi_staging_bufs(EPI, NE)>;
+  using SM = PairSmem<NE, epi_staging_bufs(EPI, NE), epi_needs_aux32(EPI)>;
   constexpr int kBStages = SM::kBStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -278,8 +284,8 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t sA = base + SM::kA, sB = base + SM::kB, sStaging = base + SM::kStaging, sLut = base + SM::kLut,
                  sBar = base + SM::kBar;
   const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8;
-  auto bar_b_full = [&](int i) { return sBar + 16 + 8 * i; };
-  auto bar_b_empty = [&](int i) { return sBar + 40 + 8 * i; };
+  auto bar_b_full = [&](int i) { return sBar + 512 + 8 * i; };   // up to 4 stages each (behind the residual barriers)
+  auto bar_b_empty = [&](int i) { return sBar + 544 + 8 * i; };
   auto bar_t_full = [&](int i) { return sBar + 64 + 8 * i; };
   auto bar_t_empty = [&](int i) { return sBar + 80 + 8 * i; };
   const uint32_t tmem_slot = sBar + 96;
