@@ -255,6 +255,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same with the descriptors given as (low word, shared high word): the low word carries the start address, so
+// stepping through panels / K slices is 32-bit arithmetic (the 64-bit form made the single issuing thread spend ~60
+// uniform-datapath instructions per B panel on descriptor composition: ~690 cycles against 256 cycles of tensor work).
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
+      : "memory");
+}
 // Make the mbarrier track completion of all tcgen05 ops previously issued by this thread
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

@@ -485,6 +485,8 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       auto desc_of = [&](uint32_t smem_addr) {
         return desc_hi | static_cast<uint64_t>(desc_lo0 | ((smem_addr & 0x3FFFFu) >> 4));
       };
+      const uint32_t desc_hi32 = static_cast<uint32_t>(desc_hi >> 32);
+      const uint32_t a_lo0 = desc_lo0 | ((sA & 0x3FFFFu) >> 4), b_lo0 = desc_lo0 | ((sB & 0x3FFFFu) >> 4);
       int stage = 0;
       uint32_t b_phase = 0;
       int acc_stage = 0;
@@ -547,45 +549,41 @@ pair_score_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int kbi = 0; kbi < kb_b; ++kbi) {
             mbar_wait(bar_b_full(stage), b_phase, 5);
             tc_fence_after_sync();
-            const uint64_t bdesc = desc_of(sB + stage * kPanelBytes);
-            // (A panel, accumulator, overwrite?) for up to two MMA groups on this B panel
-            int pan0, pan1, acc1;
-            bool two, first0, first1;
-            if (p.nterm == 1) {  // one bf16 term: msub row sub-tiles share the B panel, one accumulator each
-              pan0 = kbi;
-              pan1 = kb + kbi;
-              acc1 = 1;
-              two = p.msub == 2;
-              first0 = first1 = (kbi == 0);
-            } else if (kbi < kb) {  // B = hi:  A_hi[k] then A_lo[k], same accumulator
-              pan0 = kbi;
-              pan1 = kb + kbi;
-              acc1 = 0;
-              two = true;
-              first0 = (kbi == 0);
-              first1 = false;
-            } else {  // B = lo:  A_hi[k]
-              pan0 = kbi - kb;
-              pan1 = 0;
-              acc1 = 0;
-              two = false;
-              first0 = first1 = false;
-            }
-            const uint64_t adesc0 = desc_of(sA + pan0 * kPanelBytes);
-            const uint64_t adesc1 = desc_of(sA + pan1 * kPanelBytes);
-            const uint32_t d1 = d0 + static_cast<uint32_t>(acc1 * kBN);
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < kBK / kUmmaK; ++k)
-                umma_bf16(d0, adesc0 + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                          (first0 && k == 0) ? 0u : 1u);
-              if (two) {
+            // descriptor low words (start address >> 4 in the low 14 bits): one panel = kPanelBytes >> 4 = 1024 units
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(stage) * (kPanelBytes >> 4);
+            if (p.nterm == 1) {
+              // one bf16 term: msub row sub-tiles share the B panel, one accumulator each
+              const uint32_t a0 = a_lo0 + static_cast<uint32_t>(kbi) * (kPanelBytes >> 4);
+              const uint32_t a1 = a0 + static_cast<uint32_t>(kb) * (kPanelBytes >> 4);
+              const uint32_t acc = kbi == 0 ? 0u : 1u;
+              if (elect_one()) {
+                umma_bf16_lo(d0, a0, b_lo, desc_hi32, idesc, acc);
+                umma_bf16_lo(d0, a0 + 2, b_lo + 2, desc_hi32, idesc, 1u);
+                umma_bf16_lo(d0, a0 + 4, b_lo + 4, desc_hi32, idesc, 1u);
+                umma_bf16_lo(d0, a0 + 6, b_lo + 6, desc_hi32, idesc, 1u);
+                if (p.msub == 2) {
+                  umma_bf16_lo(d0 + kBN, a1, b_lo, desc_hi32, idesc, acc);
+                  umma_bf16_lo(d0 + kBN, a1 + 2, b_lo + 2, desc_hi32, idesc, 1u);
+                  umma_bf16_lo(d0 + kBN, a1 + 4, b_lo + 4, desc_hi32, idesc, 1u);
+                  umma_bf16_lo(d0 + kBN, a1 + 6, b_lo + 6, desc_hi32, idesc, 1u);
+                }
+                umma_commit(bar_b_empty(stage));  // frees this B stage once the MMAs above have read it
+              }
+            } else {
+              // bf16x3: B = hi -> A_hi[k] then A_lo[k]; B = lo -> A_hi[k]; all into the same accumulator
+              const bool b_is_hi = kbi < kb;
+              const uint32_t a0 = a_lo0 + static_cast<uint32_t>(b_is_hi ? kbi : kbi - kb) * (kPanelBytes >> 4);
+              const uint32_t a1 = a0 + static_cast<uint32_t>(kb) * (kPanelBytes >> 4);
+              if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < kBK / kUmmaK; ++k)
-                  umma_bf16(d1, adesc1 + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                            (first1 && k == 0) ? 0u : 1u);
+                  umma_bf16_lo(d0, a0 + 2 * k, b_lo + 2 * k, desc_hi32, idesc, (kbi == 0 && k == 0) ? 0u : 1u);
+                if (b_is_hi) {
+#pragma unroll
+                  for (int k = 0; k < kBK / kUmmaK; ++k) umma_bf16_lo(d0, a1 + 2 * k, b_lo + 2 * k, desc_hi32, idesc, 1u);
+                }
+                umma_commit(bar_b_empty(stage));
               }
-              umma_commit(bar_b_empty(stage));  // frees this B stage once the MMAs above have read it
             }
             __syncwarp();
             if (++stage == kBStages) {
